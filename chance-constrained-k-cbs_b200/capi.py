@@ -1,0 +1,380 @@
+"""ctypes binding of libcck_b200.so (include/cck_b200.h) + a thin numpy/torch-friendly mirror
+of the reference's plugin objects for this path.
+
+This module is plumbing: all arithmetic happens in the CUDA library.  It never imports the
+CPU oracle; when the shared library is missing or no sm_100 GPU is present every compute call
+raises (there is no fallback).
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_PKG, "libcck_b200.so")
+_ROOT = os.path.dirname(_PKG)
+
+OK, ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_NODEVICE = 0, 1, 2, 3, 4
+MODEL_LINEAR2D, MODEL_UNICYCLE = 0, 1
+SVC_BLACKMORE, SVC_ADAPTIVE, SVC_CHISQUARED = 0, 1, 2
+PVC_BLACKMORE, PVC_BOUNDINGBOX, PVC_CHISQUARED, PVC_ADAPTIVE_BLACKMORE, PVC_ADAPTIVE_BOUNDINGBOX = range(5)
+FLAG_FULL, FLAG_CONS_OK, FLAG_GOAL = 1, 2, 4
+
+
+class CckError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"cck_b200 error {code}: {msg}")
+        self.code = code
+
+
+class ModelParams(C.Structure):
+    _fields_ = [("model", C.c_int32), ("dim", C.c_int32), ("dt", C.c_double),
+                ("lin_Q", C.c_double * 4), ("lin_R", C.c_double * 4), ("lin_Acl", C.c_double * 4),
+                ("uni_F", C.c_double * 16), ("uni_Acl", C.c_double * 16), ("uni_Q", C.c_double * 16), ("uni_R", C.c_double * 16),
+                ("uni_gains", C.c_double * 8), ("uni_acc", C.c_double * 2), ("uni_turn", C.c_double * 2)]
+
+
+class SvcParams(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("dim", C.c_int32), ("low", C.c_double * 4), ("high", C.c_double * 4),
+                ("erf_inv_result", C.c_double), ("p_collision", C.c_double), ("sc", C.c_double), ("max_rad", C.c_double)]
+
+
+class PvcParams(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("k", C.c_int32), ("dim", C.c_int32), ("reserved", C.c_int32),
+                ("c_pair", C.c_double), ("p_coll_agnts", C.c_double), ("sc", C.c_double),
+                ("radii", C.POINTER(C.c_double)), ("pair_A", C.POINTER(C.c_double)), ("pair_B", C.POINTER(C.c_double)),
+                ("map_order", C.POINTER(C.c_int32))]
+
+
+class ConflictRun(C.Structure):
+    _fields_ = [("a", C.c_int32), ("b", C.c_int32), ("first_step", C.c_int32), ("run_len", C.c_int32)]
+
+
+class GoalParams(C.Structure):
+    _fields_ = [("gx", C.c_double), ("gy", C.c_double), ("threshold", C.c_double), ("sc", C.c_double)]
+
+
+# every symbol include/cck_b200.h declares (tests check the library exports all of them)
+SYMBOLS = [
+    "cck_ctx_create", "cck_ctx_destroy", "cck_last_error", "cck_ctx_synchronize", "cck_num_sms", "cck_launch_count",
+    "cck_model_params_default", "cck_set_model", "cck_set_obstacles", "cck_set_pvc",
+    "cck_erf_inv", "cck_chi2_quantile_2dof", "cck_split_risk", "cck_rect_robot_bounding_radius",
+    "cck_build_obstacle_tables", "cck_build_pair_halfplanes",
+    "cck_propagate", "cck_propagate_dev", "cck_is_valid", "cck_is_valid_dev",
+    "cck_propagate_while_valid", "cck_propagate_while_valid_dev",
+    "cck_validate_plan", "cck_validate_plan_dev",
+    "cck_set_constraints", "cck_satisfies_constraints", "cck_satisfies_constraints_dev",
+    "cck_expand_batch", "cck_expand_batch_dev", "cck_rollout_summary_dev", "cck_measure_fp64_peak",
+]
+
+
+def build(force=False, verbose=False):
+    """Compile libcck_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
+    src = [os.path.join(_PKG, "csrc", f) for f in ("cck_b200.cu", "cck_kernels.cuh", "cck_device.cuh")]
+    src.append(os.path.join(_ROOT, "include", "cck_b200.h"))
+    if not force and os.path.exists(_SO) and all(os.path.getmtime(_SO) >= os.path.getmtime(s) for s in src):
+        return _SO
+    out = subprocess.run(["make", "-C", os.path.join(_PKG, "csrc"), "-B"], capture_output=True, text=True)
+    if verbose or out.returncode != 0:
+        print(out.stdout[-4000:], out.stderr[-4000:])
+    if out.returncode != 0:
+        raise RuntimeError("nvcc build of libcck_b200.so failed")
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    """Load the shared library; raises loudly if it is missing (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_SO):
+        raise CckError(ERR_NODEVICE, f"{_SO} is missing: run __graft_entry__.build() (nvcc); there is no CPU fallback")
+    L = C.CDLL(_SO)
+    dp, ip, vp = C.POINTER(C.c_double), C.POINTER(C.c_int32), C.c_void_p
+    u8p = C.POINTER(C.c_uint8)
+    i64 = C.c_int64
+    L.cck_ctx_create.argtypes = [C.c_int, C.POINTER(vp)]
+    L.cck_ctx_destroy.argtypes = [vp]
+    L.cck_last_error.restype = C.c_char_p
+    L.cck_last_error.argtypes = [vp]
+    L.cck_ctx_synchronize.argtypes = [vp]
+    L.cck_num_sms.argtypes = [vp]
+    L.cck_launch_count.restype = i64
+    L.cck_launch_count.argtypes = [vp]
+    L.cck_model_params_default.argtypes = [C.c_int, C.c_double, C.POINTER(ModelParams)]
+    L.cck_set_model.argtypes = [vp, C.POINTER(ModelParams)]
+    L.cck_set_obstacles.argtypes = [vp, C.POINTER(SvcParams), vp, vp, vp, vp, C.c_int]
+    L.cck_set_pvc.argtypes = [vp, C.POINTER(PvcParams)]
+    L.cck_erf_inv.restype = C.c_double
+    L.cck_erf_inv.argtypes = [C.c_double]
+    L.cck_chi2_quantile_2dof.restype = C.c_double
+    L.cck_chi2_quantile_2dof.argtypes = [C.c_double]
+    L.cck_split_risk.restype = None
+    L.cck_split_risk.argtypes = [C.c_double, C.c_int, C.c_int, dp, dp]
+    L.cck_rect_robot_bounding_radius.restype = C.c_double
+    L.cck_rect_robot_bounding_radius.argtypes = [C.c_double] * 4
+    L.cck_build_obstacle_tables.argtypes = [C.c_int, vp, C.c_double, C.c_double, C.c_double, vp, vp, vp]
+    L.cck_build_pair_halfplanes.argtypes = [C.c_int, C.c_double, C.c_double, vp, vp]
+    L.cck_propagate.argtypes = [vp, i64, vp, i64, vp, i64, C.c_double, vp, i64]
+    L.cck_propagate_dev.argtypes = [vp, vp, i64, vp, i64, vp, i64, C.c_double, vp, i64]
+    L.cck_is_valid.argtypes = [vp, i64, vp, i64, vp]
+    L.cck_is_valid_dev.argtypes = [vp, vp, i64, vp, i64, vp]
+    L.cck_propagate_while_valid.argtypes = [vp, i64, vp, i64, vp, i64, vp, vp, i64, vp, vp, i64, C.c_int32]
+    L.cck_propagate_while_valid_dev.argtypes = [vp, vp, i64, vp, i64, vp, i64, vp, vp, i64, vp, vp, i64, C.c_int32]
+    L.cck_validate_plan.argtypes = [vp, C.c_int, vp, vp, i64, C.POINTER(ConflictRun)]
+    L.cck_validate_plan_dev.argtypes = [vp, vp, C.c_int, vp, C.c_int, vp, i64, vp]
+    L.cck_set_constraints.argtypes = [vp, C.c_int, vp, vp, vp, vp]
+    L.cck_satisfies_constraints.argtypes = [vp, i64, vp, i64, C.c_int32, vp, vp, vp]
+    L.cck_satisfies_constraints_dev.argtypes = [vp, vp, i64, vp, i64, C.c_int32, vp, vp, vp]
+    L.cck_expand_batch.argtypes = [vp, i64, vp, i64, vp, i64, vp, vp, vp, C.POINTER(GoalParams), vp, i64, vp, vp, vp, vp]
+    L.cck_expand_batch_dev.argtypes = [vp, vp, i64, vp, i64, vp, i64, vp, vp, vp, C.POINTER(GoalParams), vp, i64, vp, vp, vp, vp]
+    L.cck_rollout_summary_dev.argtypes = [vp, vp, i64, vp, vp, vp]
+    L.cck_measure_fp64_peak.argtypes = [vp, dp]
+    _lib = L
+    return L
+
+
+def _ptr(a):
+    """numpy array / torch tensor / int / None -> void* address."""
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return a
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    return a.data_ptr()   # torch tensor
+
+
+def width(dim):
+    return dim + 2 * dim * dim
+
+
+def model_params(model, dt=0.2):
+    p = ModelParams()
+    rc = lib().cck_model_params_default(model, dt, C.byref(p))
+    if rc:
+        raise CckError(rc, "cck_model_params_default")
+    return p
+
+
+def erf_inv(z):
+    return lib().cck_erf_inv(float(z))
+
+
+def chi2_quantile_2dof(p):
+    return lib().cck_chi2_quantile_2dof(float(p))
+
+
+def split_risk(p_safe, n_obstacles, n_robots):
+    a, b = C.c_double(), C.c_double()
+    lib().cck_split_risk(p_safe, n_obstacles, n_robots, C.byref(a), C.byref(b))
+    return a.value, b.value
+
+
+def rect_robot_bounding_radius(sx=0.0, sy=0.0, length=0.25, width_=0.25):
+    return lib().cck_rect_robot_bounding_radius(sx, sy, length, width_)
+
+
+def build_obstacle_tables(centres, robot_rad, length=1.0, width_=1.0):
+    c = np.ascontiguousarray(centres, dtype=np.float64).reshape(-1, 2)
+    M = len(c)
+    A, B, R = np.zeros((M, 4, 2)), np.zeros((M, 4)), np.zeros((M, 4))
+    rc = lib().cck_build_obstacle_tables(M, _ptr(c), length, width_, robot_rad, _ptr(A), _ptr(B), _ptr(R))
+    if rc:
+        raise CckError(rc, "cck_build_obstacle_tables")
+    return A, B, R
+
+
+def build_pair_halfplanes(r1, r2, bounding_box=False):
+    A, B = np.zeros((4, 2)), np.zeros(4)
+    rc = lib().cck_build_pair_halfplanes(int(bounding_box), r1, r2, _ptr(A), _ptr(B))
+    if rc:
+        raise CckError(rc, "cck_build_pair_halfplanes")
+    return A, B
+
+
+class Context:
+    """One GPU context (device tables + streams).  Mirrors what the reference holds in its
+    SpaceInformation: the installed propagator (set_model), validity checker (set_obstacles)
+    and plan validator (set_pvc)."""
+
+    def __init__(self, device=0):
+        self.L = lib()
+        h = C.c_void_p()
+        rc = self.L.cck_ctx_create(device, C.byref(h))
+        if rc:
+            raise CckError(rc, self.L.cck_last_error(None).decode())
+        self.h = h
+        self.dim = None
+        self._keep = []
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.cck_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc:
+            raise CckError(rc, self.L.cck_last_error(self.h).decode())
+
+    @property
+    def num_sms(self):
+        return self.L.cck_num_sms(self.h)
+
+    @property
+    def launch_count(self):
+        return self.L.cck_launch_count(self.h)
+
+    def synchronize(self):
+        self._ck(self.L.cck_ctx_synchronize(self.h))
+
+    def set_model(self, model, dt=0.2, params=None):
+        p = params if params is not None else model_params(model, dt)
+        self._ck(self.L.cck_set_model(self.h, C.byref(p)))
+        self.dim, self.dt, self.model = p.dim, p.dt, p.model
+        return p
+
+    def set_obstacles(self, kind, low, high, A=None, B=None, centres=None, rects=None, erf_inv_result=0.0, p_collision=0.0,
+                      sc=0.0, max_rad=0.0):
+        p = SvcParams()
+        p.kind, p.dim = kind, len(low)
+        for i in range(len(low)):
+            p.low[i], p.high[i] = float(low[i]), float(high[i])
+        p.erf_inv_result, p.p_collision, p.sc, p.max_rad = erf_inv_result, p_collision, sc, max_rad
+        M = 0 if A is None else len(A)
+        f = lambda x: None if x is None or M == 0 else np.ascontiguousarray(x, dtype=np.float64)
+        A_, B_, c_, r_ = f(A), f(B), f(centres), f(rects)
+        self._ck(self.L.cck_set_obstacles(self.h, C.byref(p), _ptr(A_), _ptr(B_), _ptr(c_), _ptr(r_), M))
+        self.M = M
+
+    def set_pvc(self, kind, k, dim, radii, pair_A, pair_B, map_order, c_pair=0.0, p_coll_agnts=0.0, sc=0.0):
+        radii = np.ascontiguousarray(radii, dtype=np.float64)
+        pair_A = np.ascontiguousarray(pair_A, dtype=np.float64)
+        pair_B = np.ascontiguousarray(pair_B, dtype=np.float64)
+        map_order = np.ascontiguousarray(map_order, dtype=np.int32)
+        p = PvcParams()
+        p.kind, p.k, p.dim = kind, k, dim
+        p.c_pair, p.p_coll_agnts, p.sc = c_pair, p_coll_agnts, sc
+        p.radii = radii.ctypes.data_as(C.POINTER(C.c_double))
+        p.pair_A = pair_A.ctypes.data_as(C.POINTER(C.c_double))
+        p.pair_B = pair_B.ctypes.data_as(C.POINTER(C.c_double))
+        p.map_order = map_order.ctypes.data_as(C.POINTER(C.c_int32))
+        self._ck(self.L.cck_set_pvc(self.h, C.byref(p)))
+        self.pvc_k, self.pvc_dim = k, dim
+
+    # ---- host-pointer entry points (numpy SoA arrays [W, n]) ----
+    def propagate(self, bel, ctrl, duration=None):
+        bel = np.ascontiguousarray(bel, dtype=np.float64)
+        ctrl = np.ascontiguousarray(ctrl, dtype=np.float64)
+        n = bel.shape[1]
+        out = np.empty_like(bel)
+        self._ck(self.L.cck_propagate(self.h, n, _ptr(bel), n, _ptr(ctrl), n, self.dt if duration is None else duration, _ptr(out), n))
+        return out
+
+    def is_valid(self, bel):
+        bel = np.ascontiguousarray(bel, dtype=np.float64)
+        n = bel.shape[1]
+        v = np.zeros(n, dtype=np.uint8)
+        self._ck(self.L.cck_is_valid(self.h, n, _ptr(bel), n, _ptr(v)))
+        return v.astype(bool)
+
+    def propagate_while_valid(self, bel, ctrl, steps, traj_T=0):
+        bel = np.ascontiguousarray(bel, dtype=np.float64)
+        ctrl = np.ascontiguousarray(ctrl, dtype=np.float64)
+        steps = np.ascontiguousarray(steps, dtype=np.int32)
+        n = bel.shape[1]
+        out = np.empty_like(bel)
+        valid = np.zeros(n, dtype=np.int32)
+        traj = np.zeros((traj_T, bel.shape[0], n)) if traj_T else None
+        self._ck(self.L.cck_propagate_while_valid(self.h, n, _ptr(bel), n, _ptr(ctrl), n, _ptr(steps), _ptr(out), n, _ptr(valid),
+                                                  _ptr(traj), n, traj_T))
+        return (out, valid, traj) if traj_T else (out, valid)
+
+    def validate_plan(self, trajs):
+        """trajs: list of SoA arrays [W, T_r].  -> (a, b, first_step, run_len) or None."""
+        k = len(trajs)
+        lens = np.array([t.shape[1] for t in trajs], dtype=np.int32)
+        W, T = trajs[0].shape[0], int(lens.max())
+        buf = np.zeros((k, W, T))
+        for r, t in enumerate(trajs):
+            buf[r, :, :t.shape[1]] = t
+        run = ConflictRun()
+        self._ck(self.L.cck_validate_plan(self.h, k, _ptr(lens), _ptr(buf), T, C.byref(run)))
+        if run.first_step < 0:
+            return None
+        return (run.a, run.b, run.first_step, run.run_len)
+
+    def set_constraints(self, ent_step, pair_ab, mu2, cov4):
+        n = len(ent_step)
+        if n == 0:
+            self._ck(self.L.cck_set_constraints(self.h, 0, None, None, None, None))
+            return
+        s = np.ascontiguousarray(ent_step, dtype=np.int32)
+        pr = np.ascontiguousarray(pair_ab, dtype=np.int32)
+        mu = np.ascontiguousarray(mu2, dtype=np.float64)
+        cv = np.ascontiguousarray(cov4, dtype=np.float64)
+        self._ck(self.L.cck_set_constraints(self.h, n, _ptr(s), _ptr(pr), _ptr(mu), _ptr(cv)))
+
+    def satisfies_constraints(self, paths, path_len, path_step0):
+        """paths: [T, W, n] SoA trajectory buffer."""
+        paths = np.ascontiguousarray(paths, dtype=np.float64)
+        T, _, n = paths.shape
+        pl = np.ascontiguousarray(path_len, dtype=np.int32)
+        s0 = np.ascontiguousarray(path_step0, dtype=np.int32)
+        ok = np.zeros(n, dtype=np.uint8)
+        self._ck(self.L.cck_satisfies_constraints(self.h, n, _ptr(paths), n, T, _ptr(pl), _ptr(s0), _ptr(ok)))
+        return ok.astype(bool)
+
+    def expand_batch(self, bel, ctrl, steps, parent_step, parent_cost, goal_xy, threshold=2.0, goal_p_safe=0.95):
+        bel = np.ascontiguousarray(bel, dtype=np.float64)
+        ctrl = np.ascontiguousarray(ctrl, dtype=np.float64)
+        steps = np.ascontiguousarray(steps, dtype=np.int32)
+        ps = np.ascontiguousarray(parent_step, dtype=np.int32)
+        pc = np.ascontiguousarray(parent_cost, dtype=np.float64)
+        n = bel.shape[1]
+        g = GoalParams(float(goal_xy[0]), float(goal_xy[1]), threshold, chi2_quantile_2dof(goal_p_safe))
+        out = np.empty_like(bel)
+        valid = np.zeros(n, dtype=np.int32)
+        cost, gd, fl = np.zeros(n), np.zeros(n), np.zeros(n, dtype=np.uint8)
+        self._ck(self.L.cck_expand_batch(self.h, n, _ptr(bel), n, _ptr(ctrl), n, _ptr(steps), _ptr(ps), _ptr(pc), C.byref(g),
+                                         _ptr(out), n, _ptr(valid), _ptr(cost), _ptr(gd), _ptr(fl)))
+        return out, valid, cost, gd, fl
+
+    # ---- device-pointer entry points (torch CUDA tensors or raw addresses) ----
+    def propagate_while_valid_dev(self, stream, n, bel, ld, ctrl, ldc, steps, out, ldo, valid, traj=None, traj_ld=0, traj_T=0):
+        self._ck(self.L.cck_propagate_while_valid_dev(self.h, stream, n, _ptr(bel), ld, _ptr(ctrl), ldc, _ptr(steps), _ptr(out), ldo,
+                                                      _ptr(valid), _ptr(traj), traj_ld, traj_T))
+
+    def propagate_dev(self, stream, n, bel, ld, ctrl, ldc, out, ldo, duration=None):
+        self._ck(self.L.cck_propagate_dev(self.h, stream, n, _ptr(bel), ld, _ptr(ctrl), ldc, self.dt if duration is None else duration,
+                                          _ptr(out), ldo))
+
+    def is_valid_dev(self, stream, n, bel, ld, valid):
+        self._ck(self.L.cck_is_valid_dev(self.h, stream, n, _ptr(bel), ld, _ptr(valid)))
+
+    def rollout_summary_dev(self, stream, n, steps, valid, out3):
+        self._ck(self.L.cck_rollout_summary_dev(self.h, stream, n, _ptr(steps), _ptr(valid), _ptr(out3)))
+
+    def measure_fp64_peak(self):
+        t = C.c_double()
+        self._ck(self.L.cck_measure_fp64_peak(self.h, C.byref(t)))
+        return t.value
+
+
+def aos_to_soa(b):
+    """[n, W] AoS records -> [W, n] SoA planes."""
+    return np.ascontiguousarray(np.asarray(b, dtype=np.float64).T)
+
+
+def soa_to_aos(b):
+    return np.ascontiguousarray(np.asarray(b).T)

@@ -1,0 +1,845 @@
+// cck_b200.cu — implementation of the C ABI declared in include/cck_b200.h.
+// Built with: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false -lineinfo ...
+#include <algorithm>
+#include <climits>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "cck_kernels.cuh"
+
+using namespace cck;
+
+// ---------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------
+struct cck_ctx {
+    int device = 0;
+    int num_sms = 0;
+    int max_smem_optin = 0;
+    cudaStream_t stream = nullptr;
+    cudaStream_t pipe[2] = {nullptr, nullptr};
+    std::string err;
+    int64_t launches = 0;
+
+    bool has_model = false;
+    cck_model_params model{};
+    LinDev lin{};
+    UniDev uni{};
+
+    bool has_svc = false;
+    SvcDev svc{};
+    unsigned char* d_tab = nullptr;
+    int tab_bytes = 0;
+    int M = 0;
+
+    bool has_pvc = false;
+    cck_pvc_params pvc_host{};
+    std::vector<double> pvc_A, pvc_B, pvc_radii;
+    std::vector<int32_t> pvc_order;
+    PvcDev pvc{};
+    double* d_pvc_A = nullptr; double* d_pvc_B = nullptr; double* d_pvc_radii = nullptr; int32_t* d_pvc_order = nullptr;
+    unsigned long long* d_key = nullptr;
+    cck_conflict_run* d_run = nullptr;
+
+    unsigned char* d_cons = nullptr;   // constraint table (nullptr = no constraints)
+    size_t cons_cap = 0;
+
+    // grow-only device scratch for the host-pointer entry points (2 pipeline slots)
+    void* d_scratch[2] = {nullptr, nullptr};
+    size_t scratch_cap[2] = {0, 0};
+};
+
+static std::string g_create_err;
+
+#define CK(ctx, call)                                                                                  \
+    do {                                                                                               \
+        cudaError_t e__ = (call);                                                                      \
+        if (e__ != cudaSuccess) {                                                                      \
+            (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e__);                          \
+            return CCK_ERR_CUDA;                                                                       \
+        }                                                                                              \
+    } while (0)
+
+static int fail(cck_ctx* ctx, int code, const std::string& msg) {
+    if (ctx) ctx->err = msg;
+    return code;
+}
+
+extern "C" int cck_ctx_create(int device, cck_ctx** out) {
+    if (!out) return CCK_ERR_INVALID;
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        g_create_err = std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                       " (libcck_b200 has no CPU fallback)";
+        return CCK_ERR_NODEVICE;
+    }
+    if (device < 0 || device >= ndev) { g_create_err = "device index out of range"; return CCK_ERR_INVALID; }
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) { g_create_err = cudaGetErrorString(e); return CCK_ERR_CUDA; }
+    if (prop.major != 10) {
+        g_create_err = "device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) +
+                       "; this library ships sm_100a code only (no fallback)";
+        return CCK_ERR_NODEVICE;
+    }
+    cck_ctx* c = new cck_ctx();
+    c->device = device;
+    c->num_sms = prop.multiProcessorCount;
+    c->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&c->pipe[0], cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&c->pipe[1], cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaMalloc(&c->d_key, sizeof(unsigned long long))) != cudaSuccess || (e = cudaMalloc(&c->d_run, sizeof(cck_conflict_run))) != cudaSuccess) {
+        g_create_err = cudaGetErrorString(e);
+        delete c;
+        return CCK_ERR_CUDA;
+    }
+    *out = c;
+    return CCK_OK;
+}
+
+extern "C" int cck_ctx_destroy(cck_ctx* c) {
+    if (!c) return CCK_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (int i = 0; i < 2; ++i) { if (c->pipe[i]) { cudaStreamSynchronize(c->pipe[i]); cudaStreamDestroy(c->pipe[i]); } cudaFree(c->d_scratch[i]); }
+    cudaFree(c->d_tab); cudaFree(c->d_pvc_A); cudaFree(c->d_pvc_B); cudaFree(c->d_pvc_radii); cudaFree(c->d_pvc_order);
+    cudaFree(c->d_key); cudaFree(c->d_run); cudaFree(c->d_cons);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return CCK_OK;
+}
+
+extern "C" const char* cck_last_error(const cck_ctx* c) { return c ? c->err.c_str() : g_create_err.c_str(); }
+extern "C" int cck_num_sms(const cck_ctx* c) { return c ? c->num_sms : 0; }
+extern "C" int64_t cck_launch_count(const cck_ctx* c) { return c ? c->launches : 0; }
+extern "C" int cck_ctx_synchronize(cck_ctx* c) {
+    if (!c) return CCK_ERR_INVALID;
+    CK(c, cudaSetDevice(c->device));
+    CK(c, cudaStreamSynchronize(c->stream));
+    CK(c, cudaStreamSynchronize(c->pipe[0]));
+    CK(c, cudaStreamSynchronize(c->pipe[1]));
+    return CCK_OK;
+}
+
+// ---------------------------------------------------------------------------
+// host-side constant builders (restating the reference's constructor arithmetic)
+// ---------------------------------------------------------------------------
+// boost::math::erf_inv: Halley iterations on erfl/erfcl in long double (Boost promotes
+// double to long double; the result is rounded to double).
+extern "C" double cck_erf_inv(double z) {
+    if (std::isnan(z) || z < -1.0 || z > 1.0) return std::nan("");
+    if (z == 1.0) return HUGE_VAL;
+    if (z == -1.0) return -HUGE_VAL;
+    if (z == 0.0) return 0.0;
+    const bool neg = z < 0;
+    const long double p = neg ? -(long double)z : (long double)z;
+    const long double q = 1.0L - p;
+    const long double lg = logl(1.0L - p * p);
+    const long double aw = 0.147L, pi = 3.14159265358979323846264338327950288L;
+    const long double t1 = 2.0L / (pi * aw) + lg / 2.0L;
+    long double x = sqrtl(sqrtl(t1 * t1 - lg / aw) - t1);
+    const long double k = 1.12837916709551257389615890312154517L;   // 2/sqrt(pi)
+    for (int it = 0; it < 60; ++it) {
+        const long double f = (p > 0.5L) ? (q - erfcl(x)) : (erfl(x) - p);
+        const long double d = k * expl(-x * x);
+        const long double dx = f / (d + x * f);
+        x -= dx;
+        if (fabsl(dx) <= 1e-21L * fabsl(x)) break;
+    }
+    const double r = (double)x;
+    return neg ? -r : r;
+}
+extern "C" double cck_chi2_quantile_2dof(double p) { return -2.0 * std::log1p(-p); }
+
+extern "C" void cck_split_risk(double p_safe, int n_obstacles, int n_robots, double* p_safe_obs, double* p_safe_agents) {
+    const double total_things = (double)(n_obstacles + n_robots);          // Instance.cpp:38
+    const double p_coll = 1 - p_safe;
+    const double p_coll_obs = (p_coll * n_obstacles) / total_things;
+    const double p_coll_agnts = (p_coll * n_robots) / total_things;
+    if (p_safe_agents) *p_safe_agents = 1 - p_coll_agnts;
+    if (p_safe_obs) *p_safe_obs = 1 - p_coll_obs;
+}
+
+namespace {
+struct P2 { double x, y; };
+typedef std::vector<P2> Ring;
+Ring rect_ring(double x, double y, double len, double width) {            // common.cpp:25-42
+    P2 bl{x - (len / 2), y - (width / 2)}, br{x + (len / 2), y - (width / 2)};
+    P2 tl{x - (len / 2), y + (width / 2)}, tr{x + (len / 2), y + (width / 2)};
+    return Ring{bl, br, tr, tl, bl};
+}
+Ring square_ring(double r) { return Ring{{-r, -r}, {r, -r}, {r, r}, {-r, r}, {-r, -r}}; }
+Ring minkowski(const Ring& a, const Ring& b) {                             // PCCBlackmoreSVC.cpp:110-145
+    Ring s1 = a, s2 = b;
+    s1.push_back(s1[1]); s2.push_back(s2[1]);
+    Ring res;
+    size_t i = 0, j = 0;
+    while ((i < s1.size() - 2 || j < s2.size() - 2) && res.size() < 64) {
+        res.push_back(P2{s1[i].x + s2[j].x, s1[i].y + s2[j].y});
+        const double ax = s1[i + 1].x - s1[i].x, ay = s1[i + 1].y - s1[i].y;
+        const double bx = s2[j + 1].x - s2[j].x, by = s2[j + 1].y - s2[j].y;
+        const double cross = (ax * by) - (ay * bx);
+        if (cross >= 0) ++i;
+        if (cross <= 0) ++j;
+    }
+    res.push_back(res.front());
+    return res;
+}
+void ring_halfplanes(const Ring& ring, double* A8, double* B4) {           // PCCBlackmoreSVC.cpp:77-108
+    for (size_t i = 0; i + 1 < ring.size() && i < 4; ++i) {
+        const double x1 = ring[i].x, y1 = ring[i].y, x2 = ring[i + 1].x, y2 = ring[i + 1].y;
+        const double a = y2 - y1, b = x1 - x2;
+        const double c = a * x1 + b * y1;
+        A8[2 * i] = a; A8[2 * i + 1] = b; B4[i] = c;
+    }
+}
+}  // namespace
+
+extern "C" double cck_rect_robot_bounding_radius(double sx, double sy, double len, double width) {
+    Ring shape = rect_ring(sx, sy, len, width);
+    double max_rad = 0.0;
+    for (const P2& p : shape) {                                            // common.cpp:68-85
+        const double x = 1.0 * p.x + 0.0 * p.y + (0 - sx);
+        const double y = -0.0 * p.x + 1.0 * p.y + (0 - sy);
+        const double r = std::sqrt((x * x) + (y * y));
+        if (r > max_rad) max_rad = r;
+    }
+    return max_rad;
+}
+
+extern "C" int cck_build_obstacle_tables(int M, const double* centres, double len, double width, double robot_rad, double* A,
+                                         double* B, double* rects) {
+    if (M < 0 || (M > 0 && (!centres || !A || !B))) return CCK_ERR_INVALID;
+    const Ring robot = square_ring(robot_rad);
+    for (int o = 0; o < M; ++o) {
+        Ring m = minkowski(robot, rect_ring(centres[2 * o], centres[2 * o + 1], len, width));
+        ring_halfplanes(m, A + 8 * o, B + 4 * o);
+        if (rects) { rects[4 * o] = m[0].x; rects[4 * o + 1] = m[0].y; rects[4 * o + 2] = m[2].x; rects[4 * o + 3] = m[2].y; }
+    }
+    return CCK_OK;
+}
+
+extern "C" int cck_build_pair_halfplanes(int bounding_box, double r1, double r2, double* A8, double* B4) {
+    if (!A8 || !B4) return CCK_ERR_INVALID;
+    Ring poly = bounding_box ? square_ring(r1 + r2) : minkowski(square_ring(r1), square_ring(r2));
+    ring_halfplanes(poly, A8, B4);
+    return CCK_OK;
+}
+
+extern "C" int cck_model_params_default(int model, double dt, cck_model_params* p) {
+    if (!p) return CCK_ERR_INVALID;
+    std::memset(p, 0, sizeof(*p));
+    p->model = model;
+    p->dt = dt;
+    const double q = std::pow(0.1, 2), r = std::pow(0.1, 2);
+    if (model == CCK_MODEL_LINEAR2D) {
+        p->dim = 2;
+        const double K = 0.3;                                               // UncertainLinearSP.h:50
+        p->lin_Q[0] = q * 1.0; p->lin_Q[3] = q * 1.0; p->lin_R[0] = r * 1.0; p->lin_R[3] = r * 1.0;
+        p->lin_Acl[0] = 1.0 - 1.0 * K; p->lin_Acl[1] = 0.0 - 0.0 * K; p->lin_Acl[2] = 0.0 - 0.0 * K; p->lin_Acl[3] = 1.0 - 1.0 * K;
+        return CCK_OK;
+    }
+    if (model == CCK_MODEL_UNICYCLE) {
+        p->dim = 4;
+        for (int i = 0; i < 4; ++i) p->uni_F[i * 4 + i] = 1.0;
+        p->uni_F[1] = dt; p->uni_F[2 * 4 + 3] = dt;                         // exp(A_ol*dt), A_ol nilpotent (:88-91)
+        const double Bd[4][2] = {{dt * dt / 2.0, 0.0}, {dt, 0.0}, {0.0, dt * dt / 2.0}, {0.0, dt}};   // :95-104
+        const double Kg[2][4] = {{2.5857, 3.4434, 0.0, 0.0}, {0.0, 0.0, 2.5857, 3.4434}};             // :58-65
+        for (int i = 0; i < 4; ++i)
+            for (int j = 0; j < 4; ++j) p->uni_Acl[i * 4 + j] = p->uni_F[i * 4 + j] - (Bd[i][0] * Kg[0][j] + Bd[i][1] * Kg[1][j]);
+        for (int i = 0; i < 4; ++i) { p->uni_Q[i * 4 + i] = q * 1.0; p->uni_R[i * 4 + i] = r * 1.0; }
+        const double g[8] = {1.0, 1.0, 0.0, 0.0, 0.0, 0.0, 1.0, 1.0};       // :76-83
+        for (int i = 0; i < 8; ++i) p->uni_gains[i] = g[i];
+        p->uni_acc[0] = -0.5; p->uni_acc[1] = 0.5; p->uni_turn[0] = -0.5; p->uni_turn[1] = 0.5;
+        return CCK_OK;
+    }
+    return CCK_ERR_INVALID;
+}
+
+extern "C" int cck_set_model(cck_ctx* c, const cck_model_params* p) {
+    if (!c || !p) return CCK_ERR_INVALID;
+    if (p->model == CCK_MODEL_LINEAR2D && p->dim != 2) return fail(c, CCK_ERR_INVALID, "linear model needs dim 2");
+    if (p->model == CCK_MODEL_UNICYCLE && p->dim != 4) return fail(c, CCK_ERR_INVALID, "unicycle model needs dim 4");
+    if (p->model != CCK_MODEL_LINEAR2D && p->model != CCK_MODEL_UNICYCLE) return fail(c, CCK_ERR_INVALID, "unknown model");
+    c->model = *p;
+    c->lin.dt = p->dt;
+    std::memcpy(c->lin.Q, p->lin_Q, sizeof(c->lin.Q)); std::memcpy(c->lin.R, p->lin_R, sizeof(c->lin.R));
+    std::memcpy(c->lin.Acl, p->lin_Acl, sizeof(c->lin.Acl));
+    std::memcpy(c->uni.F, p->uni_F, sizeof(c->uni.F)); std::memcpy(c->uni.Acl, p->uni_Acl, sizeof(c->uni.Acl));
+    std::memcpy(c->uni.Q, p->uni_Q, sizeof(c->uni.Q)); std::memcpy(c->uni.R, p->uni_R, sizeof(c->uni.R));
+    std::memcpy(c->uni.gains, p->uni_gains, sizeof(c->uni.gains));
+    c->uni.acc_lo = p->uni_acc[0]; c->uni.acc_hi = p->uni_acc[1]; c->uni.turn_lo = p->uni_turn[0]; c->uni.turn_hi = p->uni_turn[1];
+    c->has_model = true;
+    return CCK_OK;
+}
+
+// Group obstacles by bit-identical A[4][2] and lay the table out for one TMA bulk copy.
+extern "C" int cck_set_obstacles(cck_ctx* c, const cck_svc_params* p, const double* A, const double* B, const double* centres,
+                                 const double* rects, int M) {
+    if (!c || !p || M < 0) return CCK_ERR_INVALID;
+    if (M > 0 && (!A || !B)) return fail(c, CCK_ERR_INVALID, "A/B tables missing");
+    if (p->kind == CCK_SVC_ADAPTIVE && M > 0 && !centres) return fail(c, CCK_ERR_INVALID, "Adaptive SVC needs obstacle centres");
+    if (p->kind == CCK_SVC_CHISQUARED && M > 0 && !rects) return fail(c, CCK_ERR_INVALID, "ChiSquared SVC needs inflated rectangles");
+    if (p->kind < 0 || p->kind > 2 || p->dim < 1 || p->dim > 4) return fail(c, CCK_ERR_INVALID, "bad svc params");
+    CK(c, cudaSetDevice(c->device));
+
+    struct Key { uint64_t w[8]; bool operator<(const Key& o) const { return std::memcmp(w, o.w, sizeof(w)) < 0; } };
+    std::map<Key, int> cls_of;
+    std::vector<std::vector<int>> members;
+    std::vector<Key> keys;
+    for (int o = 0; o < M; ++o) {
+        Key k;
+        std::memcpy(k.w, A + 8 * o, 64);
+        auto it = cls_of.find(k);
+        if (it == cls_of.end()) { it = cls_of.emplace(k, (int)members.size()).first; members.emplace_back(); keys.push_back(k); }
+        members[it->second].push_back(o);
+    }
+    const int nc = (int)members.size();
+    TabHeader h{};
+    h.n_classes = nc; h.M = M;
+    h.off_classes = sizeof(TabHeader);
+    h.off_B = h.off_classes + nc * (int)sizeof(ClassRec);
+    h.off_centres = h.off_B + M * 32;
+    h.off_rects = h.off_centres + (centres ? M * 16 : 0);
+    h.total_bytes = h.off_rects + (rects ? M * 32 : 0);
+    h.total_bytes = (h.total_bytes + 15) & ~15;
+    if (h.total_bytes + 16 > c->max_smem_optin)
+        return fail(c, CCK_ERR_INVALID, "obstacle table (" + std::to_string(h.total_bytes) + " B) exceeds shared memory; M too large");
+    std::vector<unsigned char> buf(h.total_bytes, 0);
+    std::memcpy(buf.data(), &h, sizeof(h));
+    int pos = 0;
+    for (int k = 0; k < nc; ++k) {
+        ClassRec r{};
+        std::memcpy(r.A, keys[k].w, 64);
+        r.first = pos; r.count = (int)members[k].size();
+        std::memcpy(buf.data() + h.off_classes + k * sizeof(ClassRec), &r, sizeof(r));
+        for (int o : members[k]) { std::memcpy(buf.data() + h.off_B + pos * 32, B + 4 * o, 32); ++pos; }
+    }
+    if (centres && M) std::memcpy(buf.data() + h.off_centres, centres, (size_t)M * 16);   // original order (sum order, eta_list[0])
+    if (rects && M) std::memcpy(buf.data() + h.off_rects, rects, (size_t)M * 32);
+
+    CK(c, cudaStreamSynchronize(c->stream));
+    cudaFree(c->d_tab); c->d_tab = nullptr;
+    CK(c, cudaMalloc(&c->d_tab, h.total_bytes));
+    CK(c, cudaMemcpy(c->d_tab, buf.data(), h.total_bytes, cudaMemcpyHostToDevice));
+    c->tab_bytes = h.total_bytes;
+    c->M = M;
+
+    SvcDev& s = c->svc;
+    std::memset(&s, 0, sizeof(s));
+    s.kind = p->kind; s.dim = p->dim;
+    for (int i = 0; i < 4; ++i) { s.low[i] = p->low[i]; s.high[i] = p->high[i]; }
+    s.erf_inv_result = p->erf_inv_result; s.p_collision = p->p_collision; s.sc = p->sc; s.max_rad = p->max_rad;
+    // bg::strategy::buffer::point_circle(10): a = 0, a -= 2pi/10 (ChiSquaredBoundarySVC.cpp:58-62)
+    const double two_pi = 2.0 * M_PI, diff = two_pi / 10.0;
+    double a = 0;
+    for (int i = 0; i < 10; ++i, a -= diff) { s.dec_cos[i] = std::cos(a); s.dec_sin[i] = std::sin(a); }
+    c->has_svc = true;
+    return CCK_OK;
+}
+
+extern "C" int cck_set_pvc(cck_ctx* c, const cck_pvc_params* p) {
+    if (!c || !p) return CCK_ERR_INVALID;
+    if (p->k < 1 || p->k > CCK_MAX_ROBOTS) return fail(c, CCK_ERR_INVALID, "k out of range");
+    if (p->dim != 2 && p->dim != 4) return fail(c, CCK_ERR_INVALID, "pvc dim must be 2 or 4");
+    if (p->kind < 0 || p->kind > 4) return fail(c, CCK_ERR_INVALID, "unknown pvc kind");
+    if (!p->radii || !p->map_order || (p->kind != CCK_PVC_CHISQUARED && (!p->pair_A || !p->pair_B)))
+        return fail(c, CCK_ERR_INVALID, "pvc tables missing");
+    CK(c, cudaSetDevice(c->device));
+    const int k = p->k;
+    c->pvc_host = *p;
+    c->pvc_radii.assign(p->radii, p->radii + k);
+    c->pvc_order.assign(p->map_order, p->map_order + k);
+    c->pvc_A.assign((size_t)k * k * 8, 0.0); c->pvc_B.assign((size_t)k * k * 4, 0.0);
+    if (p->pair_A) std::memcpy(c->pvc_A.data(), p->pair_A, c->pvc_A.size() * 8);
+    if (p->pair_B) std::memcpy(c->pvc_B.data(), p->pair_B, c->pvc_B.size() * 8);
+    CK(c, cudaStreamSynchronize(c->stream));
+    cudaFree(c->d_pvc_A); cudaFree(c->d_pvc_B); cudaFree(c->d_pvc_radii); cudaFree(c->d_pvc_order);
+    c->d_pvc_A = c->d_pvc_B = c->d_pvc_radii = nullptr; c->d_pvc_order = nullptr;
+    CK(c, cudaMalloc(&c->d_pvc_A, c->pvc_A.size() * 8)); CK(c, cudaMalloc(&c->d_pvc_B, c->pvc_B.size() * 8));
+    CK(c, cudaMalloc(&c->d_pvc_radii, k * 8)); CK(c, cudaMalloc(&c->d_pvc_order, k * 4));
+    CK(c, cudaMemcpy(c->d_pvc_A, c->pvc_A.data(), c->pvc_A.size() * 8, cudaMemcpyHostToDevice));
+    CK(c, cudaMemcpy(c->d_pvc_B, c->pvc_B.data(), c->pvc_B.size() * 8, cudaMemcpyHostToDevice));
+    CK(c, cudaMemcpy(c->d_pvc_radii, c->pvc_radii.data(), k * 8, cudaMemcpyHostToDevice));
+    CK(c, cudaMemcpy(c->d_pvc_order, c->pvc_order.data(), k * 4, cudaMemcpyHostToDevice));
+    PvcDev& d = c->pvc;
+    d.kind = p->kind; d.k = k; d.dim = p->dim; d.n_pairs = k * (k - 1) / 2;
+    d.c_pair = p->c_pair; d.p_coll_agnts = p->p_coll_agnts; d.sc = p->sc;
+    d.radii = c->d_pvc_radii; d.pair_A = c->d_pvc_A; d.pair_B = c->d_pvc_B; d.map_order = c->d_pvc_order;
+    c->has_pvc = true;
+    // a new PVC invalidates the constraint table
+    cudaFree(c->d_cons); c->d_cons = nullptr; c->cons_cap = 0;
+    return CCK_OK;
+}
+
+// ---------------------------------------------------------------------------
+// launch helpers
+// ---------------------------------------------------------------------------
+static int grid_for(const cck_ctx* c, int64_t n, int threads, int ctas_per_sm) {
+    int64_t blocks = (n + threads - 1) / threads;
+    const int64_t cap = (int64_t)c->num_sms * ctas_per_sm;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+static cudaStream_t pick(cck_ctx* c, void* stream) { return stream ? (cudaStream_t)stream : c->stream; }
+
+template <typename K>
+static int set_smem(cck_ctx* c, K kernel, int bytes) {
+    if (bytes > 48 * 1024) CK(c, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    return CCK_OK;
+}
+
+static int check_ready(cck_ctx* c, bool need_svc) {
+    if (!c) return CCK_ERR_INVALID;
+    if (!c->has_model) return fail(c, CCK_ERR_INVALID, "cck_set_model has not been called");
+    if (need_svc && !c->has_svc) return fail(c, CCK_ERR_INVALID, "cck_set_obstacles has not been called");
+    if (need_svc && c->svc.dim != c->model.dim) return fail(c, CCK_ERR_INVALID, "svc dim != model dim");
+    return CCK_OK;
+}
+
+// ---------------------------------------------------------------------------
+// propagate
+// ---------------------------------------------------------------------------
+extern "C" int cck_propagate_dev(cck_ctx* c, void* stream, int64_t n, const double* bel, int64_t ld, const double* ctrl, int64_t ldc,
+                                 double duration, double* out, int64_t ldo) {
+    int rc = check_ready(c, false);
+    if (rc) return rc;
+    if (n < 0 || ld < n || ldc < n || ldo < n) return fail(c, CCK_ERR_INVALID, "bad n/ld");
+    if (n == 0) return CCK_OK;
+    CK(c, cudaSetDevice(c->device));
+    cudaStream_t s = pick(c, stream);
+    if (c->model.model == CCK_MODEL_LINEAR2D) {
+        k_propagate_lin<<<grid_for(c, n, 256, 8), 256, 0, s>>>(n, bel, ld, ctrl, ldc, out, ldo, c->lin);
+    } else {
+        k_propagate_uni<<<grid_for(c, n, 128, 8), 128, 0, s>>>(n, bel, ld, ctrl, ldc, duration, out, ldo, c->uni);
+    }
+    c->launches++;
+    CK(c, cudaGetLastError());
+    return CCK_OK;
+}
+
+// ---------------------------------------------------------------------------
+// isValid
+// ---------------------------------------------------------------------------
+extern "C" int cck_is_valid_dev(cck_ctx* c, void* stream, int64_t n, const double* bel, int64_t ld, uint8_t* valid) {
+    int rc = check_ready(c, true);
+    if (rc) return rc;
+    if (n < 0 || ld < n) return fail(c, CCK_ERR_INVALID, "bad n/ld");
+    if (n == 0) return CCK_OK;
+    CK(c, cudaSetDevice(c->device));
+    cudaStream_t s = pick(c, stream);
+    const int smem = 16 + c->tab_bytes;
+    const int g = grid_for(c, n, 256, 4);
+    const int dim = c->model.dim;
+#define LAUNCH_VALID(KIND)                                                                        \
+    do {                                                                                          \
+        if ((rc = set_smem(c, k_is_valid<KIND>, smem))) return rc;                                \
+        k_is_valid<KIND><<<g, 256, smem, s>>>(n, dim, bel, ld, valid, c->d_tab, c->tab_bytes, c->svc); \
+    } while (0)
+    if (c->svc.kind == CCK_SVC_BLACKMORE) LAUNCH_VALID(CCK_SVC_BLACKMORE);
+    else if (c->svc.kind == CCK_SVC_ADAPTIVE) LAUNCH_VALID(CCK_SVC_ADAPTIVE);
+    else LAUNCH_VALID(CCK_SVC_CHISQUARED);
+#undef LAUNCH_VALID
+    c->launches++;
+    CK(c, cudaGetLastError());
+    return CCK_OK;
+}
+
+// ---------------------------------------------------------------------------
+// propagateWhileValid / batched expansion
+// ---------------------------------------------------------------------------
+template <bool EXPAND>
+static int launch_rollout(cck_ctx* c, cudaStream_t s, const RolloutArgs& a) {
+    int rc;
+    const int smem = 16 + c->tab_bytes;
+    const int threads = 128;
+    const int g = grid_for(c, a.n, threads, 8);
+    const bool traj = a.traj != nullptr;
+#define LAUNCH_R(KERN, PAR)                                                         \
+    do {                                                                            \
+        if ((rc = set_smem(c, KERN, smem))) return rc;                              \
+        KERN<<<g, threads, smem, s>>>(a, PAR, c->svc);                              \
+    } while (0)
+#define DISPATCH_KIND(NAME, PAR, TRAJ)                                                                              \
+    do {                                                                                                            \
+        if (c->svc.kind == CCK_SVC_BLACKMORE) LAUNCH_R((NAME<CCK_SVC_BLACKMORE, TRAJ, EXPAND>), PAR);              \
+        else if (c->svc.kind == CCK_SVC_ADAPTIVE) LAUNCH_R((NAME<CCK_SVC_ADAPTIVE, TRAJ, EXPAND>), PAR);           \
+        else LAUNCH_R((NAME<CCK_SVC_CHISQUARED, TRAJ, EXPAND>), PAR);                                               \
+    } while (0)
+    if (c->model.model == CCK_MODEL_LINEAR2D) {
+        if (traj) DISPATCH_KIND(k_rollout_lin, c->lin, true); else DISPATCH_KIND(k_rollout_lin, c->lin, false);
+    } else {
+        if (traj) DISPATCH_KIND(k_rollout_uni, c->uni, true); else DISPATCH_KIND(k_rollout_uni, c->uni, false);
+    }
+#undef DISPATCH_KIND
+#undef LAUNCH_R
+    c->launches++;
+    CK(c, cudaGetLastError());
+    return CCK_OK;
+}
+
+extern "C" int cck_propagate_while_valid_dev(cck_ctx* c, void* stream, int64_t n, const double* bel, int64_t ld, const double* ctrl,
+                                             int64_t ldc, const int32_t* steps, double* out, int64_t ldo, int32_t* valid_steps,
+                                             double* traj, int64_t traj_ld, int32_t traj_T) {
+    int rc = check_ready(c, true);
+    if (rc) return rc;
+    if (n < 0 || ld < n || ldc < n || ldo < n || (traj && traj_ld < n)) return fail(c, CCK_ERR_INVALID, "bad n/ld");
+    if (n == 0) return CCK_OK;
+    CK(c, cudaSetDevice(c->device));
+    RolloutArgs a{};
+    a.n = n; a.bel = bel; a.ld = ld; a.ctrl = ctrl; a.ldc = ldc; a.steps = steps; a.out = out; a.ldo = ldo; a.valid = valid_steps;
+    a.traj = traj; a.traj_ld = traj_ld; a.traj_T = traj_T; a.tab = c->d_tab; a.tab_bytes = c->tab_bytes; a.duration = c->model.dt;
+    return launch_rollout<false>(c, pick(c, stream), a);
+}
+
+extern "C" int cck_expand_batch_dev(cck_ctx* c, void* stream, int64_t n, const double* bel, int64_t ld, const double* ctrl, int64_t ldc,
+                                    const int32_t* steps, const int32_t* parent_step, const double* parent_cost,
+                                    const cck_goal_params* goal, double* out, int64_t ldo, int32_t* valid_steps, double* cost,
+                                    double* goal_dist, uint8_t* flags) {
+    int rc = check_ready(c, true);
+    if (rc) return rc;
+    if (!goal || !parent_step || !parent_cost || !cost || !goal_dist || !flags) return fail(c, CCK_ERR_INVALID, "null argument");
+    if (n < 0 || ld < n || ldc < n || ldo < n) return fail(c, CCK_ERR_INVALID, "bad n/ld");
+    if (n == 0) return CCK_OK;
+    CK(c, cudaSetDevice(c->device));
+    RolloutArgs a{};
+    a.n = n; a.bel = bel; a.ld = ld; a.ctrl = ctrl; a.ldc = ldc; a.steps = steps; a.out = out; a.ldo = ldo; a.valid = valid_steps;
+    a.tab = c->d_tab; a.tab_bytes = c->tab_bytes; a.duration = c->model.dt;
+    a.parent_step = parent_step; a.parent_cost = parent_cost; a.cost = cost; a.goal_dist = goal_dist; a.flags = flags;
+    a.goal = *goal; a.cons = c->d_cons;
+    return launch_rollout<true>(c, pick(c, stream), a);
+}
+
+// ---------------------------------------------------------------------------
+// validatePlan
+// ---------------------------------------------------------------------------
+extern "C" int cck_validate_plan_dev(cck_ctx* c, void* stream, int k, const int32_t* lens_dev, int max_len, const double* traj,
+                                     int64_t ld, cck_conflict_run* out_dev) {
+    if (!c) return CCK_ERR_INVALID;
+    if (!c->has_pvc) return fail(c, CCK_ERR_INVALID, "cck_set_pvc has not been called");
+    if (k != c->pvc.k) return fail(c, CCK_ERR_INVALID, "k differs from cck_set_pvc");
+    if (max_len < 1 || ld < max_len) return fail(c, CCK_ERR_INVALID, "bad max_len/ld");
+    CK(c, cudaSetDevice(c->device));
+    cudaStream_t s = pick(c, stream);
+    CK(c, cudaMemsetAsync(c->d_key, 0xff, sizeof(unsigned long long), s));
+    if (c->pvc.n_pairs > 0) {
+        const int warps_per_block = 4;
+        int blocks = (max_len + warps_per_block - 1) / warps_per_block;
+        if (blocks > c->num_sms * 8) blocks = c->num_sms * 8;
+        k_validate_steps<<<blocks, 128, 0, s>>>(c->pvc, traj, ld, lens_dev, max_len, c->d_key);
+        c->launches++;
+    }
+    k_validate_finalize<<<1, 256, 0, s>>>(c->pvc, traj, ld, lens_dev, max_len, c->d_key, out_dev);
+    c->launches++;
+    CK(c, cudaGetLastError());
+    return CCK_OK;
+}
+
+// ---------------------------------------------------------------------------
+// constraints
+// ---------------------------------------------------------------------------
+extern "C" int cck_set_constraints(cck_ctx* c, int n_entries, const int32_t* ent_step, const int32_t* pair_ab, const double* mu2,
+                                   const double* cov4) {
+    if (!c) return CCK_ERR_INVALID;
+    if (!c->has_pvc) return fail(c, CCK_ERR_INVALID, "cck_set_pvc has not been called");
+    CK(c, cudaSetDevice(c->device));
+    CK(c, cudaStreamSynchronize(c->stream));
+    if (n_entries <= 0) { cudaFree(c->d_cons); c->d_cons = nullptr; c->cons_cap = 0; return CCK_OK; }
+    if (!ent_step || !pair_ab || !mu2 || !cov4) return fail(c, CCK_ERR_INVALID, "null constraint arrays");
+    int max_step = 0;
+    for (int e = 0; e < n_entries; ++e) {
+        if (ent_step[e] < 0) return fail(c, CCK_ERR_INVALID, "negative constraint step");
+        if (pair_ab[e] < 0 || pair_ab[e] >= c->pvc.k * c->pvc.k) return fail(c, CCK_ERR_INVALID, "pair index out of range");
+        max_step = std::max(max_step, ent_step[e]);
+    }
+    std::vector<int> order(n_entries);
+    for (int e = 0; e < n_entries; ++e) order[e] = e;
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return ent_step[x] < ent_step[y]; });
+    ConsHeader h{};
+    h.n_entries = n_entries; h.max_step = max_step;
+    h.off_first = sizeof(ConsHeader);
+    h.off_entries = (h.off_first + (max_step + 2) * 4 + 15) & ~15;
+    h.pvc_kind = c->pvc.kind; h.dim = c->pvc.dim; h.k = c->pvc.k;
+    h.c_pair = c->pvc.c_pair; h.p_coll_agnts = c->pvc.p_coll_agnts;
+    const size_t total = h.off_entries + (size_t)n_entries * sizeof(ConsEntry);
+    std::vector<unsigned char> buf(total, 0);
+    std::memcpy(buf.data(), &h, sizeof(h));
+    int32_t* first = reinterpret_cast<int32_t*>(buf.data() + h.off_first);
+    ConsEntry* ent = reinterpret_cast<ConsEntry*>(buf.data() + h.off_entries);
+    int e = 0;
+    for (int s = 0; s <= max_step + 1; ++s) {
+        while (e < n_entries && ent_step[order[e]] < s) ++e;
+        first[s] = e;
+    }
+    for (int i = 0; i < n_entries; ++i) {
+        const int src = order[i];
+        std::memcpy(ent[i].mu, mu2 + 2 * src, 16);
+        std::memcpy(ent[i].cov, cov4 + 4 * src, 32);
+        std::memcpy(ent[i].A, c->pvc_A.data() + (size_t)pair_ab[src] * 8, 64);
+        std::memcpy(ent[i].B, c->pvc_B.data() + (size_t)pair_ab[src] * 4, 32);
+    }
+    if (total > c->cons_cap) {
+        cudaFree(c->d_cons); c->d_cons = nullptr; c->cons_cap = 0;
+        CK(c, cudaMalloc(&c->d_cons, total));
+        c->cons_cap = total;
+    }
+    CK(c, cudaMemcpy(c->d_cons, buf.data(), total, cudaMemcpyHostToDevice));
+    return CCK_OK;
+}
+
+extern "C" int cck_satisfies_constraints_dev(cck_ctx* c, void* stream, int64_t n_paths, const double* path, int64_t ld, int32_t max_len,
+                                             const int32_t* path_len, const int32_t* path_step0, uint8_t* ok) {
+    if (!c) return CCK_ERR_INVALID;
+    if (!c->has_pvc) return fail(c, CCK_ERR_INVALID, "cck_set_pvc has not been called");
+    if (n_paths < 0 || ld < n_paths || max_len < 0) return fail(c, CCK_ERR_INVALID, "bad n/ld");
+    if (n_paths == 0) return CCK_OK;
+    CK(c, cudaSetDevice(c->device));
+    cudaStream_t s = pick(c, stream);
+    if (!c->d_cons) {   // no constraints: every path passes
+        CK(c, cudaMemsetAsync(ok, 1, (size_t)n_paths, s));
+        return CCK_OK;
+    }
+    k_constraints<<<grid_for(c, n_paths, 128, 8), 128, 0, s>>>(n_paths, c->pvc.dim, path, ld, path_len, path_step0, c->d_cons, ok);
+    c->launches++;
+    CK(c, cudaGetLastError());
+    return CCK_OK;
+}
+
+// ---------------------------------------------------------------------------
+// host-pointer entry points: H2D -> kernel -> D2H, chunked over two pipeline
+// slots/streams so copies of chunk i+1 overlap the kernel of chunk i.
+// ---------------------------------------------------------------------------
+static int ensure_scratch(cck_ctx* c, int slot, size_t bytes) {
+    if (bytes <= c->scratch_cap[slot]) return CCK_OK;
+    CK(c, cudaStreamSynchronize(c->pipe[slot]));
+    cudaFree(c->d_scratch[slot]); c->d_scratch[slot] = nullptr; c->scratch_cap[slot] = 0;
+    const size_t want = bytes + bytes / 4;
+    cudaError_t e = cudaMalloc(&c->d_scratch[slot], want);
+    if (e != cudaSuccess) { c->err = std::string("cudaMalloc scratch: ") + cudaGetErrorString(e); return CCK_ERR_NOMEM; }
+    c->scratch_cap[slot] = want;
+    return CCK_OK;
+}
+static inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+// copy `planes` planes of `cnt` elements: host (pitch ld) <-> device (pitch cnt)
+static cudaError_t h2d_planes(void* dst, const void* src, size_t elem, int64_t cnt, int64_t ld_src, int planes, cudaStream_t s) {
+    return cudaMemcpy2DAsync(dst, (size_t)cnt * elem, src, (size_t)ld_src * elem, (size_t)cnt * elem, planes, cudaMemcpyHostToDevice, s);
+}
+static cudaError_t d2h_planes(void* dst, int64_t ld_dst, const void* src, size_t elem, int64_t cnt, int planes, cudaStream_t s) {
+    return cudaMemcpy2DAsync(dst, (size_t)ld_dst * elem, src, (size_t)cnt * elem, (size_t)cnt * elem, planes, cudaMemcpyDeviceToHost, s);
+}
+
+static const int64_t kChunk = 1 << 22;   // beliefs per pipeline chunk
+
+extern "C" int cck_propagate(cck_ctx* c, int64_t n, const double* bel, int64_t ld, const double* ctrl, int64_t ldc, double duration,
+                             double* out, int64_t ldo) {
+    int rc = check_ready(c, false);
+    if (rc) return rc;
+    if (n < 0 || ld < n || ldc < n || ldo < n) return fail(c, CCK_ERR_INVALID, "bad n/ld");
+    CK(c, cudaSetDevice(c->device));
+    const int dim = c->model.dim, W = dim + 2 * dim * dim;
+    int slot = 0;
+    for (int64_t off = 0; off < n; off += kChunk, slot ^= 1) {
+        const int64_t cnt = std::min(kChunk, n - off);
+        const size_t b_in = al256((size_t)cnt * W * 8), b_c = al256((size_t)cnt * dim * 8), b_out = b_in;
+        if ((rc = ensure_scratch(c, slot, b_in + b_c + b_out))) return rc;
+        unsigned char* base = (unsigned char*)c->d_scratch[slot];
+        double* d_in = (double*)base; double* d_c = (double*)(base + b_in); double* d_out = (double*)(base + b_in + b_c);
+        cudaStream_t s = c->pipe[slot];
+        CK(c, h2d_planes(d_in, bel + off, 8, cnt, ld, W, s));
+        CK(c, h2d_planes(d_c, ctrl + off, 8, cnt, ldc, dim, s));
+        if ((rc = cck_propagate_dev(c, s, cnt, d_in, cnt, d_c, cnt, duration, d_out, cnt))) return rc;
+        CK(c, d2h_planes(out + off, ldo, d_out, 8, cnt, W, s));
+    }
+    CK(c, cudaStreamSynchronize(c->pipe[0]));
+    CK(c, cudaStreamSynchronize(c->pipe[1]));
+    return CCK_OK;
+}
+
+extern "C" int cck_is_valid(cck_ctx* c, int64_t n, const double* bel, int64_t ld, uint8_t* valid) {
+    int rc = check_ready(c, true);
+    if (rc) return rc;
+    if (n < 0 || ld < n) return fail(c, CCK_ERR_INVALID, "bad n/ld");
+    CK(c, cudaSetDevice(c->device));
+    const int dim = c->model.dim, W = dim + 2 * dim * dim;
+    int slot = 0;
+    for (int64_t off = 0; off < n; off += kChunk, slot ^= 1) {
+        const int64_t cnt = std::min(kChunk, n - off);
+        const size_t b_in = al256((size_t)cnt * W * 8), b_v = al256((size_t)cnt);
+        if ((rc = ensure_scratch(c, slot, b_in + b_v))) return rc;
+        unsigned char* base = (unsigned char*)c->d_scratch[slot];
+        cudaStream_t s = c->pipe[slot];
+        CK(c, h2d_planes(base, bel + off, 8, cnt, ld, W, s));
+        if ((rc = cck_is_valid_dev(c, s, cnt, (double*)base, cnt, base + b_in))) return rc;
+        CK(c, cudaMemcpyAsync(valid + off, base + b_in, (size_t)cnt, cudaMemcpyDeviceToHost, s));
+    }
+    CK(c, cudaStreamSynchronize(c->pipe[0]));
+    CK(c, cudaStreamSynchronize(c->pipe[1]));
+    return CCK_OK;
+}
+
+static int rollout_host(cck_ctx* c, bool expand, int64_t n, const double* bel, int64_t ld, const double* ctrl, int64_t ldc,
+                        const int32_t* steps, const int32_t* parent_step, const double* parent_cost, const cck_goal_params* goal,
+                        double* out, int64_t ldo, int32_t* valid_steps, double* traj, int64_t traj_ld, int32_t traj_T, double* cost,
+                        double* goal_dist, uint8_t* flags) {
+    int rc = check_ready(c, true);
+    if (rc) return rc;
+    if (n < 0 || ld < n || ldc < n || ldo < n || (traj && (traj_ld < n || traj_T < 1))) return fail(c, CCK_ERR_INVALID, "bad n/ld");
+    if (!bel || !ctrl || !steps || !out || !valid_steps) return fail(c, CCK_ERR_INVALID, "null argument");
+    CK(c, cudaSetDevice(c->device));
+    const int dim = c->model.dim, W = dim + 2 * dim * dim;
+    int64_t chunk = kChunk;
+    if (traj) chunk = std::max<int64_t>(1024, kChunk / (traj_T > 0 ? traj_T : 1));
+    int slot = 0;
+    for (int64_t off = 0; off < n; off += chunk, slot ^= 1) {
+        const int64_t cnt = std::min(chunk, n - off);
+        const size_t b_in = al256((size_t)cnt * W * 8), b_c = al256((size_t)cnt * dim * 8), b_i = al256((size_t)cnt * 4);
+        const size_t b_d = al256((size_t)cnt * 8), b_f = al256((size_t)cnt);
+        const size_t b_traj = traj ? al256((size_t)cnt * W * 8 * traj_T) : 0;
+        size_t total = b_in + b_c + b_i + b_in + b_i + b_traj;
+        if (expand) total += b_i + b_d + b_d + b_d + b_f;
+        if ((rc = ensure_scratch(c, slot, total))) return rc;
+        unsigned char* p = (unsigned char*)c->d_scratch[slot];
+        double* d_in = (double*)p; p += b_in;
+        double* d_c = (double*)p; p += b_c;
+        int32_t* d_steps = (int32_t*)p; p += b_i;
+        double* d_out = (double*)p; p += b_in;
+        int32_t* d_valid = (int32_t*)p; p += b_i;
+        double* d_traj = traj ? (double*)p : nullptr; p += b_traj;
+        cudaStream_t s = c->pipe[slot];
+        CK(c, h2d_planes(d_in, bel + off, 8, cnt, ld, W, s));
+        CK(c, h2d_planes(d_c, ctrl + off, 8, cnt, ldc, dim, s));
+        CK(c, cudaMemcpyAsync(d_steps, steps + off, (size_t)cnt * 4, cudaMemcpyHostToDevice, s));
+        if (!expand) {
+            if ((rc = cck_propagate_while_valid_dev(c, s, cnt, d_in, cnt, d_c, cnt, d_steps, d_out, cnt, d_valid, d_traj, cnt, traj_T))) return rc;
+        } else {
+            int32_t* d_ps = (int32_t*)p; p += b_i;
+            double* d_pc = (double*)p; p += b_d;
+            double* d_cost = (double*)p; p += b_d;
+            double* d_gd = (double*)p; p += b_d;
+            uint8_t* d_fl = (uint8_t*)p; p += b_f;
+            CK(c, cudaMemcpyAsync(d_ps, parent_step + off, (size_t)cnt * 4, cudaMemcpyHostToDevice, s));
+            CK(c, cudaMemcpyAsync(d_pc, parent_cost + off, (size_t)cnt * 8, cudaMemcpyHostToDevice, s));
+            if ((rc = cck_expand_batch_dev(c, s, cnt, d_in, cnt, d_c, cnt, d_steps, d_ps, d_pc, goal, d_out, cnt, d_valid, d_cost, d_gd, d_fl))) return rc;
+            CK(c, cudaMemcpyAsync(cost + off, d_cost, (size_t)cnt * 8, cudaMemcpyDeviceToHost, s));
+            CK(c, cudaMemcpyAsync(goal_dist + off, d_gd, (size_t)cnt * 8, cudaMemcpyDeviceToHost, s));
+            CK(c, cudaMemcpyAsync(flags + off, d_fl, (size_t)cnt, cudaMemcpyDeviceToHost, s));
+        }
+        CK(c, d2h_planes(out + off, ldo, d_out, 8, cnt, W, s));
+        CK(c, cudaMemcpyAsync(valid_steps + off, d_valid, (size_t)cnt * 4, cudaMemcpyDeviceToHost, s));
+        if (traj) CK(c, d2h_planes(traj + off, traj_ld, d_traj, 8, cnt, W * traj_T, s));
+    }
+    CK(c, cudaStreamSynchronize(c->pipe[0]));
+    CK(c, cudaStreamSynchronize(c->pipe[1]));
+    return CCK_OK;
+}
+
+extern "C" int cck_propagate_while_valid(cck_ctx* c, int64_t n, const double* bel, int64_t ld, const double* ctrl, int64_t ldc,
+                                         const int32_t* steps, double* out, int64_t ldo, int32_t* valid_steps, double* traj,
+                                         int64_t traj_ld, int32_t traj_T) {
+    return rollout_host(c, false, n, bel, ld, ctrl, ldc, steps, nullptr, nullptr, nullptr, out, ldo, valid_steps, traj, traj_ld, traj_T,
+                        nullptr, nullptr, nullptr);
+}
+
+extern "C" int cck_expand_batch(cck_ctx* c, int64_t n, const double* bel, int64_t ld, const double* ctrl, int64_t ldc,
+                                const int32_t* steps, const int32_t* parent_step, const double* parent_cost, const cck_goal_params* goal,
+                                double* out, int64_t ldo, int32_t* valid_steps, double* cost, double* goal_dist, uint8_t* flags) {
+    if (!c) return CCK_ERR_INVALID;
+    if (!goal || !parent_step || !parent_cost || !cost || !goal_dist || !flags) return fail(c, CCK_ERR_INVALID, "null argument");
+    return rollout_host(c, true, n, bel, ld, ctrl, ldc, steps, parent_step, parent_cost, goal, out, ldo, valid_steps, nullptr, 0, 0, cost,
+                        goal_dist, flags);
+}
+
+extern "C" int cck_validate_plan(cck_ctx* c, int k, const int32_t* lens, const double* traj, int64_t ld, cck_conflict_run* out) {
+    if (!c) return CCK_ERR_INVALID;
+    if (!c->has_pvc) return fail(c, CCK_ERR_INVALID, "cck_set_pvc has not been called");
+    if (!lens || !traj || !out || k != c->pvc.k) return fail(c, CCK_ERR_INVALID, "bad arguments");
+    CK(c, cudaSetDevice(c->device));
+    int max_len = 0;
+    for (int r = 0; r < k; ++r) { if (lens[r] < 1) return fail(c, CCK_ERR_INVALID, "empty trajectory"); max_len = std::max(max_len, lens[r]); }
+    if (ld < max_len) return fail(c, CCK_ERR_INVALID, "ld < max trajectory length");
+    const int W = c->pvc.dim + 2 * c->pvc.dim * c->pvc.dim;
+    const size_t b_traj = al256((size_t)k * W * max_len * 8), b_len = al256((size_t)k * 4);
+    int rc;
+    if ((rc = ensure_scratch(c, 0, b_traj + b_len))) return rc;
+    unsigned char* p = (unsigned char*)c->d_scratch[0];
+    cudaStream_t s = c->pipe[0];
+    CK(c, h2d_planes(p, traj, 8, max_len, ld, k * W, s));
+    CK(c, cudaMemcpyAsync(p + b_traj, lens, (size_t)k * 4, cudaMemcpyHostToDevice, s));
+    if ((rc = cck_validate_plan_dev(c, s, k, (int32_t*)(p + b_traj), max_len, (double*)p, max_len, c->d_run))) return rc;
+    CK(c, cudaMemcpyAsync(out, c->d_run, sizeof(cck_conflict_run), cudaMemcpyDeviceToHost, s));
+    CK(c, cudaStreamSynchronize(s));
+    return CCK_OK;
+}
+
+extern "C" int cck_satisfies_constraints(cck_ctx* c, int64_t n_paths, const double* path, int64_t ld, int32_t max_len,
+                                         const int32_t* path_len, const int32_t* path_step0, uint8_t* ok) {
+    if (!c) return CCK_ERR_INVALID;
+    if (!c->has_pvc) return fail(c, CCK_ERR_INVALID, "cck_set_pvc has not been called");
+    if (!path || !path_len || !path_step0 || !ok || n_paths < 0 || ld < n_paths || max_len < 1) return fail(c, CCK_ERR_INVALID, "bad arguments");
+    if (n_paths == 0) return CCK_OK;
+    CK(c, cudaSetDevice(c->device));
+    const int W = c->pvc.dim + 2 * c->pvc.dim * c->pvc.dim;
+    const size_t b_path = al256((size_t)n_paths * W * max_len * 8), b_i = al256((size_t)n_paths * 4), b_ok = al256((size_t)n_paths);
+    int rc;
+    if ((rc = ensure_scratch(c, 0, b_path + 2 * b_i + b_ok))) return rc;
+    unsigned char* p = (unsigned char*)c->d_scratch[0];
+    cudaStream_t s = c->pipe[0];
+    CK(c, h2d_planes(p, path, 8, n_paths, ld, W * max_len, s));
+    CK(c, cudaMemcpyAsync(p + b_path, path_len, (size_t)n_paths * 4, cudaMemcpyHostToDevice, s));
+    CK(c, cudaMemcpyAsync(p + b_path + b_i, path_step0, (size_t)n_paths * 4, cudaMemcpyHostToDevice, s));
+    if ((rc = cck_satisfies_constraints_dev(c, s, n_paths, (double*)p, n_paths, max_len, (int32_t*)(p + b_path), (int32_t*)(p + b_path + b_i),
+                                            p + b_path + 2 * b_i))) return rc;
+    CK(c, cudaMemcpyAsync(ok, p + b_path + 2 * b_i, (size_t)n_paths, cudaMemcpyDeviceToHost, s));
+    CK(c, cudaStreamSynchronize(s));
+    return CCK_OK;
+}
+
+extern "C" int cck_rollout_summary_dev(cck_ctx* c, void* stream, int64_t n, const int32_t* steps, const int32_t* valid_steps,
+                                       uint64_t* out_dev) {
+    if (!c || !steps || !valid_steps || !out_dev || n < 0) return CCK_ERR_INVALID;
+    CK(c, cudaSetDevice(c->device));
+    cudaStream_t s = pick(c, stream);
+    CK(c, cudaMemsetAsync(out_dev, 0, 3 * sizeof(uint64_t), s));
+    if (n > 0) {
+        k_summary<<<grid_for(c, n, 256, 4), 256, 0, s>>>(n, steps, valid_steps, reinterpret_cast<unsigned long long*>(out_dev));
+        c->launches++;
+        CK(c, cudaGetLastError());
+    }
+    return CCK_OK;
+}
+
+// ---------------------------------------------------------------------------
+// FP64 peak microbenchmark
+// ---------------------------------------------------------------------------
+extern "C" int cck_measure_fp64_peak(cck_ctx* c, double* tflops) {
+    if (!c || !tflops) return CCK_ERR_INVALID;
+    CK(c, cudaSetDevice(c->device));
+    double* d = nullptr;
+    CK(c, cudaMalloc(&d, 8));
+    cudaEvent_t e0, e1;
+    CK(c, cudaEventCreate(&e0)); CK(c, cudaEventCreate(&e1));
+    const int iters = 1 << 15, blocks = c->num_sms * 8, threads = 256;
+    double best = 0;
+    for (int rep = 0; rep < 5; ++rep) {
+        CK(c, cudaEventRecord(e0, c->stream));
+        k_fp64_peak<<<blocks, threads, 0, c->stream>>>(d, iters, 1.0 + rep);
+        CK(c, cudaEventRecord(e1, c->stream));
+        CK(c, cudaEventSynchronize(e1));
+        c->launches++;
+        float ms = 0;
+        CK(c, cudaEventElapsedTime(&ms, e0, e1));
+        const double flops = 2.0 * 8.0 * (double)iters * blocks * threads;
+        if (rep > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+    *tflops = best;
+    return CCK_OK;
+}

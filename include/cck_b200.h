@@ -1,0 +1,224 @@
+/* cck_b200.h — C ABI of libcck_b200.so: the B200 (sm_100a) drop-in for the
+ * belief-propagation + chance-constraint-checking hot path of CCK-CBS.
+ *
+ * Plain C, POD only, caller-owned buffers, int status codes, no exceptions and
+ * no torch/OMPL/Eigen types cross this boundary.  Each entry point names the
+ * reference interface it replaces (paths relative to the reference repo).
+ * There is NO CPU fallback: every compute entry point fails with
+ * CCK_ERR_NODEVICE / CCK_ERR_CUDA when no sm_100-class GPU is usable.
+ *
+ * Belief layout (replaces RealVectorBeliefSpace::StateType's three heap blocks,
+ * include/Spaces/RealVectorBeliefSpace.h:21-96): structure of arrays.  A belief
+ * batch is `W = dim + 2*dim*dim` planes of `n` doubles; plane f of belief i is
+ * `base[f*ld + i]` (ld >= n, in elements).  Plane order: values[0..dim),
+ * Sigma row-major, Lambda row-major (linear model: W=10; unicycle: W=36).
+ * Controls are `dim` planes with their own ld.  Trajectory buffers hold one
+ * belief batch per step: plane f of step t is `traj[(t*W + f)*ld + i]`.
+ *
+ * Host entry points take HOST pointers and do H2D / kernel / D2H on the
+ * context's stream (pinned staging owned by the context).  `_dev` entry points
+ * take DEVICE pointers plus a cudaStream_t (as void*; NULL = context stream),
+ * launch asynchronously and never synchronise.
+ */
+#ifndef CCK_B200_H
+#define CCK_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CCK_OK 0
+#define CCK_ERR_INVALID 1   /* bad argument / missing table */
+#define CCK_ERR_CUDA 2      /* a CUDA call failed; see cck_last_error */
+#define CCK_ERR_NOMEM 3
+#define CCK_ERR_NODEVICE 4  /* no usable GPU: the library never falls back to the CPU */
+
+#define CCK_MODEL_LINEAR2D 0 /* R2_UncertainLinearStatePropagator  (src/StatePropogators/UncertainLinearSP.cpp:58-111) */
+#define CCK_MODEL_UNICYCLE 1 /* DynUnicycleControlSpace            (src/StatePropogators/UncertainUnicycleSP.cpp:146-227) */
+
+#define CCK_SVC_BLACKMORE 0  /* PCCBlackmoreSVC          (src/StateValidityCheckers/PCCBlackmoreSVC.cpp:29-75) */
+#define CCK_SVC_ADAPTIVE 1   /* AdaptiveRiskBlackmoreSVC (src/StateValidityCheckers/AdaptiveRiskBlackmoreSVC.cpp:24-92) */
+#define CCK_SVC_CHISQUARED 2 /* ChiSquaredBoundarySVC    (src/StateValidityCheckers/ChiSquaredBoundarySVC.cpp:19-69) */
+
+#define CCK_PVC_BLACKMORE 0            /* MinkowskiSumBlackmorePVC   */
+#define CCK_PVC_BOUNDINGBOX 1          /* BoundingBoxBlackmorePVC    */
+#define CCK_PVC_CHISQUARED 2           /* ChiSquaredBoundaryPVC      */
+#define CCK_PVC_ADAPTIVE_BLACKMORE 3   /* AdaptiveRiskBlackmorePVC   */
+#define CCK_PVC_ADAPTIVE_BOUNDINGBOX 4 /* AdaptiveRiskBoundingBoxPVC */
+
+typedef struct cck_ctx cck_ctx;
+
+/* Model constants: the fields of the reference's propagator constructors
+ * (UncertainLinearSP.cpp:4-45, UncertainUnicycleSP.cpp:11-130) as one POD. */
+typedef struct cck_model_params {
+    int32_t model;        /* CCK_MODEL_* */
+    int32_t dim;          /* 2 or 4 */
+    double dt;            /* si->getPropagationStepSize() (OmplSetUp.cpp:186,224) */
+    double lin_Q[4], lin_R[4], lin_Acl[4];
+    double uni_F[16], uni_Acl[16], uni_Q[16], uni_R[16];
+    double uni_gains[8];  /* controller_parameters_ */
+    double uni_acc[2];    /* forward_acceleration_bounds_ */
+    double uni_turn[2];   /* turning_rate_bounds_ */
+} cck_model_params;
+
+/* State-validity-checker constants (what the reference SVC constructors compute once). */
+typedef struct cck_svc_params {
+    int32_t kind;          /* CCK_SVC_* */
+    int32_t dim;           /* state dimension whose bounds are checked */
+    double low[4], high[4];/* RealVectorBounds (OmplSetUp.cpp:195-200, 275-289) */
+    double erf_inv_result; /* Blackmore: erf_inv(1 - 2*p_coll/M)  (PCCBlackmoreSVC.cpp:10) */
+    double p_collision;    /* Adaptive:  1 - accep_prob           (AdaptiveRiskBlackmoreSVC.cpp:6) */
+    double sc;             /* ChiSquared: chi2_2 quantile         (ChiSquaredBoundarySVC.cpp:7) */
+    double max_rad;        /* ChiSquared: robot bounding radius   (ChiSquaredBoundarySVC.cpp:4) */
+} cck_svc_params;
+
+/* Plan-validity-checker constants (MinkowskiSumBlackmorePVC.cpp:4-30 and variants). */
+typedef struct cck_pvc_params {
+    int32_t kind;          /* CCK_PVC_* */
+    int32_t k;             /* number of robots (<= CCK_MAX_ROBOTS) */
+    int32_t dim;           /* 2 or 4: selects getDistribution_'s sub-block (BeliefPVC.cpp:84-113) */
+    int32_t reserved;
+    double c_pair;         /* erf_inv(1 - 2*p_coll_dist) (MinkowskiSumBlackmorePVC.cpp:178) */
+    double p_coll_agnts;   /* Adaptive PVCs: 1 - p_safe_agnts (BeliefPVC.cpp:7) */
+    double sc;             /* ChiSquared PVC: chi2_2 quantile (ChiSquaredBoundaryPVC.cpp:19) */
+    const double* radii;      /* [k] bounding radii */
+    const double* pair_A;     /* [k*k][4][2] half-plane normals, entry [a*k+b] valid for a<b */
+    const double* pair_B;     /* [k*k][4] */
+    const int32_t* map_order; /* [k] robot indices in std::map<std::string,...> name order (quirk 6) */
+} cck_pvc_params;
+#define CCK_MAX_ROBOTS 64
+
+/* One conflict run = the reference's std::vector<ConflictPtr> compressed:
+ * Conflict{a,b,first_step}, ..., Conflict{a,b,first_step+run_len-1}. */
+typedef struct cck_conflict_run {
+    int32_t a, b;          /* Conflict::agent1Idx_/agent2Idx_ (include/utils/Conflict.h:6-13) */
+    int32_t first_step;    /* -1 when the plan is conflict free */
+    int32_t run_len;
+} cck_conflict_run;
+
+/* ---- context ------------------------------------------------------------ */
+int cck_ctx_create(int device, cck_ctx** out);
+int cck_ctx_destroy(cck_ctx* ctx);
+const char* cck_last_error(const cck_ctx* ctx);   /* valid until the next call on ctx; ctx==NULL: last create error */
+int cck_ctx_synchronize(cck_ctx* ctx);
+int cck_num_sms(const cck_ctx* ctx);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+int64_t cck_launch_count(const cck_ctx* ctx);
+
+/* ---- constants ---------------------------------------------------------- */
+/* The reference constructors' constants for `model` at step size dt. */
+int cck_model_params_default(int model, double dt, cck_model_params* out);
+int cck_set_model(cck_ctx* ctx, const cck_model_params* p);
+/* Replaces the tables PCCBlackmoreSVC / AdaptiveRiskBlackmoreSVC / ChiSquaredBoundarySVC
+ * build in their constructors: A_list_ [M][4][2], B_list_ [M][4], obstacle centres [M][2]
+ * (Adaptive; may be NULL otherwise), inflated rectangles [M][4] = xlo,ylo,xhi,yhi
+ * (ChiSquared; may be NULL otherwise).  M may be 0. */
+int cck_set_obstacles(cck_ctx* ctx, const cck_svc_params* p, const double* A, const double* B,
+                      const double* centres, const double* rects, int M);
+int cck_set_pvc(cck_ctx* ctx, const cck_pvc_params* p);
+
+/* Host-side builders restating the reference's constant arithmetic (no GPU needed):
+ * Boost erf_inv / chi2 quantile call sites, Instance risk split, Minkowski half-planes. */
+double cck_erf_inv(double z);
+double cck_chi2_quantile_2dof(double p);
+/* Instance.cpp:38-44 */
+void cck_split_risk(double p_safe, int n_obstacles, int n_robots, double* p_safe_obs, double* p_safe_agents);
+/* RectangularRobot + createBoundingShape (common.cpp:117-136, 61-108) */
+double cck_rect_robot_bounding_radius(double sx, double sy, double len, double width);
+/* Unit-cell style rectangular obstacles (common.cpp:25-42) inflated by the robot's bounding
+ * square (PCCBlackmoreSVC.cpp:110-145) and converted to half-planes (:77-108). */
+int cck_build_obstacle_tables(int M, const double* centres, double len, double width, double robot_rad,
+                              double* A, double* B, double* rects);
+/* Robot-pair half-planes: Minkowski sum of the two bounding squares (MinkowskiSumBlackmorePVC.cpp:214-248)
+ * or the bounding box of r1+r2 (BoundingBoxBlackmorePVC.cpp:174-195). */
+int cck_build_pair_halfplanes(int bounding_box, double r1, double r2, double* A8, double* B4);
+
+/* ---- StatePropagator::propagate, batched --------------------------------
+ * replaces R2_UncertainLinearStatePropagator::propagate / DynUnicycleControlSpace::propagate
+ * for n independent (state, control) pairs; `duration` as in the reference signature
+ * (the linear model ignores it, quirk 1). */
+int cck_propagate(cck_ctx* ctx, int64_t n, const double* bel, int64_t ld, const double* ctrl, int64_t ldc,
+                  double duration, double* out, int64_t ldo);
+int cck_propagate_dev(cck_ctx* ctx, void* stream, int64_t n, const double* bel, int64_t ld, const double* ctrl,
+                      int64_t ldc, double duration, double* out, int64_t ldo);
+
+/* ---- StateValidityChecker::isValid, batched ----------------------------- */
+int cck_is_valid(cck_ctx* ctx, int64_t n, const double* bel, int64_t ld, uint8_t* valid);
+int cck_is_valid_dev(cck_ctx* ctx, void* stream, int64_t n, const double* bel, int64_t ld, uint8_t* valid);
+
+/* ---- SpaceInformation::propagateWhileValid, batched (the fused hot kernel) -
+ * replaces the OMPL loop called at ConstraintRespectingBSST.cpp:248: for each i,
+ * hold ctrl[i] for steps[i] steps of size dt, checking each new state with the
+ * installed SVC.  valid_steps[i] = number of leading valid steps (= index of the
+ * first violating step, or steps[i]); out = last valid state.  traj (optional,
+ * NULL to skip) receives every valid intermediate state, traj_T >= max(steps). */
+int cck_propagate_while_valid(cck_ctx* ctx, int64_t n, const double* bel, int64_t ld, const double* ctrl,
+                              int64_t ldc, const int32_t* steps, double* out, int64_t ldo, int32_t* valid_steps,
+                              double* traj, int64_t traj_ld, int32_t traj_T);
+int cck_propagate_while_valid_dev(cck_ctx* ctx, void* stream, int64_t n, const double* bel, int64_t ld,
+                                  const double* ctrl, int64_t ldc, const int32_t* steps, double* out, int64_t ldo,
+                                  int32_t* valid_steps, double* traj, int64_t traj_ld, int32_t traj_T);
+
+/* ---- PlanValidityChecker::validatePlan ----------------------------------
+ * replaces {MinkowskiSumBlackmore,BoundingBoxBlackmore,ChiSquaredBoundary,AdaptiveRisk*}PVC::validatePlan
+ * on already-interpolated trajectories (one belief per dt).  traj: robot r, plane f,
+ * step t at traj[(r*W + f)*ld + t]; lens[r] = number of states of robot r. */
+int cck_validate_plan(cck_ctx* ctx, int k, const int32_t* lens, const double* traj, int64_t ld, cck_conflict_run* out);
+int cck_validate_plan_dev(cck_ctx* ctx, void* stream, int k, const int32_t* lens_dev, int max_len, const double* traj,
+                          int64_t ld, cck_conflict_run* out_dev);
+
+/* ---- PlanValidityChecker::satisfiesConstraints, batched ------------------
+ * Constraints (BeliefConstraint, include/Constraints/BeliefConstraint.h:8-16) are
+ * flattened into entries: entry e applies at absolute step ent_step[e] and carries the
+ * constraining robot's belief as (mu[2], cov[4]) = getDistribution_ of the stored state,
+ * plus the robot-pair index pair_ab[e] = a*k+b (a<b) selecting the half-planes.
+ * Paths: n_paths candidate paths in one SoA trajectory buffer (plane f of step t of
+ * path i at path[(t*W+f)*ld + i]); path i has path_len[i] states and its first state
+ * sits at absolute step path_step0[i].  ok[i] = 1 iff every entry whose step falls on
+ * a state of path i is safe. */
+int cck_set_constraints(cck_ctx* ctx, int n_entries, const int32_t* ent_step, const int32_t* pair_ab,
+                        const double* mu2, const double* cov4);
+int cck_satisfies_constraints(cck_ctx* ctx, int64_t n_paths, const double* path, int64_t ld, int32_t max_len,
+                              const int32_t* path_len, const int32_t* path_step0, uint8_t* ok);
+int cck_satisfies_constraints_dev(cck_ctx* ctx, void* stream, int64_t n_paths, const double* path, int64_t ld,
+                                  int32_t max_len, const int32_t* path_len, const int32_t* path_step0, uint8_t* ok);
+
+/* ---- batched low-level expansion (ConstraintRespectingBSST.cpp:245-326 for K candidates) --
+ * For candidate i: parent belief, control, steps, parent's absolute step index and
+ * accumulated cost.  One launch does propagateWhileValid, the constraint check on the new
+ * segment (entries set by cck_set_constraints), the EuclideanPathLengthObjective increment
+ * and ChanceConstrainedGoal::isSatisfied.  flags bit0: propCd==cd, bit1: constraints ok,
+ * bit2: goal satisfied. */
+typedef struct cck_goal_params {
+    double gx, gy;      /* goal location */
+    double threshold;   /* goalTollorance = 2.0 (OmplSetUp.cpp:185) */
+    double sc;          /* chi2_2 quantile of 0.95 (BeliefSpaceGoals.cpp:110) */
+} cck_goal_params;
+int cck_expand_batch_dev(cck_ctx* ctx, void* stream, int64_t n, const double* bel, int64_t ld, const double* ctrl,
+                         int64_t ldc, const int32_t* steps, const int32_t* parent_step, const double* parent_cost,
+                         const cck_goal_params* goal, double* out, int64_t ldo, int32_t* valid_steps,
+                         double* cost, double* goal_dist, uint8_t* flags);
+int cck_expand_batch(cck_ctx* ctx, int64_t n, const double* bel, int64_t ld, const double* ctrl, int64_t ldc,
+                     const int32_t* steps, const int32_t* parent_step, const double* parent_cost,
+                     const cck_goal_params* goal, double* out, int64_t ldo, int32_t* valid_steps, double* cost,
+                     double* goal_dist, uint8_t* flags);
+
+/* ---- result summary (what a rank contributes to the NCCL gather) ---------------------
+ * out_dev[0] = number of candidates whose whole segment was valid (valid_steps == steps),
+ * out_dev[1] = executed belief-steps = sum_i min(valid_steps[i]+1, steps[i]),
+ * out_dev[2] = sum_i valid_steps[i].  One warp-shuffle reduction kernel. */
+int cck_rollout_summary_dev(cck_ctx* ctx, void* stream, int64_t n, const int32_t* steps, const int32_t* valid_steps,
+                            uint64_t* out_dev);
+
+/* ---- measurement helper ---------------------------------------------------
+ * FP64 pipe peak (DFMA chains, all SMs) in TFLOP/s measured on the context's device;
+ * the roofline denominator for the obstacle-check kernels (MEASURED_PEAKS.json has no
+ * FP64 entry). */
+int cck_measure_fp64_peak(cck_ctx* ctx, double* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CCK_B200_H */
