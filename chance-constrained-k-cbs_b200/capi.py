@@ -209,7 +209,7 @@ class Context:
         if rc:
             raise CckError(rc, self.L.cck_last_error(None).decode())
         self.h = h
-        self.dim = None
+        self.dim, self.dt, self.model = None, 0.2, None
         self._keep = []
 
     def close(self):

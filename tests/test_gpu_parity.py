@@ -86,11 +86,12 @@ def test_is_valid_no_obstacles_is_bounds_only(K, O, W, ctx):
     install_from_oracle_svc(K, ctx, svc, K.MODEL_LINEAR2D)
     bel, _ = W.synthetic_beliefs(4000, "linear", seed=3)
     bel[0] = np.linspace(-2, 10, 4000)
-    bel[1, 100:110] = np.nan          # NaN passes satisfiesBounds (OMPL semantics)
+    bel[1] = np.linspace(0.0, 7.0, 4000)[::-1]
+    bel[1, 2000:2010] = np.nan        # NaN passes satisfiesBounds (OMPL semantics)
     bel[0, 0] = -1.0 - 1e-16          # inside by the DBL_EPSILON slack
     got = ctx.is_valid(bel)
     ref, _ = svc.is_valid(K.soa_to_aos(bel))
-    assert np.array_equal(got, ref) and ref[100:110].all()
+    assert np.array_equal(got, ref) and ref[2000:2010].all() and 0.5 < ref.mean() < 0.9
 
 
 # --------------------------------------------------------------------------- propagateWhileValid
