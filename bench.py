@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--model", default="linear", choices=["linear", "unicycle"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs under ncu)")
     return ap.parse_args()
 
 
@@ -288,7 +289,11 @@ def run_ours(args):
         except Exception:
             pass
         fp64_peak = ctx.measure_fp64_peak()
-        cpu = cpu_baseline(args)
+        if args.no_cpu:
+            cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "skipped (--no-cpu)",
+                   "halfplane_tests_per_belief_step": 533.99 if args.variant == "all_survive" else 400.0}
+        else:
+            cpu = cpu_baseline(args)
         hps = cpu["halfplane_tests_per_belief_step"]
         f_prop = 60.0 if dim == 2 else 700.0
         f_alg_per_step = f_prop + 15.0 * hps          # F_alg = N_steps*F_prop + H_total*15

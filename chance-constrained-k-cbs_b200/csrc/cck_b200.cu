@@ -4,12 +4,14 @@
 #include <climits>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
 #include <vector>
 
 #include "cck_kernels.cuh"
+#include "cck_rollout_bm.cuh"
 
 using namespace cck;
 
@@ -24,6 +26,7 @@ struct cck_ctx {
     cudaStream_t pipe[2] = {nullptr, nullptr};
     std::string err;
     int64_t launches = 0;
+    int bpt = 2;   // beliefs per thread of the linear+Blackmore rollout kernel (CCK_BPT=0 selects the generic kernel)
 
     bool has_model = false;
     cck_model_params model{};
@@ -91,6 +94,7 @@ extern "C" int cck_ctx_create(int device, cck_ctx** out) {
     c->device = device;
     c->num_sms = prop.multiProcessorCount;
     c->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    if (const char* e2 = getenv("CCK_BPT")) { const int v = atoi(e2); if (v == 0 || v == 1 || v == 2 || v == 4) c->bpt = v; }
     if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&c->pipe[0], cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&c->pipe[1], cudaStreamNonBlocking)) != cudaSuccess ||
@@ -301,25 +305,30 @@ extern "C" int cck_set_obstacles(cck_ctx* c, const cck_svc_params* p, const doub
         members[it->second].push_back(o);
     }
     const int nc = (int)members.size();
+    int rows = 0;   // B rows incl. per-class padding to a multiple of 4
+    for (int k = 0; k < nc; ++k) rows += ((int)members[k].size() + 3) & ~3;
     TabHeader h{};
     h.n_classes = nc; h.M = M;
     h.off_classes = sizeof(TabHeader);
     h.off_B = h.off_classes + nc * (int)sizeof(ClassRec);
-    h.off_centres = h.off_B + M * 32;
+    h.off_centres = h.off_B + rows * 32;
     h.off_rects = h.off_centres + (centres ? M * 16 : 0);
     h.total_bytes = h.off_rects + (rects ? M * 32 : 0);
     h.total_bytes = (h.total_bytes + 15) & ~15;
+    h.pad = rows;
     if (h.total_bytes + 16 > c->max_smem_optin)
         return fail(c, CCK_ERR_INVALID, "obstacle table (" + std::to_string(h.total_bytes) + " B) exceeds shared memory; M too large");
     std::vector<unsigned char> buf(h.total_bytes, 0);
     std::memcpy(buf.data(), &h, sizeof(h));
     int pos = 0;
+    const double ninf[4] = {-HUGE_VAL, -HUGE_VAL, -HUGE_VAL, -HUGE_VAL};
     for (int k = 0; k < nc; ++k) {
         ClassRec r{};
         std::memcpy(r.A, keys[k].w, 64);
-        r.first = pos; r.count = (int)members[k].size();
+        r.first = pos; r.count = (int)members[k].size(); r.count_pad = (r.count + 3) & ~3;
         std::memcpy(buf.data() + h.off_classes + k * sizeof(ClassRec), &r, sizeof(r));
         for (int o : members[k]) { std::memcpy(buf.data() + h.off_B + pos * 32, B + 4 * o, 32); ++pos; }
+        for (int j = r.count; j < r.count_pad; ++j) { std::memcpy(buf.data() + h.off_B + pos * 32, ninf, 32); ++pos; }
     }
     if (centres && M) std::memcpy(buf.data() + h.off_centres, centres, (size_t)M * 16);   // original order (sum order, eta_list[0])
     if (rects && M) std::memcpy(buf.data() + h.off_rects, rects, (size_t)M * 32);
@@ -473,7 +482,19 @@ static int launch_rollout(cck_ctx* c, cudaStream_t s, const RolloutArgs& a) {
         else if (c->svc.kind == CCK_SVC_ADAPTIVE) LAUNCH_R((NAME<CCK_SVC_ADAPTIVE, TRAJ, EXPAND>), PAR);           \
         else LAUNCH_R((NAME<CCK_SVC_CHISQUARED, TRAJ, EXPAND>), PAR);                                               \
     } while (0)
-    if (c->model.model == CCK_MODEL_LINEAR2D) {
+    if (c->model.model == CCK_MODEL_LINEAR2D && c->svc.kind == CCK_SVC_BLACKMORE && c->bpt > 0) {
+        // default configuration: threshold kernel, BPT beliefs per thread
+#define LAUNCH_BM(BPT, TRAJ)                                                                             \
+    do {                                                                                                 \
+        const int gb = grid_for(c, (a.n + BPT - 1) / BPT, threads, 8);                                   \
+        if ((rc = set_smem(c, (k_rollout_lin_bm<BPT, TRAJ, EXPAND>), smem))) return rc;                  \
+        k_rollout_lin_bm<BPT, TRAJ, EXPAND><<<gb, threads, smem, s>>>(a, c->lin, c->svc);                \
+    } while (0)
+        if (c->bpt == 1) { if (traj) LAUNCH_BM(1, true); else LAUNCH_BM(1, false); }
+        else if (c->bpt == 2) { if (traj) LAUNCH_BM(2, true); else LAUNCH_BM(2, false); }
+        else { if (traj) LAUNCH_BM(4, true); else LAUNCH_BM(4, false); }
+#undef LAUNCH_BM
+    } else if (c->model.model == CCK_MODEL_LINEAR2D) {
         if (traj) DISPATCH_KIND(k_rollout_lin, c->lin, true); else DISPATCH_KIND(k_rollout_lin, c->lin, false);
     } else {
         if (traj) DISPATCH_KIND(k_rollout_uni, c->uni, true); else DISPATCH_KIND(k_rollout_uni, c->uni, false);

@@ -27,8 +27,9 @@ struct TabHeader {
 };
 struct ClassRec {
     double A[8];            // [4][2]
-    int32_t first, count;   // range in the class-sorted B array
-    double pad;
+    int32_t first, count;   // range in the class-sorted B array (rows [first, first+count) are real)
+    int32_t count_pad;      // count rounded up to a multiple of 4; padding rows hold B = -inf
+    int32_t reserved;
 };
 static_assert(sizeof(TabHeader) == 32, "header");
 static_assert(sizeof(ClassRec) == 80, "class record");
