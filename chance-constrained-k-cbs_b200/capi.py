@@ -378,3 +378,50 @@ def aos_to_soa(b):
 
 def soa_to_aos(b):
     return np.ascontiguousarray(np.asarray(b).T)
+
+
+def robot_map_order(k):
+    """Robot indices in std::map<std::string, Belief> order of the names "Robot i"
+    (lexicographic: "Robot 10" < "Robot 2"; MinkowskiSumBlackmorePVC.cpp:133, quirk 6)."""
+    return np.array(sorted(range(k), key=lambda i: f"Robot {i}"), dtype=np.int32)
+
+
+def install_pvc(ctx, kind, dim, radii, p_safe_agents, chi_p=0.9):
+    """Build the plan-validity-checker constants the reference constructors compute
+    (MinkowskiSumBlackmorePVC.cpp:4-30, BoundingBoxBlackmorePVC.cpp:4-32, ChiSquaredBoundaryPVC.cpp:4-20,
+    demos/main.cpp:105-138) with the library's host builders and install them in `ctx`."""
+    radii = np.ascontiguousarray(radii, dtype=np.float64)
+    k = len(radii)
+    p_coll_agnts = 1 - p_safe_agents
+    p_coll_dist = p_coll_agnts / (k - 1) if k > 1 else p_coll_agnts
+    c_pair = erf_inv(1 - (2 * p_coll_dist))
+    bb = kind in (PVC_BOUNDINGBOX, PVC_ADAPTIVE_BOUNDINGBOX)
+    A = np.zeros((k * k, 4, 2))
+    B = np.zeros((k * k, 4))
+    for a in range(k):
+        for b in range(a + 1, k):
+            A[a * k + b], B[a * k + b] = build_pair_halfplanes(radii[a], radii[b], bb)
+    sc = chi2_quantile_2dof(chi_p)
+    ctx.set_pvc(kind, k, dim, radii, A, B, robot_map_order(k), c_pair=c_pair, p_coll_agnts=p_coll_agnts, sc=sc)
+    return {"c_pair": c_pair, "p_coll_dist": p_coll_dist, "pair_A": A, "pair_B": B, "sc": sc}
+
+
+def constraint_entries(k, dim, constrained, constraints):
+    """Flatten BeliefConstraints for cck_set_constraints.  constraints: list of
+    (constraining_robot, steps[int], states AoS [len(steps), W]) as BeliefPVC::createConstraint
+    builds them (BeliefPVC.cpp:10-40).  Returns (ent_step, pair_ab, mu2, cov4)."""
+    ent_step, pair_ab, mu, cov = [], [], [], []
+    for other, steps, states in constraints:
+        st = np.asarray(states, dtype=np.float64).reshape(len(steps), -1)
+        lo, hi = min(constrained, other), max(constrained, other)
+        for s, b in zip(steps, st):
+            ent_step.append(int(s))
+            pair_ab.append(lo * k + hi)
+            mu.append(b[:2])
+            S, L = b[dim:dim + dim * dim], b[dim + dim * dim:]
+            if dim == 4:   # BeliefPVC::getDistribution_ picks (0,0),(0,2),(2,0),(2,2)
+                cov.append([S[0] + L[0], S[2] + L[2], S[8] + L[8], S[10] + L[10]])
+            else:
+                cov.append(S + L)
+    return (np.array(ent_step, dtype=np.int32), np.array(pair_ab, dtype=np.int32),
+            np.array(mu, dtype=np.float64).reshape(-1, 2), np.array(cov, dtype=np.float64).reshape(-1, 4))
