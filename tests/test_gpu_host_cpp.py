@@ -1,0 +1,84 @@
+"""GPU tests of the C++ host side: the OMPL-shaped adapters (one virtual call per step, as OMPL
+drives them) against the batched C-ABI launch, and the batched low-level planner + K-CBS driver
+whose plans are verified with the CPU oracle."""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT
+
+pytestmark = pytest.mark.gpu
+HOST = os.path.join(ROOT, "chance-constrained-k-cbs_b200", "host")
+
+
+def write_instance(tmp_path, g, name):
+    """MovingAI-style map + scen text rebuilt from a golden fixture (obstacle centres, starts, goals)."""
+    W, H = int(g["x_max"]), int(g["y_max"])
+    grid = [["."] * W for _ in range(H)]
+    for x, y in g["centres"]:
+        grid[int(y)][int(x)] = "@"
+    mp = tmp_path / f"{name}.map"
+    mp.write_text(f"type octile\nheight {H}\nwidth {W}\nmap\n" + "\n".join("".join(r) for r in grid) + "\n")
+    model = "2D-Uncertain-Linear-Model" if int(g["dim"]) == 2 else "Uncertain-Unicycle-Model"
+    lines = ["version 1"]
+    for s, t in zip(g["starts"], g["goals"]):
+        lines.append(f"1\t{name}.map\t{W}\t{H}\t{int(s[0])}\t{int(s[1])}\t{int(t[0])}\t{int(t[1])}\tRectangle\t{model}\t1.0")
+    sc = tmp_path / f"{name}.scen"
+    sc.write_text("\n".join(lines) + "\n")
+    return str(mp), str(sc)
+
+
+def build_host():
+    subprocess.check_call(["make", "-C", HOST, "-s"])
+
+
+def read_plan(path):
+    trajs, cur = [], None
+    for ln in open(path):
+        if ln.startswith("robot"):
+            cur = []
+            trajs.append(cur)
+        else:
+            cur.append([float(x) for x in ln.split()])
+    return [np.array(t) for t in trajs]
+
+
+def test_adapters_match_batched_launch(tmp_path):
+    build_host()
+    g = np.load(os.path.join(GOLDEN, "config4_narrow_linear_k2.npz"))
+    # the narrow-passage map is 4x7; widen it so two head-on robots meet inside the bounds
+    g2 = dict(g); g2["x_max"], g2["y_max"] = 9.0, 9.0
+    g2["centres"] = np.array([[4.0, 0.0], [4.0, 1.0], [4.0, 7.0], [4.0, 8.0]])
+    mp, sc = write_instance(tmp_path, g2, "selftest")
+    out = subprocess.run([os.path.join(HOST, "host_selftest"), mp, sc], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "host_selftest OK" in out.stdout
+
+
+@pytest.mark.parametrize("fixture,k,tmax", [("config1_empty8_linear_k2", 2, 120), ("config4_narrow_linear_k2", 2, 180)])
+def test_kcbs_plan_verified_by_oracle(O, tmp_path, fixture, k, tmax):
+    build_host()
+    g = np.load(os.path.join(GOLDEN, fixture + ".npz"))
+    mp, sc = write_instance(tmp_path, g, fixture)
+    plan_path = str(tmp_path / "plan.txt")
+    out = subprocess.run([os.path.join(HOST, "cck_plan"), "-m", mp, "-s", sc, "-k", str(k), "-t", str(tmax), "--K", "512", "--seed", "3",
+                          "--lltime", "20", "-o", plan_path], capture_output=True, text=True, timeout=tmax + 120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    res = json.loads(out.stdout.strip().splitlines()[-1])
+    assert res["solved"] and res["launches"] > 0
+    trajs = read_plan(plan_path)
+    assert len(trajs) == k
+    world = O.World.synthetic(g["centres"], float(g["x_max"]), float(g["y_max"]), k, float(g["p_safe"]))
+    svc = O.Svc(world, O.SVC_BLACKMORE, 2)
+    for r, t in enumerate(trajs):
+        assert np.array_equal(t[0, :2], g["starts"][r])                       # starts at the robot's start
+        ok, _ = svc.is_valid(t[1:])
+        assert ok.all(), f"robot {r}: oracle rejects a state of the GPU plan"
+        reached, _ = O.goal(t[-1:], 2, float(g["goals"][r, 0]), float(g["goals"][r, 1]))
+        assert reached[0], f"robot {r}: final belief does not satisfy the chance-constrained goal"
+        # consecutive states differ by one dt step of a bounded control: |dx| <= 0.2
+        assert np.abs(np.diff(t[:, :2], axis=0)).max() <= 0.2 + 1e-12
+    assert O.Pvc(world, O.PVC_BLACKMORE).validate_plan(trajs, 2) == []        # conflict free per the oracle
