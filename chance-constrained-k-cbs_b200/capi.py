@@ -65,7 +65,7 @@ SYMBOLS = [
     "cck_propagate_while_valid", "cck_propagate_while_valid_dev",
     "cck_validate_plan", "cck_validate_plan_dev",
     "cck_set_constraints", "cck_satisfies_constraints", "cck_satisfies_constraints_dev",
-    "cck_expand_batch", "cck_expand_batch_dev", "cck_rollout_summary_dev", "cck_measure_fp64_peak",
+    "cck_expand_batch", "cck_expand_batch_dev", "cck_rollout_summary_dev", "cck_select_winner_dev", "cck_measure_fp64_peak",
 ]
 
 
@@ -133,6 +133,7 @@ def lib():
     L.cck_expand_batch.argtypes = [vp, i64, vp, i64, vp, i64, vp, vp, vp, C.POINTER(GoalParams), vp, i64, vp, vp, vp, vp]
     L.cck_expand_batch_dev.argtypes = [vp, vp, i64, vp, i64, vp, i64, vp, vp, vp, C.POINTER(GoalParams), vp, i64, vp, vp, vp, vp]
     L.cck_rollout_summary_dev.argtypes = [vp, vp, i64, vp, vp, vp]
+    L.cck_select_winner_dev.argtypes = [vp, vp, i64, vp, vp, C.c_int, i64, vp]
     L.cck_measure_fp64_peak.argtypes = [vp, dp]
     _lib = L
     return L
@@ -364,6 +365,15 @@ class Context:
 
     def rollout_summary_dev(self, stream, n, steps, valid, out3):
         self._ck(self.L.cck_rollout_summary_dev(self.h, stream, n, _ptr(steps), _ptr(valid), _ptr(out3)))
+
+    def select_winner_dev(self, stream, n, cost, flags, required_mask, index_offset, out2):
+        self._ck(self.L.cck_select_winner_dev(self.h, stream, n, _ptr(cost), _ptr(flags), required_mask, index_offset, _ptr(out2)))
+
+    def expand_batch_dev(self, stream, n, bel, ld, ctrl, ldc, steps, parent_step, parent_cost, goal_xy, out, ldo, valid, cost, goal_dist, flags,
+                         threshold=2.0, goal_p_safe=0.95):
+        g = GoalParams(float(goal_xy[0]), float(goal_xy[1]), threshold, chi2_quantile_2dof(goal_p_safe))
+        self._ck(self.L.cck_expand_batch_dev(self.h, stream, n, _ptr(bel), ld, _ptr(ctrl), ldc, _ptr(steps), _ptr(parent_step), _ptr(parent_cost),
+                                             C.byref(g), _ptr(out), ldo, _ptr(valid), _ptr(cost), _ptr(goal_dist), _ptr(flags)))
 
     def measure_fp64_peak(self):
         t = C.c_double()

@@ -837,6 +837,16 @@ extern "C" int cck_rollout_summary_dev(cck_ctx* c, void* stream, int64_t n, cons
     return CCK_OK;
 }
 
+extern "C" int cck_select_winner_dev(cck_ctx* c, void* stream, int64_t n, const double* cost, const uint8_t* flags, int required_mask,
+                                     int64_t index_offset, double* out_dev) {
+    if (!c || !cost || !flags || !out_dev || n < 0) return CCK_ERR_INVALID;
+    CK(c, cudaSetDevice(c->device));
+    k_winner<<<1, 1024, 0, pick(c, stream)>>>(n, cost, flags, required_mask, index_offset, out_dev);
+    c->launches++;
+    CK(c, cudaGetLastError());
+    return CCK_OK;
+}
+
 // ---------------------------------------------------------------------------
 // FP64 peak microbenchmark
 // ---------------------------------------------------------------------------

@@ -498,6 +498,39 @@ __global__ void __launch_bounds__(256) k_summary(int64_t n, const int32_t* __res
     if ((threadIdx.x & 31) == 0) { atomicAdd(out, full); atomicAdd(out + 1, exec); atomicAdd(out + 2, vsum); }
 }
 
+// winner record: lexicographic min of (cost, index) over admissible candidates, one CTA
+__global__ void __launch_bounds__(1024) k_winner(int64_t n, const double* __restrict__ cost, const uint8_t* __restrict__ flags,
+                                                 int mask, int64_t offset, double* __restrict__ out) {
+    __shared__ double sc[32];
+    __shared__ long long si[32];
+    double bc = HUGE_VAL;
+    long long bi = -1;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+        if ((flags[i] & mask) != mask) continue;
+        const double c = cost[i];
+        if (c < bc || (c == bc && (bi < 0 || i < bi))) { bc = c; bi = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double oc = __shfl_xor_sync(0xffffffffu, bc, o);
+        const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (oi >= 0 && (bi < 0 || oc < bc || (oc == bc && oi < bi))) { bc = oc; bi = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { sc[threadIdx.x >> 5] = bc; si[threadIdx.x >> 5] = bi; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        bc = threadIdx.x < (blockDim.x >> 5) ? sc[threadIdx.x] : HUGE_VAL;
+        bi = threadIdx.x < (blockDim.x >> 5) ? si[threadIdx.x] : -1;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double oc = __shfl_xor_sync(0xffffffffu, bc, o);
+            const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (oi >= 0 && (bi < 0 || oc < bc || (oc == bc && oi < bi))) { bc = oc; bi = oi; }
+        }
+        if (threadIdx.x == 0) { out[0] = bi >= 0 ? bc : HUGE_VAL; out[1] = bi >= 0 ? (double)(offset + bi) : -1.0; }
+    }
+}
+
 // ---------------------------------------------------------------------------
 // FP64 pipe peak: 8 independent DFMA chains per thread (measurement helper)
 // ---------------------------------------------------------------------------

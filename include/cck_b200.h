@@ -212,6 +212,13 @@ int cck_expand_batch(cck_ctx* ctx, int64_t n, const double* bel, int64_t ld, con
 int cck_rollout_summary_dev(cck_ctx* ctx, void* stream, int64_t n, const int32_t* steps, const int32_t* valid_steps,
                             uint64_t* out_dev);
 
+/* Winner of a batched expansion (the candidate the planner would commit first by cost):
+ * among candidates with (flags & required_mask) == required_mask the one with the smallest
+ * cost, ties to the smallest index.  out_dev[0] = cost (+inf if none), out_dev[1] = global
+ * index (index_offset + i, as a double; -1 if none).  One per-rank record to all-gather. */
+int cck_select_winner_dev(cck_ctx* ctx, void* stream, int64_t n, const double* cost, const uint8_t* flags,
+                          int required_mask, int64_t index_offset, double* out_dev);
+
 /* ---- measurement helper ---------------------------------------------------
  * FP64 pipe peak (DFMA chains, all SMs) in TFLOP/s measured on the context's device;
  * the roofline denominator for the obstacle-check kernels (MEASURED_PEAKS.json has no

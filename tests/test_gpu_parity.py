@@ -199,3 +199,36 @@ def test_launch_count_and_errors(K, W, ctx):
     ctx.propagate(bel, ctrl)
     assert ctx.launch_count == before + 1
     assert ctx.num_sms >= 100
+
+
+def test_summary_and_winner_records(K, W, ctx):
+    """The per-rank result records that are all-gathered over NCCL (k_summary, k_winner)."""
+    import torch
+    W.install_synthetic(ctx, "linear", 256, variant="realistic")
+    n, T = 50000, 20
+    bel, ctrl = W.synthetic_beliefs(n, "linear", seed=4)
+    steps = np.random.default_rng(0).integers(0, T + 1, n).astype(np.int32)
+    out, valid = ctx.propagate_while_valid(bel, ctrl, steps)
+    dev = torch.device("cuda", 0)
+    d_steps, d_valid = torch.from_numpy(steps).to(dev), torch.from_numpy(valid).to(dev)
+    d_sum = torch.zeros(3, dtype=torch.int64, device=dev)
+    ctx.rollout_summary_dev(None, n, d_steps, d_valid, d_sum)
+    ctx.synchronize()
+    torch.cuda.synchronize()
+    ref = [int((valid == steps).sum()), int(np.where(steps > 0, np.minimum(valid + 1, steps), 0).sum()), int(valid.sum())]
+    assert d_sum.tolist() == ref
+    rng = np.random.default_rng(1)
+    cost = rng.uniform(0, 100, n)
+    flags = rng.integers(0, 8, n).astype(np.uint8)
+    adm = np.nonzero((flags & 3) == 3)[0]
+    cost[adm[[10, 500]]] = -1.0                                  # tie: lowest index wins
+    d_cost, d_flags = torch.from_numpy(cost).to(dev), torch.from_numpy(flags).to(dev)
+    rec = torch.zeros(2, dtype=torch.float64, device=dev)
+    ctx.select_winner_dev(None, n, d_cost, d_flags, 3, 1000, rec)
+    ctx.synchronize()
+    torch.cuda.synchronize()
+    assert rec.tolist() == [-1.0, float(1000 + adm[10])]
+    ctx.select_winner_dev(None, n, d_cost, torch.zeros_like(d_flags), 3, 0, rec)
+    ctx.synchronize()
+    torch.cuda.synchronize()
+    assert rec.tolist() == [float("inf"), -1.0]
