@@ -26,7 +26,7 @@ struct cck_ctx {
     cudaStream_t pipe[2] = {nullptr, nullptr};
     std::string err;
     int64_t launches = 0;
-    int bpt = 2;   // beliefs per thread of the linear+Blackmore rollout kernel (CCK_BPT=0 selects the generic kernel)
+    int bpt = 1;   // beliefs per thread of the linear+Blackmore rollout kernel (CCK_BPT=0 selects the generic kernel)
 
     bool has_model = false;
     cck_model_params model{};
@@ -37,6 +37,10 @@ struct cck_ctx {
     SvcDev svc{};
     unsigned char* d_tab = nullptr;
     int tab_bytes = 0;
+    unsigned char* d_ftab = nullptr;   // fp32 filter table (Blackmore fast path)
+    int ftab_bytes = 0;
+    double* d_exB = nullptr;           // exact fp64 rows in filter-table order
+    int32_t* d_exCls = nullptr;        // class of each row (-1: padding)
     int M = 0;
 
     bool has_pvc = false;
@@ -112,6 +116,7 @@ extern "C" int cck_ctx_destroy(cck_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     for (int i = 0; i < 2; ++i) { if (c->pipe[i]) { cudaStreamSynchronize(c->pipe[i]); cudaStreamDestroy(c->pipe[i]); } cudaFree(c->d_scratch[i]); }
+    cudaFree(c->d_ftab); cudaFree(c->d_exB); cudaFree(c->d_exCls);
     cudaFree(c->d_tab); cudaFree(c->d_pvc_A); cudaFree(c->d_pvc_B); cudaFree(c->d_pvc_radii); cudaFree(c->d_pvc_order);
     cudaFree(c->d_key); cudaFree(c->d_run); cudaFree(c->d_cons);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -340,6 +345,75 @@ extern "C" int cck_set_obstacles(cck_ctx* c, const cck_svc_params* p, const doub
     c->tab_bytes = h.total_bytes;
     c->M = M;
 
+    // ---- fp32 filter table: super-classes of normals that agree to 1e-14 relative ----
+    cudaFree(c->d_ftab); cudaFree(c->d_exB); cudaFree(c->d_exCls);
+    c->d_ftab = nullptr; c->d_exB = nullptr; c->d_exCls = nullptr; c->ftab_bytes = 0;
+    if (M > 0) {
+        std::vector<std::vector<int>> supers;          // class indices per super-class
+        for (int k = 0; k < nc; ++k) {
+            double Ak[8]; std::memcpy(Ak, keys[k].w, 64);
+            int found = -1;
+            for (size_t sidx = 0; sidx < supers.size() && found < 0; ++sidx) {
+                double Ar[8]; std::memcpy(Ar, keys[supers[sidx][0]].w, 64);
+                double scale = 0, diff = 0;
+                for (int i = 0; i < 8; ++i) { scale = std::max(scale, std::fabs(Ar[i])); diff = std::max(diff, std::fabs(Ar[i] - Ak[i])); }
+                if (std::isfinite(scale) && diff <= 1e-14 * scale) found = (int)sidx;
+            }
+            if (found < 0) { supers.emplace_back(); found = (int)supers.size() - 1; }
+            supers[found].push_back(k);
+        }
+        const int nsup = (int)supers.size();
+        int frows = 0;
+        std::vector<int> sup_rows(nsup);
+        for (int sidx = 0; sidx < nsup; ++sidx) {
+            int cnt = 0;
+            for (int k : supers[sidx]) cnt += (int)members[k].size();
+            sup_rows[sidx] = (cnt + 3) & ~3;
+            frows += sup_rows[sidx];
+        }
+        FHeader fh{};
+        fh.n_super = nsup; fh.rows_total = frows;
+        fh.off_super = sizeof(FHeader);
+        fh.off_rows = fh.off_super + nsup * (int)sizeof(SuperRec);
+        fh.total_bytes = (fh.off_rows + frows * 16 + 15) & ~15;
+        std::vector<unsigned char> fbuf(fh.total_bytes, 0);
+        std::vector<double> exB((size_t)frows * 4, -HUGE_VAL);
+        std::vector<int32_t> exCls(frows, -1);
+        std::memcpy(fbuf.data(), &fh, sizeof(fh));
+        float* frow = reinterpret_cast<float*>(fbuf.data() + fh.off_rows);
+        int rpos = 0;
+        for (int sidx = 0; sidx < nsup; ++sidx) {
+            SuperRec sr{};
+            std::memcpy(sr.A, keys[supers[sidx][0]].w, 64);
+            sr.first_row = rpos; sr.n_rows_pad = sup_rows[sidx];
+            std::memcpy(fbuf.data() + fh.off_super + sidx * sizeof(SuperRec), &sr, sizeof(sr));
+            int written = 0;
+            for (int k : supers[sidx])
+                for (int o : members[k]) {
+                    for (int i = 0; i < 4; ++i) {
+                        const double bv = B[4 * o + i];
+                        float bf = (float)bv;                       // round to nearest, then force UP
+                        if ((double)bf < bv) bf = std::nextafterf(bf, HUGE_VALF);
+                        if (std::isnan(bv)) bf = HUGE_VALF;         // never "proven": +inf <= tau fails unless tau = +inf (dead slot)
+                        frow[(size_t)(rpos + written) * 4 + i] = bf;
+                        exB[(size_t)(rpos + written) * 4 + i] = bv;
+                    }
+                    exCls[rpos + written] = k;
+                    ++written;
+                }
+            for (; written < sup_rows[sidx]; ++written)
+                for (int i = 0; i < 4; ++i) frow[(size_t)(rpos + written) * 4 + i] = -HUGE_VALF;
+            rpos += sup_rows[sidx];
+        }
+        CK(c, cudaMalloc(&c->d_ftab, fh.total_bytes));
+        CK(c, cudaMalloc(&c->d_exB, exB.size() * 8));
+        CK(c, cudaMalloc(&c->d_exCls, exCls.size() * 4));
+        CK(c, cudaMemcpy(c->d_ftab, fbuf.data(), fh.total_bytes, cudaMemcpyHostToDevice));
+        CK(c, cudaMemcpy(c->d_exB, exB.data(), exB.size() * 8, cudaMemcpyHostToDevice));
+        CK(c, cudaMemcpy(c->d_exCls, exCls.data(), exCls.size() * 4, cudaMemcpyHostToDevice));
+        c->ftab_bytes = fh.total_bytes;
+    }
+
     SvcDev& s = c->svc;
     std::memset(&s, 0, sizeof(s));
     s.kind = p->kind; s.dim = p->dim;
@@ -487,8 +561,9 @@ static int launch_rollout(cck_ctx* c, cudaStream_t s, const RolloutArgs& a) {
 #define LAUNCH_BM(BPT, TRAJ)                                                                             \
     do {                                                                                                 \
         const int gb = grid_for(c, (a.n + BPT - 1) / BPT, threads, 8);                                   \
-        if ((rc = set_smem(c, (k_rollout_lin_bm<BPT, TRAJ, EXPAND>), smem))) return rc;                  \
-        k_rollout_lin_bm<BPT, TRAJ, EXPAND><<<gb, threads, smem, s>>>(a, c->lin, c->svc);                \
+        const int fsmem = 16 + c->ftab_bytes;                                                            \
+        if ((rc = set_smem(c, (k_rollout_lin_bm<BPT, TRAJ, EXPAND>), fsmem))) return rc;                 \
+        k_rollout_lin_bm<BPT, TRAJ, EXPAND><<<gb, threads, fsmem, s>>>(a, c->lin, c->svc);               \
     } while (0)
         if (c->bpt == 1) { if (traj) LAUNCH_BM(1, true); else LAUNCH_BM(1, false); }
         else if (c->bpt == 2) { if (traj) LAUNCH_BM(2, true); else LAUNCH_BM(2, false); }
@@ -517,6 +592,7 @@ extern "C" int cck_propagate_while_valid_dev(cck_ctx* c, void* stream, int64_t n
     RolloutArgs a{};
     a.n = n; a.bel = bel; a.ld = ld; a.ctrl = ctrl; a.ldc = ldc; a.steps = steps; a.out = out; a.ldo = ldo; a.valid = valid_steps;
     a.traj = traj; a.traj_ld = traj_ld; a.traj_T = traj_T; a.tab = c->d_tab; a.tab_bytes = c->tab_bytes; a.duration = c->model.dt;
+    a.ftab = c->d_ftab; a.ftab_bytes = c->ftab_bytes; a.exB = c->d_exB; a.exCls = c->d_exCls;
     return launch_rollout<false>(c, pick(c, stream), a);
 }
 
@@ -535,6 +611,7 @@ extern "C" int cck_expand_batch_dev(cck_ctx* c, void* stream, int64_t n, const d
     a.tab = c->d_tab; a.tab_bytes = c->tab_bytes; a.duration = c->model.dt;
     a.parent_step = parent_step; a.parent_cost = parent_cost; a.cost = cost; a.goal_dist = goal_dist; a.flags = flags;
     a.goal = *goal; a.cons = c->d_cons;
+    a.ftab = c->d_ftab; a.ftab_bytes = c->ftab_bytes; a.exB = c->d_exB; a.exCls = c->d_exCls;
     return launch_rollout<true>(c, pick(c, stream), a);
 }
 

@@ -34,6 +34,12 @@ struct ClassRec {
 static_assert(sizeof(TabHeader) == 32, "header");
 static_assert(sizeof(ClassRec) == 80, "class record");
 
+// Filter table (Blackmore fast path): obstacles grouped into SUPER-classes whose normals agree to
+// 1e-14 relative (the reference's tables: one super-class), rows = B rounded UP to fp32.
+struct FHeader { int32_t n_super, rows_total, off_super, off_rows, total_bytes, pad[3]; };
+struct SuperRec { double A[8]; int32_t first_row, n_rows_pad, pad[2]; };
+static_assert(sizeof(FHeader) == 32 && sizeof(SuperRec) == 80, "filter table records");
+
 struct SvcDev {
     int32_t kind, dim;
     double low[4], high[4];

@@ -25,6 +25,9 @@ struct RolloutArgs {
     double* cost; double* goal_dist; uint8_t* flags;
     cck_goal_params goal;
     const unsigned char* cons;   // constraint table (global memory)
+    // Blackmore fast path: fp32 filter table (staged to smem) + exact rows (global, slow path only)
+    const unsigned char* ftab; int32_t ftab_bytes;
+    const double* exB; const int32_t* exCls;
 };
 
 // ---------------------------------------------------------------------------

@@ -1,27 +1,29 @@
 // cck_rollout_bm.cuh — the fused propagateWhileValid kernel for the default configuration
 // (2DUncertainLinear + PCCBlackmoreSVC), restructured around what ncu showed on the first
-// version (profiles/r1a_*): the per-obstacle loop was co-limited by LDS broadcast bandwidth
-// (2 x LDS.128 per obstacle per warp) and by DADD->DSETP dependency chains.
+// versions (profiles/r1a_*, r1b_*): the per-obstacle loop was co-limited by LDS broadcast
+// bandwidth (2 x LDS.128 per obstacle per warp) and FP64 compare/add chains, and the per-class
+// sqrt work (4 sqrt x 6..16 classes per belief-step) had become a third of the FP64 time.
 //
-//  * per class of identical normals the four inequalities  a_i.mu >= fl(B_oi + bb_i)  are
-//    turned into four thresholds tau_i with a conservative margin: B_oi <= tau_i  PROVES the
-//    reference's inequality holds (fl is monotone), so the common case is 4 DSETP per obstacle
-//    and no DADD; anything not proven safe (a real collision, or the ~1e-12-wide ambiguous
-//    band) is re-evaluated with the reference's exact expression.  Verdicts stay bit-identical.
-//  * BPT beliefs per thread share every table row loaded from shared memory, dividing the
-//    LDS traffic per belief by BPT and giving BPT x 4 independent compare chains.
+//  * CONSERVATIVE FP32 FILTER, EXACT FP64 DECISION.  For a super-class of (near-)identical
+//    normals the four inequalities  a_i.mu >= fl(B_oi + bb_i)  become four thresholds
+//    tau_i = (lhs_i - bb_i) - margin, rounded DOWN to fp32; the table holds B_oi rounded UP to
+//    fp32.  Bf_oi <= tauf_i  PROVES the reference's fp64 inequality (rounding is monotone and
+//    the margin covers the ulp-level spread of normals inside the super-class and all rounding),
+//    so the common case costs one LDS.128 and four FSETP per obstacle and touches neither the
+//    FP64 pipe nor a sqrt.  Whatever is not proven (a real collision, the ~1e-5-wide fp32 band,
+//    cancellation in a^T P a, NaN/inf operands) is decided by the reference's exact fp64
+//    expression on the obstacle's own normals (bm_exact_obstacle).  Verdicts are bit-identical.
+//  * BPT beliefs per thread share every table row loaded from shared memory.
 //  * only the current state lives in registers; a belief that dies at step r is re-played
-//    (r propagate steps, no checks: ~60 flop each) to produce its last valid state, instead of
-//    carrying a second copy of (mean, Sigma, Lambda) through the whole rollout.
+//    (r propagate steps, no checks) to produce its last valid state.
 #pragma once
 #include "cck_kernels.cuh"
 
 namespace cck {
 
 // exact reference test of one obstacle (slow path; PCCBlackmoreSVC.cpp:63-75)
-__device__ __noinline__ bool bm_exact_obstacle(const double* A8, const double2* Brow, double x, double y, double P0, double P1,
+__device__ __noinline__ bool bm_exact_obstacle(const double* A8, const double* B, double x, double y, double P0, double P1,
                                                double P2, double P3, double c) {
-    const double B[4] = {Brow[0].x, Brow[0].y, Brow[1].x, Brow[1].y};
     bool safe = false;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -34,6 +36,62 @@ __device__ __noinline__ bool bm_exact_obstacle(const double* A8, const double2* 
         safe = safe | (x * a0 + y * a1 >= B[i] + bb);
     }
     return safe;
+}
+
+// ok[b] &= "belief b is safe w.r.t. every obstacle" (PCCBlackmoreSVC.cpp:54-58), bit-exact.
+template <int BPT>
+__device__ __forceinline__ void bm_filter_check(const unsigned char* ftab, const unsigned char* gtab, const double* exB,
+                                                const int32_t* exCls, double c, const double (&x)[BPT], const double (&y)[BPT],
+                                                const double (&P)[BPT][4], const bool (&act)[BPT], bool (&ok)[BPT]) {
+    const FHeader* fh = reinterpret_cast<const FHeader*>(ftab);
+    const SuperRec* sr = reinterpret_cast<const SuperRec*>(ftab + fh->off_super);
+    const float4* rows = reinterpret_cast<const float4*>(ftab + fh->off_rows);
+    const int ns = fh->n_super;
+    for (int s = 0; s < ns; ++s) {
+        float tf[BPT][4];
+#pragma unroll
+        for (int b = 0; b < BPT; ++b) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const double a0 = sr[s].A[2 * i], a1 = sr[s].A[2 * i + 1];
+                const double t0 = a0 * P[b][0] + a1 * P[b][2];
+                const double t1 = a0 * P[b][1] + a1 * P[b][3];
+                const double q = t0 * a0 + t1 * a1;
+                // cancellation guard: |terms| of a^T P a; with q >= 2^-10 * qabs a 1e-14 spread of the normals
+                // perturbs sqrt(q) by < 1e-10 relative
+                const double qabs = fabs(a0 * a0 * P[b][0]) + fabs(a0 * a1) * (fabs(P[b][1]) + fabs(P[b][2])) + fabs(a1 * a1 * P[b][3]);
+                const double bb = 1.4142135623730951 * sqrt(q) * c;
+                const double xa = x[b] * a0, ya = y[b] * a1;
+                const double tau = ((xa + ya) - bb) - (fabs(xa) + fabs(ya) + fabs(bb)) * 3.725290298461914e-09;   // 2^-28
+                const bool good = q >= qabs * 9.765625e-4;                                                        // false for NaN
+                tf[b][i] = act[b] ? (good ? __double2float_rd(tau) : __int_as_float(0x7fc00000)) : __int_as_float(0x7f800000);
+            }
+        }
+        const int first = sr[s].first_row, cntp = sr[s].n_rows_pad;
+        for (int o = 0; o < cntp; o += 4) {
+            bool pr[BPT];
+#pragma unroll
+            for (int b = 0; b < BPT; ++b) pr[b] = true;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float4 r = rows[first + o + j];
+#pragma unroll
+                for (int b = 0; b < BPT; ++b)
+                    pr[b] = pr[b] & ((r.x <= tf[b][0]) | (r.y <= tf[b][1]) | (r.z <= tf[b][2]) | (r.w <= tf[b][3]));
+            }
+#pragma unroll
+            for (int b = 0; b < BPT; ++b) {
+                if (!pr[b] && ok[b]) {   // rare: exact fp64 decision on the obstacle's own normals
+                    const TabHeader* gh = reinterpret_cast<const TabHeader*>(gtab);
+                    const ClassRec* cls = reinterpret_cast<const ClassRec*>(gtab + gh->off_classes);
+                    for (int j = 0; j < 4 && ok[b]; ++j) {
+                        const int row = first + o + j, k = exCls[row];
+                        if (k >= 0) ok[b] = bm_exact_obstacle(cls[k].A, exB + (size_t)row * 4, x[b], y[b], P[b][0], P[b][1], P[b][2], P[b][3], c);
+                    }
+                }
+            }
+        }
+    }
 }
 
 template <int BPT>
@@ -65,12 +123,13 @@ __device__ __forceinline__ void store_planes(double* __restrict__ p, int64_t i, 
 template <int BPT, bool TRAJ, bool EXPAND>
 __global__ void __launch_bounds__(128) k_rollout_lin_bm(const __grid_constant__ RolloutArgs a, const __grid_constant__ LinDev p,
                                                         const __grid_constant__ SvcDev sp) {
-    CCK_SMEM_PROLOGUE(a)
-    const TabHeader* h = reinterpret_cast<const TabHeader*>(tab);
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+    unsigned char* ftab = smem_raw + 16;
+    stage_begin(ftab, a.ftab, (uint32_t)a.ftab_bytes, bar);
     bool waited = false;
     // vector (16-byte) plane accesses need even leading dimensions and 16-byte aligned bases
-    const bool vec = BPT > 1 && ((a.ld | a.ldc | a.ldo | a.traj_ld) & 1) == 0 &&
-                     (((uintptr_t)a.bel | (uintptr_t)a.ctrl | (uintptr_t)a.out | (uintptr_t)a.traj) & 15) == 0;
+    const bool vec = BPT > 1 && ((a.ld | a.ldc | a.ldo) & 1) == 0 && (((uintptr_t)a.bel | (uintptr_t)a.ctrl | (uintptr_t)a.out) & 15) == 0;
     const double eps = DBL_EPSILON;
     const double c = sp.erf_inv_result;
 
@@ -132,76 +191,30 @@ __global__ void __launch_bounds__(128) k_rollout_lin_bm(const __grid_constant__ 
             pstep[b] = 0;
             if (EXPAND) pstep[b] = a.parent_step[min(base + b, a.n - 1)];
         }
-        if (!waited) { stage_wait((uint32_t)a.tab_bytes, bar); waited = true; }
+        if (!waited) { stage_wait((uint32_t)a.ftab_bytes, bar); waited = true; }
 
         for (int t = 0; t < tmax; ++t) {
             bool any = false;
 #pragma unroll
-            for (int b = 0; b < BPT; ++b) any = any || alive[b];
+            for (int b = 0; b < BPT; ++b) { if (alive[b] && t >= steps[b]) alive[b] = false; any = any || alive[b]; }
             if (!any) break;
             bool ok[BPT];
+            double x[BPT], y[BPT], P[BPT][4];
 #pragma unroll
             for (int b = 0; b < BPT; ++b) {
-                if (alive[b] && t >= steps[b]) alive[b] = false;      // finished all of its steps
                 if (alive[b]) lin_step(cur[b], dux[b], duy[b], p, cur[b]);
+                x[b] = cur[b].mx; y[b] = cur[b].my;
+#pragma unroll
+                for (int f = 0; f < 4; ++f) P[b][f] = cur[b].S[f] + cur[b].L[f];
                 // satisfiesBounds (NaN passes)
-                ok[b] = !(cur[b].mx - eps > sp.high[0] || cur[b].mx + eps < sp.low[0] || cur[b].my - eps > sp.high[1] ||
-                          cur[b].my + eps < sp.low[1]);
+                ok[b] = !(x[b] - eps > sp.high[0] || x[b] + eps < sp.low[0] || y[b] - eps > sp.high[1] || y[b] + eps < sp.low[1]);
             }
-            const ClassRec* cls = reinterpret_cast<const ClassRec*>(tab + h->off_classes);
-            const double2* Bt = reinterpret_cast<const double2*>(tab + h->off_B);
-            const int nc = h->n_classes;
-            for (int k = 0; k < nc; ++k) {
-                double tau[BPT][4];
-#pragma unroll
-                for (int b = 0; b < BPT; ++b) {
-                    const double P0 = cur[b].S[0] + cur[b].L[0], P1 = cur[b].S[1] + cur[b].L[1];
-                    const double P2 = cur[b].S[2] + cur[b].L[2], P3 = cur[b].S[3] + cur[b].L[3];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const double a0 = cls[k].A[2 * i], a1 = cls[k].A[2 * i + 1];
-                        const double t0 = a0 * P0 + a1 * P2;
-                        const double t1 = a0 * P1 + a1 * P3;
-                        const double tmp = t0 * a0 + t1 * a1;
-                        const double PV = sqrt(tmp);
-                        const double bb = 1.4142135623730951 * PV * c;
-                        const double lhs = cur[b].mx * a0 + cur[b].my * a1;
-                        // B <= tau  =>  fl(B + bb) <= lhs : margin 2^-40 * (|lhs|+|bb|) >> rounding (2^-52 relative);
-                        // NaN/inf operands give tau = NaN -> nothing is "proven", the exact path decides.
-                        tau[b][i] = alive[b] ? (lhs - bb) - (fabs(lhs) + fabs(bb)) * 9.094947017729282e-13 : HUGE_VAL;
-                    }
-                }
-                const int first = cls[k].first, cnt = cls[k].count, cntp = cls[k].count_pad;
-                // branch-free over chunks of 4 table rows (padding rows are -inf: always proven)
-                for (int o = 0; o < cntp; o += 4) {
-                    bool pr[BPT];
-#pragma unroll
-                    for (int b = 0; b < BPT; ++b) pr[b] = true;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const double2 b01 = Bt[(first + o + j) * 2], b23 = Bt[(first + o + j) * 2 + 1];
-#pragma unroll
-                        for (int b = 0; b < BPT; ++b)
-                            pr[b] = pr[b] & ((b01.x <= tau[b][0]) | (b01.y <= tau[b][1]) | (b23.x <= tau[b][2]) | (b23.y <= tau[b][3]));
-                    }
-#pragma unroll
-                    for (int b = 0; b < BPT; ++b) {
-                        if (!pr[b] && ok[b]) {   // rare: a real collision or the ambiguous band -> exact reference test
-                            for (int j = 0; j < 4 && o + j < cnt; ++j)
-                                ok[b] = ok[b] && bm_exact_obstacle(cls[k].A, &Bt[(first + o + j) * 2], cur[b].mx, cur[b].my,
-                                                                   cur[b].S[0] + cur[b].L[0], cur[b].S[1] + cur[b].L[1],
-                                                                   cur[b].S[2] + cur[b].L[2], cur[b].S[3] + cur[b].L[3], c);
-                        }
-                    }
-                }
-            }
+            if (a.ftab_bytes > 0) bm_filter_check<BPT>(ftab, a.tab, a.exB, a.exCls, c, x, y, P, alive, ok);
 #pragma unroll
             for (int b = 0; b < BPT; ++b) {
                 if (!alive[b]) continue;
                 if (!ok[b]) { alive[b] = false; r[b] = t; continue; }
-                if (EXPAND && a.cons)
-                    cons_ok[b] = cons_ok[b] && constraints_ok_at(a.cons, pstep[b] + t + 1, cur[b].mx, cur[b].my, cur[b].S[0] + cur[b].L[0],
-                                                                 cur[b].S[1] + cur[b].L[1], cur[b].S[2] + cur[b].L[2], cur[b].S[3] + cur[b].L[3]);
+                if (EXPAND && a.cons) cons_ok[b] = cons_ok[b] && constraints_ok_at(a.cons, pstep[b] + t + 1, x[b], y[b], P[b][0], P[b][1], P[b][2], P[b][3]);
                 if (TRAJ && base + b < a.n) {
                     double* tp = a.traj + (int64_t)t * 10 * a.traj_ld + base + b;
                     tp[0] = cur[b].mx; tp[a.traj_ld] = cur[b].my;
@@ -260,7 +273,7 @@ __global__ void __launch_bounds__(128) k_rollout_lin_bm(const __grid_constant__ 
             }
         }
     }
-    if (!waited) stage_wait((uint32_t)a.tab_bytes, bar);
+    if (!waited) stage_wait((uint32_t)a.ftab_bytes, bar);
 }
 
 }  // namespace cck
