@@ -363,47 +363,74 @@ extern "C" int cck_set_obstacles(cck_ctx* c, const cck_svc_params* p, const doub
             supers[found].push_back(k);
         }
         const int nsup = (int)supers.size();
-        int frows = 0;
+        int frows = 0, fgroups = 0;
         std::vector<int> sup_rows(nsup);
+        std::vector<std::vector<std::pair<int, int>>> sup_members(nsup);   // (obstacle, class), Morton-sorted
         for (int sidx = 0; sidx < nsup; ++sidx) {
-            int cnt = 0;
-            for (int k : supers[sidx]) cnt += (int)members[k].size();
-            sup_rows[sidx] = (cnt + 3) & ~3;
+            auto& mem = sup_members[sidx];
+            for (int k : supers[sidx]) for (int o : members[k]) mem.emplace_back(o, k);
+            // spatial order: Morton code of the (B_1, B_2) offsets quantised to 16 bits
+            double lo1 = HUGE_VAL, hi1 = -HUGE_VAL, lo2 = HUGE_VAL, hi2 = -HUGE_VAL;
+            for (auto& m : mem) {
+                const double b1 = B[4 * m.first + 1], b2 = B[4 * m.first + 2];
+                if (std::isfinite(b1)) { lo1 = std::min(lo1, b1); hi1 = std::max(hi1, b1); }
+                if (std::isfinite(b2)) { lo2 = std::min(lo2, b2); hi2 = std::max(hi2, b2); }
+            }
+            auto quant = [](double v, double lo, double hi) -> uint32_t {
+                if (!std::isfinite(v) || !(hi > lo)) return 0u;
+                return (uint32_t)std::min(65535.0, std::max(0.0, (v - lo) / (hi - lo) * 65535.0));
+            };
+            auto spread = [](uint32_t v) { uint32_t x = v & 0xffff; x = (x | (x << 8)) & 0x00ff00ff; x = (x | (x << 4)) & 0x0f0f0f0f;
+                                           x = (x | (x << 2)) & 0x33333333; x = (x | (x << 1)) & 0x55555555; return x; };
+            auto key = [&](const std::pair<int, int>& m) { return spread(quant(B[4 * m.first + 1], lo1, hi1)) | (spread(quant(B[4 * m.first + 2], lo2, hi2)) << 1); };
+            std::stable_sort(mem.begin(), mem.end(), [&](const std::pair<int, int>& x, const std::pair<int, int>& y) { return key(x) < key(y); });
+            sup_rows[sidx] = ((int)mem.size() + CCK_GROUP - 1) / CCK_GROUP * CCK_GROUP;
             frows += sup_rows[sidx];
+            fgroups += sup_rows[sidx] / CCK_GROUP;
         }
         FHeader fh{};
-        fh.n_super = nsup; fh.rows_total = frows;
+        fh.n_super = nsup; fh.rows_total = frows; fh.groups_total = fgroups;
         fh.off_super = sizeof(FHeader);
         fh.off_rows = fh.off_super + nsup * (int)sizeof(SuperRec);
-        fh.total_bytes = (fh.off_rows + frows * 16 + 15) & ~15;
+        fh.off_groups = fh.off_rows + frows * 16;
+        fh.total_bytes = (fh.off_groups + fgroups * 16 + 15) & ~15;
+        if (fh.total_bytes + 16 > c->max_smem_optin) return fail(c, CCK_ERR_INVALID, "filter table exceeds shared memory; M too large");
         std::vector<unsigned char> fbuf(fh.total_bytes, 0);
         std::vector<double> exB((size_t)frows * 4, -HUGE_VAL);
         std::vector<int32_t> exCls(frows, -1);
         std::memcpy(fbuf.data(), &fh, sizeof(fh));
         float* frow = reinterpret_cast<float*>(fbuf.data() + fh.off_rows);
-        int rpos = 0;
+        float* fgrp = reinterpret_cast<float*>(fbuf.data() + fh.off_groups);
+        int rpos = 0, gpos = 0;
         for (int sidx = 0; sidx < nsup; ++sidx) {
             SuperRec sr{};
             std::memcpy(sr.A, keys[supers[sidx][0]].w, 64);
-            sr.first_row = rpos; sr.n_rows_pad = sup_rows[sidx];
+            sr.first_row = rpos; sr.n_rows_pad = sup_rows[sidx]; sr.first_group = gpos; sr.n_groups = sup_rows[sidx] / CCK_GROUP;
             std::memcpy(fbuf.data() + fh.off_super + sidx * sizeof(SuperRec), &sr, sizeof(sr));
             int written = 0;
-            for (int k : supers[sidx])
-                for (int o : members[k]) {
-                    for (int i = 0; i < 4; ++i) {
-                        const double bv = B[4 * o + i];
-                        float bf = (float)bv;                       // round to nearest, then force UP
-                        if ((double)bf < bv) bf = std::nextafterf(bf, HUGE_VALF);
-                        if (std::isnan(bv)) bf = HUGE_VALF;         // never "proven": +inf <= tau fails unless tau = +inf (dead slot)
-                        frow[(size_t)(rpos + written) * 4 + i] = bf;
-                        exB[(size_t)(rpos + written) * 4 + i] = bv;
-                    }
-                    exCls[rpos + written] = k;
-                    ++written;
+            for (auto& m : sup_members[sidx]) {
+                const int o = m.first;
+                for (int i = 0; i < 4; ++i) {
+                    const double bv = B[4 * o + i];
+                    float bf = (float)bv;                       // round to nearest, then force UP
+                    if ((double)bf < bv) bf = std::nextafterf(bf, HUGE_VALF);
+                    if (std::isnan(bv)) bf = HUGE_VALF;         // never "proven" by the filter
+                    frow[(size_t)(rpos + written) * 4 + i] = bf;
+                    exB[(size_t)(rpos + written) * 4 + i] = bv;
                 }
+                exCls[rpos + written] = m.second;
+                ++written;
+            }
             for (; written < sup_rows[sidx]; ++written)
                 for (int i = 0; i < 4; ++i) frow[(size_t)(rpos + written) * 4 + i] = -HUGE_VALF;
+            for (int g = 0; g < sr.n_groups; ++g)
+                for (int i = 0; i < 4; ++i) {
+                    float mx = -HUGE_VALF;
+                    for (int q = 0; q < CCK_GROUP; ++q) mx = std::max(mx, frow[(size_t)(rpos + g * CCK_GROUP + q) * 4 + i]);
+                    fgrp[(size_t)(gpos + g) * 4 + i] = mx;
+                }
             rpos += sup_rows[sidx];
+            gpos += sr.n_groups;
         }
         CK(c, cudaMalloc(&c->d_ftab, fh.total_bytes));
         CK(c, cudaMalloc(&c->d_exB, exB.size() * 8));

@@ -36,8 +36,11 @@ static_assert(sizeof(ClassRec) == 80, "class record");
 
 // Filter table (Blackmore fast path): obstacles grouped into SUPER-classes whose normals agree to
 // 1e-14 relative (the reference's tables: one super-class), rows = B rounded UP to fp32.
-struct FHeader { int32_t n_super, rows_total, off_super, off_rows, total_bytes, pad[3]; };
-struct SuperRec { double A[8]; int32_t first_row, n_rows_pad, pad[2]; };
+// Rows are sorted along a Morton curve of (B_1, B_2) and cut into GROUPS of 8; a group row holds the
+// component-wise max of its members, so one proven group row proves all 8 obstacles.
+struct FHeader { int32_t n_super, rows_total, off_super, off_rows, total_bytes, off_groups, groups_total, pad; };
+struct SuperRec { double A[8]; int32_t first_row, n_rows_pad, first_group, n_groups; };
+#define CCK_GROUP 8
 static_assert(sizeof(FHeader) == 32 && sizeof(SuperRec) == 80, "filter table records");
 
 struct SvcDev {

@@ -67,26 +67,44 @@ __device__ __forceinline__ void bm_filter_check(const unsigned char* ftab, const
                 tf[b][i] = act[b] ? (good ? __double2float_rd(tau) : __int_as_float(0x7fc00000)) : __int_as_float(0x7f800000);
             }
         }
-        const int first = sr[s].first_row, cntp = sr[s].n_rows_pad;
-        for (int o = 0; o < cntp; o += 4) {
-            bool pr[BPT];
+        // level 1 (warp-uniform, broadcast loads): group rows; level 2 (per lane): members of unproven groups
+        const float4* grp = reinterpret_cast<const float4*>(ftab + fh->off_groups) + sr[s].first_group;
+        const int ng = sr[s].n_groups, first = sr[s].first_row;
+        for (int g0 = 0; g0 < ng; g0 += 32) {
+            unsigned need[BPT];
 #pragma unroll
-            for (int b = 0; b < BPT; ++b) pr[b] = true;
+            for (int b = 0; b < BPT; ++b) need[b] = 0u;
+            const int gn = min(32, ng - g0);
+#pragma unroll 4
+            for (int j = 0; j < gn; ++j) {
+                const float4 r = grp[g0 + j];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float4 r = rows[first + o + j];
-#pragma unroll
-                for (int b = 0; b < BPT; ++b)
-                    pr[b] = pr[b] & ((r.x <= tf[b][0]) | (r.y <= tf[b][1]) | (r.z <= tf[b][2]) | (r.w <= tf[b][3]));
+                for (int b = 0; b < BPT; ++b) {
+                    const bool pv = (r.x <= tf[b][0]) | (r.y <= tf[b][1]) | (r.z <= tf[b][2]) | (r.w <= tf[b][3]);
+                    need[b] |= (pv ? 0u : 1u) << j;
+                }
             }
 #pragma unroll
             for (int b = 0; b < BPT; ++b) {
-                if (!pr[b] && ok[b]) {   // rare: exact fp64 decision on the obstacle's own normals
-                    const TabHeader* gh = reinterpret_cast<const TabHeader*>(gtab);
-                    const ClassRec* cls = reinterpret_cast<const ClassRec*>(gtab + gh->off_classes);
-                    for (int j = 0; j < 4 && ok[b]; ++j) {
-                        const int row = first + o + j, k = exCls[row];
-                        if (k >= 0) ok[b] = bm_exact_obstacle(cls[k].A, exB + (size_t)row * 4, x[b], y[b], P[b][0], P[b][1], P[b][2], P[b][3], c);
+                unsigned m = ok[b] ? need[b] : 0u;
+                while (m) {
+                    const int j = __ffs(m) - 1;
+                    m &= m - 1;
+                    const int row0 = first + (g0 + j) * CCK_GROUP;
+                    bool pr = true;
+#pragma unroll
+                    for (int q = 0; q < CCK_GROUP; ++q) {
+                        const float4 r = rows[row0 + q];
+                        pr = pr & ((r.x <= tf[b][0]) | (r.y <= tf[b][1]) | (r.z <= tf[b][2]) | (r.w <= tf[b][3]));
+                    }
+                    if (!pr) {   // rare: exact fp64 decision on the obstacles' own normals
+                        const TabHeader* gh = reinterpret_cast<const TabHeader*>(gtab);
+                        const ClassRec* cls = reinterpret_cast<const ClassRec*>(gtab + gh->off_classes);
+                        for (int q = 0; q < CCK_GROUP && ok[b]; ++q) {
+                            const int row = row0 + q, k = exCls[row];
+                            if (k >= 0) ok[b] = bm_exact_obstacle(cls[k].A, exB + (size_t)row * 4, x[b], y[b], P[b][0], P[b][1], P[b][2], P[b][3], c);
+                        }
+                        if (!ok[b]) m = 0;
                     }
                 }
             }
@@ -121,7 +139,7 @@ __device__ __forceinline__ void store_planes(double* __restrict__ p, int64_t i, 
 }
 
 template <int BPT, bool TRAJ, bool EXPAND>
-__global__ void __launch_bounds__(128) k_rollout_lin_bm(const __grid_constant__ RolloutArgs a, const __grid_constant__ LinDev p,
+__global__ void __launch_bounds__(128, (BPT == 1 ? 4 : 1)) k_rollout_lin_bm(const __grid_constant__ RolloutArgs a, const __grid_constant__ LinDev p,
                                                         const __grid_constant__ SvcDev sp) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
