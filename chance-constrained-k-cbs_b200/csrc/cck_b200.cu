@@ -26,6 +26,7 @@ struct cck_ctx {
     cudaStream_t pipe[2] = {nullptr, nullptr};
     std::string err;
     int64_t launches = 0;
+    bool refill = true;   // lane-refill rollout kernel (CCK_REFILL=0: static assignment)
     int bpt = 1;   // beliefs per thread of the linear+Blackmore rollout kernel (CCK_BPT=0 selects the generic kernel)
 
     bool has_model = false;
@@ -98,6 +99,7 @@ extern "C" int cck_ctx_create(int device, cck_ctx** out) {
     c->device = device;
     c->num_sms = prop.multiProcessorCount;
     c->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    if (const char* e3 = getenv("CCK_REFILL")) c->refill = atoi(e3) != 0;
     if (const char* e2 = getenv("CCK_BPT")) { const int v = atoi(e2); if (v == 0 || v == 1 || v == 2 || v == 4) c->bpt = v; }
     if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&c->pipe[0], cudaStreamNonBlocking)) != cudaSuccess ||
@@ -407,26 +409,30 @@ extern "C" int cck_set_obstacles(cck_ctx* c, const cck_svc_params* p, const doub
             std::memcpy(sr.A, keys[supers[sidx][0]].w, 64);
             sr.first_row = rpos; sr.n_rows_pad = sup_rows[sidx]; sr.first_group = gpos; sr.n_groups = sup_rows[sidx] / CCK_GROUP;
             std::memcpy(fbuf.data() + fh.off_super + sidx * sizeof(SuperRec), &sr, sizeof(sr));
+            // member rows are stored TRANSPOSED: member q of group g at first_row + q*n_groups + g, so lanes
+            // scanning different groups in the per-lane second level hit consecutive 16-byte words (no bank conflicts)
+            const int ngr = sr.n_groups;
+            auto slot = [&](int w) { return rpos + (w % CCK_GROUP) * ngr + (w / CCK_GROUP); };
             int written = 0;
             for (auto& m : sup_members[sidx]) {
-                const int o = m.first;
+                const int o = m.first, at = slot(written);
                 for (int i = 0; i < 4; ++i) {
                     const double bv = B[4 * o + i];
                     float bf = (float)bv;                       // round to nearest, then force UP
                     if ((double)bf < bv) bf = std::nextafterf(bf, HUGE_VALF);
                     if (std::isnan(bv)) bf = HUGE_VALF;         // never "proven" by the filter
-                    frow[(size_t)(rpos + written) * 4 + i] = bf;
-                    exB[(size_t)(rpos + written) * 4 + i] = bv;
+                    frow[(size_t)at * 4 + i] = bf;
+                    exB[(size_t)at * 4 + i] = bv;
                 }
-                exCls[rpos + written] = m.second;
+                exCls[at] = m.second;
                 ++written;
             }
             for (; written < sup_rows[sidx]; ++written)
-                for (int i = 0; i < 4; ++i) frow[(size_t)(rpos + written) * 4 + i] = -HUGE_VALF;
-            for (int g = 0; g < sr.n_groups; ++g)
+                for (int i = 0; i < 4; ++i) frow[(size_t)slot(written) * 4 + i] = -HUGE_VALF;
+            for (int g = 0; g < ngr; ++g)
                 for (int i = 0; i < 4; ++i) {
                     float mx = -HUGE_VALF;
-                    for (int q = 0; q < CCK_GROUP; ++q) mx = std::max(mx, frow[(size_t)(rpos + g * CCK_GROUP + q) * 4 + i]);
+                    for (int q = 0; q < CCK_GROUP; ++q) mx = std::max(mx, frow[(size_t)(rpos + q * ngr + g) * 4 + i]);
                     fgrp[(size_t)(gpos + g) * 4 + i] = mx;
                 }
             rpos += sup_rows[sidx];
@@ -592,7 +598,18 @@ static int launch_rollout(cck_ctx* c, cudaStream_t s, const RolloutArgs& a) {
         if ((rc = set_smem(c, (k_rollout_lin_bm<BPT, TRAJ, EXPAND>), fsmem))) return rc;                 \
         k_rollout_lin_bm<BPT, TRAJ, EXPAND><<<gb, threads, fsmem, s>>>(a, c->lin, c->svc);               \
     } while (0)
-        if (c->bpt == 1) { if (traj) LAUNCH_BM(1, true); else LAUNCH_BM(1, false); }
+        if (c->bpt == 1 && c->refill) {
+            // lane-refill kernel: each CTA owns a contiguous range and hands beliefs to idle lanes
+            const int64_t per_cta = 1024;
+            int64_t nb = (a.n + per_cta - 1) / per_cta;
+            const int gb = (int)std::min<int64_t>(nb, (int64_t)c->num_sms * 64);
+            const int fsmem = 16 + c->ftab_bytes;
+            if (traj) { if ((rc = set_smem(c, (k_rollout_lin_refill<true, EXPAND>), fsmem))) return rc;
+                        k_rollout_lin_refill<true, EXPAND><<<gb, threads, fsmem, s>>>(a, c->lin, c->svc, per_cta); }
+            else { if ((rc = set_smem(c, (k_rollout_lin_refill<false, EXPAND>), fsmem))) return rc;
+                   k_rollout_lin_refill<false, EXPAND><<<gb, threads, fsmem, s>>>(a, c->lin, c->svc, per_cta); }
+        }
+        else if (c->bpt == 1) { if (traj) LAUNCH_BM(1, true); else LAUNCH_BM(1, false); }
         else if (c->bpt == 2) { if (traj) LAUNCH_BM(2, true); else LAUNCH_BM(2, false); }
         else { if (traj) LAUNCH_BM(4, true); else LAUNCH_BM(4, false); }
 #undef LAUNCH_BM

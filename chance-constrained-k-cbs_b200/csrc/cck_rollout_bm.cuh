@@ -90,18 +90,21 @@ __device__ __forceinline__ void bm_filter_check(const unsigned char* ftab, const
                 while (m) {
                     const int j = __ffs(m) - 1;
                     m &= m - 1;
-                    const int row0 = first + (g0 + j) * CCK_GROUP;
-                    bool pr = true;
+                    const int row0 = first + (g0 + j);          // member q of this group sits at row0 + q*ng (transposed)
+                    unsigned fail = 0u;                          // members the fp32 filter could not prove safe
 #pragma unroll
                     for (int q = 0; q < CCK_GROUP; ++q) {
-                        const float4 r = rows[row0 + q];
-                        pr = pr & ((r.x <= tf[b][0]) | (r.y <= tf[b][1]) | (r.z <= tf[b][2]) | (r.w <= tf[b][3]));
+                        const float4 r = rows[row0 + q * ng];
+                        const bool pv = (r.x <= tf[b][0]) | (r.y <= tf[b][1]) | (r.z <= tf[b][2]) | (r.w <= tf[b][3]);
+                        fail |= (pv ? 0u : 1u) << q;
                     }
-                    if (!pr) {   // rare: exact fp64 decision on the obstacles' own normals
+                    if (fail) {   // rare: exact fp64 decision on those obstacles' own normals
                         const TabHeader* gh = reinterpret_cast<const TabHeader*>(gtab);
                         const ClassRec* cls = reinterpret_cast<const ClassRec*>(gtab + gh->off_classes);
-                        for (int q = 0; q < CCK_GROUP && ok[b]; ++q) {
-                            const int row = row0 + q, k = exCls[row];
+                        while (fail && ok[b]) {
+                            const int q = __ffs(fail) - 1;
+                            fail &= fail - 1;
+                            const int row = row0 + q * ng, k = exCls[row];
                             if (k >= 0) ok[b] = bm_exact_obstacle(cls[k].A, exB + (size_t)row * 4, x[b], y[b], P[b][0], P[b][1], P[b][2], P[b][3], c);
                         }
                         if (!ok[b]) m = 0;
@@ -292,6 +295,114 @@ __global__ void __launch_bounds__(128, (BPT == 1 ? 4 : 1)) k_rollout_lin_bm(cons
         }
     }
     if (!waited) stage_wait((uint32_t)a.ftab_bytes, bar);
+}
+
+// ---------------------------------------------------------------------------
+// Lane-refill variant (one belief per lane): a lane whose belief died or finished immediately
+// writes its result and pulls the next belief of the CTA's range from a shared-memory counter,
+// so warps stay full when rollouts end at different steps (the realistic workload: ~2/3 of the
+// beliefs die early).  Per-step work is identical to k_rollout_lin_bm<1,...>.
+// ---------------------------------------------------------------------------
+template <bool TRAJ, bool EXPAND>
+__global__ void __launch_bounds__(128, 4) k_rollout_lin_refill(const __grid_constant__ RolloutArgs a, const __grid_constant__ LinDev p,
+                                                               const __grid_constant__ SvcDev sp, int64_t per_cta) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ int next_rel;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+    unsigned char* ftab = smem_raw + 16;
+    stage_begin(ftab, a.ftab, (uint32_t)a.ftab_bytes, bar);
+    stage_wait((uint32_t)a.ftab_bytes, bar);
+    const double eps = DBL_EPSILON;
+    const double c = sp.erf_inv_result;
+
+    for (int64_t cta_lo = (int64_t)blockIdx.x * per_cta; cta_lo < a.n; cta_lo += (int64_t)gridDim.x * per_cta) {
+        const int64_t cta_hi = min(a.n, cta_lo + per_cta);
+        __syncthreads();
+        if (threadIdx.x == 0) next_rel = 0;
+        __syncthreads();
+        bool have = false, done = false;
+        Lin cur;
+        double dux = 0, duy = 0, x0 = 0, y0 = 0;
+        int steps = 0, t = 0, pstep = 0;
+        int64_t i = 0;
+        bool cons_ok = true;
+        cur.mx = cur.my = 0;
+#pragma unroll
+        for (int f = 0; f < 4; ++f) cur.S[f] = cur.L[f] = 0;
+        while (true) {
+            while (!have && !done) {                       // fetch the next belief of this CTA's range
+                i = cta_lo + atomicAdd(&next_rel, 1);
+                if (i >= cta_hi) { done = true; break; }
+                steps = a.steps[i];
+                if (steps <= 0) {                          // propagateWhileValid(.., 0, ..): copy, return 0
+#pragma unroll
+                    for (int f = 0; f < 10; ++f) a.out[f * a.ldo + i] = a.bel[f * a.ld + i];
+                    a.valid[i] = 0;
+                    if (EXPAND) {
+                        const double bx = a.bel[i], by = a.bel[a.ld + i];
+                        double gd;
+                        const bool g = goal_ok(a.goal, sp, bx, by, a.bel[2 * a.ld + i] + a.bel[6 * a.ld + i], a.bel[3 * a.ld + i] + a.bel[7 * a.ld + i],
+                                               a.bel[4 * a.ld + i] + a.bel[8 * a.ld + i], a.bel[5 * a.ld + i] + a.bel[9 * a.ld + i], &gd);
+                        a.cost[i] = a.parent_cost[i] + 0.0;
+                        a.goal_dist[i] = gd;
+                        a.flags[i] = (uint8_t)(1 | 2 | (g ? 4 : 0));
+                    }
+                    continue;
+                }
+                cur.mx = a.bel[i]; cur.my = a.bel[a.ld + i];
+#pragma unroll
+                for (int f = 0; f < 4; ++f) { cur.S[f] = a.bel[(2 + f) * a.ld + i]; cur.L[f] = a.bel[(6 + f) * a.ld + i]; }
+                dux = p.dt * a.ctrl[i]; duy = p.dt * a.ctrl[a.ldc + i];
+                x0 = cur.mx; y0 = cur.my;
+                t = 0; cons_ok = true;
+                if (EXPAND) pstep = a.parent_step[i];
+                have = true;
+            }
+            if (__all_sync(0xffffffffu, !have)) break;
+            bool ok[1];
+            double x[1], y[1], P[1][4];
+            const bool act[1] = {have};
+            const Lin prev = cur;                          // last valid state (restored if this step is invalid)
+            if (have) lin_step(cur, dux, duy, p, cur);
+            x[0] = cur.mx; y[0] = cur.my;
+#pragma unroll
+            for (int f = 0; f < 4; ++f) P[0][f] = cur.S[f] + cur.L[f];
+            ok[0] = !(x[0] - eps > sp.high[0] || x[0] + eps < sp.low[0] || y[0] - eps > sp.high[1] || y[0] + eps < sp.low[1]);
+            if (a.ftab_bytes > 0) bm_filter_check<1>(ftab, a.tab, a.exB, a.exCls, c, x, y, P, act, ok);
+            if (!have) continue;
+            int r = -1;                                    // >= 0: this rollout ends now with r valid steps
+            if (!ok[0]) {
+                r = t;                                     // died: the result is the last valid state
+                cur = prev;
+            } else {
+                if (EXPAND && a.cons) cons_ok = cons_ok && constraints_ok_at(a.cons, pstep + t + 1, x[0], y[0], P[0][0], P[0][1], P[0][2], P[0][3]);
+                if (TRAJ) {
+                    double* tp = a.traj + (int64_t)t * 10 * a.traj_ld + i;
+                    tp[0] = cur.mx; tp[a.traj_ld] = cur.my;
+#pragma unroll
+                    for (int f = 0; f < 4; ++f) { tp[(2 + f) * a.traj_ld] = cur.S[f]; tp[(6 + f) * a.traj_ld] = cur.L[f]; }
+                }
+                ++t;
+                if (t == steps) r = steps;
+            }
+            if (r >= 0) {
+                a.out[i] = cur.mx; a.out[a.ldo + i] = cur.my;
+#pragma unroll
+                for (int f = 0; f < 4; ++f) { a.out[(2 + f) * a.ldo + i] = cur.S[f]; a.out[(6 + f) * a.ldo + i] = cur.L[f]; }
+                a.valid[i] = r;
+                if (EXPAND) {
+                    const double d0 = x0 - cur.mx, d1 = y0 - cur.my;
+                    a.cost[i] = a.parent_cost[i] + sqrt(d0 * d0 + d1 * d1);
+                    double gd;
+                    const bool g = goal_ok(a.goal, sp, cur.mx, cur.my, cur.S[0] + cur.L[0], cur.S[1] + cur.L[1], cur.S[2] + cur.L[2],
+                                           cur.S[3] + cur.L[3], &gd);
+                    a.goal_dist[i] = gd;
+                    a.flags[i] = (uint8_t)((r == steps ? 1 : 0) | (cons_ok ? 2 : 0) | (g ? 4 : 0));
+                }
+                have = false;
+            }
+        }
+    }
 }
 
 }  // namespace cck
