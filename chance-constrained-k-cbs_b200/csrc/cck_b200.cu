@@ -11,19 +11,20 @@
 #include <vector>
 
 #include "cck_kernels.cuh"
-#include "cck_rollout_bm.cuh"
+#include "cck_rollout_grid.cuh"
 
 using namespace cck;
 
 // ---------------------------------------------------------------------------
 // context
 // ---------------------------------------------------------------------------
+#define CCK_SLOTS 4   // pipeline slots of the host-pointer entry points (H2D / kernel / D2H of different chunks overlap)
 struct cck_ctx {
     int device = 0;
     int num_sms = 0;
     int max_smem_optin = 0;
     cudaStream_t stream = nullptr;
-    cudaStream_t pipe[2] = {nullptr, nullptr};
+    cudaStream_t pipe[CCK_SLOTS] = {};
     std::string err;
     int64_t launches = 0;
     bool refill = true;   // lane-refill rollout kernel (CCK_REFILL=0: static assignment)
@@ -42,6 +43,11 @@ struct cck_ctx {
     int ftab_bytes = 0;
     double* d_exB = nullptr;           // exact fp64 rows in filter-table order
     int32_t* d_exCls = nullptr;        // class of each row (-1: padding)
+    unsigned char* d_gtab = nullptr;   // fp32 box + bitmap-grid table (Blackmore broad phase, cck_rollout_grid.cuh)
+    int gtab_bytes = 0;
+    double* d_gexB = nullptr;          // exact fp64 rows in grid-table order
+    int32_t* d_gexCls = nullptr;       // class of each row
+    int kern = 2;                      // linear+Blackmore rollout kernel: 2 grid (default), 1 group filter, 0 generic (CCK_KERNEL)
     int M = 0;
 
     bool has_pvc = false;
@@ -56,9 +62,9 @@ struct cck_ctx {
     unsigned char* d_cons = nullptr;   // constraint table (nullptr = no constraints)
     size_t cons_cap = 0;
 
-    // grow-only device scratch for the host-pointer entry points (2 pipeline slots)
-    void* d_scratch[2] = {nullptr, nullptr};
-    size_t scratch_cap[2] = {0, 0};
+    // grow-only device scratch for the host-pointer entry points (one per pipeline slot)
+    void* d_scratch[CCK_SLOTS] = {};
+    size_t scratch_cap[CCK_SLOTS] = {};
 };
 
 static std::string g_create_err;
@@ -71,6 +77,14 @@ static std::string g_create_err;
             return CCK_ERR_CUDA;                                                                       \
         }                                                                                              \
     } while (0)
+
+static cudaError_t create_pipe_streams(cck_ctx* c) {
+    for (int i = 0; i < CCK_SLOTS; ++i) {
+        const cudaError_t e = cudaStreamCreateWithFlags(&c->pipe[i], cudaStreamNonBlocking);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
 
 static int fail(cck_ctx* ctx, int code, const std::string& msg) {
     if (ctx) ctx->err = msg;
@@ -100,10 +114,10 @@ extern "C" int cck_ctx_create(int device, cck_ctx** out) {
     c->num_sms = prop.multiProcessorCount;
     c->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
     if (const char* e3 = getenv("CCK_REFILL")) c->refill = atoi(e3) != 0;
+    if (const char* e4 = getenv("CCK_KERNEL")) { const int v = atoi(e4); if (v >= 0 && v <= 2) c->kern = v; }
     if (const char* e2 = getenv("CCK_BPT")) { const int v = atoi(e2); if (v == 0 || v == 1 || v == 2 || v == 4) c->bpt = v; }
     if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess ||
-        (e = cudaStreamCreateWithFlags(&c->pipe[0], cudaStreamNonBlocking)) != cudaSuccess ||
-        (e = cudaStreamCreateWithFlags(&c->pipe[1], cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = create_pipe_streams(c)) != cudaSuccess ||
         (e = cudaMalloc(&c->d_key, sizeof(unsigned long long))) != cudaSuccess || (e = cudaMalloc(&c->d_run, sizeof(cck_conflict_run))) != cudaSuccess) {
         g_create_err = cudaGetErrorString(e);
         delete c;
@@ -117,8 +131,8 @@ extern "C" int cck_ctx_destroy(cck_ctx* c) {
     if (!c) return CCK_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    for (int i = 0; i < 2; ++i) { if (c->pipe[i]) { cudaStreamSynchronize(c->pipe[i]); cudaStreamDestroy(c->pipe[i]); } cudaFree(c->d_scratch[i]); }
-    cudaFree(c->d_ftab); cudaFree(c->d_exB); cudaFree(c->d_exCls);
+    for (int i = 0; i < CCK_SLOTS; ++i) { if (c->pipe[i]) { cudaStreamSynchronize(c->pipe[i]); cudaStreamDestroy(c->pipe[i]); } cudaFree(c->d_scratch[i]); }
+    cudaFree(c->d_ftab); cudaFree(c->d_exB); cudaFree(c->d_exCls); cudaFree(c->d_gtab); cudaFree(c->d_gexB); cudaFree(c->d_gexCls);
     cudaFree(c->d_tab); cudaFree(c->d_pvc_A); cudaFree(c->d_pvc_B); cudaFree(c->d_pvc_radii); cudaFree(c->d_pvc_order);
     cudaFree(c->d_key); cudaFree(c->d_run); cudaFree(c->d_cons);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -133,8 +147,7 @@ extern "C" int cck_ctx_synchronize(cck_ctx* c) {
     if (!c) return CCK_ERR_INVALID;
     CK(c, cudaSetDevice(c->device));
     CK(c, cudaStreamSynchronize(c->stream));
-    CK(c, cudaStreamSynchronize(c->pipe[0]));
-    CK(c, cudaStreamSynchronize(c->pipe[1]));
+    for (int i = 0; i < CCK_SLOTS; ++i) CK(c, cudaStreamSynchronize(c->pipe[i]));
     return CCK_OK;
 }
 
@@ -290,6 +303,126 @@ extern "C" int cck_set_model(cck_ctx* c, const cck_model_params* p) {
     return CCK_OK;
 }
 
+
+// ---------------------------------------------------------------------------
+// fp32 box + bitmap-grid table of the Blackmore broad phase (cck_rollout_grid.cuh).
+// Box sides are rounded OUTWARD and bumped one more ulp, so "interval misses box" in fp32
+// implies the reference's fp64 inequality for that half-plane.
+// ---------------------------------------------------------------------------
+static float f32_up(double v) {      // smallest-ish float strictly above v (>= v + 1 ulp)
+    float f = (float)v;
+    if ((double)f < v) f = std::nextafterf(f, HUGE_VALF);
+    return std::nextafterf(f, HUGE_VALF);
+}
+static float f32_down(double v) {
+    float f = (float)v;
+    if ((double)f > v) f = std::nextafterf(f, -HUGE_VALF);
+    return std::nextafterf(f, -HUGE_VALF);
+}
+
+struct GridBuild { std::vector<unsigned char> buf; std::vector<double> exB; std::vector<int32_t> exCls; };
+
+static void build_grid_table(int M, const double* A, const double* B, const std::vector<int>& cls_idx, double c, GridBuild& out) {
+    const bool c_ok = std::isfinite(c) && c >= 0.0 && c < 1e6;
+    struct Box { float xlo, ylo, xhi, yhi; };
+    std::vector<Box> box(M);
+    std::vector<int> gridded, always;
+    auto usable = [](double w) { const double a = std::fabs(w); return std::isfinite(w) && a > 1e-100 && a < 1e100; };
+    for (int o = 0; o < M; ++o) {
+        Box b{-HUGE_VALF, -HUGE_VALF, HUGE_VALF, HUGE_VALF};
+        for (int i = 0; i < 4 && c_ok; ++i) {
+            const double a0 = A[8 * o + 2 * i], a1 = A[8 * o + 2 * i + 1], bv = B[4 * o + i];
+            if (std::isnan(bv)) continue;
+            if (a1 == 0.0 && usable(a0)) {            // a0*x >= b + bb, bb/|a0| = sqrt2*c*sqrt(P00)
+                const double thr = bv / a0;
+                if (a0 > 0) b.xhi = std::min(b.xhi, f32_up(thr)); else b.xlo = std::max(b.xlo, f32_down(thr));
+            } else if (a0 == 0.0 && usable(a1)) {     // a1*y >= b + bb, bb/|a1| = sqrt2*c*sqrt(P11)
+                const double thr = bv / a1;
+                if (a1 > 0) b.yhi = std::min(b.yhi, f32_up(thr)); else b.ylo = std::max(b.ylo, f32_down(thr));
+            }
+        }
+        box[o] = b;
+        const bool finite = std::isfinite(b.xlo) && std::isfinite(b.ylo) && std::isfinite(b.xhi) && std::isfinite(b.yhi);
+        (finite ? gridded : always).push_back(o);
+    }
+    GHeader h{};
+    h.M = M; h.n_grid = (int)gridded.size(); h.R = CCK_GRID_ROWS;
+    h.k = c_ok ? f32_up(1.4142135623730951 * c * (1.0 + 1e-15)) : 0.f;
+    double sx = 0, sy = 0, x0 = HUGE_VAL, x1 = -HUGE_VAL, y0 = HUGE_VAL, y1 = -HUGE_VAL;
+    for (int o : gridded) {
+        sx = std::max(sx, (double)box[o].xhi - (double)box[o].xlo); sy = std::max(sy, (double)box[o].yhi - (double)box[o].ylo);
+        x0 = std::min(x0, (double)box[o].xlo); x1 = std::max(x1, (double)box[o].xlo);
+        y0 = std::min(y0, (double)box[o].ylo); y1 = std::max(y1, (double)box[o].ylo);
+    }
+    if (gridded.empty()) { x0 = x1 = y0 = y1 = 0; }
+    h.SX = f32_up(sx); h.SY = f32_up(sy);
+    h.gx0 = (float)x0; h.gy0 = (float)y0;
+    if ((double)h.gx0 > x0) h.gx0 = std::nextafterf(h.gx0, -HUGE_VALF);
+    if ((double)h.gy0 > y0) h.gy0 = std::nextafterf(h.gy0, -HUGE_VALF);
+    // cell size: the whole anchor range must fit the bitmap, and a cell is not finer than the typical box
+    auto inv_cell = [](double range, double s, int n) {
+        double ic = 1.0 / std::max(s, 1e-30);
+        if (range > 0) ic = std::min(ic, (n - 0.5) / range);
+        return (float)std::min(ic, 1e30);
+    };
+    h.icx = inv_cell(x1 - x0, sx, CCK_GRID_COLS); h.icy = inv_cell(y1 - y0, sy, CCK_GRID_ROWS);
+    auto fits = [&]() {
+        for (int o : gridded) {
+            const float cx = grid_cellf(box[o].xlo, h.gx0, h.icx), cy = grid_cellf(box[o].ylo, h.gy0, h.icy);
+            if (!(cx >= 0.f && cx <= (float)(CCK_GRID_COLS - 1) && cy >= 0.f && cy <= (float)(CCK_GRID_ROWS - 1))) return false;
+        }
+        return true;
+    };
+    for (int it = 0; it < 64 && !fits(); ++it) { h.icx *= 0.999f; h.icy *= 0.999f; }
+    if (!fits()) {   // cannot bin (pathological coordinates): every obstacle goes through the box test directly
+        always.insert(always.end(), gridded.begin(), gridded.end());
+        gridded.clear(); h.n_grid = 0;
+    }
+    struct Ent { int cy, cx, o; };
+    std::vector<Ent> ents;
+    for (int o : gridded) ents.push_back({(int)grid_cellf(box[o].ylo, h.gy0, h.icy), (int)grid_cellf(box[o].xlo, h.gx0, h.icx), o});
+    std::stable_sort(ents.begin(), ents.end(), [](const Ent& a, const Ent& b) { return a.cy != b.cy ? a.cy < b.cy : a.cx < b.cx; });
+    std::vector<uint64_t> occ(CCK_GRID_ROWS, 0);
+    std::vector<uint16_t> rowbase(CCK_GRID_ROWS, 0), cstart;
+    {
+        int prev_cy = -1, prev_cx = -1;
+        for (size_t e = 0; e < ents.size(); ++e) {
+            if (ents[e].cy != prev_cy || ents[e].cx != prev_cx) {
+                cstart.push_back((uint16_t)e);
+                occ[ents[e].cy] |= 1ull << ents[e].cx;
+                prev_cy = ents[e].cy; prev_cx = ents[e].cx;
+            }
+        }
+        h.n_cells = (int)cstart.size();
+        cstart.push_back((uint16_t)ents.size());
+        int acc = 0;
+        for (int r = 0; r < CCK_GRID_ROWS; ++r) { rowbase[r] = (uint16_t)acc; acc += __builtin_popcountll(occ[r]); }
+    }
+    h.Rm1 = (float)(CCK_GRID_ROWS - 1);
+    auto al = [](int v, int a) { return (v + a - 1) / a * a; };
+    h.off_occ = (int)sizeof(GHeader);
+    h.off_rowbase = h.off_occ + CCK_GRID_ROWS * 8;
+    h.off_cstart = h.off_rowbase + CCK_GRID_ROWS * 2;
+    h.off_boxes = al(h.off_cstart + (int)cstart.size() * 2, 16);
+    h.total_bytes = al(h.off_boxes + M * 16, 16);
+    out.buf.assign(h.total_bytes, 0);
+    std::memcpy(out.buf.data(), &h, sizeof(h));
+    std::memcpy(out.buf.data() + h.off_occ, occ.data(), occ.size() * 8);
+    std::memcpy(out.buf.data() + h.off_rowbase, rowbase.data(), rowbase.size() * 2);
+    std::memcpy(out.buf.data() + h.off_cstart, cstart.data(), cstart.size() * 2);
+    out.exB.assign((size_t)std::max(M, 1) * 4, 0.0);
+    out.exCls.assign(std::max(M, 1), 0);
+    int j = 0;
+    auto put = [&](int o) {
+        std::memcpy(out.buf.data() + h.off_boxes + (size_t)j * 16, &box[o], 16);
+        std::memcpy(out.exB.data() + (size_t)j * 4, B + 4 * o, 32);
+        out.exCls[j] = cls_idx[o];
+        ++j;
+    };
+    for (auto& e : ents) put(e.o);
+    for (int o : always) put(o);
+}
+
 // Group obstacles by bit-identical A[4][2] and lay the table out for one TMA bulk copy.
 extern "C" int cck_set_obstacles(cck_ctx* c, const cck_svc_params* p, const double* A, const double* B, const double* centres,
                                  const double* rects, int M) {
@@ -304,12 +437,14 @@ extern "C" int cck_set_obstacles(cck_ctx* c, const cck_svc_params* p, const doub
     std::map<Key, int> cls_of;
     std::vector<std::vector<int>> members;
     std::vector<Key> keys;
+    std::vector<int> cls_idx(M);
     for (int o = 0; o < M; ++o) {
         Key k;
         std::memcpy(k.w, A + 8 * o, 64);
         auto it = cls_of.find(k);
         if (it == cls_of.end()) { it = cls_of.emplace(k, (int)members.size()).first; members.emplace_back(); keys.push_back(k); }
         members[it->second].push_back(o);
+        cls_idx[o] = it->second;
     }
     const int nc = (int)members.size();
     int rows = 0;   // B rows incl. per-class padding to a multiple of 4
@@ -445,6 +580,21 @@ extern "C" int cck_set_obstacles(cck_ctx* c, const cck_svc_params* p, const doub
         CK(c, cudaMemcpy(c->d_exB, exB.data(), exB.size() * 8, cudaMemcpyHostToDevice));
         CK(c, cudaMemcpy(c->d_exCls, exCls.data(), exCls.size() * 4, cudaMemcpyHostToDevice));
         c->ftab_bytes = fh.total_bytes;
+    }
+    // ---- fp32 box + bitmap-grid table (the default broad phase) ----
+    cudaFree(c->d_gtab); cudaFree(c->d_gexB); cudaFree(c->d_gexCls);
+    c->d_gtab = nullptr; c->d_gexB = nullptr; c->d_gexCls = nullptr; c->gtab_bytes = 0;
+    if (M > 0) {
+        GridBuild gb;
+        build_grid_table(M, A, B, cls_idx, p->erf_inv_result, gb);
+        if (grid_smem_bytes((int)gb.buf.size()) > c->max_smem_optin) return fail(c, CCK_ERR_INVALID, "grid table exceeds shared memory; M too large");
+        CK(c, cudaMalloc(&c->d_gtab, gb.buf.size()));
+        CK(c, cudaMalloc(&c->d_gexB, gb.exB.size() * 8));
+        CK(c, cudaMalloc(&c->d_gexCls, gb.exCls.size() * 4));
+        CK(c, cudaMemcpy(c->d_gtab, gb.buf.data(), gb.buf.size(), cudaMemcpyHostToDevice));
+        CK(c, cudaMemcpy(c->d_gexB, gb.exB.data(), gb.exB.size() * 8, cudaMemcpyHostToDevice));
+        CK(c, cudaMemcpy(c->d_gexCls, gb.exCls.data(), gb.exCls.size() * 4, cudaMemcpyHostToDevice));
+        c->gtab_bytes = (int)gb.buf.size();
     }
 
     SvcDev& s = c->svc;
@@ -589,8 +739,20 @@ static int launch_rollout(cck_ctx* c, cudaStream_t s, const RolloutArgs& a) {
         else if (c->svc.kind == CCK_SVC_ADAPTIVE) LAUNCH_R((NAME<CCK_SVC_ADAPTIVE, TRAJ, EXPAND>), PAR);           \
         else LAUNCH_R((NAME<CCK_SVC_CHISQUARED, TRAJ, EXPAND>), PAR);                                               \
     } while (0)
-    if (c->model.model == CCK_MODEL_LINEAR2D && c->svc.kind == CCK_SVC_BLACKMORE && c->bpt > 0) {
-        // default configuration: threshold kernel, BPT beliefs per thread
+    if (c->model.model == CCK_MODEL_LINEAR2D && c->svc.kind == CCK_SVC_BLACKMORE && c->kern == 2) {
+        // default configuration: fp32 box/bitmap-grid broad phase + exact fp64 decision, lane refill
+        RolloutArgs g2 = a;
+        g2.ftab = c->d_gtab; g2.ftab_bytes = c->gtab_bytes; g2.exB = c->d_gexB; g2.exCls = c->d_gexCls;
+        const int per_range = 256;
+        const int64_t nr = (a.n + per_range - 1) / per_range;
+        const int gb = (int)std::min<int64_t>(nr, (int64_t)c->num_sms * 4);
+        const int gsmem = grid_smem_bytes(c->gtab_bytes);
+        if (traj) { if ((rc = set_smem(c, (k_rollout_lin_grid<true, EXPAND>), gsmem))) return rc;
+                    k_rollout_lin_grid<true, EXPAND><<<gb, CCK_GRID_THREADS, gsmem, s>>>(g2, c->lin, c->svc, per_range); }
+        else { if ((rc = set_smem(c, (k_rollout_lin_grid<false, EXPAND>), gsmem))) return rc;
+               k_rollout_lin_grid<false, EXPAND><<<gb, CCK_GRID_THREADS, gsmem, s>>>(g2, c->lin, c->svc, per_range); }
+    } else if (c->model.model == CCK_MODEL_LINEAR2D && c->svc.kind == CCK_SVC_BLACKMORE && c->kern == 1 && c->bpt > 0) {
+        // second generation: threshold (group filter) kernel, BPT beliefs per thread
 #define LAUNCH_BM(BPT, TRAJ)                                                                             \
     do {                                                                                                 \
         const int gb = grid_for(c, (a.n + BPT - 1) / BPT, threads, 8);                                   \
@@ -778,7 +940,7 @@ static cudaError_t d2h_planes(void* dst, int64_t ld_dst, const void* src, size_t
     return cudaMemcpy2DAsync(dst, (size_t)ld_dst * elem, src, (size_t)cnt * elem, (size_t)cnt * elem, planes, cudaMemcpyDeviceToHost, s);
 }
 
-static const int64_t kChunk = 1 << 22;   // beliefs per pipeline chunk
+static const int64_t kChunk = 1 << 20;   // beliefs per pipeline chunk
 
 extern "C" int cck_propagate(cck_ctx* c, int64_t n, const double* bel, int64_t ld, const double* ctrl, int64_t ldc, double duration,
                              double* out, int64_t ldo) {
@@ -788,7 +950,7 @@ extern "C" int cck_propagate(cck_ctx* c, int64_t n, const double* bel, int64_t l
     CK(c, cudaSetDevice(c->device));
     const int dim = c->model.dim, W = dim + 2 * dim * dim;
     int slot = 0;
-    for (int64_t off = 0; off < n; off += kChunk, slot ^= 1) {
+    for (int64_t off = 0; off < n; off += kChunk, slot = (slot + 1) % CCK_SLOTS) {
         const int64_t cnt = std::min(kChunk, n - off);
         const size_t b_in = al256((size_t)cnt * W * 8), b_c = al256((size_t)cnt * dim * 8), b_out = b_in;
         if ((rc = ensure_scratch(c, slot, b_in + b_c + b_out))) return rc;
@@ -800,8 +962,7 @@ extern "C" int cck_propagate(cck_ctx* c, int64_t n, const double* bel, int64_t l
         if ((rc = cck_propagate_dev(c, s, cnt, d_in, cnt, d_c, cnt, duration, d_out, cnt))) return rc;
         CK(c, d2h_planes(out + off, ldo, d_out, 8, cnt, W, s));
     }
-    CK(c, cudaStreamSynchronize(c->pipe[0]));
-    CK(c, cudaStreamSynchronize(c->pipe[1]));
+    for (int i = 0; i < CCK_SLOTS; ++i) CK(c, cudaStreamSynchronize(c->pipe[i]));
     return CCK_OK;
 }
 
@@ -812,7 +973,7 @@ extern "C" int cck_is_valid(cck_ctx* c, int64_t n, const double* bel, int64_t ld
     CK(c, cudaSetDevice(c->device));
     const int dim = c->model.dim, W = dim + 2 * dim * dim;
     int slot = 0;
-    for (int64_t off = 0; off < n; off += kChunk, slot ^= 1) {
+    for (int64_t off = 0; off < n; off += kChunk, slot = (slot + 1) % CCK_SLOTS) {
         const int64_t cnt = std::min(kChunk, n - off);
         const size_t b_in = al256((size_t)cnt * W * 8), b_v = al256((size_t)cnt);
         if ((rc = ensure_scratch(c, slot, b_in + b_v))) return rc;
@@ -822,8 +983,7 @@ extern "C" int cck_is_valid(cck_ctx* c, int64_t n, const double* bel, int64_t ld
         if ((rc = cck_is_valid_dev(c, s, cnt, (double*)base, cnt, base + b_in))) return rc;
         CK(c, cudaMemcpyAsync(valid + off, base + b_in, (size_t)cnt, cudaMemcpyDeviceToHost, s));
     }
-    CK(c, cudaStreamSynchronize(c->pipe[0]));
-    CK(c, cudaStreamSynchronize(c->pipe[1]));
+    for (int i = 0; i < CCK_SLOTS; ++i) CK(c, cudaStreamSynchronize(c->pipe[i]));
     return CCK_OK;
 }
 
@@ -840,7 +1000,7 @@ static int rollout_host(cck_ctx* c, bool expand, int64_t n, const double* bel, i
     int64_t chunk = kChunk;
     if (traj) chunk = std::max<int64_t>(1024, kChunk / (traj_T > 0 ? traj_T : 1));
     int slot = 0;
-    for (int64_t off = 0; off < n; off += chunk, slot ^= 1) {
+    for (int64_t off = 0; off < n; off += chunk, slot = (slot + 1) % CCK_SLOTS) {
         const int64_t cnt = std::min(chunk, n - off);
         const size_t b_in = al256((size_t)cnt * W * 8), b_c = al256((size_t)cnt * dim * 8), b_i = al256((size_t)cnt * 4);
         const size_t b_d = al256((size_t)cnt * 8), b_f = al256((size_t)cnt);
@@ -878,8 +1038,7 @@ static int rollout_host(cck_ctx* c, bool expand, int64_t n, const double* bel, i
         CK(c, cudaMemcpyAsync(valid_steps + off, d_valid, (size_t)cnt * 4, cudaMemcpyDeviceToHost, s));
         if (traj) CK(c, d2h_planes(traj + off, traj_ld, d_traj, 8, cnt, W * traj_T, s));
     }
-    CK(c, cudaStreamSynchronize(c->pipe[0]));
-    CK(c, cudaStreamSynchronize(c->pipe[1]));
+    for (int i = 0; i < CCK_SLOTS; ++i) CK(c, cudaStreamSynchronize(c->pipe[i]));
     return CCK_OK;
 }
 

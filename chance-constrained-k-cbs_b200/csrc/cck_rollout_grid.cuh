@@ -1,0 +1,236 @@
+// cck_rollout_grid.cuh — third generation of the fused propagateWhileValid kernel for the default
+// configuration (2DUncertainLinear + PCCBlackmoreSVC).
+//
+// ncu on the second generation (profiles/r1c_*) showed the FP64 pipe at ~55 % and the ALU pipe at
+// ~75 %: the fp32 threshold computation (4 DSQRT per belief-step) cost more FP64 issue than the
+// Kalman recursion itself, and the 32 group rows per belief-step saturated the ALU pipe (FSETP).
+// This version keeps FP64 for what must be bit-exact (the recursion, the bounds test, the exact
+// decision on unproven obstacles) and moves everything else to a CONSERVATIVE fp32 broad phase:
+//
+//  * every half-plane whose normal is axis-aligned, (±w, 0) or (0, ±w), says "safe if x - ex >= xhi",
+//    "x + ex <= xlo", … in distance units, with ex = sqrt2*c*sqrt(P00), ey = sqrt2*c*sqrt(P11).  Each
+//    obstacle therefore owns an fp32 box (xlo, ylo, xhi, yhi), rounded OUTWARD on the host; a belief
+//    whose fp32 interval [x -+ ex] x [y -+ ey] (widened by an explicit rounding margin) misses the box
+//    is PROVEN safe for the reference's fp64 inequality.  Planes that are not axis-aligned simply do
+//    not contribute a side (side = +-inf): the obstacle is then decided by the exact path.
+//  * the boxes' lower-left corners are binned into a 64-column bitmap grid in shared memory; a
+//    belief-step looks at the 3-4 bitmap rows its interval overlaps, ANDs them with a column mask and
+//    only touches the obstacles of occupied cells (a handful, usually none).  The cell function is
+//    the same monotone fp32 expression on host and device, so no margin is needed for the binning.
+//  * whatever the box test cannot prove (a real collision, the ~1e-5-wide fp32 band, non-finite
+//    operands) is decided by the reference's exact fp64 expression on the obstacle's own normals
+//    (bm_exact_obstacle).  Verdicts and first-violation steps stay bit-identical to the oracle.
+//  * lanes are refilled from a CTA-wide work counter as soon as their rollout ends, and the previous
+//    (last valid) state is stashed in shared memory instead of a second register copy.
+#pragma once
+#include "cck_rollout_bm.cuh"
+
+namespace cck {
+
+struct GHeader {                 // 80 bytes, then occ[R] (u64), rowbase[R] (u16), cstart[n_cells+1] (u16), boxes[M] (float4)
+    int32_t total_bytes, M, n_grid, n_cells;
+    int32_t R, off_occ, off_rowbase, off_cstart;
+    int32_t off_boxes, pad0;
+    float gx0, gy0, icx, icy;    // cell = floor((v - g0) * ic), clamped by the caller
+    float SX, SY;                // >= max box width / height of the gridded obstacles
+    float k;                     // >= sqrt(2) * erf_inv_result
+    float Rm1;                   // (float)(R - 1)
+    int32_t pad1[2];
+};
+static_assert(sizeof(GHeader) == 80, "grid header");
+
+#define CCK_GRID_COLS 64
+#define CCK_GRID_ROWS 64
+
+// The binning function.  Monotone non-decreasing in v (IEEE RN subtraction of a constant, RN
+// multiplication by a positive constant, floor), evaluated identically on host (table build) and
+// device (query): an anchor inside a query interval lands inside the interval's cell range.
+__host__ __device__ __forceinline__ float grid_cellf(float v, float g0, float ic) {
+#ifdef __CUDA_ARCH__
+    return floorf(__fmul_rn(__fsub_rn(v, g0), ic));
+#else
+    volatile float d = v - g0;
+    volatile float t = d * ic;
+    return floorf(t);
+#endif
+}
+
+// MUFU.SQRT: max relative error 2^-23 (PTX ISA, sqrt.approx.f32), denormal inputs flushed to zero
+__device__ __forceinline__ float sqrt_approx(float v) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
+
+// ok &= "the belief is safe w.r.t. every obstacle" (PCCBlackmoreSVC.cpp:54-58), bit-exact.
+__device__ __forceinline__ bool grid_check(const unsigned char* gt, const unsigned char* ctab, const double* exB, const int32_t* exCls,
+                                           double c, double x, double y, double P0, double P1, double P2, double P3) {
+    const GHeader* h = reinterpret_cast<const GHeader*>(gt);
+    const float4* boxes = reinterpret_cast<const float4*>(gt + h->off_boxes);
+    const TabHeader* th = reinterpret_cast<const TabHeader*>(ctab);
+    const ClassRec* cls = reinterpret_cast<const ClassRec*>(ctab + th->off_classes);
+    const float xf = __double2float_rn(x), yf = __double2float_rn(y);
+    const float p0 = __double2float_rn(P0), p3 = __double2float_rn(P3);
+    const float offd = __double2float_rn(fabs(P1) + fabs(P2));
+    // every operand finite and far from fp32 overflow, variances non-negative (false for NaN)
+    const bool fin = (fabsf(xf) + fabsf(yf)) + (p0 + p3) + offd < 1e30f && p0 >= 0.f && p3 >= 0.f;
+    if (!fin) {   // rare: decide every obstacle with the reference's expression
+        bool ok = true;
+        for (int j = 0; j < h->M && ok; ++j) ok = bm_exact_obstacle(cls[exCls[j]].A, exB + (size_t)j * 4, x, y, P0, P1, P2, P3, c);
+        return ok;
+    }
+    const float ex = h->k * sqrt_approx(p0), ey = h->k * sqrt_approx(p3);
+    // margin: 2^-18 relative covers the fp64->fp32 conversions, the fp32 sqrt/mul/add roundings (<2^-20)
+    // and the fp64 roundings of the reference's expression (2^-50); 1e-17 absolute covers denormal inputs
+    // (flushed by sqrt.approx.ftz: ex_true <= k * sqrt(1.2e-38) < 1e-18)
+    const float mx = (fabsf(xf) + ex) * 3.814697265625e-06f + 1e-17f;
+    const float my = (fabsf(yf) + ey) * 3.814697265625e-06f + 1e-17f;
+    const float xm = (xf - ex) - mx, xp = (xf + ex) + mx;
+    const float ym = (yf - ey) - my, yp = (yf + ey) + my;
+    bool ok = true;
+    // gridded obstacles: anchor (xlo, ylo) must lie in (xm - SX, xp) x (ym - SY, yp) to be unproven
+    const float clo = fmaxf(grid_cellf(__fsub_rd(xm, h->SX), h->gx0, h->icx), 0.f);
+    const float chi = fminf(grid_cellf(xp, h->gx0, h->icx), (float)(CCK_GRID_COLS - 1));
+    const float rlo = fmaxf(grid_cellf(__fsub_rd(ym, h->SY), h->gy0, h->icy), 0.f);
+    const float rhi = fminf(grid_cellf(yp, h->gy0, h->icy), h->Rm1);
+    if (clo <= chi && rlo <= rhi) {
+        const uint64_t* occ = reinterpret_cast<const uint64_t*>(gt + h->off_occ);
+        const uint16_t* rowbase = reinterpret_cast<const uint16_t*>(gt + h->off_rowbase);
+        const uint16_t* cstart = reinterpret_cast<const uint16_t*>(gt + h->off_cstart);
+        const int c0 = (int)clo, c1 = (int)chi, r1 = (int)rhi;
+        const uint64_t cm = (~0ull >> (63 - c1)) & (~0ull << c0);
+        for (int r = (int)rlo; r <= r1 && ok; ++r) {
+            const uint64_t oc = occ[r];
+            uint64_t m = oc & cm;
+            while (m && ok) {
+                const int cc = __ffsll((long long)m) - 1;
+                m &= m - 1;
+                const int cell = rowbase[r] + __popcll(oc & ((1ull << cc) - 1ull));
+                const int j1 = cstart[cell + 1];
+                for (int j = cstart[cell]; j < j1 && ok; ++j) {
+                    const float4 b = boxes[j];
+                    const bool proven = (xm >= b.z) | (xp <= b.x) | (ym >= b.w) | (yp <= b.y);
+                    if (!proven) ok = bm_exact_obstacle(cls[exCls[j]].A, exB + (size_t)j * 4, x, y, P0, P1, P2, P3, c);
+                }
+            }
+        }
+    }
+    // obstacles without a finite box (non-axis-aligned planes, unusable constants): box sides are +-inf
+    for (int j = h->n_grid; j < h->M && ok; ++j) {
+        const float4 b = boxes[j];
+        const bool proven = (xm >= b.z) | (xp <= b.x) | (ym >= b.w) | (yp <= b.y);
+        if (!proven) ok = bm_exact_obstacle(cls[exCls[j]].A, exB + (size_t)j * 4, x, y, P0, P1, P2, P3, c);
+    }
+    return ok;
+}
+
+// shared-memory carve-up: [mbarrier 16 B][grid table][work counter 16 B][stash 128 x 80 B]
+#define CCK_GRID_THREADS 128
+__host__ __device__ inline int grid_smem_bytes(int gtab_bytes) { return 16 + gtab_bytes + 16 + CCK_GRID_THREADS * 80; }
+
+template <bool TRAJ, bool EXPAND>
+__global__ void __launch_bounds__(CCK_GRID_THREADS, 4) k_rollout_lin_grid(const __grid_constant__ RolloutArgs a, const __grid_constant__ LinDev p,
+                                                                          const __grid_constant__ SvcDev sp, int per_range) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+    unsigned char* gt = smem_raw + 16;
+    int* next_k = reinterpret_cast<int*>(smem_raw + 16 + a.ftab_bytes);
+    double2* stash = reinterpret_cast<double2*>(smem_raw + 16 + a.ftab_bytes + 16) + threadIdx.x * 5;   // 80 B per thread, conflict-free STS.128
+    if (threadIdx.x == 0) *next_k = 0;
+    stage_begin(gt, a.ftab, (uint32_t)a.ftab_bytes, bar);   // __syncthreads inside
+    stage_wait((uint32_t)a.ftab_bytes, bar);
+    const double eps = DBL_EPSILON;
+    const double c = sp.erf_inv_result;
+
+    bool have = false, done = false;
+    Lin cur;
+    double dux = 0, duy = 0, x0 = 0, y0 = 0;
+    int steps = 0, t = 0, pstep = 0;
+    int64_t i = 0;
+    bool cons_ok = true;
+    cur.mx = cur.my = 0;
+#pragma unroll
+    for (int f = 0; f < 4; ++f) cur.S[f] = cur.L[f] = 0;
+    while (true) {
+        while (!have && !done) {   // fetch: the CTA owns ranges blockIdx, blockIdx+gridDim, ... of per_range beliefs
+            const int kk = atomicAdd(next_k, 1);
+            const int rg = kk / per_range;
+            i = ((int64_t)blockIdx.x + (int64_t)rg * gridDim.x) * per_range + (kk - rg * per_range);
+            if (i >= a.n) {
+                // later ranges of this CTA start even further out: nothing left once the range base is past n
+                if (((int64_t)blockIdx.x + (int64_t)rg * gridDim.x) * per_range >= a.n) { done = true; break; }
+                continue;
+            }
+            steps = a.steps[i];
+            if (steps <= 0) {      // propagateWhileValid(.., 0, ..): copy, return 0
+#pragma unroll
+                for (int f = 0; f < 10; ++f) a.out[f * a.ldo + i] = a.bel[f * a.ld + i];
+                a.valid[i] = 0;
+                if (EXPAND) {
+                    const double bx = a.bel[i], by = a.bel[a.ld + i];
+                    double gd;
+                    const bool g = goal_ok(a.goal, sp, bx, by, a.bel[2 * a.ld + i] + a.bel[6 * a.ld + i], a.bel[3 * a.ld + i] + a.bel[7 * a.ld + i],
+                                           a.bel[4 * a.ld + i] + a.bel[8 * a.ld + i], a.bel[5 * a.ld + i] + a.bel[9 * a.ld + i], &gd);
+                    a.cost[i] = a.parent_cost[i] + 0.0;
+                    a.goal_dist[i] = gd;
+                    a.flags[i] = (uint8_t)(1 | 2 | (g ? 4 : 0));
+                }
+                continue;
+            }
+            cur.mx = a.bel[i]; cur.my = a.bel[a.ld + i];
+#pragma unroll
+            for (int f = 0; f < 4; ++f) { cur.S[f] = a.bel[(2 + f) * a.ld + i]; cur.L[f] = a.bel[(6 + f) * a.ld + i]; }
+            dux = p.dt * a.ctrl[i]; duy = p.dt * a.ctrl[a.ldc + i];
+            x0 = cur.mx; y0 = cur.my;
+            t = 0; cons_ok = true;
+            if (EXPAND) pstep = a.parent_step[i];
+            have = true;
+        }
+        if (__all_sync(0xffffffffu, !have)) break;
+        if (!have) continue;
+        // stash the last valid state, advance in place
+        stash[0] = make_double2(cur.mx, cur.my);
+        stash[1] = make_double2(cur.S[0], cur.S[1]); stash[2] = make_double2(cur.S[2], cur.S[3]);
+        stash[3] = make_double2(cur.L[0], cur.L[1]); stash[4] = make_double2(cur.L[2], cur.L[3]);
+        lin_step(cur, dux, duy, p, cur);
+        const double x = cur.mx, y = cur.my;
+        const double P0 = cur.S[0] + cur.L[0], P1 = cur.S[1] + cur.L[1], P2 = cur.S[2] + cur.L[2], P3 = cur.S[3] + cur.L[3];
+        bool ok = !(x - eps > sp.high[0] || x + eps < sp.low[0] || y - eps > sp.high[1] || y + eps < sp.low[1]);   // satisfiesBounds (NaN passes)
+        if (ok && a.ftab_bytes > 0) ok = grid_check(gt, a.tab, a.exB, a.exCls, c, x, y, P0, P1, P2, P3);
+        int r = -1;                // >= 0: this rollout ends now with r valid steps
+        if (!ok) {
+            r = t;                 // died: the result is the last valid state
+            const double2 s0 = stash[0], s1 = stash[1], s2 = stash[2], s3 = stash[3], s4 = stash[4];
+            cur.mx = s0.x; cur.my = s0.y; cur.S[0] = s1.x; cur.S[1] = s1.y; cur.S[2] = s2.x; cur.S[3] = s2.y;
+            cur.L[0] = s3.x; cur.L[1] = s3.y; cur.L[2] = s4.x; cur.L[3] = s4.y;
+        } else {
+            if (EXPAND && a.cons) cons_ok = cons_ok && constraints_ok_at(a.cons, pstep + t + 1, x, y, P0, P1, P2, P3);
+            if (TRAJ) {
+                double* tp = a.traj + (int64_t)t * 10 * a.traj_ld + i;
+                tp[0] = cur.mx; tp[a.traj_ld] = cur.my;
+#pragma unroll
+                for (int f = 0; f < 4; ++f) { tp[(2 + f) * a.traj_ld] = cur.S[f]; tp[(6 + f) * a.traj_ld] = cur.L[f]; }
+            }
+            ++t;
+            if (t == steps) r = steps;
+        }
+        if (r >= 0) {
+            a.out[i] = cur.mx; a.out[a.ldo + i] = cur.my;
+#pragma unroll
+            for (int f = 0; f < 4; ++f) { a.out[(2 + f) * a.ldo + i] = cur.S[f]; a.out[(6 + f) * a.ldo + i] = cur.L[f]; }
+            a.valid[i] = r;
+            if (EXPAND) {
+                const double d0 = x0 - cur.mx, d1 = y0 - cur.my;
+                a.cost[i] = a.parent_cost[i] + sqrt(d0 * d0 + d1 * d1);
+                double gd;
+                const bool g = goal_ok(a.goal, sp, cur.mx, cur.my, cur.S[0] + cur.L[0], cur.S[1] + cur.L[1], cur.S[2] + cur.L[2],
+                                       cur.S[3] + cur.L[3], &gd);
+                a.goal_dist[i] = gd;
+                a.flags[i] = (uint8_t)((r == steps ? 1 : 0) | (cons_ok ? 2 : 0) | (g ? 4 : 0));
+            }
+            have = false;
+        }
+    }
+}
+
+}  // namespace cck
