@@ -325,23 +325,29 @@ struct GridBuild { std::vector<unsigned char> buf; std::vector<double> exB; std:
 static void build_grid_table(int M, const double* A, const double* B, const std::vector<int>& cls_idx, double c, GridBuild& out) {
     const bool c_ok = std::isfinite(c) && c >= 0.0 && c < 1e6;
     struct Box { float xlo, ylo, xhi, yhi; };
-    std::vector<Box> box(M);
+    std::vector<Box> box(M), inner(M);
     std::vector<int> gridded, always;
     auto usable = [](double w) { const double a = std::fabs(w); return std::isfinite(w) && a > 1e-100 && a < 1e100; };
     for (int o = 0; o < M; ++o) {
         Box b{-HUGE_VALF, -HUGE_VALF, HUGE_VALF, HUGE_VALF};
+        Box q{HUGE_VALF, HUGE_VALF, -HUGE_VALF, -HUGE_VALF};   // inner box: "every plane fails"; stays empty unless one plane per side
+        int sides = 0;                                          // bit per side that has exactly one usable plane
+        bool pure = c_ok;
         for (int i = 0; i < 4 && c_ok; ++i) {
             const double a0 = A[8 * o + 2 * i], a1 = A[8 * o + 2 * i + 1], bv = B[4 * o + i];
-            if (std::isnan(bv)) continue;
+            if (std::isnan(bv)) { pure = false; continue; }
             if (a1 == 0.0 && usable(a0)) {            // a0*x >= b + bb, bb/|a0| = sqrt2*c*sqrt(P00)
                 const double thr = bv / a0;
-                if (a0 > 0) b.xhi = std::min(b.xhi, f32_up(thr)); else b.xlo = std::max(b.xlo, f32_down(thr));
+                if (a0 > 0) { b.xhi = std::min(b.xhi, f32_up(thr)); q.xhi = f32_down(thr); pure = pure && !(sides & 1); sides |= 1; }
+                else { b.xlo = std::max(b.xlo, f32_down(thr)); q.xlo = f32_up(thr); pure = pure && !(sides & 2); sides |= 2; }
             } else if (a0 == 0.0 && usable(a1)) {     // a1*y >= b + bb, bb/|a1| = sqrt2*c*sqrt(P11)
                 const double thr = bv / a1;
-                if (a1 > 0) b.yhi = std::min(b.yhi, f32_up(thr)); else b.ylo = std::max(b.ylo, f32_down(thr));
-            }
+                if (a1 > 0) { b.yhi = std::min(b.yhi, f32_up(thr)); q.yhi = f32_down(thr); pure = pure && !(sides & 4); sides |= 4; }
+                else { b.ylo = std::max(b.ylo, f32_down(thr)); q.ylo = f32_up(thr); pure = pure && !(sides & 8); sides |= 8; }
+            } else pure = false;
         }
-        box[o] = b;
+        if (!pure || sides != 15) q = Box{HUGE_VALF, HUGE_VALF, -HUGE_VALF, -HUGE_VALF};
+        box[o] = b; inner[o] = q;
         const bool finite = std::isfinite(b.xlo) && std::isfinite(b.ylo) && std::isfinite(b.xhi) && std::isfinite(b.yhi);
         (finite ? gridded : always).push_back(o);
     }
@@ -404,7 +410,7 @@ static void build_grid_table(int M, const double* A, const double* B, const std:
     h.off_rowbase = h.off_occ + CCK_GRID_ROWS * 8;
     h.off_cstart = h.off_rowbase + CCK_GRID_ROWS * 2;
     h.off_boxes = al(h.off_cstart + (int)cstart.size() * 2, 16);
-    h.total_bytes = al(h.off_boxes + M * 16, 16);
+    h.total_bytes = al(h.off_boxes + 2 * M * 16, 16);
     out.buf.assign(h.total_bytes, 0);
     std::memcpy(out.buf.data(), &h, sizeof(h));
     std::memcpy(out.buf.data() + h.off_occ, occ.data(), occ.size() * 8);
@@ -415,6 +421,7 @@ static void build_grid_table(int M, const double* A, const double* B, const std:
     int j = 0;
     auto put = [&](int o) {
         std::memcpy(out.buf.data() + h.off_boxes + (size_t)j * 16, &box[o], 16);
+        std::memcpy(out.buf.data() + h.off_boxes + (size_t)(M + j) * 16, &inner[o], 16);
         std::memcpy(out.exB.data() + (size_t)j * 4, B + 4 * o, 32);
         out.exCls[j] = cls_idx[o];
         ++j;
@@ -458,8 +465,8 @@ extern "C" int cck_set_obstacles(cck_ctx* c, const cck_svc_params* p, const doub
     h.total_bytes = h.off_rects + (rects ? M * 32 : 0);
     h.total_bytes = (h.total_bytes + 15) & ~15;
     h.pad = rows;
-    if (h.total_bytes + 16 > c->max_smem_optin)
-        return fail(c, CCK_ERR_INVALID, "obstacle table (" + std::to_string(h.total_bytes) + " B) exceeds shared memory; M too large");
+    // the class table is staged into shared memory only by the generic kernels (checked at their launch);
+    // the default Blackmore rollout reads its class normals from global memory on the exact path
     std::vector<unsigned char> buf(h.total_bytes, 0);
     std::memcpy(buf.data(), &h, sizeof(h));
     int pos = 0;
@@ -531,7 +538,8 @@ extern "C" int cck_set_obstacles(cck_ctx* c, const cck_svc_params* p, const doub
         fh.off_rows = fh.off_super + nsup * (int)sizeof(SuperRec);
         fh.off_groups = fh.off_rows + frows * 16;
         fh.total_bytes = (fh.off_groups + fgroups * 16 + 15) & ~15;
-        if (fh.total_bytes + 16 > c->max_smem_optin) return fail(c, CCK_ERR_INVALID, "filter table exceeds shared memory; M too large");
+        const bool filter_fits = fh.total_bytes + 16 <= c->max_smem_optin;   // else: CCK_KERNEL=1 is refused at launch
+        if (filter_fits) {
         std::vector<unsigned char> fbuf(fh.total_bytes, 0);
         std::vector<double> exB((size_t)frows * 4, -HUGE_VAL);
         std::vector<int32_t> exCls(frows, -1);
@@ -580,6 +588,7 @@ extern "C" int cck_set_obstacles(cck_ctx* c, const cck_svc_params* p, const doub
         CK(c, cudaMemcpy(c->d_exB, exB.data(), exB.size() * 8, cudaMemcpyHostToDevice));
         CK(c, cudaMemcpy(c->d_exCls, exCls.data(), exCls.size() * 4, cudaMemcpyHostToDevice));
         c->ftab_bytes = fh.total_bytes;
+        }
     }
     // ---- fp32 box + bitmap-grid table (the default broad phase) ----
     cudaFree(c->d_gtab); cudaFree(c->d_gexB); cudaFree(c->d_gexCls);
@@ -662,6 +671,12 @@ static int set_smem(cck_ctx* c, K kernel, int bytes) {
     return CCK_OK;
 }
 
+static int check_tab_fits(cck_ctx* c) {
+    if (16 + c->tab_bytes > c->max_smem_optin)
+        return fail(c, CCK_ERR_INVALID, "obstacle table (" + std::to_string(c->tab_bytes) + " B) exceeds shared memory; M too large for this checker");
+    return CCK_OK;
+}
+
 static int check_ready(cck_ctx* c, bool need_svc) {
     if (!c) return CCK_ERR_INVALID;
     if (!c->has_model) return fail(c, CCK_ERR_INVALID, "cck_set_model has not been called");
@@ -701,6 +716,7 @@ extern "C" int cck_is_valid_dev(cck_ctx* c, void* stream, int64_t n, const doubl
     if (n == 0) return CCK_OK;
     CK(c, cudaSetDevice(c->device));
     cudaStream_t s = pick(c, stream);
+    if ((rc = check_tab_fits(c))) return rc;
     const int smem = 16 + c->tab_bytes;
     const int g = grid_for(c, n, 256, 4);
     const int dim = c->model.dim;
@@ -743,16 +759,17 @@ static int launch_rollout(cck_ctx* c, cudaStream_t s, const RolloutArgs& a) {
         // default configuration: fp32 box/bitmap-grid broad phase + exact fp64 decision, lane refill
         RolloutArgs g2 = a;
         g2.ftab = c->d_gtab; g2.ftab_bytes = c->gtab_bytes; g2.exB = c->d_gexB; g2.exCls = c->d_gexCls;
-        const int per_range = 256;
+        const int per_range = 1 << CCK_GRID_RANGE_LOG2;
         const int64_t nr = (a.n + per_range - 1) / per_range;
         const int gb = (int)std::min<int64_t>(nr, (int64_t)c->num_sms * 4);
         const int gsmem = grid_smem_bytes(c->gtab_bytes);
         if (traj) { if ((rc = set_smem(c, (k_rollout_lin_grid<true, EXPAND>), gsmem))) return rc;
-                    k_rollout_lin_grid<true, EXPAND><<<gb, CCK_GRID_THREADS, gsmem, s>>>(g2, c->lin, c->svc, per_range); }
+                    k_rollout_lin_grid<true, EXPAND><<<gb, CCK_GRID_THREADS, gsmem, s>>>(g2, c->lin, c->svc); }
         else { if ((rc = set_smem(c, (k_rollout_lin_grid<false, EXPAND>), gsmem))) return rc;
-               k_rollout_lin_grid<false, EXPAND><<<gb, CCK_GRID_THREADS, gsmem, s>>>(g2, c->lin, c->svc, per_range); }
+               k_rollout_lin_grid<false, EXPAND><<<gb, CCK_GRID_THREADS, gsmem, s>>>(g2, c->lin, c->svc); }
     } else if (c->model.model == CCK_MODEL_LINEAR2D && c->svc.kind == CCK_SVC_BLACKMORE && c->kern == 1 && c->bpt > 0) {
         // second generation: threshold (group filter) kernel, BPT beliefs per thread
+        if (c->M > 0 && c->ftab_bytes == 0) return fail(c, CCK_ERR_INVALID, "group-filter table exceeds shared memory; use the default kernel");
 #define LAUNCH_BM(BPT, TRAJ)                                                                             \
     do {                                                                                                 \
         const int gb = grid_for(c, (a.n + BPT - 1) / BPT, threads, 8);                                   \
@@ -776,8 +793,10 @@ static int launch_rollout(cck_ctx* c, cudaStream_t s, const RolloutArgs& a) {
         else { if (traj) LAUNCH_BM(4, true); else LAUNCH_BM(4, false); }
 #undef LAUNCH_BM
     } else if (c->model.model == CCK_MODEL_LINEAR2D) {
+        if ((rc = check_tab_fits(c))) return rc;
         if (traj) DISPATCH_KIND(k_rollout_lin, c->lin, true); else DISPATCH_KIND(k_rollout_lin, c->lin, false);
     } else {
+        if ((rc = check_tab_fits(c))) return rc;
         if (traj) DISPATCH_KIND(k_rollout_uni, c->uni, true); else DISPATCH_KIND(k_rollout_uni, c->uni, false);
     }
 #undef DISPATCH_KIND

@@ -27,7 +27,7 @@
 
 namespace cck {
 
-struct GHeader {                 // 80 bytes, then occ[R] (u64), rowbase[R] (u16), cstart[n_cells+1] (u16), boxes[M] (float4)
+struct GHeader {                 // 80 bytes, then occ[R] (u64), rowbase[R] (u16), cstart[n_cells+1] (u16), outer boxes[M], inner boxes[M] (float4)
     int32_t total_bytes, M, n_grid, n_cells;
     int32_t R, off_occ, off_rowbase, off_cstart;
     int32_t off_boxes, pad0;
@@ -62,13 +62,28 @@ __device__ __forceinline__ float sqrt_approx(float v) {
     return r;
 }
 
-// ok &= "the belief is safe w.r.t. every obstacle" (PCCBlackmoreSVC.cpp:54-58), bit-exact.
+// One obstacle the broad phase could not skip: outer box (proves safe), inner box (proves unsafe:
+// every plane fails with margin; +-inf for obstacles that are not one-plane-per-side boxes), else the
+// reference's fp64 expression.
+__device__ __forceinline__ bool grid_obstacle(const float4* boxes, int M, int j, float xm, float xp, float ym, float yp, float xmi,
+                                              float xpi, float ymi, float ypi, const ClassRec* cls, const double* exB,
+                                              const int32_t* exCls, double c, double x, double y, double P0, double P1, double P2,
+                                              double P3) {
+    const float4 b = boxes[j];
+    if ((xm >= b.z) | (xp <= b.x) | (ym >= b.w) | (yp <= b.y)) return true;
+    const float4 q = boxes[M + j];
+    if ((xmi < q.z) & (xpi > q.x) & (ymi < q.w) & (ypi > q.y)) return false;
+    return bm_exact_obstacle(cls[exCls[j]].A, exB + (size_t)j * 4, x, y, P0, P1, P2, P3, c);
+}
+
+// "the belief is safe w.r.t. every obstacle" (PCCBlackmoreSVC.cpp:54-58), bit-exact.
 __device__ __forceinline__ bool grid_check(const unsigned char* gt, const unsigned char* ctab, const double* exB, const int32_t* exCls,
                                            double c, double x, double y, double P0, double P1, double P2, double P3) {
     const GHeader* h = reinterpret_cast<const GHeader*>(gt);
     const float4* boxes = reinterpret_cast<const float4*>(gt + h->off_boxes);
     const TabHeader* th = reinterpret_cast<const TabHeader*>(ctab);
     const ClassRec* cls = reinterpret_cast<const ClassRec*>(ctab + th->off_classes);
+    const int M = h->M;
     const float xf = __double2float_rn(x), yf = __double2float_rn(y);
     const float p0 = __double2float_rn(P0), p3 = __double2float_rn(P3);
     const float offd = __double2float_rn(fabs(P1) + fabs(P2));
@@ -76,7 +91,7 @@ __device__ __forceinline__ bool grid_check(const unsigned char* gt, const unsign
     const bool fin = (fabsf(xf) + fabsf(yf)) + (p0 + p3) + offd < 1e30f && p0 >= 0.f && p3 >= 0.f;
     if (!fin) {   // rare: decide every obstacle with the reference's expression
         bool ok = true;
-        for (int j = 0; j < h->M && ok; ++j) ok = bm_exact_obstacle(cls[exCls[j]].A, exB + (size_t)j * 4, x, y, P0, P1, P2, P3, c);
+        for (int j = 0; j < M && ok; ++j) ok = bm_exact_obstacle(cls[exCls[j]].A, exB + (size_t)j * 4, x, y, P0, P1, P2, P3, c);
         return ok;
     }
     const float ex = h->k * sqrt_approx(p0), ey = h->k * sqrt_approx(p3);
@@ -85,8 +100,9 @@ __device__ __forceinline__ bool grid_check(const unsigned char* gt, const unsign
     // (flushed by sqrt.approx.ftz: ex_true <= k * sqrt(1.2e-38) < 1e-18)
     const float mx = (fabsf(xf) + ex) * 3.814697265625e-06f + 1e-17f;
     const float my = (fabsf(yf) + ey) * 3.814697265625e-06f + 1e-17f;
-    const float xm = (xf - ex) - mx, xp = (xf + ex) + mx;
-    const float ym = (yf - ey) - my, yp = (yf + ey) + my;
+    const float dx = xf - ex, sx = xf + ex, dy = yf - ey, sy = yf + ey;
+    const float xm = dx - mx, xp = sx + mx, ym = dy - my, yp = sy + my;       // outer interval (contains the true one)
+    const float xmi = dx + mx, xpi = sx - mx, ymi = dy + my, ypi = sy - my;   // inner interval (contained in the true one)
     bool ok = true;
     // gridded obstacles: anchor (xlo, ylo) must lie in (xm - SX, xp) x (ym - SY, yp) to be unproven
     const float clo = fmaxf(grid_cellf(__fsub_rd(xm, h->SX), h->gx0, h->icx), 0.f);
@@ -107,44 +123,85 @@ __device__ __forceinline__ bool grid_check(const unsigned char* gt, const unsign
                 m &= m - 1;
                 const int cell = rowbase[r] + __popcll(oc & ((1ull << cc) - 1ull));
                 const int j1 = cstart[cell + 1];
-                for (int j = cstart[cell]; j < j1 && ok; ++j) {
-                    const float4 b = boxes[j];
-                    const bool proven = (xm >= b.z) | (xp <= b.x) | (ym >= b.w) | (yp <= b.y);
-                    if (!proven) ok = bm_exact_obstacle(cls[exCls[j]].A, exB + (size_t)j * 4, x, y, P0, P1, P2, P3, c);
-                }
+                for (int j = cstart[cell]; j < j1 && ok; ++j)
+                    ok = grid_obstacle(boxes, M, j, xm, xp, ym, yp, xmi, xpi, ymi, ypi, cls, exB, exCls, c, x, y, P0, P1, P2, P3);
             }
         }
     }
     // obstacles without a finite box (non-axis-aligned planes, unusable constants): box sides are +-inf
-    for (int j = h->n_grid; j < h->M && ok; ++j) {
-        const float4 b = boxes[j];
-        const bool proven = (xm >= b.z) | (xp <= b.x) | (ym >= b.w) | (yp <= b.y);
-        if (!proven) ok = bm_exact_obstacle(cls[exCls[j]].A, exB + (size_t)j * 4, x, y, P0, P1, P2, P3, c);
-    }
+    for (int j = h->n_grid; j < M && ok; ++j)
+        ok = grid_obstacle(boxes, M, j, xm, xp, ym, yp, xmi, xpi, ymi, ypi, cls, exB, exCls, c, x, y, P0, P1, P2, P3);
     return ok;
 }
 
+// ---------------------------------------------------------------------------
+// cp.async (LDGSTS): per-lane prefetch of the NEXT belief into shared memory while the current
+// rollout runs, so a refill never exposes HBM latency to the warp.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem)), "l"(__cvta_generic_to_global(gmem)) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem)), "l"(__cvta_generic_to_global(gmem)) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 // shared-memory carve-up: [mbarrier 16 B][grid table][work counter 16 B][stash 128 x 80 B]
+//                         [prefetch slots: 13 planes x 128 doubles][2 planes x 128 ints]
 #define CCK_GRID_THREADS 128
-__host__ __device__ inline int grid_smem_bytes(int gtab_bytes) { return 16 + gtab_bytes + 16 + CCK_GRID_THREADS * 80; }
+#ifndef CCK_GRID_MINB
+#define CCK_GRID_MINB 4
+#endif
+#define CCK_GRID_RANGE_LOG2 8   // the work counter hands out ranges of 256 consecutive beliefs, round-robin over the CTAs
+__host__ __device__ inline int grid_smem_bytes(int gtab_bytes) {
+    return 16 + gtab_bytes + 16 + CCK_GRID_THREADS * 80 + 13 * CCK_GRID_THREADS * 8 + 2 * CCK_GRID_THREADS * 4;
+}
 
 template <bool TRAJ, bool EXPAND>
-__global__ void __launch_bounds__(CCK_GRID_THREADS, 4) k_rollout_lin_grid(const __grid_constant__ RolloutArgs a, const __grid_constant__ LinDev p,
-                                                                          const __grid_constant__ SvcDev sp, int per_range) {
+__global__ void __launch_bounds__(CCK_GRID_THREADS, CCK_GRID_MINB) k_rollout_lin_grid(const __grid_constant__ RolloutArgs a, const __grid_constant__ LinDev p,
+                                                                          const __grid_constant__ SvcDev sp) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
     unsigned char* gt = smem_raw + 16;
     int* next_k = reinterpret_cast<int*>(smem_raw + 16 + a.ftab_bytes);
     double2* stash = reinterpret_cast<double2*>(smem_raw + 16 + a.ftab_bytes + 16) + threadIdx.x * 5;   // 80 B per thread, conflict-free STS.128
+    double* slot = reinterpret_cast<double*>(smem_raw + 16 + a.ftab_bytes + 16 + CCK_GRID_THREADS * 80) + threadIdx.x;   // plane f at slot[f*128]
+    int* islot = reinterpret_cast<int*>(smem_raw + 16 + a.ftab_bytes + 16 + CCK_GRID_THREADS * 80 + 13 * CCK_GRID_THREADS * 8) + threadIdx.x;
     if (threadIdx.x == 0) *next_k = 0;
     stage_begin(gt, a.ftab, (uint32_t)a.ftab_bytes, bar);   // __syncthreads inside
-    stage_wait((uint32_t)a.ftab_bytes, bar);
     const double eps = DBL_EPSILON;
     const double c = sp.erf_inv_result;
 
-    bool have = false, done = false;
+    int64_t nxt = -1;
+    // claim the next belief of this CTA (ranges blockIdx, blockIdx+gridDim, ... of 256 beliefs) and start copying it
+    auto prefetch = [&]() {
+        nxt = -1;
+        while (true) {
+            const int kk = atomicAdd(next_k, 1);
+            const int rg = kk >> CCK_GRID_RANGE_LOG2;
+            const int64_t base = ((int64_t)blockIdx.x + (int64_t)rg * gridDim.x) << CCK_GRID_RANGE_LOG2;
+            if (base >= a.n) return;
+            const int64_t idx = base + (kk & ((1 << CCK_GRID_RANGE_LOG2) - 1));
+            if (idx < a.n) { nxt = idx; break; }
+        }
+#pragma unroll
+        for (int f = 0; f < 10; ++f) cp_async8(slot + f * CCK_GRID_THREADS, a.bel + f * a.ld + nxt);
+        cp_async8(slot + 10 * CCK_GRID_THREADS, a.ctrl + nxt);
+        cp_async8(slot + 11 * CCK_GRID_THREADS, a.ctrl + a.ldc + nxt);
+        cp_async4(islot, a.steps + nxt);
+        if (EXPAND) {
+            cp_async8(slot + 12 * CCK_GRID_THREADS, a.parent_cost + nxt);
+            cp_async4(islot + CCK_GRID_THREADS, a.parent_step + nxt);
+        }
+        cp_async_commit();
+    };
+    prefetch();
+    stage_wait((uint32_t)a.ftab_bytes, bar);
+
+    bool have = false;
     Lin cur;
-    double dux = 0, duy = 0, x0 = 0, y0 = 0;
+    double dux = 0, duy = 0, x0 = 0, y0 = 0, pcost = 0;
     int steps = 0, t = 0, pstep = 0;
     int64_t i = 0;
     bool cons_ok = true;
@@ -152,38 +209,33 @@ __global__ void __launch_bounds__(CCK_GRID_THREADS, 4) k_rollout_lin_grid(const 
 #pragma unroll
     for (int f = 0; f < 4; ++f) cur.S[f] = cur.L[f] = 0;
     while (true) {
-        while (!have && !done) {   // fetch: the CTA owns ranges blockIdx, blockIdx+gridDim, ... of per_range beliefs
-            const int kk = atomicAdd(next_k, 1);
-            const int rg = kk / per_range;
-            i = ((int64_t)blockIdx.x + (int64_t)rg * gridDim.x) * per_range + (kk - rg * per_range);
-            if (i >= a.n) {
-                // later ranges of this CTA start even further out: nothing left once the range base is past n
-                if (((int64_t)blockIdx.x + (int64_t)rg * gridDim.x) * per_range >= a.n) { done = true; break; }
-                continue;
-            }
-            steps = a.steps[i];
-            if (steps <= 0) {      // propagateWhileValid(.., 0, ..): copy, return 0
+        while (!have && nxt >= 0) {   // take the prefetched belief, start copying the one after it
+            cp_async_wait_all();
+            i = nxt;
+            cur.mx = slot[0]; cur.my = slot[CCK_GRID_THREADS];
 #pragma unroll
-                for (int f = 0; f < 10; ++f) a.out[f * a.ldo + i] = a.bel[f * a.ld + i];
+            for (int f = 0; f < 4; ++f) { cur.S[f] = slot[(2 + f) * CCK_GRID_THREADS]; cur.L[f] = slot[(6 + f) * CCK_GRID_THREADS]; }
+            dux = p.dt * slot[10 * CCK_GRID_THREADS]; duy = p.dt * slot[11 * CCK_GRID_THREADS];
+            steps = islot[0];
+            if (EXPAND) { pcost = slot[12 * CCK_GRID_THREADS]; pstep = islot[CCK_GRID_THREADS]; }
+            prefetch();
+            if (steps <= 0) {         // propagateWhileValid(.., 0, ..): copy, return 0
+                a.out[i] = cur.mx; a.out[a.ldo + i] = cur.my;
+#pragma unroll
+                for (int f = 0; f < 4; ++f) { a.out[(2 + f) * a.ldo + i] = cur.S[f]; a.out[(6 + f) * a.ldo + i] = cur.L[f]; }
                 a.valid[i] = 0;
                 if (EXPAND) {
-                    const double bx = a.bel[i], by = a.bel[a.ld + i];
                     double gd;
-                    const bool g = goal_ok(a.goal, sp, bx, by, a.bel[2 * a.ld + i] + a.bel[6 * a.ld + i], a.bel[3 * a.ld + i] + a.bel[7 * a.ld + i],
-                                           a.bel[4 * a.ld + i] + a.bel[8 * a.ld + i], a.bel[5 * a.ld + i] + a.bel[9 * a.ld + i], &gd);
-                    a.cost[i] = a.parent_cost[i] + 0.0;
+                    const bool g = goal_ok(a.goal, sp, cur.mx, cur.my, cur.S[0] + cur.L[0], cur.S[1] + cur.L[1], cur.S[2] + cur.L[2],
+                                           cur.S[3] + cur.L[3], &gd);
+                    a.cost[i] = pcost + 0.0;
                     a.goal_dist[i] = gd;
                     a.flags[i] = (uint8_t)(1 | 2 | (g ? 4 : 0));
                 }
                 continue;
             }
-            cur.mx = a.bel[i]; cur.my = a.bel[a.ld + i];
-#pragma unroll
-            for (int f = 0; f < 4; ++f) { cur.S[f] = a.bel[(2 + f) * a.ld + i]; cur.L[f] = a.bel[(6 + f) * a.ld + i]; }
-            dux = p.dt * a.ctrl[i]; duy = p.dt * a.ctrl[a.ldc + i];
             x0 = cur.mx; y0 = cur.my;
             t = 0; cons_ok = true;
-            if (EXPAND) pstep = a.parent_step[i];
             have = true;
         }
         if (__all_sync(0xffffffffu, !have)) break;
@@ -221,7 +273,7 @@ __global__ void __launch_bounds__(CCK_GRID_THREADS, 4) k_rollout_lin_grid(const 
             a.valid[i] = r;
             if (EXPAND) {
                 const double d0 = x0 - cur.mx, d1 = y0 - cur.my;
-                a.cost[i] = a.parent_cost[i] + sqrt(d0 * d0 + d1 * d1);
+                a.cost[i] = pcost + sqrt(d0 * d0 + d1 * d1);
                 double gd;
                 const bool g = goal_ok(a.goal, sp, cur.mx, cur.my, cur.S[0] + cur.L[0], cur.S[1] + cur.L[1], cur.S[2] + cur.L[2],
                                        cur.S[3] + cur.L[3], &gd);

@@ -157,6 +157,19 @@ void orc_svc_tables(void* s, double* A, double* B, double* centres, double* rect
     }
 }
 
+// Test hook: replace the half-plane tables (and the erf_inv constant) of a Blackmore checker with
+// arbitrary ones, so parity can be checked on tables the map parser never produces (rotated or
+// duplicated planes, non-finite offsets).  Only HyperplaneCCValidityChecker_ reads them.
+void orc_svc_override_tables(void* s, int M, const double* A, const double* B, double erf_inv_result) {
+    Svc& v = ((SvcH*)s)->svc;
+    v.tab.hp.assign(M, HalfPlanes{});
+    v.tab.centre.assign(M, Pt{0, 0});
+    v.tab.minkowski.assign(M, Ring(5, Pt{0, 0}));
+    for (int o = 0; o < M; ++o)
+        for (int i = 0; i < 4; ++i) { v.tab.hp[o].A[i][0] = A[o * 8 + i * 2]; v.tab.hp[o].A[i][1] = A[o * 8 + i * 2 + 1]; v.tab.hp[o].B[i] = B[o * 4 + i]; }
+    v.erf_inv_result = erf_inv_result;
+}
+
 // ---- propagation / validity (batched) ----
 void orc_propagate(int dim, double dt, double duration, long n, const double* bel, const double* ctrl, double* out) {
     if (dim == 2) {

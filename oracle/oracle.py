@@ -63,6 +63,7 @@ def lib():
         L.orc_svc_free.argtypes = [vp]
         L.orc_svc_info.argtypes = [vp, dp]
         L.orc_svc_tables.argtypes = [vp, dp, dp, dp, dp]
+        L.orc_svc_override_tables.argtypes = [vp, C.c_int, dp, dp, C.c_double]
         L.orc_propagate.argtypes = [C.c_int, C.c_double, C.c_double, C.c_long, dp, dp, dp]
         L.orc_is_valid.argtypes = [vp, C.c_int, C.c_long, dp, u8p, u64p]
         L.orc_rollout.argtypes = [vp, C.c_int, C.c_double, C.c_long, dp, dp, ip, dp, ip, dp, C.c_int, u64p, C.c_int]
@@ -199,6 +200,15 @@ class Svc:
         self.centres, self.rects = np.zeros((M, 2)), np.zeros((M, 4))
         if M:
             L.orc_svc_tables(self.h, _dp(self.A), _dp(self.B), _dp(self.centres), _dp(self.rects))
+
+    def override_tables(self, A, B, erf_inv_result):
+        """Test hook (Blackmore only): arbitrary half-plane tables A[M,4,2], B[M,4]."""
+        assert self.kind == SVC_BLACKMORE
+        self.A, self.B = _f64(A).reshape(-1, 4, 2).copy(), _f64(B).reshape(-1, 4).copy()
+        M = len(self.A)
+        self.centres, self.rects = np.zeros((M, 2)), np.zeros((M, 4))
+        self.erf_inv_result = float(erf_inv_result)
+        lib().orc_svc_override_tables(self.h, M, _dp(self.A), _dp(self.B), self.erf_inv_result)
 
     def is_valid(self, beliefs):
         b = _f64(beliefs)

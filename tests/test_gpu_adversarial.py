@@ -1,0 +1,185 @@
+"""Adversarial parity tests for the fp32 broad phase of the linear + PCCBlackmore rollout kernel
+(csrc/cck_rollout_grid.cuh).  The broad phase may only PROVE safety; everything it cannot prove is
+decided by the reference's fp64 expression, so verdicts must stay bit-identical to the oracle
+
+  * within a few ulps of the decision threshold of individual half-planes,
+  * for non-finite / degenerate beliefs (NaN, inf, negative or zero variances, huge magnitudes),
+  * for half-plane tables the map parser never produces (rotated or duplicated planes, non-finite
+    offsets, far-away coordinates, many obstacles per grid cell, unusable erf_inv constants).
+"""
+import numpy as np
+import pytest
+
+from helpers import install_from_oracle_svc, oracle_synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _rollout_both(K, ctx, svc, bel, ctrl, steps):
+    out, valid = ctx.propagate_while_valid(bel, ctrl, steps)
+    ref_out, ref_valid, _ = svc.rollout(K.soa_to_aos(bel), K.soa_to_aos(ctrl), steps, nthreads=8)
+    return K.soa_to_aos(out), valid, ref_out, ref_valid
+
+
+def _bb(a0, a1, P, c):
+    """b_bar exactly as HyperplaneCCValidityChecker_ evaluates it (numpy float64 scalars: IEEE, no FMA)."""
+    t0 = a0 * P[0] + a1 * P[2]
+    t1 = a0 * P[1] + a1 * P[3]
+    tmp = t0 * a0 + t1 * a1
+    return np.sqrt(np.float64(2.0)) * np.sqrt(tmp) * c
+
+
+def test_blackmore_threshold_ulp_sweep(K, O, W, ctx):
+    """Means placed within +-8 ulps of x*w = B + b_bar (and the y analogue) for 64 obstacles x 4 planes."""
+    world, svc = oracle_synth(O, W, 256, "realistic", 0, 2)
+    install_from_oracle_svc(K, ctx, svc, K.MODEL_LINEAR2D)
+    rng = np.random.default_rng(5)
+    base, _ = W.synthetic_beliefs(64, "linear", seed=77)
+    base[2:] *= 0.3
+    # post-step covariance of each base belief (the state the checker sees after the single step)
+    post = O.propagate(K.soa_to_aos(base), np.zeros((64, 2)), 2)
+    P = post[:, 2:6] + post[:, 6:10]
+    c = np.float64(svc.erf_inv_result)
+    cols = []
+    obs = rng.choice(256, size=64, replace=False)
+    for bi, o in enumerate(obs):
+        for i in range(4):
+            a0, a1 = np.float64(svc.A[o, i, 0]), np.float64(svc.A[o, i, 1])
+            rhs = np.float64(svc.B[o, i]) + _bb(a0, a1, P[bi], c)
+            cx, cy = svc.centres[o]
+            if a1 == 0:      # x plane: fl(x*a0) >= rhs  around x = rhs / a0, y at the obstacle centre
+                v0 = rhs / a0
+                for k in range(-8, 9):
+                    v = v0
+                    for _ in range(abs(k)):
+                        v = np.nextafter(v, np.inf if k > 0 else -np.inf)
+                    b = base[:, bi].copy(); b[0] = v; b[1] = cy
+                    cols.append(b)
+            else:
+                v0 = rhs / a1
+                for k in range(-8, 9):
+                    v = v0
+                    for _ in range(abs(k)):
+                        v = np.nextafter(v, np.inf if k > 0 else -np.inf)
+                    b = base[:, bi].copy(); b[0] = cx; b[1] = v
+                    cols.append(b)
+    bel = np.ascontiguousarray(np.stack(cols, axis=1))
+    n = bel.shape[1]
+    ctrl = np.zeros((2, n))
+    steps = np.ones(n, dtype=np.int32)
+    out, valid, ref_out, ref_valid = _rollout_both(K, ctx, svc, bel, ctrl, steps)
+    assert np.array_equal(valid, ref_valid)
+    assert np.array_equal(out, ref_out)
+    # the sweep really straddles thresholds: both verdicts occur inside many 17-point groups
+    g = ref_valid.reshape(-1, 17)
+    assert ((g.min(axis=1) == 0) & (g.max(axis=1) == 1)).sum() >= 100
+
+
+def test_blackmore_nonfinite_and_degenerate_beliefs(K, O, W, ctx):
+    world, svc = oracle_synth(O, W, 256, "realistic", 0, 2)
+    install_from_oracle_svc(K, ctx, svc, K.MODEL_LINEAR2D)
+    n = 6000
+    bel, ctrl = W.synthetic_beliefs(n, "linear", seed=123)
+    rng = np.random.default_rng(9)
+    specials = [np.nan, np.inf, -np.inf, 0.0, -0.0, 1e300, -1e300, 1e30, 1e39, 3.5e38, 1e-300, 5e-324, -1e-3, 1e-45, 1e-38]
+    for j in range(n):
+        kind = j % 6
+        if kind == 0:
+            continue                                   # untouched
+        f = rng.integers(0, 10) if kind < 4 else rng.integers(2, 10)
+        bel[f, j] = specials[rng.integers(len(specials))]
+        if kind == 5:                                   # a second special entry
+            bel[rng.integers(0, 10), j] = specials[rng.integers(len(specials))]
+    bel[2:, 100:200] = 0.0                              # zero covariance
+    bel[2:, 200:300] *= -1.0                            # negative "covariance"
+    ctrl[:, 300:320] = np.nan
+    ctrl[:, 320:340] = 1e300
+    steps = rng.integers(0, 4, size=n).astype(np.int32)
+    with np.errstate(all="ignore"):
+        out, valid, ref_out, ref_valid = _rollout_both(K, ctx, svc, bel, ctrl, steps)
+    assert np.array_equal(valid, ref_valid)
+    assert np.array_equal(out, ref_out, equal_nan=True)
+    assert 0.05 < (ref_valid == steps).mean() < 0.95
+
+
+def _random_tables(rng, M, mode, size=1.0):
+    """A[M,4,2], B[M,4] of convex quadrilateral obstacles in a 64x64 world."""
+    A, B = np.zeros((M, 4, 2)), np.zeros((M, 4))
+    for o in range(M):
+        cx, cy = rng.uniform(0, 63, 2)
+        hw, hh = rng.uniform(0.3, 1.2, 2) * size
+        th = 0.0 if mode == "axis" else rng.uniform(0, np.pi)
+        if mode == "mixed" and o % 2 == 0:
+            th = 0.0
+        w = rng.uniform(0.5, 3.0)
+        ct, st = (1.0, 0.0) if th == 0.0 else (np.cos(th), np.sin(th))
+        normals = [(st, -ct), (ct, st), (-st, ct), (-ct, -st)]     # bottom, right, top, left (outward)
+        ext = [hh, hw, hh, hw]
+        for i, ((nx, ny), e) in enumerate(zip(normals, ext)):
+            A[o, i] = (w * nx, w * ny)
+            B[o, i] = w * (nx * cx + ny * cy + e)
+    return A, B
+
+
+@pytest.mark.parametrize("mode", ["axis", "rotated", "mixed"])
+def test_blackmore_arbitrary_tables(K, O, W, ctx, mode):
+    rng = np.random.default_rng({"axis": 1, "rotated": 2, "mixed": 3}[mode])
+    world, svc = oracle_synth(O, W, 8, "realistic", 0, 2)
+    M = 200
+    A, B = _random_tables(rng, M, mode)
+    if mode == "axis":
+        # (the generator leaves both +0.0 and -0.0 components in A)  duplicated directions (two +x planes), swapped plane order, non-finite offsets
+        A[0] = [[2.0, 0.0], [1.5, 0.0], [0.0, 1.0], [0.0, -1.0]]; B[0] = [2.0 * 30.0, 1.5 * 31.0, 20.0, -18.0]
+        A[1] = A[1][[2, 0, 3, 1]]; B[1] = B[1][[2, 0, 3, 1]]
+        B[2, 1] = np.inf; B[3, 0] = -np.inf; B[4, 2] = np.nan; B[5, 1:] = np.inf
+        A[6, 3] = [0.0, 0.0]                                           # degenerate plane: 0 >= B + 0
+        A[7] *= 1e150; B[7] *= 1e150                                   # normals outside the usable range
+        B[8:12] = B[12:16]; A[8:12] = A[12:16]                          # several obstacles in one grid cell
+    svc.override_tables(A, B, 2.2)
+    install_from_oracle_svc(K, ctx, svc, K.MODEL_LINEAR2D)
+    n = 20000
+    bel, ctrl = W.synthetic_beliefs(n, "linear", seed=31)
+    bel[2:, ::3] *= 0.05
+    steps = np.full(n, 12, dtype=np.int32)
+    with np.errstate(all="ignore"):
+        out, valid, ref_out, ref_valid = _rollout_both(K, ctx, svc, bel, ctrl, steps)
+    assert np.array_equal(valid, ref_valid)
+    assert np.array_equal(out, ref_out, equal_nan=True)
+    assert 0.02 < (ref_valid == steps).mean() < 0.98
+
+
+@pytest.mark.parametrize("c", [0.0, -1.5, np.nan, np.inf, 1e-12, 7.9])
+def test_blackmore_unusual_erf_inv_constants(K, O, W, ctx, c):
+    world, svc = oracle_synth(O, W, 102, "realistic", 0, 2, seed=5)
+    svc.override_tables(svc.A, svc.B, c)
+    install_from_oracle_svc(K, ctx, svc, K.MODEL_LINEAR2D)
+    n = 8000
+    bel, ctrl = W.synthetic_beliefs(n, "linear", seed=41)
+    steps = np.full(n, 8, dtype=np.int32)
+    with np.errstate(all="ignore"):
+        out, valid, ref_out, ref_valid = _rollout_both(K, ctx, svc, bel, ctrl, steps)
+    assert np.array_equal(valid, ref_valid)
+    assert np.array_equal(out, ref_out, equal_nan=True)
+
+
+def test_blackmore_far_away_and_large_tables(K, O, W, ctx):
+    """Obstacle fields at large coordinates (fp32 ulp ~ 0.06 at 1e6) and a 4000-obstacle table."""
+    rng = np.random.default_rng(17)
+    world, svc = oracle_synth(O, W, 8, "realistic", 0, 2)
+    for off, M in ((1.0e6, 300), (0.0, 4000), (-3.0e4, 64)):
+        A, B = _random_tables(rng, M, "axis", size=0.15 if M > 1000 else 1.0)
+        A[A == 0] = 0.0
+        B[:, 1] += A[:, 1, 0] * off; B[:, 3] += A[:, 3, 0] * off        # shift the field by `off` in x
+        B[:, 2] += A[:, 2, 1] * off; B[:, 0] += A[:, 0, 1] * off        # and in y
+        svc2 = O.Svc(world, 0, 2, low=np.array([-1.0 + off, -1.0 + off]), high=np.array([64.0 + off, 64.0 + off]))
+        svc2.override_tables(A, B, 2.0)
+        install_from_oracle_svc(K, ctx, svc2, K.MODEL_LINEAR2D)
+        n = 12000
+        bel, ctrl = W.synthetic_beliefs(n, "linear", seed=51)
+        bel[0] += off; bel[1] += off
+        bel[2:, ::2] *= 0.05
+        steps = np.full(n, 10, dtype=np.int32)
+        out, valid, ref_out, ref_valid = _rollout_both(K, ctx, svc2, bel, ctrl, steps)
+        assert np.array_equal(valid, ref_valid), (off, M)
+        assert np.array_equal(out, ref_out), (off, M)
+        assert 0.02 < (ref_valid == steps).mean() < 0.98, (off, M)
