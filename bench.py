@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--model", default="linear", choices=["linear", "unicycle"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-realistic", action="store_true", help="skip the secondary realistic-variant measurement")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs under ncu)")
     return ap.parse_args()
 
@@ -282,6 +283,49 @@ def run_ours(args):
                "calls": n_e2e, "timing": "host wall clock around the blocking C-ABI call, device synchronised both sides"}
         assert torch.equal(h_valid.to(dev), d_valid), "e2e and device-resident paths disagree"
 
+    # ---- secondary: the realistic variant (obstacle field inside the world, early exits) on the same B ----
+    realistic = None
+    if args.variant == "all_survive" and not args.no_realistic:
+        ctx2 = K.Context(local)
+        W.install_synthetic(ctx2, args.model, M_OBS, variant="realistic")
+        rb, rc = W.synthetic_beliefs(B, args.model, variant="realistic", offset=rank)
+        d_rb, d_rc = torch.from_numpy(rb).to(dev), torch.from_numpy(rc).to(dev)
+        del rb, rc
+        d_rsum = torch.zeros(3, dtype=torch.int64, device=dev)
+        for _ in range(3):
+            ctx2.propagate_while_valid_dev(stream, B, d_rb, B, d_rc, B, d_steps, d_out, B, d_valid)
+        ctx2.rollout_summary_dev(stream, B, d_steps, d_valid, d_rsum)
+        barrier()
+        r_units = int(d_rsum[1].item())
+        hist = torch.bincount(d_valid.to(torch.int64), minlength=T_STEPS + 1).tolist()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            ctx2.propagate_while_valid_dev(stream, B, d_rb, B, d_rc, B, d_steps, d_out, B, d_valid)
+        e1.record()
+        barrier()
+        launches += ctx2.launch_count - 4
+        rt = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        ru = torch.tensor([r_units], dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(rt, op=dist.ReduceOp.MAX)
+            dist.all_reduce(ru, op=dist.ReduceOp.SUM)
+        realistic = {"value": int(ru[0]) * args.steps / (float(rt[0]) * 1e-3), "unit": UNIT, "belief_steps_per_launch": r_units,
+                     "kernel_ms": float(rt[0]) / args.steps,
+                     "survival_histogram_valid_steps": {"0": hist[0], "1-9": sum(hist[1:10]), "10-24": sum(hist[10:25]),
+                                                        "25-49": sum(hist[25:50]), "50": hist[50]},
+                     "note": "same B/T/M with the obstacle field inside the world (SURVEY 8d variant i): ~2/3 of the rollouts end early"}
+        del d_rb, d_rc
+        ctx2.close()
+
+    # ---- PCIe context for e2e: pinned H2D / D2H copy bandwidth of the same buffers ----
+    pcie = None
+    if not args.no_e2e:
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        e0.record(); d_bel.copy_(h_bel, non_blocking=True); e1.record(); h_out.copy_(d_out, non_blocking=True); e2.record()
+        torch.cuda.synchronize()
+        pcie = {"h2d_gbs": h_bel.numel() * 8 / (e0.elapsed_time(e1) * 1e-3) / 1e9, "d2h_gbs": h_out.numel() * 8 / (e1.elapsed_time(e2) * 1e-3) / 1e9}
+
     if rank == 0:
         peaks = {}
         try:
@@ -301,10 +345,22 @@ def run_ours(args):
         achieved_tf = per_launch_units * f_alg_per_step / (kern_ms * 1e-3) / 1e12
         bytes_per_belief = (Wd * 8 + dim * 8 + 4) + (Wd * 8 + 4)     # 184 B linear, 616 B unicycle
         hbm_gbs = B * bytes_per_belief / (kern_ms * 1e-3) / 1e9
+        # dram__bytes_read+write of one launch from the committed ncu --set full capture (per belief, scaled to B)
+        traffic = None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            key = f"{args.model}/{args.variant}"
+            if key in tj:
+                traffic = {"bytes_per_launch": tj[key]["dram_bytes_per_belief"] * B, "algorithmic_bytes_per_launch": B * bytes_per_belief,
+                           "source": tj[key]["source"]}
+        except Exception:
+            pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
-        # executed-work view: after hoisting sqrt(a^T P a) per class the irreducible FP64-pipe work is
-        # 4 compares per obstacle + ~70 instructions of propagate per belief-step
-        inst_per_step = 4.0 * M_OBS + (70.0 if dim == 2 else 900.0)
+        # executed-work view: what must stay fp64 for bit-exact results is the Kalman recursion + bounds test
+        # (linear: 111 FP64-pipe instructions per belief-step counted in the SASS of k_rollout_lin_grid and
+        # confirmed by ncu, profiles/r1d_*: no FMA contraction is allowed, so the attainable rate is the FP64
+        # ISSUE rate = DFMA peak / 2 flop); the chance check itself runs in the fp32 broad phase
+        inst_per_step = 111.0 if dim == 2 else 1100.0
         exec_tinst = per_launch_units * inst_per_step / (kern_ms * 1e-3) / 1e12
         inst_peak = fp64_peak / 2.0      # one DFMA = 2 flop = 1 FP64-pipe instruction per lane
         line = {
@@ -316,17 +372,20 @@ def run_ours(args):
                        "parallelism": f"beliefs sharded over {world} GPU(s); only a 24-byte result record per rank is all-gathered (NCCL)"},
             "kernel_ms": kern_ms, "belief_steps_per_launch": per_launch_units,
             "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak,
-                         "traffic": None,
+                         "traffic": traffic,
                          "how": "achieved = oracle-counted F_alg (%.0f flop per belief-step = %.0f + 15 x %.2f half-plane tests) x belief-steps per launch / "
                                 "CUDA-event kernel time; peak = DFMA-chain microbenchmark run live on this GPU (MEASURED_PEAKS.json has no FP64 entry)"
                                 % (f_alg_per_step, f_prop, hps)},
             "roofline_exec": {"bound": "fp64-pipe issue", "achieved": exec_tinst, "peak": inst_peak, "unit": "T lane-inst/s", "frac": exec_tinst / inst_peak,
-                              "how": "irreducible FP64-pipe lane-instructions of the class-hoisted formulation (4 DSETP per obstacle + propagate) "
-                                     "x belief-steps / kernel time vs the measured DFMA issue rate; `roofline` above credits the reference's "
-                                     "un-hoisted F_alg as SURVEY 8(d) defines it, so it can exceed 1.0"},
+                              "fp64_inst_per_belief_step": inst_per_step,
+                              "how": "FP64-pipe lane-instructions the kernel must execute for bit-exact results (Kalman recursion + bounds, "
+                                     "no FMA contraction) x belief-steps / kernel time vs the measured FP64 issue rate (DFMA peak / 2). This is the "
+                                     "number to optimise; `roofline` above credits the reference's un-strength-reduced F_alg as SURVEY 8(d) "
+                                     "defines it (the fp32 broad phase never evaluates most half-planes), so its frac exceeds 1.0"},
             "roofline_hbm": {"bound": "hbm", "achieved": hbm_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_gbs / hbm_peak,
                              "peak_source": "MEASURED_PEAKS.json (burst copy)" if "hbm_gbs" in peaks else "fallback 6650",
                              "bytes_per_belief": bytes_per_belief},
+            "realistic": realistic, "pcie": pcie,
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
         }
         print(json.dumps(line))

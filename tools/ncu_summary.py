@@ -18,7 +18,17 @@ KEEP = ['Kernel Name', 'Block Size', 'Grid Size', 'gpu__time_duration.sum', 'dra
         'smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio',
         'smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio',
         'smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio',
-        'smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio']
+        'smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_imc_miss_per_issue_active.ratio',
+        'smsp__warps_eligible.avg.per_cycle_active', 'smsp__warps_active.avg.per_cycle_active',
+        'launch__occupancy_limit_shared_mem', 'launch__occupancy_limit_blocks', 'sm__maximum_warps_per_active_cycle_pct',
+        'l1tex__t_sectors_pipe_lsu_mem_local_op_ld.sum', 'l1tex__t_sectors_pipe_lsu_mem_local_op_st.sum',
+        'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'smsp__inst_executed_op_branch.sum',
+        'sm__inst_executed_pipe_fp64_op_dfma.sum', 'smsp__thread_inst_executed.sum']
 
 
 def main(rep, out):
