@@ -11,7 +11,7 @@
 #include <vector>
 
 #include "cck_kernels.cuh"
-#include "cck_rollout_grid.cuh"
+#include "cck_rollout_uni.cuh"
 
 using namespace cck;
 
@@ -47,6 +47,7 @@ struct cck_ctx {
     int gtab_bytes = 0;
     double* d_gexB = nullptr;          // exact fp64 rows in grid-table order
     int32_t* d_gexCls = nullptr;       // class of each row
+    bool uni_sparse = false;           // unicycle matrices have the reference's exact-zero pattern
     int kern = 2;                      // linear+Blackmore rollout kernel: 2 grid (default), 1 group filter, 0 generic (CCK_KERNEL)
     int M = 0;
 
@@ -299,6 +300,21 @@ extern "C" int cck_set_model(cck_ctx* c, const cck_model_params* p) {
     std::memcpy(c->uni.Q, p->uni_Q, sizeof(c->uni.Q)); std::memcpy(c->uni.R, p->uni_R, sizeof(c->uni.R));
     std::memcpy(c->uni.gains, p->uni_gains, sizeof(c->uni.gains));
     c->uni.acc_lo = p->uni_acc[0]; c->uni.acc_hi = p->uni_acc[1]; c->uni.turn_lo = p->uni_turn[0]; c->uni.turn_hi = p->uni_turn[1];
+    // the sparse covariance step (cck_rollout_uni.cuh) needs the reference's exact-zero pattern
+    {
+        const double* F = c->uni.F; const double* A = c->uni.Acl;
+        bool ok = F[0] == 1.0 && F[5] == 1.0 && F[10] == 1.0 && F[15] == 1.0;
+        for (int i = 0; i < 16; ++i) {
+            const int r = i / 4, cc = i % 4;
+            const bool f_nz = (r == cc) || i == 1 || i == 11;
+            const bool a_nz = (r / 2) == (cc / 2);
+            if (!f_nz && F[i] != 0.0) ok = false;
+            if (!a_nz && A[i] != 0.0) ok = false;
+            if (r != cc && (c->uni.Q[i] != 0.0 || c->uni.R[i] != 0.0)) ok = false;
+            if (!std::isfinite(F[i]) || !std::isfinite(A[i]) || !std::isfinite(c->uni.Q[i]) || !std::isfinite(c->uni.R[i])) ok = false;
+        }
+        c->uni_sparse = ok;
+    }
     c->has_model = true;
     return CCK_OK;
 }
@@ -795,6 +811,24 @@ static int launch_rollout(cck_ctx* c, cudaStream_t s, const RolloutArgs& a) {
     } else if (c->model.model == CCK_MODEL_LINEAR2D) {
         if ((rc = check_tab_fits(c))) return rc;
         if (traj) DISPATCH_KIND(k_rollout_lin, c->lin, true); else DISPATCH_KIND(k_rollout_lin, c->lin, false);
+    } else if (c->uni_sparse && c->kern == 2) {
+        // unicycle, second generation: sparse covariance step, grid broad phase for Blackmore, lane refill
+        RolloutArgs g2 = a;
+        if (c->svc.kind == CCK_SVC_BLACKMORE) { g2.ftab = c->d_gtab; g2.ftab_bytes = c->gtab_bytes; g2.exB = c->d_gexB; g2.exCls = c->d_gexCls; }
+        else { if ((rc = check_tab_fits(c))) return rc; g2.ftab = c->d_tab; g2.ftab_bytes = c->tab_bytes; }
+        const int64_t nr = (a.n + (1 << CCK_GRID_RANGE_LOG2) - 1) >> CCK_GRID_RANGE_LOG2;
+        const int gb = (int)std::min<int64_t>(nr, (int64_t)c->num_sms * 2);
+        const int usmem = uni_smem_bytes(g2.ftab_bytes);
+        if (usmem > c->max_smem_optin) return fail(c, CCK_ERR_INVALID, "obstacle table exceeds shared memory; M too large");
+#define LAUNCH_U2(KIND, TRAJ)                                                                        \
+    do {                                                                                             \
+        if ((rc = set_smem(c, (k_rollout_uni2<KIND, TRAJ, EXPAND>), usmem))) return rc;              \
+        k_rollout_uni2<KIND, TRAJ, EXPAND><<<gb, CCK_UNI_THREADS, usmem, s>>>(g2, c->uni, c->svc);   \
+    } while (0)
+        if (c->svc.kind == CCK_SVC_BLACKMORE) { if (traj) LAUNCH_U2(CCK_SVC_BLACKMORE, true); else LAUNCH_U2(CCK_SVC_BLACKMORE, false); }
+        else if (c->svc.kind == CCK_SVC_ADAPTIVE) { if (traj) LAUNCH_U2(CCK_SVC_ADAPTIVE, true); else LAUNCH_U2(CCK_SVC_ADAPTIVE, false); }
+        else { if (traj) LAUNCH_U2(CCK_SVC_CHISQUARED, true); else LAUNCH_U2(CCK_SVC_CHISQUARED, false); }
+#undef LAUNCH_U2
     } else {
         if ((rc = check_tab_fits(c))) return rc;
         if (traj) DISPATCH_KIND(k_rollout_uni, c->uni, true); else DISPATCH_KIND(k_rollout_uni, c->uni, false);
