@@ -66,12 +66,14 @@ SYMBOLS = [
     "cck_validate_plan", "cck_validate_plan_dev",
     "cck_set_constraints", "cck_satisfies_constraints", "cck_satisfies_constraints_dev",
     "cck_expand_batch", "cck_expand_batch_dev", "cck_rollout_summary_dev", "cck_select_winner_dev", "cck_measure_fp64_peak",
+    "cck_tree_create", "cck_tree_destroy", "cck_tree_clear", "cck_tree_size", "cck_tree_append", "cck_tree_update",
+    "cck_tree_select", "cck_tree_nearest", "cck_belief_distance", "cck_belief_distance_lower",
 ]
 
 
 def build(force=False, verbose=False):
     """Compile libcck_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
-    src = [os.path.join(_PKG, "csrc", f) for f in ("cck_b200.cu", "cck_kernels.cuh", "cck_device.cuh", "cck_rollout_bm.cuh", "cck_rollout_grid.cuh", "cck_rollout_uni.cuh")]
+    src = [os.path.join(_PKG, "csrc", f) for f in ("cck_b200.cu", "cck_kernels.cuh", "cck_device.cuh", "cck_rollout_bm.cuh", "cck_rollout_grid.cuh", "cck_rollout_uni.cuh", "cck_tree.cuh")]
     src.append(os.path.join(_ROOT, "include", "cck_b200.h"))
     if not force and os.path.exists(_SO) and all(os.path.getmtime(_SO) >= os.path.getmtime(s) for s in src):
         return _SO
@@ -135,6 +137,17 @@ def lib():
     L.cck_rollout_summary_dev.argtypes = [vp, vp, i64, vp, vp, vp]
     L.cck_select_winner_dev.argtypes = [vp, vp, i64, vp, vp, C.c_int, i64, vp]
     L.cck_measure_fp64_peak.argtypes = [vp, dp]
+    L.cck_tree_create.argtypes = [vp, C.c_int, C.POINTER(vp)]
+    L.cck_tree_destroy.argtypes = [vp]
+    L.cck_tree_clear.argtypes = [vp]
+    L.cck_tree_size.restype = i64
+    L.cck_tree_size.argtypes = [vp]
+    L.cck_tree_append.argtypes = [vp, i64, vp, i64, vp, C.POINTER(i64)]
+    L.cck_tree_update.argtypes = [vp, i64, vp, vp, vp]
+    L.cck_tree_select.argtypes = [vp, i64, vp, i64, C.c_double, vp, vp]
+    L.cck_tree_nearest.argtypes = [vp, i64, vp, i64, vp, vp]
+    L.cck_belief_distance.argtypes = [vp, C.c_int, i64, vp, i64, vp, i64, vp]
+    L.cck_belief_distance_lower.argtypes = [vp, C.c_int, i64, vp, i64, vp]
     _lib = L
     return L
 
@@ -379,6 +392,79 @@ class Context:
         t = C.c_double()
         self._ck(self.L.cck_measure_fp64_peak(self.h, C.byref(t)))
         return t.value
+
+
+class Tree:
+    """Device-resident tree / witness set: batched selectNode / nearest-witness queries."""
+
+    def __init__(self, ctx, dim):
+        self.ctx, self.dim = ctx, dim
+        h = C.c_void_p()
+        ctx._ck(ctx.L.cck_tree_create(ctx.h, dim, C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if self.h:
+            self.ctx.L.cck_tree_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __len__(self):
+        return int(self.ctx.L.cck_tree_size(self.h))
+
+    def clear(self):
+        self.ctx._ck(self.ctx.L.cck_tree_clear(self.h))
+
+    def append(self, bel, cost):
+        bel = np.ascontiguousarray(bel, dtype=np.float64)
+        cost = np.ascontiguousarray(cost, dtype=np.float64)
+        n = bel.shape[1]
+        first = C.c_int64(0)
+        self.ctx._ck(self.ctx.L.cck_tree_append(self.h, n, _ptr(bel), n, _ptr(cost), C.byref(first)))
+        return int(first.value)
+
+    def update(self, idx, cost=None, active=None):
+        idx = np.ascontiguousarray(idx, dtype=np.int32)
+        cost = None if cost is None else np.ascontiguousarray(cost, dtype=np.float64)
+        active = None if active is None else np.ascontiguousarray(active, dtype=np.uint8)
+        self.ctx._ck(self.ctx.L.cck_tree_update(self.h, len(idx), _ptr(idx), _ptr(cost), _ptr(active)))
+
+    def select(self, samples, radius=0.2):
+        q = np.ascontiguousarray(samples, dtype=np.float64)
+        K = q.shape[1]
+        idx, dist = np.zeros(K, dtype=np.int32), np.zeros(K)
+        self.ctx._ck(self.ctx.L.cck_tree_select(self.h, K, _ptr(q), K, radius, _ptr(idx), _ptr(dist)))
+        return idx, dist
+
+    def nearest(self, queries):
+        q = np.ascontiguousarray(queries, dtype=np.float64)
+        K = q.shape[1]
+        idx, dist = np.zeros(K, dtype=np.int32), np.zeros(K)
+        self.ctx._ck(self.ctx.L.cck_tree_nearest(self.h, K, _ptr(q), K, _ptr(idx), _ptr(dist)))
+        return idx, dist
+
+
+def belief_distance(ctx, a, b, dim):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    n = a.shape[1]
+    out = np.zeros(n)
+    ctx._ck(ctx.L.cck_belief_distance(ctx.h, dim, n, _ptr(a), n, _ptr(b), n, _ptr(out)))
+    return out
+
+
+def belief_distance_lower(ctx, bel, dim):
+    """[n, n] matrix whose strict lower triangle is distance(b_i, b_q) (row q, column i < q)."""
+    bel = np.ascontiguousarray(bel, dtype=np.float64)
+    n = bel.shape[1]
+    out = np.zeros((n, n))
+    ctx._ck(ctx.L.cck_belief_distance_lower(ctx.h, dim, n, _ptr(bel), n, _ptr(out)))
+    return np.tril(out, -1)
 
 
 def aos_to_soa(b):

@@ -12,6 +12,7 @@
 
 #include "cck_kernels.cuh"
 #include "cck_rollout_uni.cuh"
+#include "cck_tree.cuh"
 
 using namespace cck;
 
@@ -1152,6 +1153,205 @@ extern "C" int cck_satisfies_constraints(cck_ctx* c, int64_t n_paths, const doub
     if ((rc = cck_satisfies_constraints_dev(c, s, n_paths, (double*)p, n_paths, max_len, (int32_t*)(p + b_path), (int32_t*)(p + b_path + b_i),
                                             p + b_path + 2 * b_i))) return rc;
     CK(c, cudaMemcpyAsync(ok, p + b_path + 2 * b_i, (size_t)n_paths, cudaMemcpyDeviceToHost, s));
+    CK(c, cudaStreamSynchronize(s));
+    return CCK_OK;
+}
+
+// ---------------------------------------------------------------------------
+// device-resident SST tree / witness set with batched belief-space
+// nearest-neighbour queries (RealVectorBeliefSpace.cpp:16-62, ConstraintRespectingBSST.cpp:119-178)
+// ---------------------------------------------------------------------------
+struct cck_tree {
+    cck_ctx* c = nullptr;
+    int dim = 2;
+    int64_t cap = 0, n = 0;
+    double* planes = nullptr;
+    uint8_t* active = nullptr;
+    void* scratch = nullptr;
+    size_t scratch_cap = 0;
+};
+
+static int tree_planes_of(int dim) { return dim + 2 * dim * dim + 1; }
+
+static int tree_scratch(cck_tree* t, size_t bytes) {
+    if (bytes <= t->scratch_cap) return CCK_OK;
+    cck_ctx* c = t->c;
+    CK(c, cudaStreamSynchronize(c->stream));
+    cudaFree(t->scratch); t->scratch = nullptr; t->scratch_cap = 0;
+    cudaError_t e = cudaMalloc(&t->scratch, bytes + bytes / 2);
+    if (e != cudaSuccess) { c->err = std::string("cudaMalloc tree scratch: ") + cudaGetErrorString(e); return CCK_ERR_NOMEM; }
+    t->scratch_cap = bytes + bytes / 2;
+    return CCK_OK;
+}
+
+static int tree_reserve(cck_tree* t, int64_t want) {
+    if (want <= t->cap) return CCK_OK;
+    cck_ctx* c = t->c;
+    int64_t ncap = std::max<int64_t>(4096, t->cap * 2);
+    while (ncap < want) ncap *= 2;
+    const int P = tree_planes_of(t->dim);
+    double* np = nullptr; uint8_t* na = nullptr;
+    if (cudaMalloc(&np, (size_t)P * ncap * 8) != cudaSuccess || cudaMalloc(&na, (size_t)ncap) != cudaSuccess) {
+        cudaFree(np); c->err = "cudaMalloc tree"; return CCK_ERR_NOMEM;
+    }
+    if (t->n > 0) {
+        CK(c, cudaMemcpy2DAsync(np, (size_t)ncap * 8, t->planes, (size_t)t->cap * 8, (size_t)t->n * 8, P, cudaMemcpyDeviceToDevice, c->stream));
+        CK(c, cudaMemcpyAsync(na, t->active, (size_t)t->n, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    CK(c, cudaStreamSynchronize(c->stream));
+    cudaFree(t->planes); cudaFree(t->active);
+    t->planes = np; t->active = na; t->cap = ncap;
+    return CCK_OK;
+}
+
+extern "C" int cck_tree_create(cck_ctx* c, int dim, cck_tree** out) {
+    if (!c || !out) return CCK_ERR_INVALID;
+    *out = nullptr;
+    if (dim != 2 && dim != 4) return fail(c, CCK_ERR_INVALID, "tree dim must be 2 or 4");
+    cck_tree* t = new cck_tree();
+    t->c = c; t->dim = dim;
+    *out = t;
+    return CCK_OK;
+}
+extern "C" int cck_tree_destroy(cck_tree* t) {
+    if (!t) return CCK_OK;
+    cudaSetDevice(t->c->device);
+    cudaStreamSynchronize(t->c->stream);
+    cudaFree(t->planes); cudaFree(t->active); cudaFree(t->scratch);
+    delete t;
+    return CCK_OK;
+}
+extern "C" int cck_tree_clear(cck_tree* t) { if (!t) return CCK_ERR_INVALID; t->n = 0; return CCK_OK; }
+extern "C" int64_t cck_tree_size(const cck_tree* t) { return t ? t->n : 0; }
+
+extern "C" int cck_tree_append(cck_tree* t, int64_t n, const double* bel, int64_t ld, const double* cost, int64_t* first) {
+    if (!t) return CCK_ERR_INVALID;
+    cck_ctx* c = t->c;
+    if (n < 0 || ld < n || (n > 0 && (!bel || !cost))) return fail(c, CCK_ERR_INVALID, "bad tree append arguments");
+    if (first) *first = t->n;
+    if (n == 0) return CCK_OK;
+    CK(c, cudaSetDevice(c->device));
+    int rc;
+    if ((rc = tree_reserve(t, t->n + n))) return rc;
+    const int W = t->dim + 2 * t->dim * t->dim;
+    const size_t b_bel = al256((size_t)n * W * 8);
+    if ((rc = tree_scratch(t, b_bel + al256((size_t)n * 8)))) return rc;
+    double* d_bel = (double*)t->scratch; double* d_cost = (double*)((unsigned char*)t->scratch + b_bel);
+    CK(c, h2d_planes(d_bel, bel, 8, n, ld, W, c->stream));
+    CK(c, cudaMemcpyAsync(d_cost, cost, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
+    TreeDev td{t->planes, t->active, t->cap};
+    const int g = grid_for(c, n, 128, 8);
+    if (t->dim == 2) k_tree_append<2><<<g, 128, 0, c->stream>>>(td, t->n, n, d_bel, n, d_cost);
+    else k_tree_append<4><<<g, 128, 0, c->stream>>>(td, t->n, n, d_bel, n, d_cost);
+    c->launches++;
+    CK(c, cudaGetLastError());
+    CK(c, cudaStreamSynchronize(c->stream));    // the host buffers may be reused by the caller
+    t->n += n;
+    return CCK_OK;
+}
+
+extern "C" int cck_tree_update(cck_tree* t, int64_t n, const int32_t* idx, const double* cost, const uint8_t* active) {
+    if (!t) return CCK_ERR_INVALID;
+    cck_ctx* c = t->c;
+    if (n < 0 || (n > 0 && !idx)) return fail(c, CCK_ERR_INVALID, "bad tree update arguments");
+    if (n == 0 || (!cost && !active)) return CCK_OK;
+    for (int64_t j = 0; j < n; ++j) if (idx[j] < 0 || idx[j] >= t->n) return fail(c, CCK_ERR_INVALID, "tree update index out of range");
+    CK(c, cudaSetDevice(c->device));
+    int rc;
+    const size_t b_i = al256((size_t)n * 4), b_c = al256((size_t)n * 8), b_a = al256((size_t)n);
+    if ((rc = tree_scratch(t, b_i + b_c + b_a))) return rc;
+    unsigned char* p = (unsigned char*)t->scratch;
+    int32_t* d_idx = (int32_t*)p; double* d_cost = (double*)(p + b_i); uint8_t* d_act = p + b_i + b_c;
+    CK(c, cudaMemcpyAsync(d_idx, idx, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+    if (cost) CK(c, cudaMemcpyAsync(d_cost, cost, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
+    if (active) CK(c, cudaMemcpyAsync(d_act, active, (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    TreeDev td{t->planes, t->active, t->cap};
+    k_tree_update<<<grid_for(c, n, 128, 8), 128, 0, c->stream>>>(td, t->dim + 2 * t->dim * t->dim, n, d_idx, cost ? d_cost : nullptr, active ? d_act : nullptr);
+    c->launches++;
+    CK(c, cudaGetLastError());
+    CK(c, cudaStreamSynchronize(c->stream));
+    return CCK_OK;
+}
+
+static int tree_query(cck_tree* t, int mode, int64_t K, const double* q, int64_t ldq, double radius, int32_t* out_idx, double* out_dist) {
+    if (!t) return CCK_ERR_INVALID;
+    cck_ctx* c = t->c;
+    if (K < 0 || ldq < K || (K > 0 && (!q || !out_idx))) return fail(c, CCK_ERR_INVALID, "bad tree query arguments");
+    if (K == 0) return CCK_OK;
+    if (K > INT_MAX) return fail(c, CCK_ERR_INVALID, "too many queries");
+    CK(c, cudaSetDevice(c->device));
+    int rc;
+    const int W = t->dim + 2 * t->dim * t->dim;
+    const size_t b_q = al256((size_t)K * W * 8), b_i = al256((size_t)K * 4), b_d = al256((size_t)K * 8);
+    if ((rc = tree_scratch(t, b_q + b_i + b_d))) return rc;
+    unsigned char* p = (unsigned char*)t->scratch;
+    double* d_q = (double*)p; int32_t* d_idx = (int32_t*)(p + b_q); double* d_dist = (double*)(p + b_q + b_i);
+    CK(c, h2d_planes(d_q, q, 8, K, ldq, W, c->stream));
+    TreeDev td{t->planes, t->active, t->cap};
+    if (t->dim == 2) {
+        if (mode == 0) k_tree_query<2, 0><<<(int)K, 128, 0, c->stream>>>(td, t->n, d_q, K, radius, d_idx, d_dist);
+        else k_tree_query<2, 1><<<(int)K, 128, 0, c->stream>>>(td, t->n, d_q, K, radius, d_idx, d_dist);
+    } else {
+        if (mode == 0) k_tree_query<4, 0><<<(int)K, 128, 0, c->stream>>>(td, t->n, d_q, K, radius, d_idx, d_dist);
+        else k_tree_query<4, 1><<<(int)K, 128, 0, c->stream>>>(td, t->n, d_q, K, radius, d_idx, d_dist);
+    }
+    c->launches++;
+    CK(c, cudaGetLastError());
+    CK(c, cudaMemcpyAsync(out_idx, d_idx, (size_t)K * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (out_dist) CK(c, cudaMemcpyAsync(out_dist, d_dist, (size_t)K * 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    return CCK_OK;
+}
+
+extern "C" int cck_tree_select(cck_tree* t, int64_t K, const double* samples, int64_t lds, double selection_radius, int32_t* out_idx,
+                               double* out_dist) {
+    return tree_query(t, 0, K, samples, lds, selection_radius, out_idx, out_dist);
+}
+extern "C" int cck_tree_nearest(cck_tree* t, int64_t K, const double* queries, int64_t ldq, int32_t* out_idx, double* out_dist) {
+    return tree_query(t, 1, K, queries, ldq, 0.0, out_idx, out_dist);
+}
+
+extern "C" int cck_belief_distance_lower(cck_ctx* c, int dim, int64_t n, const double* bel, int64_t ld, double* out) {
+    if (!c) return CCK_ERR_INVALID;
+    if ((dim != 2 && dim != 4) || n < 0 || ld < n || n > 8192 || (n > 0 && (!bel || !out))) return fail(c, CCK_ERR_INVALID, "bad distance-matrix arguments (n <= 8192)");
+    if (n == 0) return CCK_OK;
+    CK(c, cudaSetDevice(c->device));
+    int rc;
+    const int W = dim + 2 * dim * dim;
+    const size_t b_in = al256((size_t)n * W * 8), b_o = al256((size_t)n * n * 8);
+    if ((rc = ensure_scratch(c, 0, b_in + b_o))) return rc;
+    unsigned char* p = (unsigned char*)c->d_scratch[0];
+    double* d_b = (double*)p; double* d_o = (double*)(p + b_in);
+    cudaStream_t s = c->pipe[0];
+    CK(c, h2d_planes(d_b, bel, 8, n, ld, W, s));
+    if (dim == 2) k_distance_lower<2><<<(int)n, 128, 0, s>>>(n, d_b, n, d_o);
+    else k_distance_lower<4><<<(int)n, 128, 0, s>>>(n, d_b, n, d_o);
+    c->launches++;
+    CK(c, cudaGetLastError());
+    CK(c, cudaMemcpyAsync(out, d_o, (size_t)n * n * 8, cudaMemcpyDeviceToHost, s));   // entries with i >= q are unspecified
+    CK(c, cudaStreamSynchronize(s));
+    return CCK_OK;
+}
+
+extern "C" int cck_belief_distance(cck_ctx* c, int dim, int64_t n, const double* a, int64_t lda, const double* b, int64_t ldb, double* out) {
+    if (!c) return CCK_ERR_INVALID;
+    if ((dim != 2 && dim != 4) || n < 0 || lda < n || ldb < n || (n > 0 && (!a || !b || !out))) return fail(c, CCK_ERR_INVALID, "bad distance arguments");
+    if (n == 0) return CCK_OK;
+    CK(c, cudaSetDevice(c->device));
+    int rc;
+    const int W = dim + 2 * dim * dim;
+    const size_t b_in = al256((size_t)n * W * 8), b_o = al256((size_t)n * 8);
+    if ((rc = ensure_scratch(c, 0, 2 * b_in + b_o))) return rc;
+    unsigned char* p = (unsigned char*)c->d_scratch[0];
+    double* d_a = (double*)p; double* d_b = (double*)(p + b_in); double* d_o = (double*)(p + 2 * b_in);
+    cudaStream_t s = c->pipe[0];
+    CK(c, h2d_planes(d_a, a, 8, n, lda, W, s));
+    CK(c, h2d_planes(d_b, b, 8, n, ldb, W, s));
+    if (dim == 2) k_belief_distance<2><<<grid_for(c, n, 128, 8), 128, 0, s>>>(n, d_a, n, d_b, n, d_o);
+    else k_belief_distance<4><<<grid_for(c, n, 128, 8), 128, 0, s>>>(n, d_a, n, d_b, n, d_o);
+    c->launches++;
+    CK(c, cudaGetLastError());
+    CK(c, cudaMemcpyAsync(out, d_o, (size_t)n * 8, cudaMemcpyDeviceToHost, s));
     CK(c, cudaStreamSynchronize(s));
     return CCK_OK;
 }

@@ -1,0 +1,272 @@
+// cck_tree.cuh — SURVEY §8(f) row 2: RealVectorBeliefSpace::distance (src/Spaces/RealVectorBeliefSpace.cpp:16-62)
+// and the two nearest-neighbour queries the low-level planner issues every iteration,
+// selectNode (ConstraintRespectingBSST.cpp:119-148) and findClosestWitness (:150-178),
+// as brute-force batched reductions over a device-resident tree.
+//
+//   distance(s1, s2) = | ||mu1 - mu2||^2 + trace(C1 + C2 - 2 (C2^1/2 C1 C2^1/2)^1/2) |,   0 if the means coincide
+//
+// with C = Sigma + Lambda and ^1/2 the symmetric square root (SelfAdjointEigenSolver::operatorSqrt,
+// which reads the lower triangle).  The eigen-decomposition is a cyclic Jacobi iteration on the
+// symmetric part; the CPU oracle runs the same operation sequence, so distances and the selected
+// indices are bit-identical to it (Eigen's tridiagonal QL agrees to rounding).
+//
+// Layout: items (tree nodes or witnesses) are SoA planes of `cap` doubles:
+//   mean[DIM] | cov[DIM*DIM] | sqrtcov[DIM*DIM] | cost ; plus an `active` byte plane.
+// sqrtcov is filled once per item at append time.  One CTA scans all items for one query; lanes
+// reduce (key, index) pairs lexicographically so ties resolve to the lowest index, exactly like the
+// sequential scan.
+#pragma once
+#include "cck_device.cuh"
+
+namespace cck {
+
+// symmetric square root of the lower-triangle-symmetrised A (DIM x DIM): out = V diag(sqrt(max(l,0))) V^T.
+// DIAG_ONLY: only out[i*DIM+i] is produced (that is all the trace needs).
+template <int DIM, bool DIAG_ONLY>
+__host__ __device__ inline void sym_sqrt(const double* Ain, double* out) {
+    double A[DIM * DIM], V[DIM * DIM];
+#pragma unroll
+    for (int i = 0; i < DIM; ++i)
+#pragma unroll
+        for (int j = 0; j < DIM; ++j) {
+            A[i * DIM + j] = Ain[(i > j ? i : j) * DIM + (i > j ? j : i)];
+            V[i * DIM + j] = i == j ? 1.0 : 0.0;
+        }
+    for (int sweep = 0; sweep < 60; ++sweep) {
+        double off = 0;
+#pragma unroll
+        for (int i = 0; i < DIM; ++i)
+#pragma unroll
+            for (int j = 0; j < DIM; ++j)
+                if (j < i) off += A[i * DIM + j] * A[i * DIM + j];
+        if (off < 1e-300) break;
+#pragma unroll
+        for (int p = 0; p < DIM; ++p)
+#pragma unroll
+            for (int q = 0; q < DIM; ++q) {
+                if (q <= p) continue;
+                if (fabs(A[p * DIM + q]) < 1e-300) continue;
+                const double th = (A[q * DIM + q] - A[p * DIM + p]) / (2 * A[p * DIM + q]);
+                const double t = (th >= 0 ? 1.0 : -1.0) / (fabs(th) + sqrt(th * th + 1));
+                const double c = 1 / sqrt(t * t + 1), s = t * c;
+#pragma unroll
+                for (int k = 0; k < DIM; ++k) { const double akp = A[k * DIM + p], akq = A[k * DIM + q]; A[k * DIM + p] = c * akp - s * akq; A[k * DIM + q] = s * akp + c * akq; }
+#pragma unroll
+                for (int k = 0; k < DIM; ++k) { const double apk = A[p * DIM + k], aqk = A[q * DIM + k]; A[p * DIM + k] = c * apk - s * aqk; A[q * DIM + k] = s * apk + c * aqk; }
+#pragma unroll
+                for (int k = 0; k < DIM; ++k) { const double vkp = V[k * DIM + p], vkq = V[k * DIM + q]; V[k * DIM + p] = c * vkp - s * vkq; V[k * DIM + q] = s * vkp + c * vkq; }
+            }
+    }
+    double sq[DIM];
+#pragma unroll
+    for (int k = 0; k < DIM; ++k) sq[k] = sqrt(A[k * DIM + k] > 0.0 ? A[k * DIM + k] : 0.0);
+#pragma unroll
+    for (int i = 0; i < DIM; ++i)
+#pragma unroll
+        for (int j = 0; j < DIM; ++j) {
+            if (DIAG_ONLY && i != j) continue;
+            double acc = 0;
+#pragma unroll
+            for (int k = 0; k < DIM; ++k) acc += V[i * DIM + k] * sq[k] * V[j * DIM + k];
+            out[i * DIM + j] = acc;
+        }
+}
+
+// trace(C1 + C2 - 2 (S2 C1 S2)^1/2) with S2 = C2^1/2 given
+template <int DIM>
+__host__ __device__ inline double cov_term(const double* C1, const double* C2, const double* S2) {
+    double t[DIM * DIM], m[DIM * DIM], s3[DIM * DIM];
+#pragma unroll
+    for (int i = 0; i < DIM; ++i)
+#pragma unroll
+        for (int j = 0; j < DIM; ++j) {
+            double a = 0;
+#pragma unroll
+            for (int k = 0; k < DIM; ++k) a += S2[i * DIM + k] * C1[k * DIM + j];
+            t[i * DIM + j] = a;
+        }
+#pragma unroll
+    for (int i = 0; i < DIM; ++i)
+#pragma unroll
+        for (int j = 0; j < DIM; ++j) {
+            double a = 0;
+#pragma unroll
+            for (int k = 0; k < DIM; ++k) a += t[i * DIM + k] * S2[k * DIM + j];
+            m[i * DIM + j] = a;
+        }
+    sym_sqrt<DIM, true>(m, s3);
+    double tr = 0;
+#pragma unroll
+    for (int i = 0; i < DIM; ++i) tr += C1[i * DIM + i] + C2[i * DIM + i] - 2 * s3[i * DIM + i];
+    return tr;
+}
+
+struct TreeDev {
+    double* planes;      // [DIM + 2*DIM*DIM + 1][cap]
+    uint8_t* active;     // [cap]
+    int64_t cap;
+};
+template <int DIM> __host__ __device__ constexpr int tree_planes() { return DIM + 2 * DIM * DIM + 1; }
+
+// fill cov / sqrtcov / cost / active of items [first, first+n) from SoA belief records (device)
+template <int DIM>
+__global__ void __launch_bounds__(128) k_tree_append(TreeDev tr, int64_t first, int64_t n, const double* __restrict__ bel, int64_t ld,
+                                                     const double* __restrict__ cost) {
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = first + j;
+        double C[DIM * DIM], S[DIM * DIM];
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) tr.planes[d * tr.cap + i] = bel[d * ld + j];
+#pragma unroll
+        for (int f = 0; f < DIM * DIM; ++f) C[f] = bel[(DIM + f) * ld + j] + bel[(DIM + DIM * DIM + f) * ld + j];
+        sym_sqrt<DIM, false>(C, S);
+#pragma unroll
+        for (int f = 0; f < DIM * DIM; ++f) { tr.planes[(DIM + f) * tr.cap + i] = C[f]; tr.planes[(DIM + DIM * DIM + f) * tr.cap + i] = S[f]; }
+        tr.planes[(DIM + 2 * DIM * DIM) * tr.cap + i] = cost[j];
+        tr.active[i] = 1;
+    }
+}
+
+__global__ void __launch_bounds__(128) k_tree_update(TreeDev tr, int planes_cost, int64_t n, const int32_t* __restrict__ idx,
+                                                     const double* __restrict__ cost, const uint8_t* __restrict__ active) {
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = idx[j];
+        if (cost) tr.planes[(int64_t)planes_cost * tr.cap + i] = cost[j];
+        if (active) tr.active[i] = active[j];
+    }
+}
+
+struct KeyIdx { double key; long long idx; };
+__device__ __forceinline__ void keyidx_min(KeyIdx& a, double k, long long i) {
+    if (i >= 0 && (a.idx < 0 || k < a.key || (k == a.key && i < a.idx))) { a.key = k; a.idx = i; }
+}
+__device__ __forceinline__ void keyidx_warp(KeyIdx& a) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double k = __shfl_xor_sync(0xffffffffu, a.key, o);
+        const long long i = __shfl_xor_sync(0xffffffffu, a.idx, o);
+        keyidx_min(a, k, i);
+    }
+}
+
+// MODE 0 (selectNode): query = sample, item = tree node; distance(sample, node) uses the NODE's sqrt
+//   (cov_term(C_sample, C_node)); among active nodes: best cost within `radius`, else nearest.
+// MODE 1 (findClosestWitness): query = new node, item = witness; cov_term(C_witness, C_query) uses the
+//   QUERY's sqrt; plain nearest, no active filter.
+// One CTA per query.  out_idx[q] = chosen item or -1, out_dist[q] = its distance.
+template <int DIM, int MODE>
+__global__ void __launch_bounds__(128) k_tree_query(TreeDev tr, int64_t n_items, const double* __restrict__ qbel, int64_t ldq, double radius,
+                                                    int32_t* __restrict__ out_idx, double* __restrict__ out_dist) {
+    const int64_t q = blockIdx.x;
+    double qm[DIM], qC[DIM * DIM], qS[DIM * DIM];
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) qm[d] = qbel[d * ldq + q];
+#pragma unroll
+    for (int f = 0; f < DIM * DIM; ++f) qC[f] = qbel[(DIM + f) * ldq + q] + qbel[(DIM + DIM * DIM + f) * ldq + q];
+    if (MODE == 1) sym_sqrt<DIM, false>(qC, qS);
+    KeyIdx best{0.0, -1}, near{0.0, -1}, bestd{0.0, -1};
+    for (int64_t i = threadIdx.x; i < n_items; i += blockDim.x) {
+        if (MODE == 0 && !tr.active[i]) continue;
+        double d2 = 0;
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) { const double e = qm[d] - tr.planes[d * tr.cap + i]; d2 += e * e; }
+        double dist = 0;
+        if (d2 != 0) {
+            double C[DIM * DIM], S[DIM * DIM];
+#pragma unroll
+            for (int f = 0; f < DIM * DIM; ++f) C[f] = tr.planes[(DIM + f) * tr.cap + i];
+            if (MODE == 0) {
+#pragma unroll
+                for (int f = 0; f < DIM * DIM; ++f) S[f] = tr.planes[(DIM + DIM * DIM + f) * tr.cap + i];
+                dist = fabs(d2 + cov_term<DIM>(qC, C, S));
+            } else {
+                dist = fabs(d2 + cov_term<DIM>(C, qC, qS));
+            }
+        }
+        if (MODE == 0 && dist <= radius) {
+            const double cst = tr.planes[(DIM + 2 * DIM * DIM) * tr.cap + i];
+            if (best.idx < 0 || cst < best.key) { best.key = cst; best.idx = i; bestd.key = dist; bestd.idx = i; }
+        }
+        if (near.idx < 0 || dist < near.key) { near.key = dist; near.idx = i; }
+    }
+    // block reduction (lexicographic (key, index): ties -> lowest index, as the sequential scan)
+    __shared__ double s_key[2][4];
+    __shared__ long long s_idx[2][4];
+    __shared__ double s_bd[4];
+    keyidx_warp(near);
+    // for `best` the distance of the winner travels with it
+    {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double k = __shfl_xor_sync(0xffffffffu, best.key, o);
+            const long long i = __shfl_xor_sync(0xffffffffu, best.idx, o);
+            const double dd = __shfl_xor_sync(0xffffffffu, bestd.key, o);
+            if (i >= 0 && (best.idx < 0 || k < best.key || (k == best.key && i < best.idx))) { best.key = k; best.idx = i; bestd.key = dd; }
+        }
+    }
+    const int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) { s_key[0][w] = near.key; s_idx[0][w] = near.idx; s_key[1][w] = best.key; s_idx[1][w] = best.idx; s_bd[w] = bestd.key; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        KeyIdx n2{0.0, -1}, b2{0.0, -1};
+        double bd = 0;
+        for (int k = 0; k < 4; ++k) {
+            keyidx_min(n2, s_key[0][k], s_idx[0][k]);
+            const long long bi = s_idx[1][k];
+            if (bi >= 0 && (b2.idx < 0 || s_key[1][k] < b2.key || (s_key[1][k] == b2.key && bi < b2.idx))) { b2.key = s_key[1][k]; b2.idx = bi; bd = s_bd[k]; }
+        }
+        if (MODE == 0 && b2.idx >= 0) { out_idx[q] = (int32_t)b2.idx; if (out_dist) out_dist[q] = bd; }
+        else { out_idx[q] = (int32_t)n2.idx; if (out_dist) out_dist[q] = n2.idx >= 0 ? n2.key : HUGE_VAL; }
+    }
+}
+
+// lower triangle of the pairwise matrix of one batch: out[q*n + i] = distance(b_i, b_q) for i < q
+// (findClosestWitness between candidates of the same launch: witness = earlier candidate i, node = q)
+template <int DIM>
+__global__ void __launch_bounds__(128) k_distance_lower(int64_t n, const double* __restrict__ bel, int64_t ld, double* __restrict__ out) {
+    const int64_t q = blockIdx.x;
+    double qm[DIM], qC[DIM * DIM], qS[DIM * DIM];
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) qm[d] = bel[d * ld + q];
+#pragma unroll
+    for (int f = 0; f < DIM * DIM; ++f) qC[f] = bel[(DIM + f) * ld + q] + bel[(DIM + DIM * DIM + f) * ld + q];
+    sym_sqrt<DIM, false>(qC, qS);
+    for (int64_t i = threadIdx.x; i < q; i += blockDim.x) {
+        double d2 = 0;
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) { const double e = bel[d * ld + i] - qm[d]; d2 += e * e; }
+        double dist = 0;
+        if (d2 != 0) {
+            double C[DIM * DIM];
+#pragma unroll
+            for (int f = 0; f < DIM * DIM; ++f) C[f] = bel[(DIM + f) * ld + i] + bel[(DIM + DIM * DIM + f) * ld + i];
+            dist = fabs(d2 + cov_term<DIM>(C, qC, qS));
+        }
+        out[q * n + i] = dist;
+    }
+}
+
+// plain batched distance(a_i, b_i) (second argument's sqrt, as RealVectorBeliefSpace::distance(state1, state2))
+template <int DIM>
+__global__ void __launch_bounds__(128) k_belief_distance(int64_t n, const double* __restrict__ a, int64_t lda, const double* __restrict__ b,
+                                                         int64_t ldb, double* __restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double d2 = 0;
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) { const double e = a[d * lda + i] - b[d * ldb + i]; d2 += e * e; }
+        double dist = 0;
+        if (d2 != 0) {
+            double C1[DIM * DIM], C2[DIM * DIM], S2[DIM * DIM];
+#pragma unroll
+            for (int f = 0; f < DIM * DIM; ++f) {
+                C1[f] = a[(DIM + f) * lda + i] + a[(DIM + DIM * DIM + f) * lda + i];
+                C2[f] = b[(DIM + f) * ldb + i] + b[(DIM + DIM * DIM + f) * ldb + i];
+            }
+            sym_sqrt<DIM, false>(C2, S2);
+            dist = fabs(d2 + cov_term<DIM>(C1, C2, S2));
+        }
+        out[i] = dist;
+    }
+}
+
+}  // namespace cck

@@ -23,48 +23,33 @@
 namespace cck_b200 {
 
 // ---------------------------------------------------------------------------
-// RealVectorBeliefSpace::distance (src/Spaces/RealVectorBeliefSpace.cpp:16-62): squared mean
-// distance + trace(C1 + C2 - 2 (C2^1/2 C1 C2^1/2)^1/2), |.| of the total.  The covariance of a
-// tree node depends only on its depth (the recursion is control independent), so the trace term
-// is memoised per (depth, depth) / (sample diag, depth) instead of three eigen-solves per call.
+// RealVectorBeliefSpace::distance (src/Spaces/RealVectorBeliefSpace.cpp:16-62) drives both
+// nearest-neighbour structures of the planner (nn_ for selectNode, witnesses_ for
+// findClosestWitness).  Both live on the GPU as cck_tree objects: one brute-force batched launch
+// answers the K selectNode queries of an iteration, one more the K nearest-witness queries, and a
+// lower-triangular distance matrix of the batch lets the host replay the reference's SEQUENTIAL
+// witness rules exactly (a candidate must see the witnesses created by earlier candidates of the
+// same launch).
 // ---------------------------------------------------------------------------
-struct SymEig {
-    // Jacobi eigen-decomposition of the symmetric part (lower triangle, as SelfAdjointEigenSolver reads it)
-    static void sqrt_sym(const double* Ain, int n, double* out) {
-        double A[16], V[16];
-        for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) { A[i * n + j] = Ain[std::max(i, j) * n + std::min(i, j)]; V[i * n + j] = i == j; }
-        for (int sweep = 0; sweep < 60; ++sweep) {
-            double off = 0;
-            for (int i = 0; i < n; ++i) for (int j = 0; j < i; ++j) off += A[i * n + j] * A[i * n + j];
-            if (off < 1e-300) break;
-            for (int p = 0; p < n; ++p)
-                for (int q = p + 1; q < n; ++q) {
-                    if (std::fabs(A[p * n + q]) < 1e-300) continue;
-                    const double th = (A[q * n + q] - A[p * n + p]) / (2 * A[p * n + q]);
-                    const double t = (th >= 0 ? 1.0 : -1.0) / (std::fabs(th) + std::sqrt(th * th + 1));
-                    const double c = 1 / std::sqrt(t * t + 1), s = t * c;
-                    for (int k = 0; k < n; ++k) { const double akp = A[k * n + p], akq = A[k * n + q]; A[k * n + p] = c * akp - s * akq; A[k * n + q] = s * akp + c * akq; }
-                    for (int k = 0; k < n; ++k) { const double apk = A[p * n + k], aqk = A[q * n + k]; A[p * n + k] = c * apk - s * aqk; A[q * n + k] = s * apk + c * aqk; }
-                    for (int k = 0; k < n; ++k) { const double vkp = V[k * n + p], vkq = V[k * n + q]; V[k * n + p] = c * vkp - s * vkq; V[k * n + q] = s * vkp + c * vkq; }
-                }
-        }
-        for (int i = 0; i < n; ++i)
-            for (int j = 0; j < n; ++j) {
-                double acc = 0;
-                for (int k = 0; k < n; ++k) acc += V[i * n + k] * std::sqrt(std::max(A[k * n + k], 0.0)) * V[j * n + k];
-                out[i * n + j] = acc;
-            }
+class DeviceTree {
+public:
+    DeviceTree(const GpuContextPtr& gpu, int dim) : gpu_(gpu) { gpu_->check(cck_tree_create(gpu_->get(), dim, &t_), "cck_tree_create"); }
+    ~DeviceTree() { cck_tree_destroy(t_); }
+    DeviceTree(const DeviceTree&) = delete;
+    DeviceTree& operator=(const DeviceTree&) = delete;
+    void clear() { gpu_->check(cck_tree_clear(t_), "cck_tree_clear"); }
+    int64_t size() const { return cck_tree_size(t_); }
+    void append(int64_t n, const double* bel_soa, int64_t ld, const double* cost) { gpu_->check(cck_tree_append(t_, n, bel_soa, ld, cost, nullptr), "cck_tree_append"); }
+    void deactivate(const std::vector<int32_t>& idx) {
+        if (idx.empty()) return;
+        std::vector<uint8_t> z(idx.size(), 0);
+        gpu_->check(cck_tree_update(t_, (int64_t)idx.size(), idx.data(), nullptr, z.data()), "cck_tree_update");
     }
-    static double cov_term(const double* C1, const double* C2, int n) {
-        double s2[16], t[16], m[16], s3[16];
-        sqrt_sym(C2, n, s2);
-        for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) { double a = 0; for (int k = 0; k < n; ++k) a += s2[i * n + k] * C1[k * n + j]; t[i * n + j] = a; }
-        for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) { double a = 0; for (int k = 0; k < n; ++k) a += t[i * n + k] * s2[k * n + j]; m[i * n + j] = a; }
-        sqrt_sym(m, n, s3);
-        double tr = 0;
-        for (int i = 0; i < n; ++i) tr += C1[i * n + i] + C2[i * n + i] - 2 * s3[i * n + i];
-        return tr;
-    }
+    void select(int64_t K, const double* samples, int64_t lds, double radius, int32_t* out) { gpu_->check(cck_tree_select(t_, K, samples, lds, radius, out, nullptr), "cck_tree_select"); }
+    void nearest(int64_t K, const double* q, int64_t ldq, int32_t* idx, double* dist) { gpu_->check(cck_tree_nearest(t_, K, q, ldq, idx, dist), "cck_tree_nearest"); }
+private:
+    GpuContextPtr gpu_;
+    cck_tree* t_ = nullptr;
 };
 
 struct PlannerParams {
@@ -89,7 +74,7 @@ public:
         bool inactive = false;
         int numChildren = 0;
     };
-    struct Witness { std::vector<double> state; int depth; int rep; };
+    struct Witness { int rep; };
 
     BatchedBSST(InstancePtr inst, int robot, const std::string& svc_name, const std::string& pvc_name, PlannerParams prm, int device = 0)
         : inst_(std::move(inst)), robot_(robot), prm_(prm), rng_(prm.seed + 7919 * (uint64_t)robot) {
@@ -97,6 +82,8 @@ public:
         dim_ = r.getDynamicsModel() == "Uncertain-Unicycle-Model" ? 4 : 2;
         W_ = belief_width(dim_);
         gpu_ = std::make_shared<GpuContext>(device);
+        nodes_dev_ = std::make_unique<DeviceTree>(gpu_, dim_);
+        wit_dev_ = std::make_unique<DeviceTree>(gpu_, dim_);
         // spaces + bounds (OmplSetUp.cpp:194-207 / 263-289)
         auto space = std::make_shared<RealVectorBeliefSpace>(dim_);
         ob::RealVectorBounds b(dim_);
@@ -136,7 +123,7 @@ public:
 
     // ConstraintRespectingPlanner::updateConstraints + clear
     void updateConstraints(const std::vector<ConstraintPtr>& c) { constraints_ = c; clear(); }
-    void clear() { motions_.clear(); witnesses_.clear(); cov_cache_.clear(); }
+    void clear() { motions_.clear(); witnesses_.clear(); nodes_dev_->clear(); wit_dev_->clear(); }
 
     // solve(seconds): returns the interpolated trajectory (one state per dt) or empty
     Trajectory solve(double seconds, double* cost_out = nullptr) {
@@ -145,29 +132,39 @@ public:
         if (motions_.empty()) {
             Motion m; m.state = start_;
             motions_.push_back(m);
-            find_closest_witness((int)motions_.size() - 1, true);
+            const double zero = 0.0;
+            nodes_dev_->append(1, start_.data(), 1, &zero);      // one record: SoA with ld = 1 is the record itself
+            witnesses_.push_back(Witness{0});
+            wit_dev_->append(1, start_.data(), 1, &zero);
         }
         const int K = prm_.K;
-        std::vector<double> bel((size_t)W_ * K), ctrl((size_t)dim_ * K), out((size_t)W_ * K), pcost(K), cost(K), gdist(K);
-        std::vector<int32_t> steps(K), pstep(K), valid(K);
+        std::vector<double> bel((size_t)W_ * K), ctrl((size_t)dim_ * K), out((size_t)W_ * K), pcost(K), cost(K), gdist(K), samples((size_t)W_ * K);
+        std::vector<int32_t> steps(K), pstep(K), valid(K), parent(K);
         std::vector<uint8_t> flags(K);
-        std::vector<int> parent(K);
         std::uniform_real_distribution<double> U01(0.0, 1.0);
         int solution = -1;
         while (solution < 0) {
             if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > seconds) break;
-            // ---- sample K candidates (ConstraintRespectingBSST.cpp:226-247) ----
+            // ---- sample K (state, control, duration) triples (ConstraintRespectingBSST.cpp:226-247) ----
+            std::fill(samples.begin(), samples.end(), 0.0);
             for (int j = 0; j < K; ++j) {
-                double rs[4], diag[2];
+                double rs[4];
                 if (U01(rng_) < prm_.goal_bias) { rs[0] = goal_.gx; rs[1] = goal_.gy; for (int d = 2; d < dim_; ++d) rs[d] = uni(sbounds_.low[d], sbounds_.high[d]); }
                 else for (int d = 0; d < dim_; ++d) rs[d] = uni(sbounds_.low[d], sbounds_.high[d]);
-                diag[0] = U01(rng_) * max_eig_; diag[1] = U01(rng_) * max_eig_;           // :235-236
-                const int n = select_node(rs, diag);
-                parent[j] = n;
-                const Motion& m = motions_[n];
-                for (int f = 0; f < W_; ++f) bel[(size_t)f * K + j] = m.state[f];
+                for (int d = 0; d < dim_; ++d) samples[(size_t)d * K + j] = rs[d];
+                // the sample carries sigma = diag(d0, d1, 0.01..), lambda = 0.01 I (allocState default + :235-236)
+                for (int d = 0; d < dim_; ++d) { samples[(size_t)(dim_ + d * dim_ + d) * K + j] = 0.01; samples[(size_t)(dim_ + dim_ * dim_ + d * dim_ + d) * K + j] = 0.01; }
+                samples[(size_t)(dim_ + 0) * K + j] = U01(rng_) * max_eig_;
+                samples[(size_t)(dim_ + dim_ + 1) * K + j] = U01(rng_) * max_eig_;
                 for (int d = 0; d < dim_; ++d) ctrl[(size_t)d * K + j] = uni(cbounds_.low[d], cbounds_.high[d]);
                 steps[j] = prm_.min_steps + (int)(rng_() % (uint64_t)(prm_.max_steps - prm_.min_steps + 1));
+            }
+            // ---- ONE launch: selectNode for all K samples (:119-148) ----
+            nodes_dev_->select(K, samples.data(), K, prm_.selection_radius, parent.data());
+            stats_.launches++;
+            for (int j = 0; j < K; ++j) {
+                const Motion& m = motions_[parent[j]];
+                for (int f = 0; f < W_; ++f) bel[(size_t)f * K + j] = m.state[f];
                 pstep[j] = m.depth; pcost[j] = m.accCost;
             }
             // ---- ONE launch: K x (<=10 steps) propagate + check (+ constraints, cost, goal) ----
@@ -175,31 +172,7 @@ public:
                                          valid.data(), cost.data(), gdist.data(), flags.data()), "cck_expand_batch");
             stats_.launches++; stats_.candidates += K;
             // ---- commit in sample order with the reference's witness rules (:250-326) ----
-            for (int j = 0; j < K && solution < 0; ++j) {
-                if (!(flags[j] & 1)) continue;                               // propCd != cd
-                Motion m;
-                m.state.resize(W_);
-                for (int f = 0; f < W_; ++f) m.state[f] = out[(size_t)f * K + j];
-                for (int d = 0; d < dim_; ++d) m.ctrl[d] = ctrl[(size_t)d * K + j];
-                m.steps = steps[j]; m.parent = parent[j]; m.depth = motions_[parent[j]].depth + steps[j]; m.accCost = cost[j];
-                motions_.push_back(m);
-                const int idx = (int)motions_.size() - 1;
-                const int w = find_closest_witness(idx, false);
-                Witness& wit = witnesses_[w];
-                const bool is_new = wit.rep == idx;
-                if (!(is_new || m.accCost < motions_[wit.rep].accCost)) { motions_.pop_back(); continue; }
-                if (!constraints_.empty() && !(flags[j] & 2)) {             // satisfiesConstraints failed (:300)
-                    if (is_new) witnesses_.pop_back();
-                    motions_.pop_back();
-                    continue;
-                }
-                if (!is_new) { prune(wit.rep); wit.rep = idx; }
-                motions_[parent[j]].numChildren++;
-                stats_.accepted++;
-                const double c00 = m.state[dim_] + m.state[dim_ + dim_ * dim_], c11 = m.state[dim_ + dim_ + 1] + m.state[dim_ + dim_ * dim_ + dim_ + 1];
-                if (c00 > max_eig_) max_eig_ = c00; else if (c11 > max_eig_) max_eig_ = c11;     // :313-320
-                if (flags[j] & 4) solution = idx;                            // goal->isSatisfied (:326)
-            }
+            solution = commit(K, out, ctrl, steps, parent, cost, flags);
         }
         stats_.nodes = (int64_t)motions_.size();
         stats_.seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
@@ -211,68 +184,79 @@ public:
 private:
     double uni(double lo, double hi) { return lo + (hi - lo) * std::uniform_real_distribution<double>(0.0, 1.0)(rng_); }
 
-    // covariance (Sigma + Lambda) of a tree state
-    void cov_of(const std::vector<double>& s, double* C) const { for (int f = 0; f < dim_ * dim_; ++f) C[f] = s[dim_ + f] + s[dim_ + dim_ * dim_ + f]; }
-
-    double cov_term_nodes(int d1, const std::vector<double>& s1, int d2, const std::vector<double>& s2) {
-        const uint64_t key = ((uint64_t)(uint32_t)d1 << 32) | (uint32_t)d2;
-        auto it = cov_cache_.find(key);
-        if (it != cov_cache_.end()) return it->second;
-        double C1[16], C2[16];
-        cov_of(s1, C1); cov_of(s2, C2);
-        const double v = SymEig::cov_term(C1, C2, dim_);
-        cov_cache_[key] = v;
-        return v;
-    }
-
-    // selectNode (ConstraintRespectingBSST.cpp:119-148): best-cost active node within the selection
-    // radius of the sample, else the nearest active node.  The sample carries sigma = diag(d0, d1, 0.01..),
-    // lambda = 0.01 I (allocState default).
-    int select_node(const double* rs, const double* diag) {
-        double Cs[16] = {0};
-        for (int i = 0; i < dim_; ++i) Cs[i * dim_ + i] = 0.02;
-        Cs[0] = diag[0] + 0.01; Cs[dim_ + 1] = diag[1] + 0.01;
-        std::unordered_map<int, double> term;   // per-depth covariance term for this sample
-        int best = -1, nearest = -1;
-        double best_cost = std::numeric_limits<double>::infinity(), nd = std::numeric_limits<double>::infinity();
-        for (int i = 0; i < (int)motions_.size(); ++i) {
-            const Motion& m = motions_[i];
-            if (m.inactive) continue;
-            double d2 = 0;
-            for (int d = 0; d < dim_; ++d) { const double e = rs[d] - m.state[d]; d2 += e * e; }
-            double dist = 0;
-            if (d2 != 0) {
-                auto it = term.find(m.depth);
-                if (it == term.end()) { double Cm[16]; cov_of(m.state, Cm); it = term.emplace(m.depth, SymEig::cov_term(Cs, Cm, dim_)).first; }
-                dist = std::fabs(d2 + it->second);
+    // Commit the survivors of one launch.  The reference handles one candidate at a time: findClosestWitness
+    // (:150-178) sees every witness created so far, including those of earlier candidates of the same batch.
+    // Here: one launch finds each survivor's nearest PRE-BATCH witness, one more the lower-triangular distance
+    // matrix among the survivors; the loop below then replays the sequential rules with table look-ups only.
+    int commit(int K, const std::vector<double>& out, const std::vector<double>& ctrl, const std::vector<int32_t>& steps,
+               const std::vector<int32_t>& parent, const std::vector<double>& cost, const std::vector<uint8_t>& flags) {
+        std::vector<int> surv;
+        for (int j = 0; j < K; ++j) if (flags[j] & 1) surv.push_back(j);          // propCd == cd
+        int solution = -1;
+        const int kMaxChunk = 2048;
+        for (size_t c0 = 0; c0 < surv.size() && solution < 0; c0 += kMaxChunk) {
+            const int S = (int)std::min<size_t>(kMaxChunk, surv.size() - c0);
+            std::vector<double> q((size_t)W_ * S), qcost(S);
+            for (int s = 0; s < S; ++s) { const int j = surv[c0 + s]; for (int f = 0; f < W_; ++f) q[(size_t)f * S + s] = out[(size_t)f * K + j]; qcost[s] = cost[j]; }
+            std::vector<int32_t> widx(S);
+            std::vector<double> wdist(S), lower((size_t)S * S);
+            wit_dev_->nearest(S, q.data(), S, widx.data(), wdist.data());
+            gpu_->check(cck_belief_distance_lower(gpu_->get(), dim_, S, q.data(), S, lower.data()), "cck_belief_distance_lower");
+            stats_.launches += 2;
+            std::vector<std::pair<int, int>> fresh;       // (survivor s, witness index) of witnesses created in this chunk
+            std::vector<int32_t> deact;
+            std::vector<int> new_nodes;                   // survivors appended to the tree, in order
+            const size_t wit_before = witnesses_.size();
+            for (int s = 0; s < S && solution < 0; ++s) {
+                const int j = surv[c0 + s];
+                int w = widx[s];
+                double cd = w >= 0 ? wdist[s] : std::numeric_limits<double>::infinity();
+                for (const auto& fw : fresh) { const double d = lower[(size_t)s * S + fw.first]; if (d < cd) { cd = d; w = fw.second; } }
+                const int idx = (int)motions_.size();
+                bool is_new = false;
+                if (w < 0 || cd > prm_.pruning_radius) { witnesses_.push_back(Witness{idx}); w = (int)witnesses_.size() - 1; fresh.emplace_back(s, w); is_new = true; }
+                Witness& wit = witnesses_[w];
+                if (!(is_new || cost[j] < motions_[wit.rep].accCost)) continue;
+                if (!constraints_.empty() && !(flags[j] & 2)) {                 // satisfiesConstraints failed (:300)
+                    if (is_new) { witnesses_.pop_back(); fresh.pop_back(); }
+                    continue;
+                }
+                Motion m;
+                m.state.resize(W_);
+                for (int f = 0; f < W_; ++f) m.state[f] = out[(size_t)f * K + j];
+                for (int d = 0; d < dim_; ++d) m.ctrl[d] = ctrl[(size_t)d * K + j];
+                m.steps = steps[j]; m.parent = parent[j]; m.depth = motions_[parent[j]].depth + steps[j]; m.accCost = cost[j];
+                motions_.push_back(m);
+                new_nodes.push_back(s);
+                if (!is_new) { prune(wit.rep, deact); wit.rep = idx; }
+                motions_[parent[j]].numChildren++;
+                stats_.accepted++;
+                const double c00 = m.state[dim_] + m.state[dim_ + dim_ * dim_], c11 = m.state[dim_ + dim_ + 1] + m.state[dim_ + dim_ * dim_ + dim_ + 1];
+                if (c00 > max_eig_) max_eig_ = c00; else if (c11 > max_eig_) max_eig_ = c11;     // :313-320
+                if (flags[j] & 4) solution = idx;                                // goal->isSatisfied (:326)
             }
-            if (dist <= prm_.selection_radius && m.accCost < best_cost) { best_cost = m.accCost; best = i; }
-            if (dist < nd) { nd = dist; nearest = i; }
+            // mirror the chunk's changes on the device: new nodes, new witnesses, deactivated representatives
+            if (!new_nodes.empty()) {
+                const int n = (int)new_nodes.size();
+                std::vector<double> nb((size_t)W_ * n), nc(n);
+                for (int a = 0; a < n; ++a) { for (int f = 0; f < W_; ++f) nb[(size_t)f * n + a] = q[(size_t)f * S + new_nodes[a]]; nc[a] = qcost[new_nodes[a]]; }
+                nodes_dev_->append(n, nb.data(), n, nc.data());
+            }
+            if (witnesses_.size() > wit_before) {
+                const int n = (int)fresh.size();
+                std::vector<double> wb((size_t)W_ * n), wc(n, 0.0);
+                for (int a = 0; a < n; ++a) for (int f = 0; f < W_; ++f) wb[(size_t)f * n + a] = q[(size_t)f * S + fresh[a].first];
+                wit_dev_->append(n, wb.data(), n, wc.data());
+            }
+            nodes_dev_->deactivate(deact);
         }
-        return best >= 0 ? best : nearest;
-    }
-
-    // findClosestWitness (:150-178)
-    int find_closest_witness(int node, bool) {
-        const Motion& m = motions_[node];
-        int closest = -1;
-        double cd = std::numeric_limits<double>::infinity();
-        for (int w = 0; w < (int)witnesses_.size(); ++w) {
-            double d2 = 0;
-            for (int d = 0; d < dim_; ++d) { const double e = witnesses_[w].state[d] - m.state[d]; d2 += e * e; }
-            const double dist = d2 == 0 ? 0.0 : std::fabs(d2 + cov_term_nodes(witnesses_[w].depth, witnesses_[w].state, m.depth, m.state));
-            if (dist < cd) { cd = dist; closest = w; }
-        }
-        if (closest < 0 || cd > prm_.pruning_radius) {
-            witnesses_.push_back(Witness{m.state, m.depth, node});
-            return (int)witnesses_.size() - 1;
-        }
-        return closest;
+        return solution;
     }
 
     // the old representative becomes inactive; childless inactive nodes are dropped up the tree (:357-381)
-    void prune(int old_rep) {
+    void prune(int old_rep, std::vector<int32_t>& deact) {
         motions_[old_rep].inactive = true;
+        deact.push_back(old_rep);          // mirrored on the device after this chunk's nodes are appended
         int cur = old_rep;
         while (cur >= 0 && motions_[cur].inactive && motions_[cur].numChildren == 0) {
             const int par = motions_[cur].parent;
@@ -314,7 +298,7 @@ private:
     std::vector<ConstraintPtr> constraints_;
     std::vector<Motion> motions_;
     std::vector<Witness> witnesses_;
-    std::unordered_map<uint64_t, double> cov_cache_;
+    std::unique_ptr<DeviceTree> nodes_dev_, wit_dev_;
     double max_eig_ = 10.0;                                            // :221
     PlannerStats stats_;
 };

@@ -225,6 +225,32 @@ int cck_select_winner_dev(cck_ctx* ctx, void* stream, int64_t n, const double* c
  * FP64 entry). */
 int cck_measure_fp64_peak(cck_ctx* ctx, double* tflops);
 
+/* ---- belief-space nearest neighbours over a device-resident tree ----
+ * RealVectorBeliefSpace::distance (src/Spaces/RealVectorBeliefSpace.cpp:16-62):
+ *   | ||mu1-mu2||^2 + trace(C1 + C2 - 2 (C2^1/2 C1 C2^1/2)^1/2) |, 0 when the means coincide, C = Sigma + Lambda.
+ * A cck_tree holds tree nodes (or witnesses): belief record, accumulated cost, active flag.
+ *   cck_tree_select   replaces ConstraintRespectingBSST::selectNode (:119-148) for K samples at once:
+ *                     best-cost ACTIVE node within selection_radius of the sample, else the nearest active node.
+ *   cck_tree_nearest  replaces the nearest-witness query of findClosestWitness (:150-178): argmin distance
+ *                     over all items (ties -> lowest index), the caller compares out_dist with the pruning radius.
+ * Belief records are SoA [W][ld] host arrays as everywhere else; indices are item positions in append order. */
+typedef struct cck_tree cck_tree;
+int cck_tree_create(cck_ctx* ctx, int dim, cck_tree** out);
+int cck_tree_destroy(cck_tree* tree);
+int cck_tree_clear(cck_tree* tree);
+int64_t cck_tree_size(const cck_tree* tree);
+int cck_tree_append(cck_tree* tree, int64_t n, const double* bel, int64_t ld, const double* cost, int64_t* first_index);
+int cck_tree_update(cck_tree* tree, int64_t n, const int32_t* idx, const double* cost /* or NULL */, const uint8_t* active /* or NULL */);
+int cck_tree_select(cck_tree* tree, int64_t K, const double* samples, int64_t lds, double selection_radius, int32_t* out_idx,
+                    double* out_dist /* or NULL */);
+int cck_tree_nearest(cck_tree* tree, int64_t K, const double* queries, int64_t ldq, int32_t* out_idx, double* out_dist /* or NULL */);
+/* distance(a_i, b_i) for n pairs (RealVectorBeliefSpace::distance(state1 = a, state2 = b)) */
+int cck_belief_distance(cck_ctx* ctx, int dim, int64_t n, const double* a, int64_t lda, const double* b, int64_t ldb, double* out);
+/* out[q*n + i] = distance(b_i, b_q) for i < q (n <= 8192; other entries unspecified): the witness tests between
+ * candidates committed from the same launch, so the sequential witness rules can be replayed on the host exactly */
+int cck_belief_distance_lower(cck_ctx* ctx, int dim, int64_t n, const double* bel, int64_t ld, double* out);
+
+
 #ifdef __cplusplus
 }
 #endif

@@ -450,6 +450,87 @@ inline void split_risk(Instance& inst, double p_safe) {
 }
 
 // ---------------------------------------------------------------------------
+// f2: RealVectorBeliefSpace::distance (src/Spaces/RealVectorBeliefSpace.cpp:16-62) and the two
+// nearest-neighbour rules of the low-level planner (ConstraintRespectingBSST.cpp:119-178).
+// Eigen's SelfAdjointEigenSolver (lower triangle, operatorSqrt = V sqrt(D) V^T) is restated as a
+// cyclic Jacobi iteration; Eigen's tridiagonal QL agrees to rounding, not bit for bit.
+// ---------------------------------------------------------------------------
+inline void sym_operator_sqrt(const double* Ain, int n, double* out) {
+    double A[16], V[16];
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j) { A[i * n + j] = Ain[std::max(i, j) * n + std::min(i, j)]; V[i * n + j] = (i == j) ? 1.0 : 0.0; }
+    for (int sweep = 0; sweep < 60; ++sweep) {
+        double off = 0;
+        for (int i = 0; i < n; ++i) for (int j = 0; j < i; ++j) off += A[i * n + j] * A[i * n + j];
+        if (off < 1e-300) break;
+        for (int p = 0; p < n; ++p)
+            for (int q = p + 1; q < n; ++q) {
+                if (std::fabs(A[p * n + q]) < 1e-300) continue;
+                const double th = (A[q * n + q] - A[p * n + p]) / (2 * A[p * n + q]);
+                const double t = (th >= 0 ? 1.0 : -1.0) / (std::fabs(th) + std::sqrt(th * th + 1));
+                const double c = 1 / std::sqrt(t * t + 1), sn = t * c;
+                for (int k = 0; k < n; ++k) { const double akp = A[k * n + p], akq = A[k * n + q]; A[k * n + p] = c * akp - sn * akq; A[k * n + q] = sn * akp + c * akq; }
+                for (int k = 0; k < n; ++k) { const double apk = A[p * n + k], aqk = A[q * n + k]; A[p * n + k] = c * apk - sn * aqk; A[q * n + k] = sn * apk + c * aqk; }
+                for (int k = 0; k < n; ++k) { const double vkp = V[k * n + p], vkq = V[k * n + q]; V[k * n + p] = c * vkp - sn * vkq; V[k * n + q] = sn * vkp + c * vkq; }
+            }
+    }
+    double sq[4];
+    for (int k = 0; k < n; ++k) sq[k] = std::sqrt(A[k * n + k] > 0.0 ? A[k * n + k] : 0.0);
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j) {
+            double acc = 0;
+            for (int k = 0; k < n; ++k) acc += V[i * n + k] * sq[k] * V[j * n + k];
+            out[i * n + j] = acc;
+        }
+}
+
+// b1, b2: belief records [D + 2 D^2]
+inline double belief_distance(const double* b1, const double* b2, int D) {
+    double d2 = 0;                                                                    // :22-27
+    for (int i = 0; i < D; ++i) { const double e = b1[i] - b2[i]; d2 += e * e; }
+    if (d2 == 0) return 0.0;
+    double C1[16], C2[16], S2[16], t[16], m[16], S3[16];
+    for (int f = 0; f < D * D; ++f) { C1[f] = b1[D + f] + b1[D + D * D + f]; C2[f] = b2[D + f] + b2[D + D * D + f]; }   // getCovariance, :30-31
+    sym_operator_sqrt(C2, D, S2);                                                     // :35-36
+    for (int i = 0; i < D; ++i) for (int j = 0; j < D; ++j) { double a = 0; for (int k = 0; k < D; ++k) a += S2[i * D + k] * C1[k * D + j]; t[i * D + j] = a; }
+    for (int i = 0; i < D; ++i) for (int j = 0; j < D; ++j) { double a = 0; for (int k = 0; k < D; ++k) a += t[i * D + k] * S2[k * D + j]; m[i * D + j] = a; }   // :37
+    sym_operator_sqrt(m, D, S3);                                                      // :38-39
+    double tr = 0;
+    for (int i = 0; i < D; ++i) tr += C1[i * D + i] + C2[i * D + i] - 2 * S3[i * D + i];
+    return std::fabs(d2 + tr);                                                        // :41, :62
+}
+
+// selectNode (:119-148): best-cost active node within the selection radius of the sample, else the nearest
+// active one.  distance(sample, node): the node is the second argument.
+inline int select_node(const double* nodes, const double* cost, const unsigned char* active, long n, const double* sample, int D,
+                       double selection_radius, double* dist_out) {
+    const int W = D + 2 * D * D;
+    int best = -1, nearest = -1;
+    double best_cost = HUGE_VAL, best_d = 0, nd = HUGE_VAL;
+    for (long i = 0; i < n; ++i) {
+        if (!active[i]) continue;
+        const double d = belief_distance(sample, nodes + i * W, D);
+        if (d <= selection_radius && (best < 0 || cost[i] < best_cost)) { best_cost = cost[i]; best = (int)i; best_d = d; }
+        if (nearest < 0 || d < nd) { nd = d; nearest = (int)i; }
+    }
+    if (dist_out) *dist_out = best >= 0 ? best_d : (nearest >= 0 ? nd : HUGE_VAL);
+    return best >= 0 ? best : nearest;
+}
+
+// nearest witness (:150-178): distance(witness, node), the query node is the second argument
+inline int nearest_witness(const double* witnesses, long n, const double* node, int D, double* dist_out) {
+    const int W = D + 2 * D * D;
+    int closest = -1;
+    double cd = HUGE_VAL;
+    for (long i = 0; i < n; ++i) {
+        const double d = belief_distance(witnesses + i * W, node, D);
+        if (closest < 0 || d < cd) { cd = d; closest = (int)i; }
+    }
+    if (dist_out) *dist_out = cd;
+    return closest;
+}
+
+// ---------------------------------------------------------------------------
 // a4/a5/a6: state validity checkers
 // ---------------------------------------------------------------------------
 struct Counters { uint64_t n_steps = 0, n_halfplane = 0, n_obstacle = 0; };

@@ -304,4 +304,19 @@ void orc_goal(int dim, long n, const double* bel, double gx, double gy, double t
     }
 }
 
+// ---- f2: belief-space distance and the planner's nearest-neighbour rules (AoS records) ----
+void orc_belief_distance(int dim, long n, const double* a, const double* b, double* out) {
+    const int W = dim + 2 * dim * dim;
+    for (long i = 0; i < n; ++i) out[i] = belief_distance(a + i * W, b + i * W, dim);
+}
+void orc_select_nodes(int dim, long n_nodes, const double* nodes, const double* cost, const unsigned char* active, long K, const double* samples,
+                      double radius, int* out_idx, double* out_dist) {
+    const int W = dim + 2 * dim * dim;
+    for (long q = 0; q < K; ++q) out_idx[q] = select_node(nodes, cost, active, n_nodes, samples + q * W, dim, radius, out_dist + q);
+}
+void orc_nearest_witness(int dim, long n_wit, const double* wit, long K, const double* queries, int* out_idx, double* out_dist) {
+    const int W = dim + 2 * dim * dim;
+    for (long q = 0; q < K; ++q) out_idx[q] = nearest_witness(wit, n_wit, queries + q * W, dim, out_dist + q);
+}
+
 }  // extern "C"

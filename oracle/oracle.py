@@ -79,6 +79,9 @@ def lib():
         L.orc_satisfies_constraints.restype = C.c_int
         L.orc_satisfies_constraints.argtypes = [vp, C.c_int, C.c_int, dp, C.c_double, C.c_int, C.c_int, ip, ip, ip, dp]
         L.orc_goal.argtypes = [C.c_int, C.c_long, dp, C.c_double, C.c_double, C.c_double, C.c_double, u8p, dp]
+        L.orc_belief_distance.argtypes = [C.c_int, C.c_long, dp, dp, dp]
+        L.orc_select_nodes.argtypes = [C.c_int, C.c_long, dp, dp, u8p, C.c_long, dp, C.c_double, ip, dp]
+        L.orc_nearest_witness.argtypes = [C.c_int, C.c_long, dp, C.c_long, dp, ip, dp]
         _lib = L
     return _lib
 
@@ -303,3 +306,30 @@ def goal(beliefs, dim, gx, gy, threshold=2.0, p_safe=0.95):
     dist = np.zeros(len(b))
     lib().orc_goal(dim, len(b), _dp(b), gx, gy, threshold, p_safe, ok.ctypes.data_as(C.POINTER(C.c_ubyte)), _dp(dist))
     return ok.astype(bool), dist
+
+
+def belief_distance(a, b, dim):
+    """RealVectorBeliefSpace::distance(a_i, b_i) for AoS records [n, W]."""
+    a, b = _f64(a), _f64(b)
+    out = np.zeros(len(a))
+    lib().orc_belief_distance(dim, len(a), _dp(a), _dp(b), _dp(out))
+    return out
+
+
+def select_nodes(nodes, cost, active, samples, dim, radius=0.2):
+    """selectNode for each sample against the AoS node set -> (index, distance)."""
+    nodes, cost, samples = _f64(nodes), _f64(cost), _f64(samples)
+    act = np.ascontiguousarray(active, dtype=np.uint8)
+    idx = np.zeros(len(samples), dtype=np.int32)
+    dist = np.zeros(len(samples))
+    lib().orc_select_nodes(dim, len(nodes), _dp(nodes), _dp(cost), act.ctypes.data_as(C.POINTER(C.c_ubyte)), len(samples), _dp(samples),
+                           radius, _ip(idx), _dp(dist))
+    return idx, dist
+
+
+def nearest_witness(witnesses, queries, dim):
+    witnesses, queries = _f64(witnesses), _f64(queries)
+    idx = np.zeros(len(queries), dtype=np.int32)
+    dist = np.zeros(len(queries))
+    lib().orc_nearest_witness(dim, len(witnesses), _dp(witnesses), len(queries), _dp(queries), _ip(idx), _dp(dist))
+    return idx, dist
