@@ -12,6 +12,7 @@
 // [1,10] steps (OmplSetUp.cpp:225); controls uniform in the control bounds.
 #pragma once
 #include <chrono>
+#include <future>
 #include <cmath>
 #include <limits>
 #include <queue>
@@ -266,22 +267,36 @@ private:
         }
     }
 
-    // root -> solution path, interpolated to one state per dt (PathControl::interpolate):
-    // the intermediate states are re-propagated on the GPU in trajectory mode.
+    // root -> solution path, interpolated to one state per dt (PathControl::interpolate,
+    // ConstraintRespectingBSST.cpp:283-298): ALL segments are re-propagated by ONE trajectory-mode launch
+    // (segment s = belief s of the batch, its parent state, held control and step count).
     Trajectory extract(int sol) {
         std::vector<int> chain;
         for (int c = sol; c >= 0; c = motions_[c].parent) chain.push_back(c);
         std::reverse(chain.begin(), chain.end());
         Trajectory tr;
         tr.push_back(BeliefState{dim_, motions_[chain[0]].state});
-        for (size_t s = 1; s < chain.size(); ++s) {
-            const Motion& m = motions_[chain[s]];
-            const Motion& p = motions_[chain[s - 1]];
-            std::vector<double> traj((size_t)m.steps * W_), fin(W_);
-            int32_t st = m.steps, valid = 0;
-            gpu_->check(cck_propagate_while_valid(gpu_->get(), 1, p.state.data(), 1, m.ctrl, 1, &st, fin.data(), 1, &valid, traj.data(), 1, m.steps), "interpolate");
-            for (int t = 0; t < m.steps; ++t) tr.push_back(BeliefState{dim_, std::vector<double>(traj.begin() + (size_t)t * W_, traj.begin() + (size_t)(t + 1) * W_)});
+        const int n = (int)chain.size() - 1;
+        if (n <= 0) return tr;
+        int T = 0;
+        for (int s = 1; s <= n; ++s) T = std::max(T, motions_[chain[s]].steps);
+        std::vector<double> bel((size_t)W_ * n), ctrl((size_t)dim_ * n), fin((size_t)W_ * n), traj((size_t)T * W_ * n);
+        std::vector<int32_t> st(n), valid(n);
+        for (int s = 0; s < n; ++s) {
+            const Motion& m = motions_[chain[s + 1]];
+            const Motion& p = motions_[chain[s]];
+            for (int f = 0; f < W_; ++f) bel[(size_t)f * n + s] = p.state[f];
+            for (int d = 0; d < dim_; ++d) ctrl[(size_t)d * n + s] = m.ctrl[d];
+            st[s] = m.steps;
         }
+        gpu_->check(cck_propagate_while_valid(gpu_->get(), n, bel.data(), n, ctrl.data(), n, st.data(), fin.data(), n, valid.data(), traj.data(), n, T), "interpolate");
+        stats_.launches++;
+        for (int s = 0; s < n; ++s)
+            for (int t = 0; t < st[s]; ++t) {
+                std::vector<double> v(W_);
+                for (int f = 0; f < W_; ++f) v[f] = traj[((size_t)t * W_ + f) * n + s];
+                tr.push_back(BeliefState{dim_, std::move(v)});
+            }
         return tr;
     }
 
@@ -345,18 +360,30 @@ public:
             const std::vector<ConflictPtr> confs = pv->validatePlan(cur->plan);      // :289
             if (confs.empty()) { res.solved = true; res.plan = cur->plan; res.cost = cur->cost; break; }
             const int agents[2] = {confs.front()->agent1Idx_, confs.front()->agent2Idx_};
-            for (int a : agents) {                                       // :389-467 (two independent replans)
-                auto child = std::make_shared<Node>(*cur);
-                child->cons.push_back(pv->createConstraint(cur->plan, confs, a));
+            // :389-467: the two child replans are independent (different agents, each planner owns its context,
+            // stream and device trees), so they run concurrently — on different GPUs when n_devices > 1
+            std::shared_ptr<Node> child[2];
+            std::future<Trajectory> job[2];
+            for (int i = 0; i < 2; ++i) {
+                const int a = agents[i];
+                child[i] = std::make_shared<Node>(*cur);
+                child[i]->cons.push_back(pv->createConstraint(cur->plan, confs, a));
                 std::vector<ConstraintPtr> mine;
-                for (const auto& c : child->cons) if (c->getConstrainedAgent() == a) mine.push_back(c);
+                for (const auto& c : child[i]->cons) if (c->getConstrainedAgent() == a) mine.push_back(c);
                 planners_[a]->updateConstraints(mine);
                 res.replans++;
-                Trajectory t = planners_[a]->solve(ll_seconds_);
+                BatchedBSST* pl = planners_[a].get();
+                const double secs = ll_seconds_;
+                if (agents[0] != agents[1]) job[i] = std::async(std::launch::async, [pl, secs] { return pl->solve(secs); });
+                else { std::promise<Trajectory> pr; pr.set_value(pl->solve(secs)); job[i] = pr.get_future(); }
+            }
+            for (int i = 0; i < 2; ++i) {
+                const int a = agents[i];
+                Trajectory t = job[i].get();
                 if (t.empty()) continue;                                 // failed replans are dropped (the reference re-queues them at infinite cost)
-                child->cost += 0.2 * ((double)t.size() - (double)child->plan[a].size());
-                child->plan[a] = std::move(t);
-                pq.push(child);
+                child[i]->cost += 0.2 * ((double)t.size() - (double)child[i]->plan[a].size());
+                child[i]->plan[a] = std::move(t);
+                pq.push(child[i]);
             }
         }
         res.seconds = elapsed();
