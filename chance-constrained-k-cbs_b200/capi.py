@@ -12,7 +12,7 @@ import subprocess
 import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_PKG, "libcck_b200.so")
+_SO = os.environ.get("CCK_SO") or os.path.join(_PKG, "libcck_b200.so")   # CCK_SO: alternative build (kernel tuning experiments)
 _ROOT = os.path.dirname(_PKG)
 
 OK, ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_NODEVICE = 0, 1, 2, 3, 4

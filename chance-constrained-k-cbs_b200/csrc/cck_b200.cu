@@ -812,7 +812,7 @@ static int launch_rollout(cck_ctx* c, cudaStream_t s, const RolloutArgs& a) {
     } else if (c->model.model == CCK_MODEL_LINEAR2D) {
         if ((rc = check_tab_fits(c))) return rc;
         if (traj) DISPATCH_KIND(k_rollout_lin, c->lin, true); else DISPATCH_KIND(k_rollout_lin, c->lin, false);
-    } else if (c->uni_sparse && c->kern == 2) {
+    } else if (c->uni_sparse && c->kern >= 2) {
         // unicycle, second generation: sparse covariance step, grid broad phase for Blackmore, lane refill
         RolloutArgs g2 = a;
         if (c->svc.kind == CCK_SVC_BLACKMORE) { g2.ftab = c->d_gtab; g2.ftab_bytes = c->gtab_bytes; g2.exB = c->d_gexB; g2.exCls = c->d_gexCls; }

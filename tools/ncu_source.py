@@ -35,3 +35,12 @@ for s in range(0, len(body), blk):
         ops[op] = ops.get(op, 0) + 1
     top = ' '.join(f"{k}:{v}" for k, v in sorted(ops.items(), key=lambda kv: -kv[1])[:6])
     print(f"+0x{int(chunk[0][ia],16)-base:05x} inst {100*inst/tot_inst:5.1f}%  avg_thr {thr/max(inst,1):5.1f}  samples {100*samp/max(tot_samp,1):5.1f}%  {top}")
+
+# top individual instructions by stall samples
+if len(sys.argv) > 3:
+    col = sys.argv[3]
+    ic = hdr.index(col)
+    top = sorted(body, key=lambda r: -int(r[ic]))[:25]
+    print(f"--- top instructions by {col}")
+    for r in top:
+        print(f"+0x{int(r[ia],16)-base:05x} {int(r[ic]):7d} inst={r[iinst]:>10s} thr/inst={int(r[ithr])/max(int(r[iinst]),1):5.1f}  {r[isrc][:90]}")
