@@ -318,6 +318,44 @@ def run_ours(args):
         del d_rb, d_rc
         ctx2.close()
 
+    # ---- secondary: M = 0 trajectory mode (config-1 shape: bounds-only checker, every intermediate belief written
+    #      for the plan validator) -- the HBM-bound regime of the path ----
+    m0 = None
+    if args.variant == "all_survive" and args.model == "linear" and not args.no_realistic:
+        Bm = min(B, 1 << 22)
+        ctx3 = K.Context(local)
+        W.install_synthetic(ctx3, "linear", 0, variant="all_survive")
+        d_traj = torch.empty((T_STEPS * Wd, Bm), dtype=torch.float64, device=dev)
+        for _ in range(3):
+            ctx3.propagate_while_valid_dev(stream, Bm, d_bel, B, d_ctrl, B, d_steps, d_out, B, d_valid, traj=d_traj, traj_ld=Bm, traj_T=T_STEPS)
+        barrier()
+        assert int((d_valid[:Bm] == T_STEPS).sum().item()) == Bm
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            ctx3.propagate_while_valid_dev(stream, Bm, d_bel, B, d_ctrl, B, d_steps, d_out, B, d_valid, traj=d_traj, traj_ld=Bm, traj_T=T_STEPS)
+        e1.record()
+        barrier()
+        launches += args.steps
+        mt = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(mt, op=dist.ReduceOp.MAX)
+        m_ms = float(mt[0]) / args.steps
+        m_rate = Bm * T_STEPS / (m_ms * 1e-3)
+        bytes_per_step = Wd * 8 + (Wd * 8 + dim * 8 + 4 + Wd * 8 + 4) / T_STEPS          # 80 + 184/T
+        peaks0 = {}
+        try:
+            peaks0 = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hp = peaks0.get("hbm_gbs", 6650.0)
+        m0 = {"value": m_rate * world, "unit": UNIT, "beliefs_per_gpu": Bm, "kernel_ms": m_ms,
+              "roofline": {"bound": "hbm", "achieved": m_rate * bytes_per_step / 1e9, "peak": hp, "unit": "GB/s",
+                           "frac": m_rate * bytes_per_step / 1e9 / hp, "bytes_per_belief_step": bytes_per_step},
+              "note": "M = 0 (bounds-only checker, config-1 shape), trajectory mode: 80 B written per belief-step"}
+        del d_traj
+        ctx3.close()
+
     # ---- PCIe context for e2e: pinned H2D / D2H copy bandwidth of the same buffers ----
     pcie = None
     if not args.no_e2e:
@@ -385,7 +423,7 @@ def run_ours(args):
             "roofline_hbm": {"bound": "hbm", "achieved": hbm_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_gbs / hbm_peak,
                              "peak_source": "MEASURED_PEAKS.json (burst copy)" if "hbm_gbs" in peaks else "fallback 6650",
                              "bytes_per_belief": bytes_per_belief},
-            "realistic": realistic, "pcie": pcie,
+            "realistic": realistic, "m0_trajectory": m0, "pcie": pcie,
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
         }
         print(json.dumps(line))

@@ -70,6 +70,7 @@ struct cck_ctx {
 };
 
 static std::string g_create_err;
+static int64_t kChunk = 1 << 20;   // beliefs per pipeline chunk of the host-pointer entry points (CCK_CHUNK_LOG2 overrides, tuning only)
 
 #define CK(ctx, call)                                                                                  \
     do {                                                                                               \
@@ -116,6 +117,7 @@ extern "C" int cck_ctx_create(int device, cck_ctx** out) {
     c->num_sms = prop.multiProcessorCount;
     c->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
     if (const char* e3 = getenv("CCK_REFILL")) c->refill = atoi(e3) != 0;
+    if (const char* e5 = getenv("CCK_CHUNK_LOG2")) { const int v = atoi(e5); if (v >= 10 && v <= 26) kChunk = (int64_t)1 << v; }
     if (const char* e4 = getenv("CCK_KERNEL")) { const int v = atoi(e4); if (v >= 0 && v <= 2) c->kern = v; }
     if (const char* e2 = getenv("CCK_BPT")) { const int v = atoi(e2); if (v == 0 || v == 1 || v == 2 || v == 4) c->bpt = v; }
     if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess ||
@@ -733,10 +735,18 @@ extern "C" int cck_is_valid_dev(cck_ctx* c, void* stream, int64_t n, const doubl
     if (n == 0) return CCK_OK;
     CK(c, cudaSetDevice(c->device));
     cudaStream_t s = pick(c, stream);
+    const int dim = c->model.dim;
+    if (c->svc.kind == CCK_SVC_BLACKMORE && c->kern == 2) {   // fp32 box/bitmap-grid broad phase + exact decision
+        const int gsm = 16 + c->gtab_bytes;
+        if ((rc = set_smem(c, k_is_valid_grid, gsm))) return rc;
+        k_is_valid_grid<<<grid_for(c, n, 256, 4), 256, gsm, s>>>(n, dim, bel, ld, valid, c->d_gtab, c->gtab_bytes, c->d_tab, c->d_gexB, c->d_gexCls, c->svc);
+        c->launches++;
+        CK(c, cudaGetLastError());
+        return CCK_OK;
+    }
     if ((rc = check_tab_fits(c))) return rc;
     const int smem = 16 + c->tab_bytes;
     const int g = grid_for(c, n, 256, 4);
-    const int dim = c->model.dim;
 #define LAUNCH_VALID(KIND)                                                                        \
     do {                                                                                          \
         if ((rc = set_smem(c, k_is_valid<KIND>, smem))) return rc;                                \
@@ -994,7 +1004,6 @@ static cudaError_t d2h_planes(void* dst, int64_t ld_dst, const void* src, size_t
     return cudaMemcpy2DAsync(dst, (size_t)ld_dst * elem, src, (size_t)cnt * elem, (size_t)cnt * elem, planes, cudaMemcpyDeviceToHost, s);
 }
 
-static const int64_t kChunk = 1 << 20;   // beliefs per pipeline chunk
 
 extern "C" int cck_propagate(cck_ctx* c, int64_t n, const double* bel, int64_t ld, const double* ctrl, int64_t ldc, double duration,
                              double* out, int64_t ldo) {

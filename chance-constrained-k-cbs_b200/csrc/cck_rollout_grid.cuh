@@ -134,6 +134,32 @@ __device__ __forceinline__ bool grid_check(const unsigned char* gt, const unsign
     return ok;
 }
 
+// PCCBlackmoreSVC::isValid, batched (row a4), through the same broad phase: bounds, then grid_check.
+__global__ void __launch_bounds__(256) k_is_valid_grid(int64_t n, int dim, const double* __restrict__ bel, int64_t ld, uint8_t* __restrict__ valid,
+                                                       const unsigned char* __restrict__ ggtab, int32_t gtab_bytes, const unsigned char* __restrict__ ctab,
+                                                       const double* __restrict__ exB, const int32_t* __restrict__ exCls, const __grid_constant__ SvcDev sp) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+    unsigned char* gt = smem_raw + 16;
+    stage_begin(gt, ggtab, (uint32_t)gtab_bytes, bar);
+    bool waited = false;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double v[4] = {0, 0, 0, 0};
+        const int dd = dim * dim;
+        for (int f = 0; f < dim; ++f) v[f] = bel[f * ld + i];
+        // (Sigma+Lambda).block<2,2>(0,0)  (PCCBlackmoreSVC.cpp:41)
+        const double P0 = bel[(dim + 0) * ld + i] + bel[(dim + dd + 0) * ld + i];
+        const double P1 = bel[(dim + 1) * ld + i] + bel[(dim + dd + 1) * ld + i];
+        const double P2 = bel[(dim + dim) * ld + i] + bel[(dim + dd + dim) * ld + i];
+        const double P3 = bel[(dim + dim + 1) * ld + i] + bel[(dim + dd + dim + 1) * ld + i];
+        if (!waited) { stage_wait((uint32_t)gtab_bytes, bar); waited = true; }
+        bool ok = bounds_ok(sp, v);
+        if (ok && gtab_bytes > 0) ok = grid_check(gt, ctab, exB, exCls, sp.erf_inv_result, v[0], v[1], P0, P1, P2, P3);
+        valid[i] = ok ? 1 : 0;
+    }
+    if (!waited) stage_wait((uint32_t)gtab_bytes, bar);   // never exit with a copy in flight
+}
+
 // ---------------------------------------------------------------------------
 // cp.async (LDGSTS): per-lane prefetch of the NEXT belief into shared memory while the current
 // rollout runs, so a refill never exposes HBM latency to the warp.

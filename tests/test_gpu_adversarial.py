@@ -16,6 +16,9 @@ pytestmark = pytest.mark.gpu
 
 
 def _rollout_both(K, ctx, svc, bel, ctrl, steps):
+    # isValid on the start states goes through the same broad phase (k_is_valid_grid)
+    with np.errstate(all="ignore"):
+        assert np.array_equal(ctx.is_valid(bel), svc.is_valid(K.soa_to_aos(bel))[0])
     out, valid = ctx.propagate_while_valid(bel, ctrl, steps)
     ref_out, ref_valid, _ = svc.rollout(K.soa_to_aos(bel), K.soa_to_aos(ctrl), steps, nthreads=8)
     return K.soa_to_aos(out), valid, ref_out, ref_valid
