@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-realistic", action="store_true", help="skip the secondary realistic-variant measurement")
+    ap.add_argument("--no-solve", action="store_true", help="skip the short live CCK-CBS solve-time sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs under ncu)")
     return ap.parse_args()
 
@@ -401,6 +402,22 @@ def run_ours(args):
         inst_per_step = 111.0 if dim == 2 else 1100.0
         exec_tinst = per_launch_units * inst_per_step / (kern_ms * 1e-3) / 1e12
         inst_peak = fp64_peak / 2.0      # one DFMA = 2 flop = 1 FP64-pipe instruction per lane
+        # ---- second half of BASELINE.json's metric: CCK-CBS solve time, short live sample (full distribution:
+        #      tools/solve_bench.py -> profiles/r1_solve_times.json) ----
+        solve = None
+        if world == 1 and not args.no_solve and not args.no_cpu:
+            try:
+                out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "solve_bench.py"), "--seeds", "5", "--time", "20", "--only", "k=4"],
+                                     capture_output=True, text=True, timeout=300)
+                solve = {}
+                for ln in out.stdout.splitlines():
+                    if ln.startswith("config"):
+                        lab, js = ln.split(" {", 1)
+                        d = json.loads("{" + js)
+                        solve[lab] = {k: d[k] for k in ("seeds", "solved", "seconds_median", "seconds_p90", "K", "candidates_median", "cbs_nodes_median")}
+                solve["how"] = "K-CBS over the batched GPU BSST (host/cck_plan), instances rebuilt from tests/golden; wall seconds per solve"
+            except Exception as e:  # noqa: BLE001
+                solve = {"error": str(e)[:200]}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -423,7 +440,7 @@ def run_ours(args):
             "roofline_hbm": {"bound": "hbm", "achieved": hbm_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_gbs / hbm_peak,
                              "peak_source": "MEASURED_PEAKS.json (burst copy)" if "hbm_gbs" in peaks else "fallback 6650",
                              "bytes_per_belief": bytes_per_belief},
-            "realistic": realistic, "m0_trajectory": m0, "pcie": pcie,
+            "realistic": realistic, "m0_trajectory": m0, "solve_time": solve, "pcie": pcie,
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
         }
         print(json.dumps(line))
