@@ -385,6 +385,8 @@ static void build_grid_table(int M, const double* A, const double* B, const std:
     if ((double)h.gx0 > x0) h.gx0 = std::nextafterf(h.gx0, -HUGE_VALF);
     if ((double)h.gy0 > y0) h.gy0 = std::nextafterf(h.gy0, -HUGE_VALF);
     // cell size: the whole anchor range must fit the bitmap, and a cell is not finer than the typical box
+    // (measured: spreading the range over all 64 columns/rows cuts false candidates 0.54 -> 0.38 per belief-step
+    // but adds bitmap rows to every query; realistic sweep 29.5 -> 28.4 G/s, so the coarser cells stay)
     auto inv_cell = [](double range, double s, int n) {
         double ic = 1.0 / std::max(s, 1e-30);
         if (range > 0) ic = std::min(ic, (n - 0.5) / range);
