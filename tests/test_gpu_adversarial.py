@@ -186,3 +186,32 @@ def test_blackmore_far_away_and_large_tables(K, O, W, ctx):
         assert np.array_equal(valid, ref_valid), (off, M)
         assert np.array_equal(out, ref_out), (off, M)
         assert 0.02 < (ref_valid == steps).mean() < 0.98, (off, M)
+
+
+@pytest.mark.parametrize("kind", [0, 2])
+def test_unicycle_sparse_step_degenerate_inputs(K, O, W, ctx, kind):
+    """The second-generation unicycle kernel skips the exact-zero terms of F, A_cl_d, Q, R; beliefs with
+    non-finite covariance entries (where 0*inf = NaN matters) must take the dense step.  Zero, negative and
+    huge-but-finite covariances stay on the sparse path.  Covariances are bit-exact, means within 1e-9."""
+    world, svc = oracle_synth(O, W, 40, "realistic", kind, 4, seed=31)
+    install_from_oracle_svc(K, ctx, svc, K.MODEL_UNICYCLE)
+    n = 3000
+    bel, ctrl = W.synthetic_beliefs(n, "unicycle", seed=61)
+    bel[4:, :] *= 0.02
+    rng = np.random.default_rng(13)
+    # the chi-squared checker's polygon predicates are only defined for finite coordinates (Boost.Geometry
+    # with NaN vertices is outside the reference's contract), so it gets the finite specials only
+    specials = [np.nan, np.inf, -np.inf, 0.0, -0.0, 1e200, -1e-3, 1e-300] if kind == 0 else [0.0, -0.0, 1e3, -1e-3, 1e-300]
+    for j in range(0, n, 3):
+        bel[rng.integers(4, 36), j] = specials[rng.integers(len(specials))]
+    bel[4:, 1:300:3] = 0.0
+    steps = rng.integers(1, 6, size=n).astype(np.int32)
+    with np.errstate(all="ignore"):
+        out, valid = ctx.propagate_while_valid(bel, ctrl, steps)
+        ref_out, ref_valid, _ = svc.rollout(K.soa_to_aos(bel), K.soa_to_aos(ctrl), steps, nthreads=8)
+    out = K.soa_to_aos(out)
+    mism = np.nonzero(valid != ref_valid)[0]
+    assert len(mism) <= 2, f"{len(mism)} verdict mismatches"
+    ok = np.ones(n, bool); ok[mism] = False
+    assert np.array_equal(out[ok][:, 4:], ref_out[ok][:, 4:], equal_nan=True)          # Sigma, Lambda: no transcendental
+    assert np.allclose(out[ok][:, :4], ref_out[ok][:, :4], rtol=1e-9, atol=1e-12, equal_nan=True)
