@@ -64,6 +64,9 @@ struct cck_ctx {
     unsigned char* d_cons = nullptr;   // constraint table (nullptr = no constraints)
     size_t cons_cap = 0;
 
+    // pinned staging block of the small-batch path (planner-sized launches: one H2D, one launch, one D2H)
+    unsigned char* h_stage = nullptr;
+    size_t h_stage_cap = 0;
     // grow-only device scratch for the host-pointer entry points (one per pipeline slot)
     void* d_scratch[CCK_SLOTS] = {};
     size_t scratch_cap[CCK_SLOTS] = {};
@@ -135,6 +138,7 @@ extern "C" int cck_ctx_destroy(cck_ctx* c) {
     if (!c) return CCK_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    cudaFreeHost(c->h_stage);
     for (int i = 0; i < CCK_SLOTS; ++i) { if (c->pipe[i]) { cudaStreamSynchronize(c->pipe[i]); cudaStreamDestroy(c->pipe[i]); } cudaFree(c->d_scratch[i]); }
     cudaFree(c->d_ftab); cudaFree(c->d_exB); cudaFree(c->d_exCls); cudaFree(c->d_gtab); cudaFree(c->d_gexB); cudaFree(c->d_gexCls);
     cudaFree(c->d_tab); cudaFree(c->d_pvc_A); cudaFree(c->d_pvc_B); cudaFree(c->d_pvc_radii); cudaFree(c->d_pvc_order);
@@ -788,14 +792,14 @@ static int launch_rollout(cck_ctx* c, cudaStream_t s, const RolloutArgs& a) {
         // default configuration: fp32 box/bitmap-grid broad phase + exact fp64 decision, lane refill
         RolloutArgs g2 = a;
         g2.ftab = c->d_gtab; g2.ftab_bytes = c->gtab_bytes; g2.exB = c->d_gexB; g2.exCls = c->d_gexCls;
-        const int per_range = 1 << CCK_GRID_RANGE_LOG2;
-        const int64_t nr = (a.n + per_range - 1) / per_range;
+        const int rl2 = rollout_range_log2(a.n);
+        const int64_t nr = (a.n + ((int64_t)1 << rl2) - 1) >> rl2;
         const int gb = (int)std::min<int64_t>(nr, (int64_t)c->num_sms * 4);
         const int gsmem = grid_smem_bytes(c->gtab_bytes);
         if (traj) { if ((rc = set_smem(c, (k_rollout_lin_grid<true, EXPAND>), gsmem))) return rc;
-                    k_rollout_lin_grid<true, EXPAND><<<gb, CCK_GRID_THREADS, gsmem, s>>>(g2, c->lin, c->svc); }
+                    k_rollout_lin_grid<true, EXPAND><<<gb, CCK_GRID_THREADS, gsmem, s>>>(g2, c->lin, c->svc, rl2); }
         else { if ((rc = set_smem(c, (k_rollout_lin_grid<false, EXPAND>), gsmem))) return rc;
-               k_rollout_lin_grid<false, EXPAND><<<gb, CCK_GRID_THREADS, gsmem, s>>>(g2, c->lin, c->svc); }
+               k_rollout_lin_grid<false, EXPAND><<<gb, CCK_GRID_THREADS, gsmem, s>>>(g2, c->lin, c->svc, rl2); }
     } else if (c->model.model == CCK_MODEL_LINEAR2D && c->svc.kind == CCK_SVC_BLACKMORE && c->kern == 1 && c->bpt > 0) {
         // second generation: threshold (group filter) kernel, BPT beliefs per thread
         if (c->M > 0 && c->ftab_bytes == 0) return fail(c, CCK_ERR_INVALID, "group-filter table exceeds shared memory; use the default kernel");
@@ -829,14 +833,15 @@ static int launch_rollout(cck_ctx* c, cudaStream_t s, const RolloutArgs& a) {
         RolloutArgs g2 = a;
         if (c->svc.kind == CCK_SVC_BLACKMORE) { g2.ftab = c->d_gtab; g2.ftab_bytes = c->gtab_bytes; g2.exB = c->d_gexB; g2.exCls = c->d_gexCls; }
         else { if ((rc = check_tab_fits(c))) return rc; g2.ftab = c->d_tab; g2.ftab_bytes = c->tab_bytes; }
-        const int64_t nr = (a.n + (1 << CCK_GRID_RANGE_LOG2) - 1) >> CCK_GRID_RANGE_LOG2;
+        const int rl2 = rollout_range_log2(a.n);
+        const int64_t nr = (a.n + ((int64_t)1 << rl2) - 1) >> rl2;
         const int gb = (int)std::min<int64_t>(nr, (int64_t)c->num_sms * 2);
         const int usmem = uni_smem_bytes(g2.ftab_bytes);
         if (usmem > c->max_smem_optin) return fail(c, CCK_ERR_INVALID, "obstacle table exceeds shared memory; M too large");
 #define LAUNCH_U2(KIND, TRAJ)                                                                        \
     do {                                                                                             \
         if ((rc = set_smem(c, (k_rollout_uni2<KIND, TRAJ, EXPAND>), usmem))) return rc;              \
-        k_rollout_uni2<KIND, TRAJ, EXPAND><<<gb, CCK_UNI_THREADS, usmem, s>>>(g2, c->uni, c->svc);   \
+        k_rollout_uni2<KIND, TRAJ, EXPAND><<<gb, CCK_UNI_THREADS, usmem, s>>>(g2, c->uni, c->svc, rl2);   \
     } while (0)
         if (c->svc.kind == CCK_SVC_BLACKMORE) { if (traj) LAUNCH_U2(CCK_SVC_BLACKMORE, true); else LAUNCH_U2(CCK_SVC_BLACKMORE, false); }
         else if (c->svc.kind == CCK_SVC_ADAPTIVE) { if (traj) LAUNCH_U2(CCK_SVC_ADAPTIVE, true); else LAUNCH_U2(CCK_SVC_ADAPTIVE, false); }
@@ -1052,6 +1057,55 @@ extern "C" int cck_is_valid(cck_ctx* c, int64_t n, const double* bel, int64_t ld
     return CCK_OK;
 }
 
+// Planner-sized batches (n <= 16384, no trajectory output): the ~14 small copies of the chunked path cost more
+// than the launch itself, so everything is packed into ONE pinned staging block: one H2D, one launch, one D2H.
+static int rollout_host_small(cck_ctx* c, bool expand, int64_t n, const double* bel, int64_t ld, const double* ctrl, int64_t ldc,
+                              const int32_t* steps, const int32_t* parent_step, const double* parent_cost, const cck_goal_params* goal,
+                              double* out, int64_t ldo, int32_t* valid_steps, double* cost, double* goal_dist, uint8_t* flags) {
+    int rc;
+    const int dim = c->model.dim, W = dim + 2 * dim * dim;
+    const size_t b_in = al256((size_t)n * W * 8), b_c = al256((size_t)n * dim * 8), b_i = al256((size_t)n * 4), b_d = al256((size_t)n * 8), b_f = al256((size_t)n);
+    const size_t in_bytes = b_in + b_c + b_i + (expand ? b_i + b_d : 0);
+    const size_t out_bytes = b_in + b_i + (expand ? 2 * b_d + b_f : 0);
+    const size_t total = in_bytes + out_bytes;
+    if (total > c->h_stage_cap) {
+        CK(c, cudaStreamSynchronize(c->pipe[0]));
+        cudaFreeHost(c->h_stage); c->h_stage = nullptr; c->h_stage_cap = 0;
+        if (cudaHostAlloc((void**)&c->h_stage, total * 2, cudaHostAllocDefault) != cudaSuccess) { c->err = "cudaHostAlloc staging"; return CCK_ERR_NOMEM; }
+        c->h_stage_cap = total * 2;
+    }
+    if ((rc = ensure_scratch(c, 0, total))) return rc;
+    unsigned char* h = c->h_stage;
+    unsigned char* d = (unsigned char*)c->d_scratch[0];
+    size_t o = 0;
+    const size_t o_bel = o; o += b_in;
+    const size_t o_ctrl = o; o += b_c;
+    const size_t o_steps = o; o += b_i;
+    size_t o_ps = 0, o_pc = 0;
+    if (expand) { o_ps = o; o += b_i; o_pc = o; o += b_d; }
+    const size_t o_out = o; o += b_in;
+    const size_t o_valid = o; o += b_i;
+    size_t o_cost = 0, o_gd = 0, o_fl = 0;
+    if (expand) { o_cost = o; o += b_d; o_gd = o; o += b_d; o_fl = o; o += b_f; }
+    for (int f = 0; f < W; ++f) std::memcpy(h + o_bel + (size_t)f * n * 8, bel + (size_t)f * ld, (size_t)n * 8);
+    for (int f = 0; f < dim; ++f) std::memcpy(h + o_ctrl + (size_t)f * n * 8, ctrl + (size_t)f * ldc, (size_t)n * 8);
+    std::memcpy(h + o_steps, steps, (size_t)n * 4);
+    if (expand) { std::memcpy(h + o_ps, parent_step, (size_t)n * 4); std::memcpy(h + o_pc, parent_cost, (size_t)n * 8); }
+    cudaStream_t s = c->pipe[0];
+    CK(c, cudaMemcpyAsync(d, h, in_bytes, cudaMemcpyHostToDevice, s));
+    if (!expand) rc = cck_propagate_while_valid_dev(c, s, n, (double*)(d + o_bel), n, (double*)(d + o_ctrl), n, (int32_t*)(d + o_steps), (double*)(d + o_out), n,
+                                                    (int32_t*)(d + o_valid), nullptr, 0, 0);
+    else rc = cck_expand_batch_dev(c, s, n, (double*)(d + o_bel), n, (double*)(d + o_ctrl), n, (int32_t*)(d + o_steps), (int32_t*)(d + o_ps), (double*)(d + o_pc),
+                                   goal, (double*)(d + o_out), n, (int32_t*)(d + o_valid), (double*)(d + o_cost), (double*)(d + o_gd), d + o_fl);
+    if (rc) return rc;
+    CK(c, cudaMemcpyAsync(h + in_bytes, d + in_bytes, out_bytes, cudaMemcpyDeviceToHost, s));
+    CK(c, cudaStreamSynchronize(s));
+    for (int f = 0; f < W; ++f) std::memcpy(out + (size_t)f * ldo, h + o_out + (size_t)f * n * 8, (size_t)n * 8);
+    std::memcpy(valid_steps, h + o_valid, (size_t)n * 4);
+    if (expand) { std::memcpy(cost, h + o_cost, (size_t)n * 8); std::memcpy(goal_dist, h + o_gd, (size_t)n * 8); std::memcpy(flags, h + o_fl, (size_t)n); }
+    return CCK_OK;
+}
+
 static int rollout_host(cck_ctx* c, bool expand, int64_t n, const double* bel, int64_t ld, const double* ctrl, int64_t ldc,
                         const int32_t* steps, const int32_t* parent_step, const double* parent_cost, const cck_goal_params* goal,
                         double* out, int64_t ldo, int32_t* valid_steps, double* traj, int64_t traj_ld, int32_t traj_T, double* cost,
@@ -1061,6 +1115,8 @@ static int rollout_host(cck_ctx* c, bool expand, int64_t n, const double* bel, i
     if (n < 0 || ld < n || ldc < n || ldo < n || (traj && (traj_ld < n || traj_T < 1))) return fail(c, CCK_ERR_INVALID, "bad n/ld");
     if (!bel || !ctrl || !steps || !out || !valid_steps) return fail(c, CCK_ERR_INVALID, "null argument");
     CK(c, cudaSetDevice(c->device));
+    if (n > 0 && n <= 16384 && !traj)
+        return rollout_host_small(c, expand, n, bel, ld, ctrl, ldc, steps, parent_step, parent_cost, goal, out, ldo, valid_steps, cost, goal_dist, flags);
     const int dim = c->model.dim, W = dim + 2 * dim * dim;
     int64_t chunk = kChunk;
     if (traj) chunk = std::max<int64_t>(1024, kChunk / (traj_T > 0 ? traj_T : 1));

@@ -179,14 +179,17 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 #ifndef CCK_GRID_MINB
 #define CCK_GRID_MINB 4
 #endif
-#define CCK_GRID_RANGE_LOG2 8   // the work counter hands out ranges of 256 consecutive beliefs, round-robin over the CTAs
+// the work counter hands out ranges of 2^range_log2 consecutive beliefs, round-robin over the CTAs: 256 for the
+// big sweeps (coalesced refills), 128 = one belief per lane for planner-sized batches (latency: every candidate of a
+// K <= 75k launch starts immediately on its own lane)
+__host__ inline int rollout_range_log2(int64_t n) { return n >= ((int64_t)1 << 22) ? 8 : 7; }
 __host__ __device__ inline int grid_smem_bytes(int gtab_bytes) {
     return 16 + gtab_bytes + 16 + CCK_GRID_THREADS * 80 + 13 * CCK_GRID_THREADS * 8 + 2 * CCK_GRID_THREADS * 4;
 }
 
 template <bool TRAJ, bool EXPAND>
 __global__ void __launch_bounds__(CCK_GRID_THREADS, CCK_GRID_MINB) k_rollout_lin_grid(const __grid_constant__ RolloutArgs a, const __grid_constant__ LinDev p,
-                                                                          const __grid_constant__ SvcDev sp) {
+                                                                          const __grid_constant__ SvcDev sp, const int range_log2) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
     unsigned char* gt = smem_raw + 16;
@@ -205,10 +208,10 @@ __global__ void __launch_bounds__(CCK_GRID_THREADS, CCK_GRID_MINB) k_rollout_lin
         nxt = -1;
         while (true) {
             const int kk = atomicAdd(next_k, 1);
-            const int rg = kk >> CCK_GRID_RANGE_LOG2;
-            const int64_t base = ((int64_t)blockIdx.x + (int64_t)rg * gridDim.x) << CCK_GRID_RANGE_LOG2;
+            const int rg = kk >> range_log2;
+            const int64_t base = ((int64_t)blockIdx.x + (int64_t)rg * gridDim.x) << range_log2;
             if (base >= a.n) return;
-            const int64_t idx = base + (kk & ((1 << CCK_GRID_RANGE_LOG2) - 1));
+            const int64_t idx = base + (kk & ((1 << range_log2) - 1));
             if (idx < a.n) { nxt = idx; break; }
         }
 #pragma unroll

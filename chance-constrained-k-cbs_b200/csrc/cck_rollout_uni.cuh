@@ -96,7 +96,7 @@ __host__ __device__ inline int uni_smem_bytes(int tab_bytes) { return 16 + tab_b
 
 template <int KIND, bool TRAJ, bool EXPAND>
 __global__ void __launch_bounds__(CCK_UNI_THREADS, 2) k_rollout_uni2(const __grid_constant__ RolloutArgs a, const __grid_constant__ UniDev p,
-                                                                    const __grid_constant__ SvcDev sp) {
+                                                                    const __grid_constant__ SvcDev sp, const int range_log2) {
     // KIND == Blackmore: a.ftab is the grid table (staged), a.tab the class table (global, exact path only);
     // other kinds: a.ftab == a.tab is the class table (staged)
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -142,10 +142,10 @@ __global__ void __launch_bounds__(CCK_UNI_THREADS, 2) k_rollout_uni2(const __gri
     while (true) {
         while (!have && !done) {   // the CTA owns ranges blockIdx, blockIdx+gridDim, ... of 256 beliefs
             const int kk = atomicAdd(next_k, 1);
-            const int rg = kk >> CCK_GRID_RANGE_LOG2;
-            const int64_t base = ((int64_t)blockIdx.x + (int64_t)rg * gridDim.x) << CCK_GRID_RANGE_LOG2;
+            const int rg = kk >> range_log2;
+            const int64_t base = ((int64_t)blockIdx.x + (int64_t)rg * gridDim.x) << range_log2;
             if (base >= a.n) { done = true; break; }
-            i = base + (kk & ((1 << CCK_GRID_RANGE_LOG2) - 1));
+            i = base + (kk & ((1 << range_log2) - 1));
             if (i >= a.n) continue;
 #pragma unroll
             for (int f = 0; f < 4; ++f) { v[f] = a.bel[f * a.ld + i]; u[f] = a.ctrl[f * a.ldc + i]; }
