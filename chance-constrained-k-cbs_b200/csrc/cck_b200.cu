@@ -742,7 +742,7 @@ extern "C" int cck_is_valid_dev(cck_ctx* c, void* stream, int64_t n, const doubl
     CK(c, cudaSetDevice(c->device));
     cudaStream_t s = pick(c, stream);
     const int dim = c->model.dim;
-    if (c->svc.kind == CCK_SVC_BLACKMORE && c->kern == 2) {   // fp32 box/bitmap-grid broad phase + exact decision
+    if (c->svc.kind == CCK_SVC_BLACKMORE && c->kern >= 2) {   // fp32 box/bitmap-grid broad phase + exact decision
         const int gsm = 16 + c->gtab_bytes;
         if ((rc = set_smem(c, k_is_valid_grid, gsm))) return rc;
         k_is_valid_grid<<<grid_for(c, n, 256, 4), 256, gsm, s>>>(n, dim, bel, ld, valid, c->d_gtab, c->gtab_bytes, c->d_tab, c->d_gexB, c->d_gexCls, c->svc);
