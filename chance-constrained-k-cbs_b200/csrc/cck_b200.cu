@@ -49,6 +49,7 @@ struct cck_ctx {
     double* d_gexB = nullptr;          // exact fp64 rows in grid-table order
     int32_t* d_gexCls = nullptr;       // class of each row
     bool uni_sparse = false;           // unicycle matrices have the reference's exact-zero pattern
+    GridConst gconst{};                // header scalars of the grid table + fp32 bounds (kernel constants)
     int kern = 2;                      // linear+Blackmore rollout kernel: 2 grid (default), 1 group filter, 0 generic (CCK_KERNEL)
     int M = 0;
 
@@ -618,6 +619,8 @@ extern "C" int cck_set_obstacles(cck_ctx* c, const cck_svc_params* p, const doub
     // ---- fp32 box + bitmap-grid table (the default broad phase) ----
     cudaFree(c->d_gtab); cudaFree(c->d_gexB); cudaFree(c->d_gexCls);
     c->d_gtab = nullptr; c->d_gexB = nullptr; c->d_gexCls = nullptr; c->gtab_bytes = 0;
+    c->gconst = GridConst{};
+    c->gconst.blx = f32_up(p->low[0]); c->gconst.bhx = f32_down(p->high[0]); c->gconst.bly = f32_up(p->low[1]); c->gconst.bhy = f32_down(p->high[1]);
     if (M > 0) {
         GridBuild gb;
         build_grid_table(M, A, B, cls_idx, p->erf_inv_result, gb);
@@ -629,6 +632,11 @@ extern "C" int cck_set_obstacles(cck_ctx* c, const cck_svc_params* p, const doub
         CK(c, cudaMemcpy(c->d_gexB, gb.exB.data(), gb.exB.size() * 8, cudaMemcpyHostToDevice));
         CK(c, cudaMemcpy(c->d_gexCls, gb.exCls.data(), gb.exCls.size() * 4, cudaMemcpyHostToDevice));
         c->gtab_bytes = (int)gb.buf.size();
+        GHeader gh;
+        std::memcpy(&gh, gb.buf.data(), sizeof(gh));
+        const GridConst keep = c->gconst;
+        c->gconst = GridConst{gh.k, gh.SX, gh.SY, gh.gx0, gh.gy0, gh.icx, gh.icy, gh.Rm1, gh.M, gh.n_grid, gh.off_occ, gh.off_rowbase, gh.off_cstart, gh.off_boxes,
+                              keep.blx, keep.bhx, keep.bly, keep.bhy};
     }
 
     SvcDev& s = c->svc;
@@ -745,7 +753,7 @@ extern "C" int cck_is_valid_dev(cck_ctx* c, void* stream, int64_t n, const doubl
     if (c->svc.kind == CCK_SVC_BLACKMORE && c->kern >= 2) {   // fp32 box/bitmap-grid broad phase + exact decision
         const int gsm = 16 + c->gtab_bytes;
         if ((rc = set_smem(c, k_is_valid_grid, gsm))) return rc;
-        k_is_valid_grid<<<grid_for(c, n, 256, 4), 256, gsm, s>>>(n, dim, bel, ld, valid, c->d_gtab, c->gtab_bytes, c->d_tab, c->d_gexB, c->d_gexCls, c->svc);
+        k_is_valid_grid<<<grid_for(c, n, 256, 4), 256, gsm, s>>>(n, dim, bel, ld, valid, c->d_gtab, c->gtab_bytes, c->d_tab, c->d_gexB, c->d_gexCls, c->svc, c->gconst);
         c->launches++;
         CK(c, cudaGetLastError());
         return CCK_OK;
@@ -797,9 +805,9 @@ static int launch_rollout(cck_ctx* c, cudaStream_t s, const RolloutArgs& a) {
         const int gb = (int)std::min<int64_t>(nr, (int64_t)c->num_sms * 4);
         const int gsmem = grid_smem_bytes(c->gtab_bytes);
         if (traj) { if ((rc = set_smem(c, (k_rollout_lin_grid<true, EXPAND>), gsmem))) return rc;
-                    k_rollout_lin_grid<true, EXPAND><<<gb, CCK_GRID_THREADS, gsmem, s>>>(g2, c->lin, c->svc, rl2); }
+                    k_rollout_lin_grid<true, EXPAND><<<gb, CCK_GRID_THREADS, gsmem, s>>>(g2, c->lin, c->svc, c->gconst, rl2); }
         else { if ((rc = set_smem(c, (k_rollout_lin_grid<false, EXPAND>), gsmem))) return rc;
-               k_rollout_lin_grid<false, EXPAND><<<gb, CCK_GRID_THREADS, gsmem, s>>>(g2, c->lin, c->svc, rl2); }
+               k_rollout_lin_grid<false, EXPAND><<<gb, CCK_GRID_THREADS, gsmem, s>>>(g2, c->lin, c->svc, c->gconst, rl2); }
     } else if (c->model.model == CCK_MODEL_LINEAR2D && c->svc.kind == CCK_SVC_BLACKMORE && c->kern == 1 && c->bpt > 0) {
         // second generation: threshold (group filter) kernel, BPT beliefs per thread
         if (c->M > 0 && c->ftab_bytes == 0) return fail(c, CCK_ERR_INVALID, "group-filter table exceeds shared memory; use the default kernel");
@@ -841,7 +849,7 @@ static int launch_rollout(cck_ctx* c, cudaStream_t s, const RolloutArgs& a) {
 #define LAUNCH_U2(KIND, TRAJ)                                                                        \
     do {                                                                                             \
         if ((rc = set_smem(c, (k_rollout_uni2<KIND, TRAJ, EXPAND>), usmem))) return rc;              \
-        k_rollout_uni2<KIND, TRAJ, EXPAND><<<gb, CCK_UNI_THREADS, usmem, s>>>(g2, c->uni, c->svc, rl2);   \
+        k_rollout_uni2<KIND, TRAJ, EXPAND><<<gb, CCK_UNI_THREADS, usmem, s>>>(g2, c->uni, c->svc, c->gconst, rl2);   \
     } while (0)
         if (c->svc.kind == CCK_SVC_BLACKMORE) { if (traj) LAUNCH_U2(CCK_SVC_BLACKMORE, true); else LAUNCH_U2(CCK_SVC_BLACKMORE, false); }
         else if (c->svc.kind == CCK_SVC_ADAPTIVE) { if (traj) LAUNCH_U2(CCK_SVC_ADAPTIVE, true); else LAUNCH_U2(CCK_SVC_ADAPTIVE, false); }

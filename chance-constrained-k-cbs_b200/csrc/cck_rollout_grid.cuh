@@ -39,6 +39,14 @@ struct GHeader {                 // 80 bytes, then occ[R] (u64), rowbase[R] (u16
 };
 static_assert(sizeof(GHeader) == 80, "grid header");
 
+// header scalars as kernel constants (constant-bank operands instead of ~10 LDS per belief-step) + the state
+// bounds rounded INWARD to fp32 (pre-check of satisfiesBounds)
+struct GridConst {
+    float k, SX, SY, gx0, gy0, icx, icy, Rm1;
+    int32_t M, n_grid, off_occ, off_rowbase, off_cstart, off_boxes;
+    float blx, bhx, bly, bhy;
+};
+
 #define CCK_GRID_COLS 64
 #define CCK_GRID_ROWS 64
 
@@ -77,9 +85,9 @@ __device__ __forceinline__ bool grid_obstacle(const float4* boxes, int M, int j,
 }
 
 // "the belief is safe w.r.t. every obstacle" (PCCBlackmoreSVC.cpp:54-58), bit-exact.
-__device__ __forceinline__ bool grid_check(const unsigned char* gt, const unsigned char* ctab, const double* exB, const int32_t* exCls,
-                                           double c, double x, double y, double P0, double P1, double P2, double P3) {
-    const GHeader* h = reinterpret_cast<const GHeader*>(gt);
+__device__ __forceinline__ bool grid_check(const GridConst& g, const unsigned char* gt, const unsigned char* ctab, const double* exB,
+                                           const int32_t* exCls, double c, double x, double y, double P0, double P1, double P2, double P3) {
+    const GridConst* h = &g;
     const float4* boxes = reinterpret_cast<const float4*>(gt + h->off_boxes);
     const TabHeader* th = reinterpret_cast<const TabHeader*>(ctab);
     const ClassRec* cls = reinterpret_cast<const ClassRec*>(ctab + th->off_classes);
@@ -137,7 +145,8 @@ __device__ __forceinline__ bool grid_check(const unsigned char* gt, const unsign
 // PCCBlackmoreSVC::isValid, batched (row a4), through the same broad phase: bounds, then grid_check.
 __global__ void __launch_bounds__(256) k_is_valid_grid(int64_t n, int dim, const double* __restrict__ bel, int64_t ld, uint8_t* __restrict__ valid,
                                                        const unsigned char* __restrict__ ggtab, int32_t gtab_bytes, const unsigned char* __restrict__ ctab,
-                                                       const double* __restrict__ exB, const int32_t* __restrict__ exCls, const __grid_constant__ SvcDev sp) {
+                                                       const double* __restrict__ exB, const int32_t* __restrict__ exCls, const __grid_constant__ SvcDev sp,
+                                                       const __grid_constant__ GridConst g) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
     unsigned char* gt = smem_raw + 16;
@@ -154,7 +163,7 @@ __global__ void __launch_bounds__(256) k_is_valid_grid(int64_t n, int dim, const
         const double P3 = bel[(dim + dim + 1) * ld + i] + bel[(dim + dd + dim + 1) * ld + i];
         if (!waited) { stage_wait((uint32_t)gtab_bytes, bar); waited = true; }
         bool ok = bounds_ok(sp, v);
-        if (ok && gtab_bytes > 0) ok = grid_check(gt, ctab, exB, exCls, sp.erf_inv_result, v[0], v[1], P0, P1, P2, P3);
+        if (ok && gtab_bytes > 0) ok = grid_check(g, gt, ctab, exB, exCls, sp.erf_inv_result, v[0], v[1], P0, P1, P2, P3);
         valid[i] = ok ? 1 : 0;
     }
     if (!waited) stage_wait((uint32_t)gtab_bytes, bar);   // never exit with a copy in flight
@@ -189,7 +198,8 @@ __host__ __device__ inline int grid_smem_bytes(int gtab_bytes) {
 
 template <bool TRAJ, bool EXPAND>
 __global__ void __launch_bounds__(CCK_GRID_THREADS, CCK_GRID_MINB) k_rollout_lin_grid(const __grid_constant__ RolloutArgs a, const __grid_constant__ LinDev p,
-                                                                          const __grid_constant__ SvcDev sp, const int range_log2) {
+                                                                          const __grid_constant__ SvcDev sp, const __grid_constant__ GridConst g,
+                                                                          const int range_log2) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
     unsigned char* gt = smem_raw + 16;
@@ -276,8 +286,12 @@ __global__ void __launch_bounds__(CCK_GRID_THREADS, CCK_GRID_MINB) k_rollout_lin
         lin_step(cur, dux, duy, p, cur);
         const double x = cur.mx, y = cur.my;
         const double P0 = cur.S[0] + cur.L[0], P1 = cur.S[1] + cur.L[1], P2 = cur.S[2] + cur.L[2], P3 = cur.S[3] + cur.L[3];
-        bool ok = !(x - eps > sp.high[0] || x + eps < sp.low[0] || y - eps > sp.high[1] || y + eps < sp.low[1]);   // satisfiesBounds (NaN passes)
-        if (ok && a.ftab_bytes > 0) ok = grid_check(gt, a.tab, a.exB, a.exCls, c, x, y, P0, P1, P2, P3);
+        // satisfiesBounds (NaN passes): the mean rounded to fp32 strictly inside the inward-rounded bounds proves it
+        // (RN is monotone: xf < bhx <= high implies x < high); otherwise the exact fp64 test decides
+        const float xf = __double2float_rn(x), yf = __double2float_rn(y);
+        bool ok = (xf > g.blx) & (xf < g.bhx) & (yf > g.bly) & (yf < g.bhy);
+        if (!ok) ok = !(x - eps > sp.high[0] || x + eps < sp.low[0] || y - eps > sp.high[1] || y + eps < sp.low[1]);
+        if (ok && a.ftab_bytes > 0) ok = grid_check(g, gt, a.tab, a.exB, a.exCls, c, x, y, P0, P1, P2, P3);
         int r = -1;                // >= 0: this rollout ends now with r valid steps
         if (!ok) {
             r = t;                 // died: the result is the last valid state

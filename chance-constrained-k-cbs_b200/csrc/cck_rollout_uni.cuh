@@ -96,7 +96,8 @@ __host__ __device__ inline int uni_smem_bytes(int tab_bytes) { return 16 + tab_b
 
 template <int KIND, bool TRAJ, bool EXPAND>
 __global__ void __launch_bounds__(CCK_UNI_THREADS, 2) k_rollout_uni2(const __grid_constant__ RolloutArgs a, const __grid_constant__ UniDev p,
-                                                                    const __grid_constant__ SvcDev sp, const int range_log2) {
+                                                                    const __grid_constant__ SvcDev sp, const __grid_constant__ GridConst g,
+                                                                    const int range_log2) {
     // KIND == Blackmore: a.ftab is the grid table (staged), a.tab the class table (global, exact path only);
     // other kinds: a.ftab == a.tab is the class table (staged)
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -191,7 +192,7 @@ __global__ void __launch_bounds__(CCK_UNI_THREADS, 2) k_rollout_uni2(const __gri
         const double P0 = S[0] + L[0], P1 = S[1] + L[1], P2 = S[4] + L[4], P3 = S[5] + L[5];   // (x, xdot) block, quirk 2
         bool ok = bounds_ok(sp, v);
         if (ok && has_obstacles) {
-            if (KIND == CCK_SVC_BLACKMORE) ok = grid_check(tab, a.tab, a.exB, a.exCls, c, v[0], v[1], P0, P1, P2, P3);
+            if (KIND == CCK_SVC_BLACKMORE) ok = grid_check(g, tab, a.tab, a.exB, a.exCls, c, v[0], v[1], P0, P1, P2, P3);
             else if (KIND == CCK_SVC_ADAPTIVE) ok = halfplane_check<true>(tab, v[0], v[1], P0, P1, P2, P3, adaptive_c(sp, tab, v[0], v[1]));
             else ok = chisq_check(sp, tab, v[0], v[1], P0, P1, P2, P3);
         }
