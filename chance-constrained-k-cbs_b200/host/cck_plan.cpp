@@ -2,6 +2,7 @@
 // belief models, running the batched GPU low-level planner under the K-CBS search.
 //   cck_plan -m maps/x.map -s scens/x.scen -k 2 [--solver K-CBS] [--lowlevel BSST] [--svc Blackmore]
 //            [--pvc Blackmore] [-p 0.9] [-t 300] [--K 1024] [--seed 1] [--lltime 5] [--devices 1] [--output plan.txt]
+//            [--export DIR]   (the reference's exportBeliefPlan files: DIR/agentNN.txt, DIR/agentNN_covs.txt; DIR must exist)
 // Prints one JSON line; --output writes the plan as text: per robot a line "robot r T W" followed by T rows.
 #include <cstdio>
 #include <cstdlib>
@@ -12,7 +13,7 @@
 using namespace cck_b200;
 
 int main(int argc, char** argv) {
-    std::string map, scen, solver = "K-CBS", lowlevel = "BSST", svc = "Blackmore", pvc = "Blackmore", output;
+    std::string map, scen, solver = "K-CBS", lowlevel = "BSST", svc = "Blackmore", pvc = "Blackmore", output, export_dir;
     int k = 1, K = 1024, devices = 1;
     double p_safe = 0.9, time_s = 300.0, lltime = 5.0;
     uint64_t seed = 1;
@@ -33,6 +34,7 @@ int main(int argc, char** argv) {
         else if (a == "--seed") seed = std::strtoull(next().c_str(), nullptr, 10);
         else if (a == "--devices") devices = std::atoi(next().c_str());
         else if (a == "-o" || a == "--output") output = next();
+        else if (a == "--export") export_dir = next();
         else { std::fprintf(stderr, "unknown flag %s\n", a.c_str()); return 2; }
     }
     if (solver != "K-CBS" || lowlevel != "BSST") { std::fprintf(stderr, "only --solver K-CBS --lowlevel BSST are in scope\n"); return 2; }
@@ -48,6 +50,7 @@ int main(int argc, char** argv) {
                     "\"tree_nodes\": %lld, \"obstacles\": %zu, \"agents\": %d, \"K\": %d}\n",
                     r.solved ? "true" : "false", r.seconds, r.cost, r.nodes_expanded, r.replans, (long long)launches, (long long)cands, (long long)nodes,
                     inst->getObstacles().size(), k, K);
+        if (!export_dir.empty() && r.solved) exportBeliefPlan(r.paths, export_dir);
         if (!output.empty() && r.solved) {
             FILE* f = std::fopen(output.c_str(), "w");
             for (int i = 0; i < k; ++i) {

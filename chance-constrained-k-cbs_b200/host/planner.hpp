@@ -12,6 +12,7 @@
 // [1,10] steps (OmplSetUp.cpp:225); controls uniform in the control bounds.
 #pragma once
 #include <chrono>
+#include <fstream>
 #include <future>
 #include <cmath>
 #include <limits>
@@ -59,6 +60,15 @@ struct PlannerParams {
     double goal_threshold = 2.0, goal_p_safe = 0.95;   // ChanceConstrainedGoal(si, goal, 2.0, 0.95)  (OmplSetUp.cpp:239)
     int min_steps = 1, max_steps = 10;
     uint64_t seed = 1;
+};
+
+// The solution as the reference's PathControl holds it (ConstraintRespectingBSST.cpp:327-349): tree-node states,
+// the control held on each segment and its duration in seconds (steps * stepSize).
+struct SegmentPath {
+    int dim = 2;
+    std::vector<std::vector<double>> states;     // n+1 belief records [W]
+    std::vector<std::vector<double>> controls;   // n control vectors [dim]
+    std::vector<double> durations;               // n durations (seconds)
 };
 
 struct PlannerStats { int64_t launches = 0, candidates = 0, accepted = 0, nodes = 0; double seconds = 0; };
@@ -121,6 +131,7 @@ public:
     const GpuContextPtr& gpu() const { return gpu_; }
     int dim() const { return dim_; }
     const PlannerStats& stats() const { return stats_; }
+    const SegmentPath& lastSolutionPath() const { return last_path_; }   // segments of the last trajectory solve() returned
 
     // ConstraintRespectingPlanner::updateConstraints + clear
     void updateConstraints(const std::vector<ConstraintPtr>& c) { constraints_ = c; clear(); }
@@ -277,6 +288,13 @@ private:
         Trajectory tr;
         tr.push_back(BeliefState{dim_, motions_[chain[0]].state});
         const int n = (int)chain.size() - 1;
+        last_path_ = SegmentPath{};
+        last_path_.dim = dim_;
+        for (size_t s = 0; s < chain.size(); ++s) {
+            const Motion& m = motions_[chain[s]];
+            last_path_.states.push_back(m.state);
+            if (s > 0) { last_path_.controls.emplace_back(m.ctrl, m.ctrl + dim_); last_path_.durations.push_back(0.2 * m.steps); }
+        }
         if (n <= 0) return tr;
         int T = 0;
         for (int s = 1; s <= n; ++s) T = std::max(T, motions_[chain[s]].steps);
@@ -316,6 +334,7 @@ private:
     std::unique_ptr<DeviceTree> nodes_dev_, wit_dev_;
     double max_eig_ = 10.0;                                            // :221
     PlannerStats stats_;
+    SegmentPath last_path_;
 };
 
 // ---------------------------------------------------------------------------
@@ -323,7 +342,7 @@ private:
 // conflict spawns two children, one per involved agent, each re-planned under the union of that
 // agent's constraints along the branch.  (The merge block is unimplemented in the reference.)
 // ---------------------------------------------------------------------------
-struct KCBSResult { bool solved = false; Plan plan; double cost = 0, seconds = 0; int nodes_expanded = 0, replans = 0; };
+struct KCBSResult { bool solved = false; Plan plan; std::vector<SegmentPath> paths; double cost = 0, seconds = 0; int nodes_expanded = 0, replans = 0; };
 
 class KCBS {
 public:
@@ -335,7 +354,7 @@ public:
     BatchedBSST& planner(int r) { return *planners_[r]; }
 
     KCBSResult solve(double seconds) {
-        struct Node { Plan plan; double cost; std::vector<ConstraintPtr> cons; };
+        struct Node { Plan plan; std::vector<SegmentPath> paths; double cost; std::vector<ConstraintPtr> cons; };
         auto cmp = [](const std::shared_ptr<Node>& a, const std::shared_ptr<Node>& b) { return a->cost > b->cost; };
         std::priority_queue<std::shared_ptr<Node>, std::vector<std::shared_ptr<Node>>, decltype(cmp)> pq(cmp);
         const auto t0 = std::chrono::steady_clock::now();
@@ -351,6 +370,7 @@ public:
             if (t.empty()) { res.seconds = elapsed(); return res; }
             root->cost += 0.2 * (double)(t.size() - 1);                 // sum of control durations (KCBSNode::updatePlanAndCost)
             root->plan.push_back(std::move(t));
+            root->paths.push_back(planners_[r]->lastSolutionPath());
         }
         pq.push(root);
         const PlanValidityCheckerPtr& pv = planners_[0]->getPlanValidator();
@@ -358,7 +378,7 @@ public:
             auto cur = pq.top(); pq.pop();
             res.nodes_expanded++;
             const std::vector<ConflictPtr> confs = pv->validatePlan(cur->plan);      // :289
-            if (confs.empty()) { res.solved = true; res.plan = cur->plan; res.cost = cur->cost; break; }
+            if (confs.empty()) { res.solved = true; res.plan = cur->plan; res.paths = cur->paths; res.cost = cur->cost; break; }
             const int agents[2] = {confs.front()->agent1Idx_, confs.front()->agent2Idx_};
             // :389-467: the two child replans are independent (different agents, each planner owns its context,
             // stream and device trees), so they run concurrently — on different GPUs when n_devices > 1
@@ -383,6 +403,7 @@ public:
                 if (t.empty()) continue;                                 // failed replans are dropped (the reference re-queues them at infinite cost)
                 child[i]->cost += 0.2 * ((double)t.size() - (double)child[i]->plan[a].size());
                 child[i]->plan[a] = std::move(t);
+                child[i]->paths[a] = planners_[a]->lastSolutionPath();
                 pq.push(child[i]);
             }
         }
@@ -394,5 +415,31 @@ private:
     double ll_seconds_;
     std::vector<std::unique_ptr<BatchedBSST>> planners_;
 };
+
+// exportBeliefPlan (src/utils/postProcess.cpp:381-417): solutions/<name>/agentNN.txt in OMPL's
+// PathControl::printAsMatrix layout (first row: start state and zeros for control + duration; then one row per
+// segment: node state, control, duration) and agentNN_covs.txt with Sigma + Lambda (row-major) of every node,
+// both with the default ostream precision the reference writes.
+inline void exportBeliefPlan(const std::vector<SegmentPath>& plan, const std::string& dir) {
+    for (size_t i = 0; i < plan.size(); ++i) {
+        const SegmentPath& p = plan[i];
+        const std::string num = (i < 10 ? "0" : "") + std::to_string(i);
+        std::ofstream file(dir + "/agent" + num + ".txt");
+        const int d = p.dim;
+        for (int f = 0; f < d; ++f) file << p.states[0][f] << " ";
+        for (int f = 0; f < d + 1; ++f) file << "0 ";
+        file << '\n';
+        for (size_t s = 0; s < p.controls.size(); ++s) {
+            for (int f = 0; f < d; ++f) file << p.states[s + 1][f] << " ";
+            for (int f = 0; f < d; ++f) file << p.controls[s][f] << ' ';
+            file << p.durations[s] << '\n';
+        }
+        std::ofstream covs(dir + "/agent" + num + "_covs.txt");
+        for (const auto& st : p.states) {
+            for (int f = 0; f < d * d; ++f) covs << st[d + f] + st[d + d * d + f] << " ";
+            covs << std::endl;
+        }
+    }
+}
 
 }  // namespace cck_b200

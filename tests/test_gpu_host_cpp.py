@@ -82,3 +82,29 @@ def test_kcbs_plan_verified_by_oracle(O, tmp_path, fixture, k, tmax):
         # consecutive states differ by one dt step of a bounded control: |dx| <= 0.2
         assert np.abs(np.diff(t[:, :2], axis=0)).max() <= 0.2 + 1e-12
     assert O.Pvc(world, O.PVC_BLACKMORE).validate_plan(trajs, 2) == []        # conflict free per the oracle
+
+
+def test_export_belief_plan_format(tmp_path):
+    """exportBeliefPlan (postProcess.cpp:381-417): agentNN.txt rows = state | control | duration (first row zeros),
+    agentNN_covs.txt rows = Sigma + Lambda; the segment durations add up to the interpolated plan's length."""
+    build_host()
+    g = np.load(os.path.join(GOLDEN, "config1_empty8_linear_k2.npz"))
+    mp, sc = write_instance(tmp_path, g, "exp")
+    exp = tmp_path / "solutions"
+    exp.mkdir()
+    plan_path = str(tmp_path / "plan.txt")
+    out = subprocess.run([os.path.join(HOST, "cck_plan"), "-m", mp, "-s", sc, "-k", "2", "-t", "60", "--K", "512", "--seed", "5", "--lltime", "20",
+                          "-o", plan_path, "--export", str(exp)], capture_output=True, text=True, timeout=180)
+    assert out.returncode == 0, out.stdout + out.stderr
+    trajs = read_plan(plan_path)
+    for r in range(2):
+        rows = np.loadtxt(exp / f"agent0{r}.txt", ndmin=2)
+        covs = np.loadtxt(exp / f"agent0{r}_covs.txt", ndmin=2)
+        assert rows.shape[1] == 2 + 2 + 1 and covs.shape == (rows.shape[0], 4)
+        assert np.array_equal(rows[0], [g["starts"][r, 0], g["starts"][r, 1], 0, 0, 0])
+        assert np.all(np.abs(rows[1:, 2:4]) <= 1.0) and np.all(rows[1:, 4] >= 0.2 - 1e-9) and np.all(rows[1:, 4] <= 2.0 + 1e-9)
+        steps = np.rint(rows[1:, 4] / 0.2).astype(int)
+        assert steps.sum() == len(trajs[r]) - 1                      # durations cover the interpolated trajectory
+        idx = np.concatenate([[0], np.cumsum(steps)])
+        assert np.allclose(rows[:, :2], trajs[r][idx, :2], rtol=1e-5, atol=1e-5)    # node states = interpolated states at segment ends
+        assert np.allclose(covs, trajs[r][idx, 2:6] + trajs[r][idx, 6:10], rtol=1e-5, atol=1e-7)
