@@ -67,7 +67,7 @@ SYMBOLS = [
     "cck_set_constraints", "cck_satisfies_constraints", "cck_satisfies_constraints_dev",
     "cck_expand_batch", "cck_expand_batch_dev", "cck_rollout_summary_dev", "cck_select_winner_dev", "cck_measure_fp64_peak",
     "cck_tree_create", "cck_tree_destroy", "cck_tree_clear", "cck_tree_size", "cck_tree_append", "cck_tree_update",
-    "cck_tree_select", "cck_tree_nearest", "cck_belief_distance", "cck_belief_distance_lower",
+    "cck_tree_select", "cck_tree_nearest", "cck_belief_distance", "cck_belief_distance_lower", "cck_belief_distance_cols",
 ]
 
 
@@ -148,6 +148,7 @@ def lib():
     L.cck_tree_nearest.argtypes = [vp, i64, vp, i64, vp, vp]
     L.cck_belief_distance.argtypes = [vp, C.c_int, i64, vp, i64, vp, i64, vp]
     L.cck_belief_distance_lower.argtypes = [vp, C.c_int, i64, vp, i64, vp]
+    L.cck_belief_distance_cols.argtypes = [vp, C.c_int, i64, vp, i64, C.c_int32, vp, vp]
     _lib = L
     return L
 
@@ -465,6 +466,18 @@ def belief_distance_lower(ctx, bel, dim):
     out = np.zeros((n, n))
     ctx._ck(ctx.L.cck_belief_distance_lower(ctx.h, dim, n, _ptr(bel), n, _ptr(out)))
     return np.tril(out, -1)
+
+
+def belief_distance_cols(ctx, bel, dim, cols):
+    """[n, nf]: entry (q, a) = distance(b_cols[a], b_q) where cols[a] < q (0 elsewhere)."""
+    bel = np.ascontiguousarray(bel, dtype=np.float64)
+    cols = np.ascontiguousarray(cols, dtype=np.int32)
+    n, nf = bel.shape[1], len(cols)
+    out = np.zeros((n, max(nf, 1)))
+    ctx._ck(ctx.L.cck_belief_distance_cols(ctx.h, dim, n, _ptr(bel), n, nf, _ptr(cols), _ptr(out)))
+    out = out[:, :nf]
+    out[np.arange(n)[:, None] <= cols[None, :]] = 0.0
+    return out
 
 
 def aos_to_soa(b):

@@ -64,6 +64,7 @@ struct cck_ctx {
 
     unsigned char* d_cons = nullptr;   // constraint table (nullptr = no constraints)
     size_t cons_cap = 0;
+    int cons_bytes = 0;                // size of the current constraint table (staged into shared memory when small)
 
     // pinned staging block of the small-batch path (planner-sized launches: one H2D, one launch, one D2H)
     unsigned char* h_stage = nullptr;
@@ -803,7 +804,7 @@ static int launch_rollout(cck_ctx* c, cudaStream_t s, const RolloutArgs& a) {
         const int rl2 = rollout_range_log2(a.n);
         const int64_t nr = (a.n + ((int64_t)1 << rl2) - 1) >> rl2;
         const int gb = (int)std::min<int64_t>(nr, (int64_t)c->num_sms * 4);
-        const int gsmem = grid_smem_bytes(c->gtab_bytes);
+        const int gsmem = grid_smem_bytes(c->gtab_bytes) + (EXPAND ? a.cons_smem_bytes : 0);
         if (traj) { if ((rc = set_smem(c, (k_rollout_lin_grid<true, EXPAND>), gsmem))) return rc;
                     k_rollout_lin_grid<true, EXPAND><<<gb, CCK_GRID_THREADS, gsmem, s>>>(g2, c->lin, c->svc, c->gconst, rl2); }
         else { if ((rc = set_smem(c, (k_rollout_lin_grid<false, EXPAND>), gsmem))) return rc;
@@ -844,7 +845,7 @@ static int launch_rollout(cck_ctx* c, cudaStream_t s, const RolloutArgs& a) {
         const int rl2 = rollout_range_log2(a.n);
         const int64_t nr = (a.n + ((int64_t)1 << rl2) - 1) >> rl2;
         const int gb = (int)std::min<int64_t>(nr, (int64_t)c->num_sms * 2);
-        const int usmem = uni_smem_bytes(g2.ftab_bytes);
+        const int usmem = uni_smem_bytes(g2.ftab_bytes) + (EXPAND ? a.cons_smem_bytes : 0);
         if (usmem > c->max_smem_optin) return fail(c, CCK_ERR_INVALID, "obstacle table exceeds shared memory; M too large");
 #define LAUNCH_U2(KIND, TRAJ)                                                                        \
     do {                                                                                             \
@@ -896,6 +897,7 @@ extern "C" int cck_expand_batch_dev(cck_ctx* c, void* stream, int64_t n, const d
     a.tab = c->d_tab; a.tab_bytes = c->tab_bytes; a.duration = c->model.dt;
     a.parent_step = parent_step; a.parent_cost = parent_cost; a.cost = cost; a.goal_dist = goal_dist; a.flags = flags;
     a.goal = *goal; a.cons = c->d_cons;
+    a.cons_smem_bytes = (c->d_cons && c->cons_bytes <= CCK_CONS_SMEM_MAX) ? c->cons_bytes : 0;   // small tables are copied into shared memory by each CTA
     a.ftab = c->d_ftab; a.ftab_bytes = c->ftab_bytes; a.exB = c->d_exB; a.exCls = c->d_exCls;
     return launch_rollout<true>(c, pick(c, stream), a);
 }
@@ -934,7 +936,7 @@ extern "C" int cck_set_constraints(cck_ctx* c, int n_entries, const int32_t* ent
     if (!c->has_pvc) return fail(c, CCK_ERR_INVALID, "cck_set_pvc has not been called");
     CK(c, cudaSetDevice(c->device));
     CK(c, cudaStreamSynchronize(c->stream));
-    if (n_entries <= 0) { cudaFree(c->d_cons); c->d_cons = nullptr; c->cons_cap = 0; return CCK_OK; }
+    if (n_entries <= 0) { cudaFree(c->d_cons); c->d_cons = nullptr; c->cons_cap = 0; c->cons_bytes = 0; return CCK_OK; }
     if (!ent_step || !pair_ab || !mu2 || !cov4) return fail(c, CCK_ERR_INVALID, "null constraint arrays");
     int max_step = 0;
     for (int e = 0; e < n_entries; ++e) {
@@ -970,10 +972,11 @@ extern "C" int cck_set_constraints(cck_ctx* c, int n_entries, const int32_t* ent
     }
     if (total > c->cons_cap) {
         cudaFree(c->d_cons); c->d_cons = nullptr; c->cons_cap = 0;
-        CK(c, cudaMalloc(&c->d_cons, total));
+        CK(c, cudaMalloc(&c->d_cons, total + 16));
         c->cons_cap = total;
     }
     CK(c, cudaMemcpy(c->d_cons, buf.data(), total, cudaMemcpyHostToDevice));
+    c->cons_bytes = (int)((total + 15) & ~(size_t)15);
     return CCK_OK;
 }
 
@@ -1404,6 +1407,31 @@ extern "C" int cck_belief_distance_lower(cck_ctx* c, int dim, int64_t n, const d
     c->launches++;
     CK(c, cudaGetLastError());
     CK(c, cudaMemcpyAsync(out, d_o, (size_t)n * n * 8, cudaMemcpyDeviceToHost, s));   // entries with i >= q are unspecified
+    CK(c, cudaStreamSynchronize(s));
+    return CCK_OK;
+}
+
+extern "C" int cck_belief_distance_cols(cck_ctx* c, int dim, int64_t n, const double* bel, int64_t ld, int32_t nf, const int32_t* cols, double* out) {
+    if (!c) return CCK_ERR_INVALID;
+    if ((dim != 2 && dim != 4) || n < 0 || ld < n || nf < 0 || n > 65536 || (n > 0 && nf > 0 && (!bel || !cols || !out)))
+        return fail(c, CCK_ERR_INVALID, "bad distance-columns arguments (n <= 65536)");
+    if (n == 0 || nf == 0) return CCK_OK;
+    for (int a = 0; a < nf; ++a) if (cols[a] < 0 || cols[a] >= n) return fail(c, CCK_ERR_INVALID, "distance column out of range");
+    CK(c, cudaSetDevice(c->device));
+    int rc;
+    const int W = dim + 2 * dim * dim;
+    const size_t b_in = al256((size_t)n * W * 8), b_c = al256((size_t)nf * 4), b_o = al256((size_t)n * nf * 8);
+    if ((rc = ensure_scratch(c, 0, b_in + b_c + b_o))) return rc;
+    unsigned char* p = (unsigned char*)c->d_scratch[0];
+    double* d_b = (double*)p; int32_t* d_c = (int32_t*)(p + b_in); double* d_o = (double*)(p + b_in + b_c);
+    cudaStream_t s = c->pipe[0];
+    CK(c, h2d_planes(d_b, bel, 8, n, ld, W, s));
+    CK(c, cudaMemcpyAsync(d_c, cols, (size_t)nf * 4, cudaMemcpyHostToDevice, s));
+    if (dim == 2) k_distance_cols<2><<<(int)n, 128, 0, s>>>(n, d_b, n, nf, d_c, d_o);
+    else k_distance_cols<4><<<(int)n, 128, 0, s>>>(n, d_b, n, nf, d_c, d_o);
+    c->launches++;
+    CK(c, cudaGetLastError());
+    CK(c, cudaMemcpyAsync(out, d_o, (size_t)n * nf * 8, cudaMemcpyDeviceToHost, s));   // entries with cols[a] >= q are unspecified
     CK(c, cudaStreamSynchronize(s));
     return CCK_OK;
 }

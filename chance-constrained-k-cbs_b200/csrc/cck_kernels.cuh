@@ -10,6 +10,7 @@
 
 namespace cck {
 
+#define CCK_CONS_SMEM_MAX 16384
 struct RolloutArgs {
     int64_t n;
     const double* bel; int64_t ld;
@@ -25,6 +26,7 @@ struct RolloutArgs {
     double* cost; double* goal_dist; uint8_t* flags;
     cck_goal_params goal;
     const unsigned char* cons;   // constraint table (global memory)
+    int32_t cons_smem_bytes;     // > 0: the table is small, every CTA copies it into shared memory first (multiple of 16)
     // Blackmore fast path: fp32 filter table (staged to smem) + exact rows (global, slow path only)
     const unsigned char* ftab; int32_t ftab_bytes;
     const double* exB; const int32_t* exCls;

@@ -208,6 +208,15 @@ __global__ void __launch_bounds__(CCK_GRID_THREADS, CCK_GRID_MINB) k_rollout_lin
     double* slot = reinterpret_cast<double*>(smem_raw + 16 + a.ftab_bytes + 16 + CCK_GRID_THREADS * 80) + threadIdx.x;   // plane f at slot[f*128]
     int* islot = reinterpret_cast<int*>(smem_raw + 16 + a.ftab_bytes + 16 + CCK_GRID_THREADS * 80 + 13 * CCK_GRID_THREADS * 8) + threadIdx.x;
     if (threadIdx.x == 0) *next_k = 0;
+    // EXPAND: a small constraint table is copied behind the prefetch slots (a dependent global load per step and
+    // candidate is what a planner-sized launch would otherwise wait for)
+    const unsigned char* cons = a.cons;
+    if (EXPAND && a.cons_smem_bytes > 0) {
+        unsigned char* sc = smem_raw + grid_smem_bytes(a.ftab_bytes);
+        for (int o = threadIdx.x * 16; o < a.cons_smem_bytes; o += CCK_GRID_THREADS * 16)
+            *reinterpret_cast<uint4*>(sc + o) = *reinterpret_cast<const uint4*>(a.cons + o);
+        cons = sc;
+    }
     stage_begin(gt, a.ftab, (uint32_t)a.ftab_bytes, bar);   // __syncthreads inside
     const double eps = DBL_EPSILON;
     const double c = sp.erf_inv_result;
@@ -299,7 +308,7 @@ __global__ void __launch_bounds__(CCK_GRID_THREADS, CCK_GRID_MINB) k_rollout_lin
             cur.mx = s0.x; cur.my = s0.y; cur.S[0] = s1.x; cur.S[1] = s1.y; cur.S[2] = s2.x; cur.S[3] = s2.y;
             cur.L[0] = s3.x; cur.L[1] = s3.y; cur.L[2] = s4.x; cur.L[3] = s4.y;
         } else {
-            if (EXPAND && a.cons) cons_ok = cons_ok && constraints_ok_at(a.cons, pstep + t + 1, x, y, P0, P1, P2, P3);
+            if (EXPAND && cons) cons_ok = cons_ok && constraints_ok_at(cons, pstep + t + 1, x, y, P0, P1, P2, P3);
             if (TRAJ) {
                 double* tp = a.traj + (int64_t)t * 10 * a.traj_ld + i;
                 tp[0] = cur.mx; tp[a.traj_ld] = cur.my;

@@ -106,6 +106,13 @@ __global__ void __launch_bounds__(CCK_UNI_THREADS, 2) k_rollout_uni2(const __gri
     int* next_k = reinterpret_cast<int*>(smem_raw + 16 + a.ftab_bytes);
     double* stash = reinterpret_cast<double*>(smem_raw + 16 + a.ftab_bytes + 16) + threadIdx.x;   // plane f at stash[f*128]
     if (threadIdx.x == 0) *next_k = 0;
+    const unsigned char* cons = a.cons;
+    if (EXPAND && a.cons_smem_bytes > 0) {   // small constraint table: shared memory copy (see k_rollout_lin_grid)
+        unsigned char* sc = smem_raw + uni_smem_bytes(a.ftab_bytes);
+        for (int o = threadIdx.x * 16; o < a.cons_smem_bytes; o += CCK_UNI_THREADS * 16)
+            *reinterpret_cast<uint4*>(sc + o) = *reinterpret_cast<const uint4*>(a.cons + o);
+        cons = sc;
+    }
     stage_begin(tab, a.ftab, (uint32_t)a.ftab_bytes, bar);
     stage_wait((uint32_t)a.ftab_bytes, bar);
     const double c = sp.erf_inv_result;
@@ -204,9 +211,9 @@ __global__ void __launch_bounds__(CCK_UNI_THREADS, 2) k_rollout_uni2(const __gri
 #pragma unroll
             for (int f = 0; f < 16; ++f) { S[f] = stash[(4 + f) * CCK_UNI_THREADS]; L[f] = stash[(20 + f) * CCK_UNI_THREADS]; }
         } else {
-            if (EXPAND && a.cons) {
+            if (EXPAND && cons) {
                 // getDistribution_ picks entries (0,0),(0,2),(2,0),(2,2) (BeliefPVC.cpp:94-97)
-                cons_ok = cons_ok && constraints_ok_at(a.cons, pstep + t + 1, v[0], v[1], S[0] + L[0], S[2] + L[2], S[8] + L[8], S[10] + L[10]);
+                cons_ok = cons_ok && constraints_ok_at(cons, pstep + t + 1, v[0], v[1], S[0] + L[0], S[2] + L[2], S[8] + L[8], S[10] + L[10]);
             }
             if (TRAJ) {
                 double* tp = a.traj + (int64_t)t * 36 * a.traj_ld + i;

@@ -246,6 +246,36 @@ __global__ void __launch_bounds__(128) k_distance_lower(int64_t n, const double*
     }
 }
 
+// selected columns of the same matrix: out[q*nf + a] = distance(b_cols[a], b_q) for cols[a] < q.  Only candidates
+// that are farther than the pruning radius from every existing witness can become witnesses themselves, so the
+// planner asks for those columns only (usually a handful once the tree is established).
+template <int DIM>
+__global__ void __launch_bounds__(128) k_distance_cols(int64_t n, const double* __restrict__ bel, int64_t ld, int nf,
+                                                       const int32_t* __restrict__ cols, double* __restrict__ out) {
+    const int64_t q = blockIdx.x;
+    double qm[DIM], qC[DIM * DIM], qS[DIM * DIM];
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) qm[d] = bel[d * ld + q];
+#pragma unroll
+    for (int f = 0; f < DIM * DIM; ++f) qC[f] = bel[(DIM + f) * ld + q] + bel[(DIM + DIM * DIM + f) * ld + q];
+    sym_sqrt<DIM, false>(qC, qS);
+    for (int a = threadIdx.x; a < nf; a += blockDim.x) {
+        const int64_t i = cols[a];
+        if (i >= q) continue;
+        double d2 = 0;
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) { const double e = bel[d * ld + i] - qm[d]; d2 += e * e; }
+        double dist = 0;
+        if (d2 != 0) {
+            double C[DIM * DIM];
+#pragma unroll
+            for (int f = 0; f < DIM * DIM; ++f) C[f] = bel[(DIM + f) * ld + i] + bel[(DIM + DIM * DIM + f) * ld + i];
+            dist = fabs(d2 + cov_term<DIM>(C, qC, qS));
+        }
+        out[q * nf + a] = dist;
+    }
+}
+
 // plain batched distance(a_i, b_i) (second argument's sqrt, as RealVectorBeliefSpace::distance(state1, state2))
 template <int DIM>
 __global__ void __launch_bounds__(128) k_belief_distance(int64_t n, const double* __restrict__ a, int64_t lda, const double* __restrict__ b,

@@ -211,10 +211,20 @@ private:
             std::vector<double> q((size_t)W_ * S), qcost(S);
             for (int s = 0; s < S; ++s) { const int j = surv[c0 + s]; for (int f = 0; f < W_; ++f) q[(size_t)f * S + s] = out[(size_t)f * K + j]; qcost[s] = cost[j]; }
             std::vector<int32_t> widx(S);
-            std::vector<double> wdist(S), lower((size_t)S * S);
+            std::vector<double> wdist(S);
             wit_dev_->nearest(S, q.data(), S, widx.data(), wdist.data());
-            gpu_->check(cck_belief_distance_lower(gpu_->get(), dim_, S, q.data(), S, lower.data()), "cck_belief_distance_lower");
-            stats_.launches += 2;
+            stats_.launches++;
+            // only survivors farther than the pruning radius from every existing witness can become witnesses:
+            // their columns of the batch's distance matrix are all the sequential replay needs
+            std::vector<int32_t> cols;
+            std::vector<int> col_of(S, -1);
+            for (int s = 0; s < S; ++s) if (widx[s] < 0 || wdist[s] > prm_.pruning_radius) { col_of[s] = (int)cols.size(); cols.push_back(s); }
+            const int nf = (int)cols.size();
+            std::vector<double> dcols((size_t)S * std::max(nf, 1));
+            if (nf > 0) {
+                gpu_->check(cck_belief_distance_cols(gpu_->get(), dim_, S, q.data(), S, nf, cols.data(), dcols.data()), "cck_belief_distance_cols");
+                stats_.launches++;
+            }
             std::vector<std::pair<int, int>> fresh;       // (survivor s, witness index) of witnesses created in this chunk
             std::vector<int32_t> deact;
             std::vector<int> new_nodes;                   // survivors appended to the tree, in order
@@ -223,7 +233,7 @@ private:
                 const int j = surv[c0 + s];
                 int w = widx[s];
                 double cd = w >= 0 ? wdist[s] : std::numeric_limits<double>::infinity();
-                for (const auto& fw : fresh) { const double d = lower[(size_t)s * S + fw.first]; if (d < cd) { cd = d; w = fw.second; } }
+                for (const auto& fw : fresh) { const double d = dcols[(size_t)s * nf + col_of[fw.first]]; if (d < cd) { cd = d; w = fw.second; } }
                 const int idx = (int)motions_.size();
                 bool is_new = false;
                 if (w < 0 || cd > prm_.pruning_radius) { witnesses_.push_back(Witness{idx}); w = (int)witnesses_.size() - 1; fresh.emplace_back(s, w); is_new = true; }

@@ -249,6 +249,9 @@ int cck_belief_distance(cck_ctx* ctx, int dim, int64_t n, const double* a, int64
 /* out[q*n + i] = distance(b_i, b_q) for i < q (n <= 8192; other entries unspecified): the witness tests between
  * candidates committed from the same launch, so the sequential witness rules can be replayed on the host exactly */
 int cck_belief_distance_lower(cck_ctx* ctx, int dim, int64_t n, const double* bel, int64_t ld, double* out);
+/* the same matrix restricted to nf columns: out[q*nf + a] = distance(b_cols[a], b_q) for cols[a] < q.  Only candidates farther
+ * than the pruning radius from every existing witness can become witnesses, so the planner asks for those columns only */
+int cck_belief_distance_cols(cck_ctx* ctx, int dim, int64_t n, const double* bel, int64_t ld, int32_t nf, const int32_t* cols, double* out);
 
 
 #ifdef __cplusplus

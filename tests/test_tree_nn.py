@@ -100,6 +100,10 @@ def test_gpu_distance_lower_matrix(K, O, ctx, dim):
         ref = O.belief_distance(b[:q], np.repeat(b[q:q + 1], q, axis=0), dim)
         assert np.array_equal(got[q, :q], ref)
     assert got[7, 3] == 0.0
+    cols = np.array([0, 3, 5, 120, 298], dtype=np.int32)
+    sub = K.belief_distance_cols(ctx, K.aos_to_soa(b), dim, cols)
+    assert np.array_equal(sub, got[:, cols])
+    assert K.belief_distance_cols(ctx, K.aos_to_soa(b), dim, np.zeros(0, dtype=np.int32)).shape == (300, 0)
 
 
 @pytest.mark.gpu
