@@ -637,7 +637,7 @@ extern "C" int cck_set_obstacles(cck_ctx* c, const cck_svc_params* p, const doub
         std::memcpy(&gh, gb.buf.data(), sizeof(gh));
         const GridConst keep = c->gconst;
         c->gconst = GridConst{gh.k, gh.SX, gh.SY, gh.gx0, gh.gy0, gh.icx, gh.icy, gh.Rm1, gh.M, gh.n_grid, gh.off_occ, gh.off_rowbase, gh.off_cstart, gh.off_boxes,
-                              keep.blx, keep.bhx, keep.bly, keep.bhy};
+                              keep.blx, keep.bhx, keep.bly, keep.bhy, (int32_t)sizeof(TabHeader), 0};
     }
 
     SvcDev& s = c->svc;
@@ -799,6 +799,7 @@ static int launch_rollout(cck_ctx* c, cudaStream_t s, const RolloutArgs& a) {
     } while (0)
     if (c->model.model == CCK_MODEL_LINEAR2D && c->svc.kind == CCK_SVC_BLACKMORE && c->kern == 2) {
         // default configuration: fp32 box/bitmap-grid broad phase + exact fp64 decision, lane refill
+        if (a.n > (int64_t)INT_MAX) return fail(c, CCK_ERR_INVALID, "more than 2^31-1 beliefs in one launch");
         RolloutArgs g2 = a;
         g2.ftab = c->d_gtab; g2.ftab_bytes = c->gtab_bytes; g2.exB = c->d_gexB; g2.exCls = c->d_gexCls;
         const int rl2 = rollout_range_log2(a.n);

@@ -45,6 +45,7 @@ struct GridConst {
     float k, SX, SY, gx0, gy0, icx, icy, Rm1;
     int32_t M, n_grid, off_occ, off_rowbase, off_cstart, off_boxes;
     float blx, bhx, bly, bhy;
+    int32_t off_classes, pad;   // byte offset of the ClassRec array inside the (global) class table
 };
 
 #define CCK_GRID_COLS 64
@@ -89,8 +90,7 @@ __device__ __forceinline__ bool grid_check(const GridConst& g, const unsigned ch
                                            const int32_t* exCls, double c, double x, double y, double P0, double P1, double P2, double P3) {
     const GridConst* h = &g;
     const float4* boxes = reinterpret_cast<const float4*>(gt + h->off_boxes);
-    const TabHeader* th = reinterpret_cast<const TabHeader*>(ctab);
-    const ClassRec* cls = reinterpret_cast<const ClassRec*>(ctab + th->off_classes);
+    const ClassRec* cls = reinterpret_cast<const ClassRec*>(ctab + h->off_classes);   // a kernel constant: no header load per step
     const int M = h->M;
     const float xf = __double2float_rn(x), yf = __double2float_rn(y);
     const float p0 = __double2float_rn(P0), p3 = __double2float_rn(P3);
@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(CCK_GRID_THREADS, CCK_GRID_MINB) k_rollout_lin
     const double eps = DBL_EPSILON;
     const double c = sp.erf_inv_result;
 
-    int64_t nxt = -1;
+    int nxt = -1;                  // belief indices fit 32 bits (the launcher refuses n >= 2^31)
     // claim the next belief of this CTA (ranges blockIdx, blockIdx+gridDim, ... of 256 beliefs) and start copying it
     auto prefetch = [&]() {
         nxt = -1;
@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(CCK_GRID_THREADS, CCK_GRID_MINB) k_rollout_lin
             const int64_t base = ((int64_t)blockIdx.x + (int64_t)rg * gridDim.x) << range_log2;
             if (base >= a.n) return;
             const int64_t idx = base + (kk & ((1 << range_log2) - 1));
-            if (idx < a.n) { nxt = idx; break; }
+            if (idx < a.n) { nxt = (int)idx; break; }
         }
 #pragma unroll
         for (int f = 0; f < 10; ++f) cp_async8(slot + f * CCK_GRID_THREADS, a.bel + f * a.ld + nxt);
@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(CCK_GRID_THREADS, CCK_GRID_MINB) k_rollout_lin
     Lin cur;
     double dux = 0, duy = 0, x0 = 0, y0 = 0, pcost = 0;
     int steps = 0, t = 0, pstep = 0;
-    int64_t i = 0;
+    int i = 0;
     bool cons_ok = true;
     cur.mx = cur.my = 0;
 #pragma unroll
