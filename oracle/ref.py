@@ -1,0 +1,112 @@
+"""ctypes wrapper over oracle/_ref/libcck_ref.so: the REFERENCE'S OWN SOURCES for the headline path
+(Instance/Robot/Obstacle, R2_UncertainLinearStatePropagator, PCCBlackmoreSVC) compiled from /root/reference
+against the stand-in headers of oracle/shim/.  TEST INFRASTRUCTURE: used to pin the oracle and to generate
+the golden vectors tests/golden/ref_*.npz (oracle/gen_ref_golden.py).  Available only where /root/reference
+is mounted (this container); the prebuilt .so travels to the GPU box, the sources do not."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_ref", "libcck_ref.so")
+REFERENCE = "/root/reference"
+SOURCES = ["src/utils/common.cpp", "src/utils/Instance.cpp", "src/StatePropogators/UncertainLinearSP.cpp",
+           "src/StateValidityCheckers/PCCBlackmoreSVC.cpp"]
+
+
+def available():
+    return os.path.exists(_SO)
+
+
+def build(force=False):
+    """Compile the reference sources where they lie (Release flags of its CMakeLists: -O3 -DNDEBUG, C++17,
+    baseline x86-64).  Returns the library path, or None when /root/reference is not mounted."""
+    if not os.path.isdir(REFERENCE):
+        return _SO if os.path.exists(_SO) else None
+    srcs = [os.path.join(REFERENCE, s) for s in SOURCES]
+    deps = srcs + [os.path.join(_HERE, "ref_capi.cpp")] + [os.path.join(_HERE, "shim", f) for f in ("shim_eigen.hpp", "shim_boost.hpp", "shim_ompl.hpp")]
+    if not force and os.path.exists(_SO) and all(os.path.getmtime(_SO) >= os.path.getmtime(d) for d in deps):
+        return _SO
+    subprocess.check_call(["make", "-C", _HERE, "-s", "ref"])
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = C.CDLL(_SO)
+        dp, ip, vp, u8p = C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_void_p, C.POINTER(C.c_ubyte)
+        L.ref_world_create.restype = vp
+        L.ref_world_create.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_double]
+        L.ref_world_free.argtypes = [vp]
+        L.ref_world_info.argtypes = [vp, dp]
+        L.ref_world_obstacles.argtypes = [vp, dp]
+        L.ref_world_robots.argtypes = [vp, dp]
+        L.ref_svc_create.restype = vp
+        L.ref_svc_create.argtypes = [vp, C.c_int, dp, dp, C.c_double]
+        L.ref_svc_free.argtypes = [vp]
+        L.ref_svc_tables.argtypes = [vp, dp, dp, dp]
+        L.ref_is_valid.argtypes = [vp, C.c_long, dp, u8p]
+        L.ref_propagate.argtypes = [vp, C.c_long, dp, dp, dp]
+        L.ref_rollout.argtypes = [vp, C.c_long, dp, dp, ip, dp, ip]
+        _lib = L
+    return _lib
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+class World:
+    def __init__(self, map_path, scen_path, k, p_safe):
+        self.h = lib().ref_world_create(map_path.encode(), scen_path.encode(), k, p_safe)
+        info = np.zeros(6)
+        lib().ref_world_info(self.h, _dp(info))
+        self.n_obstacles, self.n_robots = int(info[0]), int(info[1])
+        self.x_max, self.y_max, self.p_safe_obs, self.p_safe_agents = info[2:6]
+        self.centres = np.zeros((self.n_obstacles, 2))
+        if self.n_obstacles:
+            lib().ref_world_obstacles(self.h, _dp(self.centres))
+        r = np.zeros((self.n_robots, 5))
+        lib().ref_world_robots(self.h, _dp(r))
+        self.starts, self.goals, self.bounding_rad = r[:, 0:2].copy(), r[:, 2:4].copy(), r[:, 4].copy()
+
+
+class Svc:
+    """PCCBlackmoreSVC + R2_UncertainLinearStatePropagator wired as OmplSetUp.cpp:183-228 does."""
+
+    def __init__(self, world, robot=0, step=0.2):
+        self.world = world
+        self.low = np.array([-1.0, -1.0])
+        self.high = np.array([world.x_max, world.y_max], dtype=np.float64)
+        self.h = lib().ref_svc_create(world.h, robot, _dp(self.low), _dp(self.high), step)
+        M = world.n_obstacles
+        self.A, self.B = np.zeros((M, 4, 2)), np.zeros((M, 4))
+        info = np.zeros(3)
+        lib().ref_svc_tables(self.h, _dp(self.A), _dp(self.B), _dp(info))
+        self.erf_inv_result, self.p_collision = info[0], info[1]
+
+    def is_valid(self, bel):
+        b = np.ascontiguousarray(bel, dtype=np.float64)
+        out = np.zeros(len(b), dtype=np.uint8)
+        lib().ref_is_valid(self.h, len(b), _dp(b), out.ctypes.data_as(C.POINTER(C.c_ubyte)))
+        return out.astype(bool)
+
+    def propagate(self, bel, ctrl):
+        b, u = np.ascontiguousarray(bel, dtype=np.float64), np.ascontiguousarray(ctrl, dtype=np.float64)
+        out = np.zeros_like(b)
+        lib().ref_propagate(self.h, len(b), _dp(b), _dp(u), _dp(out))
+        return out
+
+    def rollout(self, bel, ctrl, steps):
+        b, u = np.ascontiguousarray(bel, dtype=np.float64), np.ascontiguousarray(ctrl, dtype=np.float64)
+        st = np.ascontiguousarray(steps, dtype=np.int32)
+        out = np.zeros_like(b)
+        valid = np.zeros(len(b), dtype=np.int32)
+        lib().ref_rollout(self.h, len(b), _dp(b), _dp(u), st.ctypes.data_as(C.POINTER(C.c_int)), _dp(out), valid.ctypes.data_as(C.POINTER(C.c_int)))
+        return out, valid

@@ -1,0 +1,151 @@
+// shim_ompl.hpp — TEST INFRASTRUCTURE.  The OMPL 1.6 types the reference's belief space, linear propagator and
+// PCCBlackmoreSVC are written against (State::as<T>, RealVectorStateSpace::StateType, control::StatePropagator,
+// base::StateValidityChecker, SpaceInformation::getPropagationStepSize / satisfiesBounds with OMPL's
+// RealVectorBounds test: v - eps > high || v + eps < low, eps = DBL_EPSILON), no planning machinery.
+#pragma once
+#include <cfloat>
+#include <iostream>
+#include <limits>
+#include <memory>
+#include <string>
+#include <vector>
+
+#define OMPL_CLASS_FORWARD(C) class C; typedef std::shared_ptr<C> C##Ptr
+#define OMPL_INFORM(...) ((void)0)
+#define OMPL_WARN(...) ((void)0)
+#define OMPL_ERROR(...) ((void)0)
+#define OMPL_DEBUG(...) ((void)0)
+
+namespace ompl {
+namespace base {
+
+class State {
+public:
+    template <class T> const T* as() const { return static_cast<const T*>(this); }
+    template <class T> T* as() { return static_cast<T*>(this); }
+protected:
+    State() = default;
+    ~State() = default;
+};
+
+enum StateSpaceType { STATE_SPACE_UNKNOWN = 0, STATE_SPACE_REAL_VECTOR = 1 };
+
+struct RealVectorBounds {
+    std::vector<double> low, high;
+    explicit RealVectorBounds(unsigned dim = 0) : low(dim, 0.0), high(dim, 0.0) {}
+};
+
+class StateSpace {
+public:
+    virtual ~StateSpace() = default;
+    const std::string& getName() const { return name_; }
+    void setName(const std::string& n) { name_ = n; }
+    virtual State* allocState() const = 0;
+    virtual void freeState(State*) const = 0;
+    virtual void copyState(State*, const State*) const = 0;
+    virtual double distance(const State*, const State*) const = 0;
+    virtual void printState(const State*, std::ostream&) const {}
+    virtual bool satisfiesBounds(const State*) const = 0;
+protected:
+    int type_ = STATE_SPACE_UNKNOWN;
+    std::string name_ = "Space";
+};
+
+class RealVectorStateSpace : public StateSpace {
+public:
+    class StateType : public State {
+    public:
+        StateType() = default;
+        double* values = nullptr;
+    };
+    explicit RealVectorStateSpace(unsigned dim = 0) : dimension_(dim), bounds_(dim) {}
+    unsigned getDimension() const { return dimension_; }
+    void setBounds(const RealVectorBounds& b) { bounds_ = b; }
+    const RealVectorBounds& getBounds() const { return bounds_; }
+    State* allocState() const override { auto* s = new StateType(); s->values = new double[dimension_]; return s; }
+    void freeState(State* s) const override { auto* r = static_cast<StateType*>(s); delete[] r->values; delete r; }
+    void copyState(State* d, const State* s) const override {
+        for (unsigned i = 0; i < dimension_; ++i) static_cast<StateType*>(d)->values[i] = static_cast<const StateType*>(s)->values[i];
+    }
+    double distance(const State*, const State*) const override { return 0; }
+    void printState(const State*, std::ostream&) const override {}
+    // RealVectorStateSpace::satisfiesBounds (OMPL 1.6, src/ompl/base/spaces/src/RealVectorStateSpace.cpp)
+    bool satisfiesBounds(const State* state) const override {
+        const auto* r = static_cast<const StateType*>(state);
+        for (unsigned i = 0; i < dimension_; ++i)
+            if (r->values[i] - std::numeric_limits<double>::epsilon() > bounds_.high[i] ||
+                r->values[i] + std::numeric_limits<double>::epsilon() < bounds_.low[i])
+                return false;
+        return true;
+    }
+protected:
+    unsigned dimension_;
+    RealVectorBounds bounds_;
+};
+
+using StateSpacePtr = std::shared_ptr<StateSpace>;
+
+class SpaceInformation {
+public:
+    explicit SpaceInformation(StateSpacePtr s) : space_(std::move(s)) {}
+    virtual ~SpaceInformation() = default;
+    const StateSpacePtr& getStateSpace() const { return space_; }
+    bool satisfiesBounds(const State* s) const { return space_->satisfiesBounds(s); }
+protected:
+    StateSpacePtr space_;
+};
+using SpaceInformationPtr = std::shared_ptr<SpaceInformation>;
+
+class StateValidityChecker {
+public:
+    explicit StateValidityChecker(const SpaceInformationPtr& si) : si_(si.get()) {}
+    explicit StateValidityChecker(SpaceInformation* si) : si_(si) {}
+    virtual ~StateValidityChecker() = default;
+    virtual bool isValid(const State*) const = 0;
+protected:
+    SpaceInformation* si_;
+};
+
+}  // namespace base
+
+namespace control {
+
+class Control {
+public:
+    template <class T> const T* as() const { return static_cast<const T*>(this); }
+    template <class T> T* as() { return static_cast<T*>(this); }
+protected:
+    Control() = default;
+    ~Control() = default;
+};
+
+class RealVectorControlSpace {
+public:
+    class ControlType : public Control {
+    public:
+        double* values = nullptr;
+    };
+};
+
+class SpaceInformation : public base::SpaceInformation {
+public:
+    explicit SpaceInformation(base::StateSpacePtr s) : base::SpaceInformation(std::move(s)) {}
+    void setPropagationStepSize(double s) { step_ = s; }
+    double getPropagationStepSize() const { return step_; }
+private:
+    double step_ = 0.05;
+};
+using SpaceInformationPtr = std::shared_ptr<SpaceInformation>;
+
+class StatePropagator {
+public:
+    explicit StatePropagator(const SpaceInformationPtr& si) : si_(si.get()) {}
+    virtual ~StatePropagator() = default;
+    virtual void propagate(const base::State*, const Control*, double, base::State*) const = 0;
+    virtual bool canPropagateBackward() const { return true; }
+protected:
+    SpaceInformation* si_;
+};
+
+}  // namespace control
+}  // namespace ompl

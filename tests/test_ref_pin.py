@@ -1,0 +1,123 @@
+"""Pinning against the REFERENCE'S OWN SOURCES for the headline path.
+
+oracle/_ref/libcck_ref.so is built (in the container where /root/reference is mounted) from the reference's
+Instance.cpp, common.cpp, UncertainLinearSP.cpp and PCCBlackmoreSVC.cpp, compiled where they lie against the
+stand-in Eigen/Boost/OMPL headers of oracle/shim/ (every matrix product on this path has inner dimension 2, so
+the stand-in's evaluation order cannot differ from Eigen's).  tests/golden/ref_*.npz hold its outputs
+(oracle/gen_ref_golden.py).  Checked here, bit for bit:
+
+  * the oracle against the committed reference vectors (everywhere, no reference needed),
+  * the oracle against the live reference build on all of the reference's linear-model maps (this container),
+  * the CUDA path against the reference vectors (B200).
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+
+FILES = sorted(glob.glob(os.path.join(GOLDEN, "ref_*.npz")))
+IDS = [os.path.basename(f)[:-4] for f in FILES]
+
+
+def test_reference_vectors_present():
+    assert len(FILES) >= 4
+
+
+@pytest.mark.parametrize("path", FILES, ids=IDS)
+def test_oracle_matches_reference_vectors(O, path):
+    g = np.load(path)
+    k = int(g["k"])
+    w = O.World.synthetic(g["centres"], float(g["x_max"]), float(g["y_max"]), k, float(g["p_safe"]))
+    # risk split (Instance.cpp:38-44), robot bounding radius (common.cpp:61-108)
+    assert w.p_safe_obs == float(g["p_safe_obs"]) and w.p_safe_agents == float(g["p_safe_agents"])
+    svc = O.Svc(w, O.SVC_BLACKMORE, 2)
+    assert svc.max_rad == float(g["bounding_rad"][0])
+    # Minkowski half-plane tables and the erf_inv constant (PCCBlackmoreSVC.cpp:3-25, 77-145)
+    assert np.array_equal(svc.A, g["A"]) and np.array_equal(svc.B, g["B"])
+    assert svc.erf_inv_result == float(g["erf_inv_result"]) and svc.p_collision == float(g["p_collision"])
+    b, u, steps = g["beliefs"], g["controls"], g["steps"]
+    assert np.array_equal(O.propagate(b, u, 2), g["propagate"])                       # UncertainLinearSP.cpp:58-111
+    assert np.array_equal(svc.is_valid(b)[0], g["is_valid"])                           # PCCBlackmoreSVC.cpp:29-75
+    fin, nval, _ = svc.rollout(b, u, steps)
+    assert np.array_equal(nval, g["rollout_valid"]) and np.array_equal(fin, g["rollout_final"])
+    assert 0.2 < g["is_valid"].mean() < 0.95
+
+
+def test_oracle_matches_live_reference_build(O):
+    """All linear-model scenario files of the reference, parsed by the reference's own Instance.cpp."""
+    from oracle import ref as R
+    if not os.path.isdir(R.REFERENCE):
+        pytest.skip("/root/reference is not mounted here (the committed reference vectors cover this box)")
+    R.build()
+    scens = sorted(glob.glob(os.path.join(R.REFERENCE, "scens", "*2DUncertainLinear*.scen")))
+    assert scens
+    checked = 0
+    for sc in scens:
+        base = os.path.basename(sc)
+        mp = os.path.join(R.REFERENCE, "maps", base.split("-Rectangles")[0].split("-2DUncertainLinear")[0] + ".map")
+        if not os.path.exists(mp):
+            continue
+        rows = 0          # leading well-formed (tab-separated) robot rows; the reference's tokenizer walk is UB on the others
+        with open(sc) as f:
+            for ln in f.read().splitlines()[1:]:
+                if len(ln.split("\t")) < 10 or "Rectangle" not in ln:    # PointRobot has no bounding shape (quirk 11)
+                    break
+                rows += 1
+        if rows == 0:
+            continue
+        ow_probe = O.World.from_files(mp, sc, 1, 0.9)
+        if ow_probe.map_overrun:          # the reference parser indexes past the row string there (UB, quirk 13)
+            continue
+        for k in sorted({1, min(2, rows), min(5, rows), rows} - {0}):
+            rw = R.World(mp, sc, k, 0.9)
+            ow = O.World.from_files(mp, sc, k, 0.9)
+            assert rw.n_obstacles == ow.n_obstacles and np.array_equal(rw.centres, ow.centres), base
+            assert (rw.x_max, rw.y_max) == (ow.x_max, ow.y_max)
+            assert rw.p_safe_obs == ow.p_safe_obs and rw.p_safe_agents == ow.p_safe_agents
+            assert np.array_equal(rw.starts, ow.starts) and np.array_equal(rw.goals, ow.goals) and np.array_equal(rw.bounding_rad, ow.bounding_rad)
+            rs, os_ = R.Svc(rw), O.Svc(ow, O.SVC_BLACKMORE, 2)
+            assert np.array_equal(rs.A, os_.A) and np.array_equal(rs.B, os_.B) and rs.erf_inv_result == os_.erf_inv_result, (base, k)
+            rng = np.random.default_rng(k)
+            n = 1500
+            b = np.zeros((n, 10))
+            b[:, 0] = rng.uniform(-1.5, rw.x_max + 0.5, n); b[:, 1] = rng.uniform(-1.5, rw.y_max + 0.5, n)
+            L = rng.uniform(0.01, 0.2, (n, 2, 3))
+            for o, off in enumerate((2, 6)):
+                b[:, off] = L[:, o, 0] ** 2; b[:, off + 1] = b[:, off + 2] = L[:, o, 0] * L[:, o, 1]; b[:, off + 3] = L[:, o, 1] ** 2 + L[:, o, 2] ** 2
+            u = rng.uniform(-1, 1, (n, 2))
+            steps = rng.integers(0, 11, n).astype(np.int32)
+            assert np.array_equal(rs.propagate(b, u), O.propagate(b, u, 2))
+            assert np.array_equal(rs.is_valid(b), os_.is_valid(b)[0])
+            rf, rv = rs.rollout(b, u, steps)
+            of, ov, _ = os_.rollout(b, u, steps)
+            assert np.array_equal(rv, ov) and np.array_equal(rf, of)
+            checked += 1
+    assert checked >= 8
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", FILES, ids=IDS)
+def test_cuda_path_matches_reference_vectors(K, ctx, path):
+    """The product path (host table builders + kernels through the C ABI) against the reference's outputs."""
+    g = np.load(path)
+    k, M = int(g["k"]), int(g["n_obstacles"])
+    ctx.set_model(K.MODEL_LINEAR2D)
+    rad = K.rect_robot_bounding_radius(float(g["starts"][0, 0]), float(g["starts"][0, 1]))
+    assert rad == float(g["bounding_rad"][0])
+    p_safe_obs, p_safe_agents = K.split_risk(float(g["p_safe"]), M, k)
+    assert p_safe_obs == float(g["p_safe_obs"]) and p_safe_agents == float(g["p_safe_agents"])
+    A, B, rects = K.build_obstacle_tables(g["centres"], rad)
+    if M:
+        assert np.array_equal(A, g["A"]) and np.array_equal(B, g["B"])
+    c = K.erf_inv(1 - 2 * ((1 - p_safe_obs) / M)) if M else 0.0
+    assert c == float(g["erf_inv_result"])
+    ctx.set_obstacles(K.SVC_BLACKMORE, np.array([-1.0, -1.0]), np.array([float(g["x_max"]), float(g["y_max"])]), A, B, g["centres"], rects,
+                      erf_inv_result=c, p_collision=1 - p_safe_obs)
+    bel, ctrl = K.aos_to_soa(g["beliefs"]), K.aos_to_soa(g["controls"])
+    assert np.array_equal(K.soa_to_aos(ctx.propagate(bel, ctrl)), g["propagate"])
+    assert np.array_equal(ctx.is_valid(bel), g["is_valid"])
+    out, valid = ctx.propagate_while_valid(bel, ctrl, g["steps"])
+    assert np.array_equal(valid, g["rollout_valid"]) and np.array_equal(K.soa_to_aos(out), g["rollout_final"])
