@@ -8,13 +8,13 @@
 //
 // PARITY: the reference ships no tests, golden vectors or fixtures and its CMake
 // build needs OMPL 1.6.0, Eigen3 and Boost (absent, no network).
-//   PINNED (bit for bit, tests/test_ref_pin.py): the headline path — Instance/Robot/Obstacle parsing and
-//   geometry, R2_UncertainLinearStatePropagator::propagate, PCCBlackmoreSVC (Minkowski half-planes, erf_inv
-//   constant, isValid) — against the reference's OWN sources compiled where they lie against the stand-in
+//   PINNED (bit for bit, tests/test_ref_pin.py): the default-configuration path — Instance/Robot/Obstacle parsing
+//   and geometry, R2_UncertainLinearStatePropagator::propagate, PCCBlackmoreSVC (Minkowski half-planes, erf_inv
+//   constant, isValid), MinkowskiSumBlackmorePVC / BoundingBoxBlackmorePVC / BeliefPVC (validatePlan,
+//   createConstraint, satisfiesConstraints) — against the reference's OWN sources compiled where they lie against the stand-in
 //   headers of oracle/shim/ (oracle/_ref, oracle/ref_capi.cpp) and against the vectors generated from that
 //   build (tests/golden/ref_*.npz).
-//   PARITY UNPINNED for everything else (unicycle, adaptive / chi-squared checkers, plan validity checkers,
-//   goal, distance): checked only against (i) closed-form known answers derived from the reference's
+//   PARITY UNPINNED for everything else (unicycle, adaptive / chi-squared checkers, goal, distance): checked only against (i) closed-form known answers derived from the reference's
 //   formulas, (ii) scipy for erf_inv / chi-square quantiles, (iii) self-consistency.
 // Third-party arithmetic restated (source not under /root/reference):
 //   Boost.Math erf_inv, quantile(chi_squared(2)); Eigen 2x2/4x4 inverse(),

@@ -12,8 +12,9 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "_ref", "libcck_ref.so")
 REFERENCE = "/root/reference"
-SOURCES = ["src/utils/common.cpp", "src/utils/Instance.cpp", "src/StatePropogators/UncertainLinearSP.cpp",
-           "src/StateValidityCheckers/PCCBlackmoreSVC.cpp"]
+SOURCES = ["src/utils/common.cpp", "src/utils/Instance.cpp", "src/utils/Conflict.cpp", "src/StatePropogators/UncertainLinearSP.cpp",
+           "src/StateValidityCheckers/PCCBlackmoreSVC.cpp", "src/Constraints/BeliefConstraint.cpp", "src/PlanValidityCheckers/BeliefPVC.cpp",
+           "src/PlanValidityCheckers/MinkowskiSumBlackmorePVC.cpp", "src/PlanValidityCheckers/BoundingBoxBlackmorePVC.cpp"]
 
 
 def available():
@@ -26,7 +27,7 @@ def build(force=False):
     if not os.path.isdir(REFERENCE):
         return _SO if os.path.exists(_SO) else None
     srcs = [os.path.join(REFERENCE, s) for s in SOURCES]
-    deps = srcs + [os.path.join(_HERE, "ref_capi.cpp")] + [os.path.join(_HERE, "shim", f) for f in ("shim_eigen.hpp", "shim_boost.hpp", "shim_ompl.hpp")]
+    deps = srcs + [os.path.join(_HERE, "ref_capi.cpp")] + [os.path.join(_HERE, "shim", f) for f in ("shim_eigen.hpp", "shim_boost.hpp", "shim_ompl.hpp", "utils/MultiRobotProblemDefinition.h")]
     if not force and os.path.exists(_SO) and all(os.path.getmtime(_SO) >= os.path.getmtime(d) for d in deps):
         return _SO
     subprocess.check_call(["make", "-C", _HERE, "-s", "ref"])
@@ -54,6 +55,17 @@ def lib():
         L.ref_is_valid.argtypes = [vp, C.c_long, dp, u8p]
         L.ref_propagate.argtypes = [vp, C.c_long, dp, dp, dp]
         L.ref_rollout.argtypes = [vp, C.c_long, dp, dp, ip, dp, ip]
+        L.ref_pvc_create.restype = vp
+        L.ref_pvc_create.argtypes = [vp, C.c_int, C.c_double]
+        L.ref_pvc_free.argtypes = [vp]
+        L.ref_pvc_info.argtypes = [vp, dp]
+        L.ref_pvc_pair_halfplanes.argtypes = [vp, C.c_int, C.c_int, dp, dp]
+        L.ref_validate_plan.restype = C.c_int
+        L.ref_validate_plan.argtypes = [vp, C.c_int, ip, dp, ip, C.c_int]
+        L.ref_create_constraint.restype = C.c_int
+        L.ref_create_constraint.argtypes = [vp, C.c_int, ip, dp, C.c_int, ip, dp, dp, C.c_int]
+        L.ref_satisfies_constraints.restype = C.c_int
+        L.ref_satisfies_constraints.argtypes = [vp, C.c_int, dp, C.c_int, C.c_int, ip, ip, ip, dp]
         _lib = L
     return _lib
 
@@ -110,3 +122,56 @@ class Svc:
         valid = np.zeros(len(b), dtype=np.int32)
         lib().ref_rollout(self.h, len(b), _dp(b), _dp(u), st.ctypes.data_as(C.POINTER(C.c_int)), _dp(out), valid.ctypes.data_as(C.POINTER(C.c_int)))
         return out, valid
+
+
+def _ip(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int))
+
+
+class Pvc:
+    """MinkowskiSumBlackmorePVC (kind 0) / BoundingBoxBlackmorePVC (kind 1) as demos/main.cpp:100-112 wires them
+    (p_safe = Instance::getPsafeAgents()).  Paths are interpolated trajectories [T_r, 10]."""
+
+    def __init__(self, world, kind=0, step=0.2):
+        self.world, self.kind, self.k = world, kind, world.n_robots
+        self.h = lib().ref_pvc_create(world.h, kind, step)
+        info = np.zeros(3)
+        lib().ref_pvc_info(self.h, _dp(info))
+        self.p_coll_agnts, self.p_coll_dist, self.c_pair = info
+
+    def pair_halfplanes(self, a, b):
+        A, B = np.zeros((4, 2)), np.zeros(4)
+        lib().ref_pvc_pair_halfplanes(self.h, a, b, _dp(A), _dp(B))
+        return A, B
+
+    def _pack(self, trajs):
+        lens = np.array([len(t) for t in trajs], dtype=np.int32)
+        states = np.ascontiguousarray(np.concatenate([np.asarray(t, dtype=np.float64).reshape(-1, 10) for t in trajs], axis=0))
+        return lens, states
+
+    def validate_plan(self, trajs):
+        lens, states = self._pack(trajs)
+        cap = int(lens.max()) + 2
+        out = np.zeros((cap, 3), dtype=np.int32)
+        n = lib().ref_validate_plan(self.h, len(trajs), _ip(lens), _dp(states), _ip(out), cap)
+        return [tuple(int(x) for x in out[i]) for i in range(n)]
+
+    def create_constraint(self, trajs, robot):
+        """createConstraint(plan, validatePlan(plan), robot) -> (constrained, constraining, times, states) or None."""
+        lens, states = self._pack(trajs)
+        cap = int(lens.max()) + 2
+        info = np.zeros(2, dtype=np.int32)
+        times, cst = np.zeros(cap), np.zeros((cap, 10))
+        n = lib().ref_create_constraint(self.h, len(trajs), _ip(lens), _dp(states), robot, _ip(info), _dp(times), _dp(cst), cap)
+        if n == 0:
+            return None
+        return int(info[0]), int(info[1]), times[:n].copy(), cst[:n].copy()
+
+    def satisfies_constraints(self, path, constrained, constraints):
+        """constraints: list of (constraining_robot, steps[int], states[len(steps), 10])."""
+        p = np.ascontiguousarray(np.asarray(path, dtype=np.float64).reshape(-1, 10))
+        cr = np.array([c[0] for c in constraints], dtype=np.int32)
+        nt = np.array([len(c[1]) for c in constraints], dtype=np.int32)
+        st = np.ascontiguousarray(np.concatenate([np.asarray(c[1], dtype=np.int32) for c in constraints]), dtype=np.int32)
+        states = np.ascontiguousarray(np.concatenate([np.asarray(c[2], dtype=np.float64).reshape(-1, 10) for c in constraints], axis=0))
+        return bool(lib().ref_satisfies_constraints(self.h, len(p), _dp(p), constrained, len(constraints), _ip(cr), _ip(nt), _ip(st), _dp(states)))

@@ -1,4 +1,4 @@
-// ref_capi.cpp — TEST INFRASTRUCTURE: C entry points over the REFERENCE'S OWN SOURCES for the headline path,
+// ref_capi.cpp — TEST INFRASTRUCTURE: C entry points over the REFERENCE'S OWN SOURCES for the default-configuration path,
 // compiled from where they lie under /root/reference (never copied):
 //   src/utils/common.cpp, src/utils/Instance.cpp                 (map/scen parser, obstacles, robots, risk split)
 //   src/StatePropogators/UncertainLinearSP.cpp                    (R2_UncertainLinearStatePropagator::propagate)
@@ -61,8 +61,8 @@ struct RefSvc {
     std::shared_ptr<R2_UncertainLinearStatePropagator> prop;
 };
 struct Quiet {   // Instance's constructor prints every obstacle
+    std::ostringstream sink;     // declared (hence constructed) before `old` uses it
     std::streambuf* old;
-    std::ostringstream sink;
     Quiet() : old(std::cout.rdbuf(sink.rdbuf())) {}
     ~Quiet() { std::cout.rdbuf(old); }
 };
@@ -184,6 +184,130 @@ void ref_rollout(void* s, long n, const double* bel, const double* ctrl, const i
         valid[i] = r;
     }
     S->space->freeState(state); S->space->freeState(result);
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------
+// Plan validity checkers: src/PlanValidityCheckers/BeliefPVC.cpp, MinkowskiSumBlackmorePVC.cpp,
+// BoundingBoxBlackmorePVC.cpp, src/Constraints/BeliefConstraint.cpp, src/utils/Conflict.cpp compiled in place.
+// MultiRobotProblemDefinition is the stand-in of oracle/shim/utils/ (a holder of Instance + SpaceInformation),
+// oc::PathControl the stand-in of shim_ompl.hpp (already-interpolated paths only).
+// ---------------------------------------------------------------------------
+#define private public
+#define protected public
+#include "PlanValidityCheckers/MinkowskiSumBlackmorePVC.h"
+#include "PlanValidityCheckers/BoundingBoxBlackmorePVC.h"
+#undef private
+#undef protected
+
+namespace {
+struct RefPvc {
+    RefWorld* world;
+    std::vector<oc::SpaceInformationPtr> sis;
+    MultiRobotProblemDefinitionPtr pdef;
+    std::shared_ptr<BeliefPVC> pvc;
+    int kind;
+};
+oc::PathControl make_path(RefPvc* P, int robot, int len, const double* states, double step) {
+    oc::PathControl path(P->sis[robot]);
+    auto* st = P->sis[robot]->allocState()->as<RealVectorBeliefSpace::StateType>();
+    for (int t = 0; t < len; ++t) {
+        load(st, states + (size_t)t * 10, 2);
+        if (t == 0) path.append(st); else path.append(st, step);
+    }
+    P->sis[robot]->freeState(st);
+    return path;
+}
+}  // namespace
+
+extern "C" {
+
+void* ref_pvc_create(void* w, int kind, double step) {
+    RefWorld* W = (RefWorld*)w;
+    RefPvc* P = new RefPvc();
+    P->world = W; P->kind = kind;
+    const auto robots = W->inst->getRobots();
+    for (size_t r = 0; r < robots.size(); ++r) {
+        auto space = std::make_shared<RealVectorBeliefSpace>(2);
+        auto si = std::make_shared<oc::SpaceInformation>(space);
+        si->setPropagationStepSize(step);
+        P->sis.push_back(si);
+    }
+    P->pdef = std::make_shared<MultiRobotProblemDefinition>(W->inst, P->sis);
+    if (kind == 0) P->pvc = std::make_shared<MinkowskiSumBlackmorePVC>(P->pdef, W->inst->getPsafeAgents());      // demos/main.cpp:103
+    else P->pvc = std::make_shared<BoundingBoxBlackmorePVC>(P->pdef, W->inst->getPsafeAgents());
+    return P;
+}
+void ref_pvc_free(void* p) { delete (RefPvc*)p; }
+// out: p_coll_agnts, p_coll_dist, erf_inv(1 - 2 p_coll_dist) as the stand-in erf_inv evaluates it
+void ref_pvc_info(void* p, double* out) {
+    RefPvc* P = (RefPvc*)p;
+    out[0] = P->pvc->p_coll_agnts_;
+    const double pd = P->kind == 0 ? std::static_pointer_cast<MinkowskiSumBlackmorePVC>(P->pvc)->p_coll_dist_
+                                   : std::static_pointer_cast<BoundingBoxBlackmorePVC>(P->pvc)->p_coll_dist_;
+    out[1] = pd;
+    out[2] = boost::math::erf_inv(1 - (2 * pd));
+}
+// half-planes of the pair (a, b), a < b, as stored in halfPlane_map_
+void ref_pvc_pair_halfplanes(void* p, int a, int b, double* A8, double* B4) {
+    RefPvc* P = (RefPvc*)p;
+    const std::string key = std::to_string(a) + "," + std::to_string(b);
+    auto& hp = P->kind == 0 ? std::static_pointer_cast<MinkowskiSumBlackmorePVC>(P->pvc)->halfPlane_map_
+                            : std::static_pointer_cast<BoundingBoxBlackmorePVC>(P->pvc)->halfPlane_map_;
+    const auto& pr = hp.at(key);
+    for (int i = 0; i < 4; ++i) { A8[2 * i] = pr.first(i, 0); A8[2 * i + 1] = pr.first(i, 1); B4[i] = pr.second(i, 0); }
+}
+// validatePlan on interpolated trajectories: lens[k], states concatenated AoS; out rows (a, b, step); returns count
+int ref_validate_plan(void* p, int k, const int* lens, const double* states, int* out, int cap) {
+    RefPvc* P = (RefPvc*)p;
+    Plan plan;
+    size_t off = 0;
+    const double step = P->sis[0]->getPropagationStepSize();
+    for (int r = 0; r < k; ++r) { plan.push_back(make_path(P, r, lens[r], states + off * 10, step)); off += lens[r]; }
+    std::vector<ConflictPtr> confs = P->pvc->validatePlan(plan);
+    int n = 0;
+    for (auto& c : confs) { if (n < cap) { out[3 * n] = c->agent1Idx_; out[3 * n + 1] = c->agent2Idx_; out[3 * n + 2] = c->timeStep_; } ++n; }
+    return n;
+}
+// createConstraint(plan, validatePlan(plan), robot): returns the number of entries; out_info = {constrained, constraining};
+// times[cap], states[cap][10]
+int ref_create_constraint(void* p, int k, const int* lens, const double* states, int robot, int* out_info, double* times, double* cstates, int cap) {
+    RefPvc* P = (RefPvc*)p;
+    Plan plan;
+    size_t off = 0;
+    const double step = P->sis[0]->getPropagationStepSize();
+    for (int r = 0; r < k; ++r) { plan.push_back(make_path(P, r, lens[r], states + off * 10, step)); off += lens[r]; }
+    std::vector<ConflictPtr> confs = P->pvc->validatePlan(plan);
+    if (confs.empty()) return 0;
+    ConstraintPtr c = P->pvc->createConstraint(plan, confs, robot);
+    out_info[0] = c->getConstrainedAgent(); out_info[1] = c->getConstrainingAgent();
+    const auto ts = c->getTimes();
+    const auto ss = c->as<BeliefConstraint>()->getStates();
+    for (size_t i = 0; i < ts.size() && (int)i < cap; ++i) { times[i] = ts[i]; store(ss[i]->as<RealVectorBeliefSpace::StateType>(), cstates + i * 10, 2); }
+    return (int)ts.size();
+}
+// satisfiesConstraints(path, constraints): constraints given as (constraining robot, n_times, steps[], states[][10])
+int ref_satisfies_constraints(void* p, int n_path, const double* path_states, int constrained, int n_cons, const int* constraining,
+                              const int* n_times, const int* steps, const double* cstates) {
+    RefPvc* P = (RefPvc*)p;
+    const double step = P->sis[0]->getPropagationStepSize();
+    oc::PathControl path = make_path(P, constrained, n_path, path_states, step);
+    std::vector<ConstraintPtr> cons;
+    size_t off = 0;
+    for (int c = 0; c < n_cons; ++c) {
+        std::vector<double> times;
+        std::vector<ob::State*> sts;
+        for (int i = 0; i < n_times[c]; ++i) {
+            times.push_back(steps[off + i] * step);                                        // BeliefPVC.cpp:23
+            auto* st = P->sis[constraining[c]]->allocState()->as<RealVectorBeliefSpace::StateType>();
+            load(st, cstates + (off + i) * 10, 2);
+            sts.push_back(st);
+        }
+        off += n_times[c];
+        cons.push_back(std::make_shared<BeliefConstraint>(constrained, constraining[c], times, sts));
+    }
+    return P->pvc->satisfiesConstraints(path, cons) ? 1 : 0;
 }
 
 }  // extern "C"

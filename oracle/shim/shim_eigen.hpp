@@ -6,6 +6,12 @@
 // (the reference builds for baseline x86-64: CMakeLists.txt:6-8).  The 2x2 inverse follows Eigen's
 // compute_inverse_size2_helper (adjugate times 1/det).  NOT a general Eigen replacement.
 #pragma once
+// Eigen/Core includes <emmintrin.h> on x86-64 (SSE2 vectorisation is on by default), which reaches <stdlib.h>
+// through <mm_malloc.h>; libstdc++'s <stdlib.h> wrapper does `using std::abs;`.  That is what makes the reference's
+// UNQUALIFIED `abs(t - current_time) < 1E-9` in *PVC::satisfiesConstraints the floating-point overload — with
+// <cmath>/<cstdlib> alone it would be int abs(int) and match every constraint time within +-1 s.  The stand-in
+// must reproduce that include, or the reference sources compiled here would behave differently.
+#include <emmintrin.h>
 #include <cassert>
 #include <cmath>
 #include <cstddef>
@@ -20,6 +26,7 @@ class Matrix {
 public:
     Matrix() : r_(R == Dynamic ? 0 : R), c_(C == Dynamic ? 0 : C), d_((size_t)r_ * c_, T(0)) {}
     Matrix(int r, int c) : r_(r), c_(c), d_((size_t)r * c, T(0)) {}
+    explicit Matrix(int n) : r_(n), c_(1), d_((size_t)n, T(0)) {}   // VectorXd mu(2)
     // Vector2d{a, b}
     Matrix(T a, T b) : r_(R == Dynamic ? 2 : R), c_(C == Dynamic ? 1 : C), d_((size_t)r_ * c_, T(0)) { d_[0] = a; d_[1] = b; }
     template <int R2, int C2, int O2>

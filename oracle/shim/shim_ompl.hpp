@@ -3,7 +3,12 @@
 // base::StateValidityChecker, SpaceInformation::getPropagationStepSize / satisfiesBounds with OMPL's
 // RealVectorBounds test: v - eps > high || v + eps < low, eps = DBL_EPSILON), no planning machinery.
 #pragma once
+#include <algorithm>
 #include <cfloat>
+#include <map>
+#include <unordered_map>
+#include <cmath>
+#include <stdexcept>
 #include <iostream>
 #include <limits>
 #include <memory>
@@ -91,6 +96,10 @@ public:
     virtual ~SpaceInformation() = default;
     const StateSpacePtr& getStateSpace() const { return space_; }
     bool satisfiesBounds(const State* s) const { return space_->satisfiesBounds(s); }
+    State* allocState() const { return space_->allocState(); }
+    void freeState(State* s) const { space_->freeState(s); }
+    void copyState(State* d, const State* s) const { space_->copyState(d, s); }
+    State* cloneState(const State* s) const { State* c = space_->allocState(); space_->copyState(c, s); return c; }
 protected:
     StateSpacePtr space_;
 };
@@ -145,6 +154,38 @@ public:
     virtual bool canPropagateBackward() const { return true; }
 protected:
     SpaceInformation* si_;
+};
+
+// PathControl: states / control durations with OMPL's value semantics (copies own their states).  Only paths that
+// are ALREADY interpolated (every control lasts one propagation step) are supported: interpolate() then has
+// nothing to do, exactly as in OMPL (steps <= 1 keeps state, control and duration).
+class PathControl {
+public:
+    explicit PathControl(const base::SpaceInformationPtr& si) : si_(si) {}
+    PathControl(const PathControl& o) : si_(o.si_), durations_(o.durations_) { for (auto* s : o.states_) states_.push_back(si_->cloneState(s)); }
+    PathControl& operator=(const PathControl& o) {
+        if (this != &o) { clear(); si_ = o.si_; durations_ = o.durations_; for (auto* s : o.states_) states_.push_back(si_->cloneState(s)); }
+        return *this;
+    }
+    ~PathControl() { clear(); }
+    void append(const base::State* s) { states_.push_back(si_->cloneState(s)); }
+    void append(const base::State* s, double duration) { states_.push_back(si_->cloneState(s)); durations_.push_back(duration); }
+    void interpolate() {
+        const double res = static_cast<const SpaceInformation*>(si_.get())->getPropagationStepSize();
+        for (double d : durations_)
+            if ((int)std::floor(0.5 + d / res) > 1) throw std::runtime_error("shim PathControl: feed interpolated paths");
+    }
+    std::size_t getStateCount() const { return states_.size(); }
+    std::size_t getControlCount() const { return durations_.size(); }
+    base::State* getState(unsigned i) { return states_[i]; }
+    const base::State* getState(unsigned i) const { return states_[i]; }
+    std::vector<base::State*>& getStates() { return states_; }
+    double getControlDuration(unsigned i) const { return durations_[i]; }
+private:
+    void clear() { for (auto* s : states_) si_->freeState(s); states_.clear(); }
+    base::SpaceInformationPtr si_;
+    std::vector<base::State*> states_;
+    std::vector<double> durations_;
 };
 
 }  // namespace control

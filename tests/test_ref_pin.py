@@ -46,6 +46,50 @@ def test_oracle_matches_reference_vectors(O, path):
     assert 0.2 < g["is_valid"].mean() < 0.95
 
 
+def _plans(g):
+    k = int(g["k"])
+    lens, states = g["plan_lens"], g["plan_states"]
+    off, plans = 0, []
+    for i in range(len(lens)):
+        trajs = []
+        for r in range(k):
+            trajs.append(states[off:off + lens[i, r]]); off += lens[i, r]
+        plans.append(trajs)
+    return plans
+
+
+@pytest.mark.parametrize("path", FILES, ids=IDS)
+def test_oracle_pvc_matches_reference_vectors(O, path):
+    """validatePlan / createConstraint / satisfiesConstraints of MinkowskiSumBlackmorePVC and BoundingBoxBlackmorePVC
+    (reference sources) on random ragged plans: earliest conflict in std::map name order, the follow-up loop, robots
+    waiting at their last state, constraint times/states, the floating-point time match."""
+    g = np.load(path)
+    k = int(g["k"])
+    w = O.World.synthetic(g["centres"], float(g["x_max"]), float(g["y_max"]), k, float(g["p_safe"]))
+    plans = _plans(g)
+    for okind, tag in ((O.PVC_BLACKMORE, "mink"), (O.PVC_BOUNDINGBOX, "bbox")):
+        pv = O.Pvc(w, okind)
+        assert np.array_equal(np.array([pv.p_coll_agnts, pv.p_coll_dist, pv.c_pair]), g[f"{tag}_info"])
+        A, B = pv.pair_halfplanes(0, 1)
+        assert np.array_equal(A, g[f"{tag}_hp_A"]) and np.array_equal(B, g[f"{tag}_hp_B"])
+        ref_c, ref_s = g[f"{tag}_conflicts"], g[f"{tag}_satisfies"]
+        n_conf = 0
+        for i, trajs in enumerate(plans):
+            c = pv.validate_plan(trajs, 2)
+            exp = [tuple(int(x) for x in row[1:]) for row in ref_c[ref_c[:, 0] == i]]
+            assert c == exp, (tag, i)
+            if not c:
+                assert (ref_s[i] == -1).all()
+                continue
+            n_conf += 1
+            a, other, steps = c[0][0], c[0][1], [x[2] for x in c]
+            cstates = np.array([trajs[other][min(s, len(trajs[other]) - 1)] for s in steps])     # BeliefPVC.cpp:24-36
+            for j in range(ref_s.shape[1]):
+                probe = g["probe_states"][i, j, :g["probe_len"][i, j]]
+                assert pv.satisfies_constraints(probe, 2, a, [(other, steps, cstates)]) == bool(ref_s[i, j]), (tag, i, j)
+        assert n_conf >= 10 and 0.05 < (ref_s[ref_s >= 0] == 0).mean() < 0.95
+
+
 def test_oracle_matches_live_reference_build(O):
     """All linear-model scenario files of the reference, parsed by the reference's own Instance.cpp."""
     from oracle import ref as R
@@ -94,8 +138,49 @@ def test_oracle_matches_live_reference_build(O):
             rf, rv = rs.rollout(b, u, steps)
             of, ov, _ = os_.rollout(b, u, steps)
             assert np.array_equal(rv, ov) and np.array_equal(rf, of)
+            if k > 1 and "random-32-32-10" in base:      # plan validity checkers, live
+                for kind, okind in ((0, O.PVC_BLACKMORE), (1, O.PVC_BOUNDINGBOX)):
+                    rp, op = R.Pvc(rw, kind), O.Pvc(ow, okind)
+                    assert (rp.p_coll_agnts, rp.p_coll_dist, rp.c_pair) == (op.p_coll_agnts, op.p_coll_dist, op.c_pair)
+                    for _ in range(15):
+                        trajs = []
+                        for r in range(k):
+                            T = int(rng.integers(3, 30))
+                            t = np.zeros((T, 10))
+                            t[:, :2] = np.cumsum(rng.uniform(-0.2, 0.2, (T, 2)), axis=0) + rng.uniform(0, 2.0 + 0.1 * k, 2)
+                            t[:, 2] = t[:, 5] = rng.uniform(0.001, 0.03); t[:, 6] = t[:, 9] = rng.uniform(0.001, 0.03)
+                            trajs.append(t)
+                        assert rp.validate_plan(trajs) == op.validate_plan(trajs, 2), (base, k, kind)
             checked += 1
     assert checked >= 8
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", FILES, ids=IDS)
+def test_cuda_pvc_matches_reference_vectors(K, ctx, path):
+    """cck_validate_plan / cck_satisfies_constraints against the reference's plan checkers."""
+    g = np.load(path)
+    k = int(g["k"])
+    ctx.set_model(K.MODEL_LINEAR2D)
+    rad = K.rect_robot_bounding_radius()
+    plans = _plans(g)
+    for kind, tag in ((K.PVC_BLACKMORE, "mink"), (K.PVC_BOUNDINGBOX, "bbox")):
+        K.install_pvc(ctx, kind, 2, [rad] * k, float(g["p_safe_agents"]))
+        ref_c, ref_s = g[f"{tag}_conflicts"], g[f"{tag}_satisfies"]
+        for i, trajs in enumerate(plans):
+            exp = ref_c[ref_c[:, 0] == i]
+            run = ctx.validate_plan([K.aos_to_soa(t) for t in trajs])
+            if len(exp) == 0:
+                assert run is None, (tag, i)
+                continue
+            assert run == (int(exp[0, 1]), int(exp[0, 2]), int(exp[0, 3]), len(exp)), (tag, i, run, exp[0])
+            a, other, steps = int(exp[0, 1]), int(exp[0, 2]), [int(x) for x in exp[:, 3]]
+            cstates = np.array([trajs[other][min(s, len(trajs[other]) - 1)] for s in steps])
+            ctx.set_constraints(*K.constraint_entries(k, 2, a, [(other, steps, cstates)]))
+            n_probe = ref_s.shape[1]
+            soa = np.ascontiguousarray(g["probe_states"][i].transpose(1, 2, 0))        # [T, W, n]
+            ok = ctx.satisfies_constraints(soa, g["probe_len"][i], np.zeros(n_probe, dtype=np.int32))
+            assert np.array_equal(ok, ref_s[i].astype(bool)), (tag, i)
 
 
 @pytest.mark.gpu
