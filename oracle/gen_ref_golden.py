@@ -101,10 +101,24 @@ def main():
         w = R.World(f"{R.REFERENCE}/maps/{mp}.map", f"{R.REFERENCE}/scens/{sc}.scen", k, 0.9)
         s = R.Svc(w)
         b, u, steps = beliefs(3000, w.x_max, w.y_max, 20240501 + k)
+        pv = {}
         prop = s.propagate(b, u)
         valid = s.is_valid(b)
         fin, nval = s.rollout(b, u, steps)
         pv = pvc_vectors(w, k, 777 + k) if k > 1 else {}
+        if k == 4 and w.n_obstacles > 0:      # adaptive-risk checkers (their erf_inv at data-dependent arguments is the stand-in's): structure pin
+            sa = R.Svc(w, kind=1)
+            pv["adaptive_is_valid"] = sa.is_valid(b[:500])
+            lens, states = pv["plan_lens"], pv["plan_states"]
+            for kind, tag in ((2, "amink"), (3, "abbox")):
+                ap = R.Pvc(w, kind)
+                confs, off = [], 0
+                for i in range(25):
+                    trajs = []
+                    for r in range(k):
+                        trajs.append(states[off:off + lens[i, r]]); off += lens[i, r]
+                    confs.append(np.array([[i, a_, b_, s_] for a_, b_, s_ in ap.validate_plan(trajs)], dtype=np.int32).reshape(-1, 4))
+                pv[f"{tag}_conflicts"] = np.concatenate(confs, axis=0)
         np.savez_compressed(os.path.join(out_dir, name + ".npz"), map=mp, scen=sc, k=k, p_safe=0.9, **pv,
                             n_obstacles=w.n_obstacles, x_max=w.x_max, y_max=w.y_max, centres=w.centres, starts=w.starts, goals=w.goals,
                             bounding_rad=w.bounding_rad, p_safe_obs=w.p_safe_obs, p_safe_agents=w.p_safe_agents,

@@ -13,7 +13,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "_ref", "libcck_ref.so")
 REFERENCE = "/root/reference"
 SOURCES = ["src/utils/common.cpp", "src/utils/Instance.cpp", "src/utils/Conflict.cpp", "src/StatePropogators/UncertainLinearSP.cpp",
-           "src/StateValidityCheckers/PCCBlackmoreSVC.cpp", "src/Constraints/BeliefConstraint.cpp", "src/PlanValidityCheckers/BeliefPVC.cpp",
+           "src/StateValidityCheckers/PCCBlackmoreSVC.cpp", "src/StateValidityCheckers/AdaptiveRiskBlackmoreSVC.cpp",
+           "src/PlanValidityCheckers/AdaptiveRiskBlackmorePVC.cpp", "src/PlanValidityCheckers/AdaptiveRiskBoundingBoxPVC.cpp", "src/Constraints/BeliefConstraint.cpp", "src/PlanValidityCheckers/BeliefPVC.cpp",
            "src/PlanValidityCheckers/MinkowskiSumBlackmorePVC.cpp", "src/PlanValidityCheckers/BoundingBoxBlackmorePVC.cpp"]
 
 
@@ -50,6 +51,8 @@ def lib():
         L.ref_world_robots.argtypes = [vp, dp]
         L.ref_svc_create.restype = vp
         L.ref_svc_create.argtypes = [vp, C.c_int, dp, dp, C.c_double]
+        L.ref_svc_create_kind.restype = vp
+        L.ref_svc_create_kind.argtypes = [vp, C.c_int, C.c_int, dp, dp, C.c_double]
         L.ref_svc_free.argtypes = [vp]
         L.ref_svc_tables.argtypes = [vp, dp, dp, dp]
         L.ref_is_valid.argtypes = [vp, C.c_long, dp, u8p]
@@ -92,11 +95,12 @@ class World:
 class Svc:
     """PCCBlackmoreSVC + R2_UncertainLinearStatePropagator wired as OmplSetUp.cpp:183-228 does."""
 
-    def __init__(self, world, robot=0, step=0.2):
+    def __init__(self, world, robot=0, step=0.2, kind=0):
+        """kind 0: PCCBlackmoreSVC, kind 1: AdaptiveRiskBlackmoreSVC (its erf_inv is the stand-in's)."""
         self.world = world
         self.low = np.array([-1.0, -1.0])
         self.high = np.array([world.x_max, world.y_max], dtype=np.float64)
-        self.h = lib().ref_svc_create(world.h, robot, _dp(self.low), _dp(self.high), step)
+        self.h = lib().ref_svc_create_kind(world.h, kind, robot, _dp(self.low), _dp(self.high), step)
         M = world.n_obstacles
         self.A, self.B = np.zeros((M, 4, 2)), np.zeros((M, 4))
         info = np.zeros(3)
@@ -129,7 +133,8 @@ def _ip(a):
 
 
 class Pvc:
-    """MinkowskiSumBlackmorePVC (kind 0) / BoundingBoxBlackmorePVC (kind 1) as demos/main.cpp:100-112 wires them
+    """MinkowskiSumBlackmorePVC (kind 0) / BoundingBoxBlackmorePVC (1) / AdaptiveRiskBlackmorePVC (2) /
+    AdaptiveRiskBoundingBoxPVC (3) as demos/main.cpp:100-125 wires them
     (p_safe = Instance::getPsafeAgents()).  Paths are interpolated trajectories [T_r, 10]."""
 
     def __init__(self, world, kind=0, step=0.2):

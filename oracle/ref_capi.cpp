@@ -28,6 +28,7 @@
 
 #define private public      // test glue only: read A_list_, B_list_, erf_inv_result_ of the reference's checker
 #include "StateValidityCheckers/PCCBlackmoreSVC.h"
+#include "StateValidityCheckers/AdaptiveRiskBlackmoreSVC.h"
 #undef private
 #include "StatePropogators/UncertainLinearSP.h"
 
@@ -57,7 +58,9 @@ struct RefWorld { InstancePtr inst; };
 struct RefSvc {
     std::shared_ptr<RealVectorBeliefSpace> space;
     oc::SpaceInformationPtr si;
-    std::shared_ptr<PCCBlackmoreSVC> svc;
+    std::shared_ptr<PCCBlackmoreSVC> pcc;                 // kind 0
+    std::shared_ptr<AdaptiveRiskBlackmoreSVC> adaptive;   // kind 1
+    ob::StateValidityChecker* svc = nullptr;
     std::shared_ptr<R2_UncertainLinearStatePropagator> prop;
 };
 struct Quiet {   // Instance's constructor prints every obstacle
@@ -110,7 +113,10 @@ void ref_world_robots(void* w, double* out) {
 }
 
 // the wiring of set_up_ConstraintBSST_MP_Problems for the linear model (src/utils/OmplSetUp.cpp:183-228)
-void* ref_svc_create(void* w, int robot, const double* low, const double* high, double step) {
+void* ref_svc_create_kind(void* w, int kind, int robot, const double* low, const double* high, double step);
+void* ref_svc_create(void* w, int robot, const double* low, const double* high, double step) { return ref_svc_create_kind(w, 0, robot, low, high, step); }
+// kind 0: PCCBlackmoreSVC, kind 1: AdaptiveRiskBlackmoreSVC (OmplSetUp.cpp:213-222)
+void* ref_svc_create_kind(void* w, int kind, int robot, const double* low, const double* high, double step) {
     RefWorld* W = (RefWorld*)w;
     RefSvc* s = new RefSvc();
     s->space = std::make_shared<RealVectorBeliefSpace>(2);
@@ -119,14 +125,22 @@ void* ref_svc_create(void* w, int robot, const double* low, const double* high, 
     s->space->setBounds(b);
     s->si = std::make_shared<oc::SpaceInformation>(s->space);
     s->si->setPropagationStepSize(step);
-    s->svc = std::make_shared<PCCBlackmoreSVC>(s->si, W->inst, W->inst->getRobots()[robot], W->inst->getPsafeObs());
+    if (kind == 0) { s->pcc = std::make_shared<PCCBlackmoreSVC>(s->si, W->inst, W->inst->getRobots()[robot], W->inst->getPsafeObs()); s->svc = s->pcc.get(); }
+    else { s->adaptive = std::make_shared<AdaptiveRiskBlackmoreSVC>(s->si, W->inst, W->inst->getRobots()[robot], W->inst->getPsafeObs()); s->svc = s->adaptive.get(); }
     s->prop = std::make_shared<R2_UncertainLinearStatePropagator>(s->si);
     return s;
 }
 void ref_svc_free(void* s) { delete (RefSvc*)s; }
 // A[M][4][2], B[M][4]; info: erf_inv_result, p_collision, n_obstacles
 void ref_svc_tables(void* s, double* A, double* B, double* info) {
-    const PCCBlackmoreSVC& v = *((RefSvc*)s)->svc;
+    if (!((RefSvc*)s)->pcc) {
+        const AdaptiveRiskBlackmoreSVC& v = *((RefSvc*)s)->adaptive;
+        for (size_t o = 0; o < v.A_list_.size(); ++o)
+            for (int i = 0; i < 4; ++i) { A[o * 8 + i * 2] = v.A_list_[o](i, 0); A[o * 8 + i * 2 + 1] = v.A_list_[o](i, 1); B[o * 4 + i] = v.B_list_[o](i, 0); }
+        info[0] = 0.0; info[1] = v.p_collision_; info[2] = (double)v.A_list_.size();
+        return;
+    }
+    const PCCBlackmoreSVC& v = *((RefSvc*)s)->pcc;
     for (size_t o = 0; o < v.A_list_.size(); ++o)
         for (int i = 0; i < 4; ++i) { A[o * 8 + i * 2] = v.A_list_[o](i, 0); A[o * 8 + i * 2 + 1] = v.A_list_[o](i, 1); B[o * 4 + i] = v.B_list_[o](i, 0); }
     info[0] = v.n_obstacles_ > 0 ? v.erf_inv_result_ : 0.0; info[1] = v.p_collision_; info[2] = v.n_obstacles_;
@@ -198,6 +212,8 @@ void ref_rollout(void* s, long n, const double* bel, const double* ctrl, const i
 #define protected public
 #include "PlanValidityCheckers/MinkowskiSumBlackmorePVC.h"
 #include "PlanValidityCheckers/BoundingBoxBlackmorePVC.h"
+#include "PlanValidityCheckers/AdaptiveRiskBlackmorePVC.h"
+#include "PlanValidityCheckers/AdaptiveRiskBoundingBoxPVC.h"
 #undef private
 #undef protected
 
@@ -235,8 +251,10 @@ void* ref_pvc_create(void* w, int kind, double step) {
         P->sis.push_back(si);
     }
     P->pdef = std::make_shared<MultiRobotProblemDefinition>(W->inst, P->sis);
-    if (kind == 0) P->pvc = std::make_shared<MinkowskiSumBlackmorePVC>(P->pdef, W->inst->getPsafeAgents());      // demos/main.cpp:103
-    else P->pvc = std::make_shared<BoundingBoxBlackmorePVC>(P->pdef, W->inst->getPsafeAgents());
+    if (kind == 0) P->pvc = std::make_shared<MinkowskiSumBlackmorePVC>(P->pdef, W->inst->getPsafeAgents());      // demos/main.cpp:100-125
+    else if (kind == 1) P->pvc = std::make_shared<BoundingBoxBlackmorePVC>(P->pdef, W->inst->getPsafeAgents());
+    else if (kind == 2) P->pvc = std::make_shared<AdaptiveRiskBlackmorePVC>(P->pdef, W->inst->getPsafeAgents());
+    else P->pvc = std::make_shared<AdaptiveRiskBoundingBoxPVC>(P->pdef, W->inst->getPsafeAgents());
     return P;
 }
 void ref_pvc_free(void* p) { delete (RefPvc*)p; }
@@ -244,6 +262,7 @@ void ref_pvc_free(void* p) { delete (RefPvc*)p; }
 void ref_pvc_info(void* p, double* out) {
     RefPvc* P = (RefPvc*)p;
     out[0] = P->pvc->p_coll_agnts_;
+    if (P->kind >= 2) { out[1] = 0; out[2] = 0; return; }       // adaptive checkers allocate the risk per state
     const double pd = P->kind == 0 ? std::static_pointer_cast<MinkowskiSumBlackmorePVC>(P->pvc)->p_coll_dist_
                                    : std::static_pointer_cast<BoundingBoxBlackmorePVC>(P->pvc)->p_coll_dist_;
     out[1] = pd;
@@ -254,7 +273,9 @@ void ref_pvc_pair_halfplanes(void* p, int a, int b, double* A8, double* B4) {
     RefPvc* P = (RefPvc*)p;
     const std::string key = std::to_string(a) + "," + std::to_string(b);
     auto& hp = P->kind == 0 ? std::static_pointer_cast<MinkowskiSumBlackmorePVC>(P->pvc)->halfPlane_map_
-                            : std::static_pointer_cast<BoundingBoxBlackmorePVC>(P->pvc)->halfPlane_map_;
+             : P->kind == 1 ? std::static_pointer_cast<BoundingBoxBlackmorePVC>(P->pvc)->halfPlane_map_
+             : P->kind == 2 ? std::static_pointer_cast<AdaptiveRiskBlackmorePVC>(P->pvc)->halfPlane_map_
+                            : std::static_pointer_cast<AdaptiveRiskBoundingBoxPVC>(P->pvc)->halfPlane_map_;
     const auto& pr = hp.at(key);
     for (int i = 0; i < 4; ++i) { A8[2 * i] = pr.first(i, 0); A8[2 * i + 1] = pr.first(i, 1); B4[i] = pr.second(i, 0); }
 }

@@ -124,7 +124,7 @@ namespace math {
 template <class T> T erf_inv(T z) {
     if (z <= -1 || z >= 1) return z <= -1 ? -INFINITY : INFINITY;
     long double lo = -7.0L, hi = 7.0L;   // erfl(7) == 1 in long double
-    for (int it = 0; it < 200; ++it) {
+    for (int it = 0; it < 90; ++it) {          // 14 / 2^90 is far below the long double ulp
         const long double mid = 0.5L * (lo + hi);
         if (erfl(mid) < (long double)z) lo = mid; else hi = mid;
     }

@@ -90,6 +90,26 @@ def test_oracle_pvc_matches_reference_vectors(O, path):
         assert n_conf >= 10 and 0.05 < (ref_s[ref_s >= 0] == 0).mean() < 0.95
 
 
+def test_oracle_adaptive_checkers_match_reference_vectors(O):
+    """AdaptiveRiskBlackmoreSVC::isValid (eta_list[0] for every obstacle, quirk 4) and the adaptive plan checkers
+    (per-state risk allocation over the active robots in map order).  The reference's erf_inv at data-dependent
+    arguments is Boost's; the reference build used the stand-in's, so this pins the structure, not the last ulp."""
+    g = np.load(os.path.join(GOLDEN, "ref_config2_random32_10_k4.npz"))
+    k = int(g["k"])
+    w = O.World.synthetic(g["centres"], float(g["x_max"]), float(g["y_max"]), k, float(g["p_safe"]))
+    sa = O.Svc(w, O.SVC_ADAPTIVE, 2)
+    ref = g["adaptive_is_valid"]
+    assert np.array_equal(sa.is_valid(g["beliefs"][:len(ref)])[0], ref) and 0.2 < ref.mean() < 0.9
+    plans = _plans(g)
+    for okind, tag in ((O.PVC_ADAPTIVE_BLACKMORE, "amink"), (O.PVC_ADAPTIVE_BOUNDINGBOX, "abbox")):
+        pv = O.Pvc(w, okind)
+        ref_c = g[f"{tag}_conflicts"]
+        for i in range(25):
+            exp = [tuple(int(x) for x in row[1:]) for row in ref_c[ref_c[:, 0] == i]]
+            assert pv.validate_plan(plans[i], 2) == exp, (tag, i)
+        assert len(ref_c) > 50
+
+
 def test_oracle_matches_live_reference_build(O):
     """All linear-model scenario files of the reference, parsed by the reference's own Instance.cpp."""
     from oracle import ref as R
@@ -153,6 +173,33 @@ def test_oracle_matches_live_reference_build(O):
                         assert rp.validate_plan(trajs) == op.validate_plan(trajs, 2), (base, k, kind)
             checked += 1
     assert checked >= 8
+
+
+@pytest.mark.gpu
+def test_cuda_adaptive_checkers_match_reference_vectors(K, ctx):
+    """Device erfinv vs the reference build's erf_inv: verdicts equal outside the +-1e-6 band (<= 1 % mismatches)."""
+    g = np.load(os.path.join(GOLDEN, "ref_config2_random32_10_k4.npz"))
+    k, M = int(g["k"]), int(g["n_obstacles"])
+    ctx.set_model(K.MODEL_LINEAR2D)
+    rad = K.rect_robot_bounding_radius()
+    A, B, rects = K.build_obstacle_tables(g["centres"], rad)
+    p_coll = 1 - float(g["p_safe_obs"])
+    ctx.set_obstacles(K.SVC_ADAPTIVE, np.array([-1.0, -1.0]), np.array([float(g["x_max"]), float(g["y_max"])]), A, B, g["centres"], rects,
+                      erf_inv_result=0.0, p_collision=p_coll)
+    ref = g["adaptive_is_valid"]
+    got = ctx.is_valid(K.aos_to_soa(g["beliefs"][:len(ref)]))
+    assert (got != ref).sum() <= max(2, len(ref) // 100)
+    plans = _plans(g)
+    for kind, tag in ((K.PVC_ADAPTIVE_BLACKMORE, "amink"), (K.PVC_ADAPTIVE_BOUNDINGBOX, "abbox")):
+        K.install_pvc(ctx, kind, 2, [rad] * k, float(g["p_safe_agents"]))
+        ref_c = g[f"{tag}_conflicts"]
+        bad = 0
+        for i in range(25):
+            exp = ref_c[ref_c[:, 0] == i]
+            run = ctx.validate_plan([K.aos_to_soa(t) for t in plans[i]])
+            want = None if len(exp) == 0 else (int(exp[0, 1]), int(exp[0, 2]), int(exp[0, 3]), len(exp))
+            bad += (run != want)
+        assert bad <= 1, (tag, bad)
 
 
 @pytest.mark.gpu
