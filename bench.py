@@ -78,6 +78,40 @@ def oracle_time(args, O, W, svc, n, threads, offset=1000):
     return dt, int(cnt[0]), int(cnt[1])
 
 
+def reference_sources_timing(args, W):
+    """Informational: the reference's OWN sources (oracle/_ref, compiled against the stand-in headers of oracle/shim/)
+    on a small sample of the same workload, one thread (the reference is single-threaded).  Not the official
+    baseline: the stand-in Matrix heap-allocates where Eigen's fixed-size types do not, so this under-states a real
+    build of the reference; the (faster) oracle port above is the conservative number."""
+    try:
+        import tempfile
+        from oracle import ref as R
+        if args.model != "linear" or not R.available():
+            return None
+        centres = W.synthetic_obstacles(M_OBS, W.SEED, args.variant)
+        width = int(centres[:, 0].max()) + 2 if args.variant == "all_survive" else W.WORLD    # the parser sets x_max = map width
+        with tempfile.TemporaryDirectory() as d:
+            rows = [["."] * width for _ in range(W.WORLD)]
+            for x, y in centres:
+                rows[int(y)][int(x)] = "@"
+            mp, sc = os.path.join(d, "synthetic.map"), os.path.join(d, "synthetic.scen")
+            open(mp, "w").write(f"type octile\nheight {W.WORLD}\nwidth {width}\nmap\n" + "\n".join("".join(r) for r in rows) + "\n")
+            open(sc, "w").write("version 1\n" + "".join(f"{i}\tsynthetic.map\t{width}\t{W.WORLD}\t{2 + i}\t2\t{5 + i}\t5\tRectangle\t2D-Uncertain-Linear-Model\t1.0\n" for i in range(4)))
+            world = R.World(mp, sc, 4, 0.9)
+            svc = R.Svc(world)
+        n = 512
+        bel, ctrl = W.synthetic_beliefs(n, "linear", variant=args.variant, offset=3000)
+        steps = np.full(n, T_STEPS, dtype=np.int32)
+        t0 = time.perf_counter()
+        _, valid = svc.rollout(np.ascontiguousarray(bel.T), np.ascontiguousarray(ctrl.T), steps)
+        dt = time.perf_counter() - t0
+        units = int(np.minimum(valid.astype(np.int64) + 1, T_STEPS).sum())
+        return {"single_thread_value": units / dt, "unit": UNIT, "sample": f"{n} beliefs ({units} belief-steps, {dt:.1f} s)",
+                "note": "reference sources + stand-in Eigen/Boost/OMPL headers (oracle/_ref); informational, see DESIGN.md section 4"}
+    except Exception as e:  # noqa: BLE001
+        return {"error": str(e)[:200]}
+
+
 def cpu_baseline(args):
     """Oracle timed on all host cores on a bounded sample of the same workload."""
     O, W, svc = oracle_setup(args)
@@ -89,7 +123,8 @@ def cpu_baseline(args):
     dt1, nsteps1, _ = oracle_time(args, O, W, svc, max(2048, n // (4 * cores)), 1)
     return {"value": nsteps / dt, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"{n} beliefs x {T_STEPS} steps x {M_OBS} obstacles ({nsteps} belief-steps, {dt:.1f} s, std::thread over beliefs)",
-            "single_thread_value": nsteps1 / dt1, "halfplane_tests_per_belief_step": nhp / nsteps}
+            "single_thread_value": nsteps1 / dt1, "halfplane_tests_per_belief_step": nhp / nsteps,
+            "reference_sources": reference_sources_timing(args, W)}
 
 
 def run_reference(args):
