@@ -625,19 +625,26 @@ extern "C" int cck_set_obstacles(cck_ctx* c, const cck_svc_params* p, const doub
     if (M > 0) {
         GridBuild gb;
         build_grid_table(M, A, B, cls_idx, p->erf_inv_result, gb);
-        if (grid_smem_bytes((int)gb.buf.size()) > c->max_smem_optin) return fail(c, CCK_ERR_INVALID, "grid table exceeds shared memory; M too large");
+        if (M > 65535) return fail(c, CCK_ERR_INVALID, "more than 65535 obstacles");
+        GHeader gh0;
+        std::memcpy(&gh0, gb.buf.data(), sizeof(gh0));
+        // small tables are staged whole; for large M only the header + bitmap + cell list (<= 9 KB) go to shared memory
+        // and the box arrays (32 B per obstacle) are read from global memory
+        const bool boxes_in_smem = gb.buf.size() <= 24 * 1024;
+        const int stage_bytes = boxes_in_smem ? (int)gb.buf.size() : gh0.off_boxes;
+        if (grid_smem_bytes(stage_bytes) > c->max_smem_optin) return fail(c, CCK_ERR_INVALID, "grid table exceeds shared memory");
         CK(c, cudaMalloc(&c->d_gtab, gb.buf.size()));
         CK(c, cudaMalloc(&c->d_gexB, gb.exB.size() * 8));
         CK(c, cudaMalloc(&c->d_gexCls, gb.exCls.size() * 4));
         CK(c, cudaMemcpy(c->d_gtab, gb.buf.data(), gb.buf.size(), cudaMemcpyHostToDevice));
         CK(c, cudaMemcpy(c->d_gexB, gb.exB.data(), gb.exB.size() * 8, cudaMemcpyHostToDevice));
         CK(c, cudaMemcpy(c->d_gexCls, gb.exCls.data(), gb.exCls.size() * 4, cudaMemcpyHostToDevice));
-        c->gtab_bytes = (int)gb.buf.size();
-        GHeader gh;
-        std::memcpy(&gh, gb.buf.data(), sizeof(gh));
+        c->gtab_bytes = stage_bytes;
+        const GHeader& gh = gh0;
         const GridConst keep = c->gconst;
         c->gconst = GridConst{gh.k, gh.SX, gh.SY, gh.gx0, gh.gy0, gh.icx, gh.icy, gh.Rm1, gh.M, gh.n_grid, gh.off_occ, gh.off_rowbase, gh.off_cstart, gh.off_boxes,
-                              keep.blx, keep.bhx, keep.bly, keep.bhy, (int32_t)sizeof(TabHeader), 0};
+                              keep.blx, keep.bhx, keep.bly, keep.bhy, (int32_t)sizeof(TabHeader), 0,
+                              boxes_in_smem ? nullptr : reinterpret_cast<const float4*>(c->d_gtab + gh.off_boxes)};
     }
 
     SvcDev& s = c->svc;

@@ -46,6 +46,7 @@ struct GridConst {
     int32_t M, n_grid, off_occ, off_rowbase, off_cstart, off_boxes;
     float blx, bhx, bly, bhy;
     int32_t off_classes, pad;   // byte offset of the ClassRec array inside the (global) class table
+    const float4* boxes_global; // non-null: the box arrays are too large for shared memory and are read from global (L1/L2)
 };
 
 #define CCK_GRID_COLS 64
@@ -89,7 +90,7 @@ __device__ __forceinline__ bool grid_obstacle(const float4* boxes, int M, int j,
 __device__ __forceinline__ bool grid_check(const GridConst& g, const unsigned char* gt, const unsigned char* ctab, const double* exB,
                                            const int32_t* exCls, double c, double x, double y, double P0, double P1, double P2, double P3) {
     const GridConst* h = &g;
-    const float4* boxes = reinterpret_cast<const float4*>(gt + h->off_boxes);
+    const float4* boxes = h->boxes_global ? h->boxes_global : reinterpret_cast<const float4*>(gt + h->off_boxes);
     const ClassRec* cls = reinterpret_cast<const ClassRec*>(ctab + h->off_classes);   // a kernel constant: no header load per step
     const int M = h->M;
     const float xf = __double2float_rn(x), yf = __double2float_rn(y);
