@@ -67,7 +67,7 @@ SYMBOLS = [
     "cck_set_constraints", "cck_satisfies_constraints", "cck_satisfies_constraints_dev",
     "cck_expand_batch", "cck_expand_batch_dev", "cck_rollout_summary_dev", "cck_select_winner_dev", "cck_measure_fp64_peak",
     "cck_tree_create", "cck_tree_destroy", "cck_tree_clear", "cck_tree_size", "cck_tree_append", "cck_tree_update",
-    "cck_tree_select", "cck_tree_nearest", "cck_belief_distance", "cck_belief_distance_lower", "cck_belief_distance_cols",
+    "cck_tree_select", "cck_tree_nearest", "cck_belief_distance", "cck_belief_distance_lower", "cck_belief_distance_cols", "cck_build_grid_table",
 ]
 
 
@@ -147,6 +147,7 @@ def lib():
     L.cck_tree_select.argtypes = [vp, i64, vp, i64, C.c_double, vp, vp]
     L.cck_tree_nearest.argtypes = [vp, i64, vp, i64, vp, vp]
     L.cck_belief_distance.argtypes = [vp, C.c_int, i64, vp, i64, vp, i64, vp]
+    L.cck_build_grid_table.argtypes = [C.c_int, vp, vp, C.c_double, vp, i64, C.POINTER(i64), vp]
     L.cck_belief_distance_lower.argtypes = [vp, C.c_int, i64, vp, i64, vp]
     L.cck_belief_distance_cols.argtypes = [vp, C.c_int, i64, vp, i64, C.c_int32, vp, vp]
     _lib = L
@@ -466,6 +467,36 @@ def belief_distance_lower(ctx, bel, dim):
     out = np.zeros((n, n))
     ctx._ck(ctx.L.cck_belief_distance_lower(ctx.h, dim, n, _ptr(bel), n, _ptr(out)))
     return np.tril(out, -1)
+
+
+def build_grid_table(A, B, erf_inv_result):
+    """Host-only: parse the grid table cck_set_obstacles would upload.  Returns a dict with the header scalars,
+    occ[R] (uint64), rowbase, cstart, outer / inner boxes [M, 4] = (xlo, ylo, xhi, yhi) in row order, and order[M]."""
+    A = np.ascontiguousarray(A, dtype=np.float64).reshape(-1, 4, 2)
+    B = np.ascontiguousarray(B, dtype=np.float64).reshape(-1, 4)
+    M = len(A)
+    L = lib()
+    nbytes = C.c_int64(0)
+    rc = L.cck_build_grid_table(M, _ptr(A), _ptr(B), float(erf_inv_result), None, 0, C.byref(nbytes), None)
+    if rc:
+        raise CckError(rc, "cck_build_grid_table")
+    buf = np.zeros(nbytes.value, dtype=np.uint8)
+    order = np.zeros(max(M, 1), dtype=np.int32)
+    rc = L.cck_build_grid_table(M, _ptr(A), _ptr(B), float(erf_inv_result), _ptr(buf), nbytes.value, C.byref(nbytes), _ptr(order))
+    if rc:
+        raise CckError(rc, "cck_build_grid_table")
+    hi = buf[:40].view(np.int32)
+    hf = buf[40:72].view(np.float32)
+    t = {"total_bytes": int(hi[0]), "M": int(hi[1]), "n_grid": int(hi[2]), "n_cells": int(hi[3]), "R": int(hi[4]),
+         "gx0": hf[0], "gy0": hf[1], "icx": hf[2], "icy": hf[3], "SX": hf[4], "SY": hf[5], "k": hf[6], "Rm1": hf[7]}
+    off_occ, off_rb, off_cs, off_bx = int(hi[5]), int(hi[6]), int(hi[7]), int(hi[8])
+    t["occ"] = buf[off_occ:off_occ + 8 * t["R"]].view(np.uint64).copy()
+    t["rowbase"] = buf[off_rb:off_rb + 2 * t["R"]].view(np.uint16).copy()
+    t["cstart"] = buf[off_cs:off_cs + 2 * (t["n_cells"] + 1)].view(np.uint16).copy()
+    t["outer"] = buf[off_bx:off_bx + 16 * M].view(np.float32).reshape(M, 4).copy()
+    t["inner"] = buf[off_bx + 16 * M:off_bx + 32 * M].view(np.float32).reshape(M, 4).copy()
+    t["order"] = order[:M].copy()
+    return t
 
 
 def belief_distance_cols(ctx, bel, dim, cols):

@@ -345,7 +345,7 @@ static float f32_down(double v) {
     return std::nextafterf(f, -HUGE_VALF);
 }
 
-struct GridBuild { std::vector<unsigned char> buf; std::vector<double> exB; std::vector<int32_t> exCls; };
+struct GridBuild { std::vector<unsigned char> buf; std::vector<double> exB; std::vector<int32_t> exCls; std::vector<int32_t> order; };
 
 static void build_grid_table(int M, const double* A, const double* B, const std::vector<int>& cls_idx, double c, GridBuild& out) {
     const bool c_ok = std::isfinite(c) && c >= 0.0 && c < 1e6;
@@ -372,6 +372,14 @@ static void build_grid_table(int M, const double* A, const double* B, const std:
             } else pure = false;
         }
         if (!pure || sides != 15) q = Box{HUGE_VALF, HUGE_VALF, -HUGE_VALF, -HUGE_VALF};
+        // sides beyond the magnitudes the broad phase accepts (|x|, P < 1e30) become infinite, so that one far-away
+        // plane cannot stretch the bitmap grid: towards "never proven" from 1e30 on (always allowed), towards "always
+        // proven" only beyond 1e31 (x -+ ex stays below 1.01e30 for every belief that passes the finiteness guard)
+        auto clamp_hi = [](float v) { return v > 1e30f ? HUGE_VALF : (v < -1e31f ? -HUGE_VALF : v); };   // proven if x - ex >= v
+        auto clamp_lo = [](float v) { return v < -1e30f ? -HUGE_VALF : (v > 1e31f ? HUGE_VALF : v); };   // proven if x + ex <= v
+        b.xhi = clamp_hi(b.xhi); b.yhi = clamp_hi(b.yhi); b.xlo = clamp_lo(b.xlo); b.ylo = clamp_lo(b.ylo);
+        if (!(std::fabs(b.xlo) < 1e30f && std::fabs(b.ylo) < 1e30f && std::fabs(b.xhi) < 1e30f && std::fabs(b.yhi) < 1e30f))
+            q = Box{HUGE_VALF, HUGE_VALF, -HUGE_VALF, -HUGE_VALF};
         box[o] = b; inner[o] = q;
         const bool finite = std::isfinite(b.xlo) && std::isfinite(b.ylo) && std::isfinite(b.xhi) && std::isfinite(b.yhi);
         (finite ? gridded : always).push_back(o);
@@ -451,10 +459,31 @@ static void build_grid_table(int M, const double* A, const double* B, const std:
         std::memcpy(out.buf.data() + h.off_boxes + (size_t)(M + j) * 16, &inner[o], 16);
         std::memcpy(out.exB.data() + (size_t)j * 4, B + 4 * o, 32);
         out.exCls[j] = cls_idx[o];
+        out.order.push_back(o);
         ++j;
     };
     for (auto& e : ents) put(e.o);
     for (int o : always) put(o);
+}
+
+// Host-only: the serialised grid table cck_set_obstacles would upload (no GPU, no context needed), so that its
+// invariants can be tested on a CPU-only machine: layout = GHeader (80 B: int32 total_bytes, M, n_grid, n_cells, R,
+// off_occ, off_rowbase, off_cstart, off_boxes, pad; float gx0, gy0, icx, icy, SX, SY, k, Rm1; 2 x int32 pad), uint64 occ[R],
+// uint16 rowbase[R], uint16 cstart[n_cells+1], float4 outer[M], float4 inner[M] (xlo, ylo, xhi, yhi).  order[j] = index of
+// the obstacle stored in row j.
+extern "C" int cck_build_grid_table(int M, const double* A, const double* B, double erf_inv_result, unsigned char* out, int64_t cap,
+                                    int64_t* bytes, int32_t* order) {
+    if (M < 0 || (M > 0 && (!A || !B)) || !bytes) return CCK_ERR_INVALID;
+    GridBuild gb;
+    std::vector<int> cls_idx(std::max(M, 1), 0);
+    build_grid_table(M, A, B, cls_idx, erf_inv_result, gb);
+    *bytes = (int64_t)gb.buf.size();
+    if (out) {
+        if (cap < (int64_t)gb.buf.size()) return CCK_ERR_INVALID;
+        std::memcpy(out, gb.buf.data(), gb.buf.size());
+    }
+    if (order) for (int j = 0; j < M; ++j) order[j] = gb.order[j];
+    return CCK_OK;
 }
 
 // Group obstacles by bit-identical A[4][2] and lay the table out for one TMA bulk copy.

@@ -225,6 +225,13 @@ int cck_select_winner_dev(cck_ctx* ctx, void* stream, int64_t n, const double* c
  * FP64 entry). */
 int cck_measure_fp64_peak(cck_ctx* ctx, double* tflops);
 
+/* Host-only (no GPU, no context): the serialised fp32 box + bitmap-grid table that cck_set_obstacles builds for the
+ * PCCBlackmoreSVC broad phase (PCCBlackmoreSVC.cpp:54-75 is what it must never contradict).  Exposed so that the
+ * table's invariants — every obstacle binned into its own cell, boxes rounded outward / inward by at least one ulp —
+ * can be tested without a device.  `out` may be NULL to query `*bytes`; order[j] = obstacle stored in row j. */
+int cck_build_grid_table(int M, const double* A, const double* B, double erf_inv_result, unsigned char* out, int64_t cap,
+                         int64_t* bytes, int32_t* order);
+
 /* ---- belief-space nearest neighbours over a device-resident tree ----
  * RealVectorBeliefSpace::distance (src/Spaces/RealVectorBeliefSpace.cpp:16-62):
  *   | ||mu1-mu2||^2 + trace(C1 + C2 - 2 (C2^1/2 C1 C2^1/2)^1/2) |, 0 when the means coincide, C = Sigma + Lambda.

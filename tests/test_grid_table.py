@@ -1,0 +1,209 @@
+"""CPU-only tests of the fp32 box + bitmap-grid broad phase of the PCCBlackmore rollout kernels
+(csrc/cck_rollout_grid.cuh): the table is built by host code (cck_build_grid_table needs no GPU), and the device's
+fp32 query is re-enacted here in numpy float32 arithmetic (IEEE round-to-nearest, like the kernel's FADD/FMUL).
+
+What must hold for verdicts to stay bit-identical to PCCBlackmoreSVC::isValid (PCCBlackmoreSVC.cpp:54-75):
+  1. every obstacle with a finite box is binned into exactly the cell the monotone cell function assigns to it,
+  2. outer boxes contain, inner boxes are contained in, the exact thresholds b/a with at least one fp32 ulp to spare,
+  3. "interval misses the outer box" (proven safe) implies the reference's fp64 predicate is TRUE,
+     "interval inside the inner box" (proven unsafe) implies it is FALSE,
+  4. every obstacle that is not proven safe lies in the queried cell window (or in the always-list).
+"""
+import numpy as np
+import pytest
+
+f32 = np.float32
+
+
+def _tables(K, W, which, rng):
+    rad = K.rect_robot_bounding_radius()
+    if which == "synthetic":
+        centres = W.synthetic_obstacles(256, W.SEED, "realistic")
+        A, B, _ = K.build_obstacle_tables(centres, rad)
+    elif which == "far":
+        centres = W.synthetic_obstacles(256, W.SEED, "all_survive")
+        A, B, _ = K.build_obstacle_tables(centres, rad)
+    elif which == "dense32":
+        cells = rng.choice(32 * 32, size=102, replace=False)
+        centres = np.stack([cells % 32, cells // 32], axis=1).astype(np.float64)
+        A, B, _ = K.build_obstacle_tables(centres, rad)
+    else:   # arbitrary: axis-aligned boxes of random size/scale, some rotated, some with non-finite or duplicated planes
+        M = 300
+        A, B = np.zeros((M, 4, 2)), np.zeros((M, 4))
+        for o in range(M):
+            cx, cy = rng.uniform(0, 63, 2)
+            hw, hh = rng.uniform(0.2, 1.5, 2)
+            w = rng.uniform(0.5, 3.0)
+            th = rng.uniform(0, np.pi) if o % 5 == 0 else 0.0
+            ct, st = (1.0, 0.0) if th == 0.0 else (np.cos(th), np.sin(th))
+            for i, ((nx, ny), e) in enumerate(zip([(st, -ct), (ct, st), (-st, ct), (-ct, -st)], [hh, hw, hh, hw])):
+                A[o, i] = (w * nx, w * ny)
+                B[o, i] = w * (nx * cx + ny * cy + e)
+        B[3, 1] = np.inf; B[7, 0] = -np.inf; B[11, 2] = np.nan
+        A[13] = [[2.0, 0.0], [1.5, 0.0], [0.0, 1.0], [0.0, -1.0]]; B[13] = [60.0, 46.5, 20.0, -18.0]
+    return A, B
+
+
+def _exact_safe(A, B, x, y, P, c):
+    """HyperplaneCCValidityChecker_ per (belief, obstacle): [n, M] bool, float64 in the reference's operation order."""
+    a0, a1 = A[None, :, :, 0], A[None, :, :, 1]                       # [1, M, 4]
+    P0, P1, P2, P3 = (P[:, k][:, None, None] for k in range(4))
+    with np.errstate(all="ignore"):
+        t0 = a0 * P0 + a1 * P2
+        t1 = a0 * P1 + a1 * P3
+        tmp = t0 * a0 + t1 * a1
+        bb = np.sqrt(np.float64(2.0)) * np.sqrt(tmp) * c
+        ok = (x[:, None, None] * a0 + y[:, None, None] * a1) >= (B[None, :, :] + bb)
+    return ok.any(axis=2)
+
+
+def _device_query(t, x, y, P, sqrt_err=0.0):
+    """The kernel's fp32 prologue (grid_check), in numpy float32.  sqrt_err perturbs the approximate sqrt."""
+    xf, yf = x.astype(f32), y.astype(f32)
+    p0, p3 = P[:, 0].astype(f32), P[:, 3].astype(f32)
+    offd = (np.abs(P[:, 1]) + np.abs(P[:, 2])).astype(f32)
+    with np.errstate(all="ignore"):
+        fin = ((np.abs(xf) + np.abs(yf)) + (p0 + p3) + offd < f32(1e30)) & (p0 >= 0) & (p3 >= 0)
+        s0 = (np.sqrt(p0) * f32(1.0 + sqrt_err)).astype(f32)
+        s3 = (np.sqrt(p3) * f32(1.0 + sqrt_err)).astype(f32)
+        ex, ey = f32(t["k"]) * s0, f32(t["k"]) * s3
+        mx = (np.abs(xf) + ex) * f32(3.814697265625e-06) + f32(1e-17)
+        my = (np.abs(yf) + ey) * f32(3.814697265625e-06) + f32(1e-17)
+        dx, sx, dy, sy = xf - ex, xf + ex, yf - ey, yf + ey
+    q = {"fin": fin, "xm": dx - mx, "xp": sx + mx, "ym": dy - my, "yp": sy + my,
+         "xmi": dx + mx, "xpi": sx - mx, "ymi": dy + my, "ypi": sy - my}
+    return q
+
+
+def _cell(v, g0, ic):
+    with np.errstate(all="ignore"):
+        return np.floor((v.astype(f32) - f32(g0)) * f32(ic))
+
+
+def _sub_rd(a, b):
+    """fp32 subtraction rounded towards -inf (__fsub_rd)."""
+    with np.errstate(all="ignore"):
+        exact = a.astype(np.float64) - np.float64(b)
+        r = exact.astype(f32)
+        r = np.where(r.astype(np.float64) > exact, np.nextafter(r, f32(-np.inf)), r)
+    return r.astype(f32)
+
+
+@pytest.mark.parametrize("which", ["synthetic", "far", "dense32", "arbitrary"])
+def test_grid_table_invariants(K, W, which):
+    rng = np.random.default_rng(3)
+    A, B = _tables(K, W, which, rng)
+    M = len(A)
+    c = 2.2
+    t = K.capi.build_grid_table(A, B, c)
+    assert t["M"] == M and sorted(t["order"].tolist()) == list(range(M))
+    ng = t["n_grid"]
+    outer, inner, order = t["outer"], t["inner"], t["order"]
+    assert np.isfinite(outer[:ng]).all() and not np.isfinite(outer[ng:]).all(axis=1).any()
+    assert float(t["k"]) >= np.sqrt(2.0) * c
+    # 1. binning: cell function, bitmap bit, popcount rank, CSR range
+    cx = _cell(outer[:ng, 0], t["gx0"], t["icx"]).astype(int)
+    cy = _cell(outer[:ng, 1], t["gy0"], t["icy"]).astype(int)
+    assert (cx >= 0).all() and (cx <= 63).all() and (cy >= 0).all() and (cy < t["R"]).all()
+    for j in range(ng):
+        occ = int(t["occ"][cy[j]])
+        assert (occ >> int(cx[j])) & 1
+        cell = int(t["rowbase"][cy[j]]) + bin(occ & ((1 << int(cx[j])) - 1)).count("1")
+        assert t["cstart"][cell] <= j < t["cstart"][cell + 1]
+    assert sum(bin(int(o)).count("1") for o in t["occ"]) == t["n_cells"] and t["cstart"][-1] == ng
+    if ng:
+        assert float(t["SX"]) >= (outer[:ng, 2].astype(np.float64) - outer[:ng, 0]).max()
+        assert float(t["SY"]) >= (outer[:ng, 3].astype(np.float64) - outer[:ng, 1]).max()
+    # 2. box sides vs the exact thresholds b/a of the axis-aligned planes, with >= 1 ulp to spare.  Several planes of
+    #    the same direction are OR-ed by the reference, so the weakest threshold (min for +, max for -) defines the side.
+    for j in range(M):
+        o = order[j]
+        thr = {"+x": [], "-x": [], "+y": [], "-y": []}
+        for i in range(4):
+            a0, a1, b = A[o, i, 0], A[o, i, 1], B[o, i]
+            if np.isnan(b) or not (np.isfinite(a0) and np.isfinite(a1)):
+                continue
+            if a1 == 0 and 1e-100 < abs(a0) < 1e100:
+                thr["+x" if a0 > 0 else "-x"].append(b / a0)
+            elif a0 == 0 and 1e-100 < abs(a1) < 1e100:
+                thr["+y" if a1 > 0 else "-y"].append(b / a1)
+        with np.errstate(all="ignore"):
+            for key, col, up in (("+x", 2, True), ("+y", 3, True), ("-x", 0, False), ("-y", 1, False)):
+                side = outer[j, col]
+                if not thr[key]:
+                    assert side == (np.inf if up else -np.inf)
+                    continue
+                e = min(thr[key]) if up else max(thr[key])
+                if up:
+                    assert float(side) >= e and (np.isinf(side) or float(np.nextafter(side, f32(-np.inf))) >= e)
+                else:
+                    assert float(side) <= e and (np.isinf(side) or float(np.nextafter(side, f32(np.inf))) <= e)
+        if np.isfinite(inner[j]).all():      # inner box strictly inside the outer one
+            assert inner[j, 0] > outer[j, 0] and inner[j, 1] > outer[j, 1] and inner[j, 2] < outer[j, 2] and inner[j, 3] < outer[j, 3]
+
+
+@pytest.mark.parametrize("which", ["synthetic", "dense32", "arbitrary"])
+@pytest.mark.parametrize("sqrt_err", [0.0, 2.0 ** -22, -(2.0 ** -22)])
+def test_fp32_broad_phase_never_contradicts_the_fp64_predicate(K, W, which, sqrt_err):
+    rng = np.random.default_rng(11)
+    A, B = _tables(K, W, which, rng)
+    M = len(A)
+    c = 2.2
+    t = K.capi.build_grid_table(A, B, c)
+    outer, inner, order, ng = t["outer"], t["inner"], t["order"], t["n_grid"]
+    Ao, Bo = A[order], B[order]                                      # rows in table order
+    n = 40000
+    span = 64.0 if which != "dense32" else 32.0
+    x, y = rng.uniform(-1.5, span + 0.5, n), rng.uniform(-1.5, span + 0.5, n)
+    Lc = rng.uniform(0.01, 0.35, (n, 3))
+    P = np.stack([Lc[:, 0] ** 2, Lc[:, 0] * Lc[:, 1], Lc[:, 0] * Lc[:, 1], Lc[:, 1] ** 2 + Lc[:, 2] ** 2], axis=1)
+    P[::11] *= 1e-6                                                  # tiny covariances
+    # a third of the beliefs sit within a few fp32 ulps of a box side widened by their own (ex, ey)
+    kf = float(t["k"])
+    sel = rng.integers(0, max(ng, 1), n)
+    for side in range(4):
+        idx = np.arange(side, n, 12)
+        if ng == 0:
+            break
+        jj = sel[idx]
+        e = kf * np.sqrt(P[idx, 0] if side in (0, 2) else P[idx, 3])
+        jitter = rng.uniform(-3e-5, 3e-5, len(idx))
+        if side == 0:
+            x[idx] = outer[jj, 2] + e + jitter; y[idx] = (outer[jj, 1].astype(np.float64) + outer[jj, 3]) / 2
+        elif side == 2:
+            x[idx] = outer[jj, 0] - e + jitter; y[idx] = (outer[jj, 1].astype(np.float64) + outer[jj, 3]) / 2
+        elif side == 1:
+            y[idx] = outer[jj, 3] + e + jitter; x[idx] = (outer[jj, 0].astype(np.float64) + outer[jj, 2]) / 2
+        else:
+            y[idx] = outer[jj, 1] - e + jitter; x[idx] = (outer[jj, 0].astype(np.float64) + outer[jj, 2]) / 2
+    q = _device_query(t, x, y, P, sqrt_err)
+    fin = q["fin"]
+    assert fin.all()
+    exact = _exact_safe(Ao, Bo, x, y, P, c)                          # [n, M]
+    with np.errstate(all="ignore"):
+        proven_safe = ((q["xm"][:, None] >= outer[None, :, 2]) | (q["xp"][:, None] <= outer[None, :, 0]) |
+                       (q["ym"][:, None] >= outer[None, :, 3]) | (q["yp"][:, None] <= outer[None, :, 1]))
+        proven_unsafe = ((q["xmi"][:, None] < inner[None, :, 2]) & (q["xpi"][:, None] > inner[None, :, 0]) &
+                         (q["ymi"][:, None] < inner[None, :, 3]) & (q["ypi"][:, None] > inner[None, :, 1]))
+    # 3. the broad phase may only prove what the fp64 predicate says
+    assert not (proven_safe & ~exact).any()
+    assert not (proven_unsafe & exact).any()
+    assert not (proven_safe & proven_unsafe).any()
+    undecided = ~proven_safe & ~proven_unsafe
+    if which == "arbitrary":      # a fifth of those obstacles is rotated: no box, always decided by the exact expression
+        assert proven_safe.mean() > 0.7 and proven_unsafe.any() and undecided[:, np.isfinite(outer).all(axis=1)].mean() < 0.01
+    else:
+        assert proven_safe.mean() > 0.9 and proven_unsafe.any() and undecided.mean() < 0.01
+    # 4. every obstacle that is not proven safe is found through the bitmap window (or sits in the always-list)
+    clo = np.maximum(_cell(_sub_rd(q["xm"], t["SX"]), t["gx0"], t["icx"]), 0)
+    chi = np.minimum(_cell(q["xp"], t["gx0"], t["icx"]), 63)
+    rlo = np.maximum(_cell(_sub_rd(q["ym"], t["SY"]), t["gy0"], t["icy"]), 0)
+    rhi = np.minimum(_cell(q["yp"], t["gy0"], t["icy"]), t["Rm1"])
+    if ng:
+        cx = _cell(outer[:ng, 0], t["gx0"], t["icx"])
+        cy = _cell(outer[:ng, 1], t["gy0"], t["icy"])
+        in_window = ((cx[None, :] >= clo[:, None]) & (cx[None, :] <= chi[:, None]) &
+                     (cy[None, :] >= rlo[:, None]) & (cy[None, :] <= rhi[:, None]))
+        assert not (~proven_safe[:, :ng] & ~in_window).any()
+        # the window is not vacuous: it skips most of the table
+        assert in_window.mean() < 0.05
