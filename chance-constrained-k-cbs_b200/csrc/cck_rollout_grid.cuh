@@ -75,32 +75,48 @@ __device__ __forceinline__ float sqrt_approx(float v) {
 // One obstacle the broad phase could not skip: outer box (proves safe), inner box (proves unsafe:
 // every plane fails with margin; +-inf for obstacles that are not one-plane-per-side boxes), else the
 // reference's fp64 expression.
-__device__ __forceinline__ bool grid_obstacle(const float4* boxes, int M, int j, float xm, float xp, float ym, float yp, float xmi,
-                                              float xpi, float ymi, float ypi, const ClassRec* cls, const double* exB,
-                                              const int32_t* exCls, double c, double x, double y, double P0, double P1, double P2,
-                                              double P3) {
+template <class Exact>
+__device__ __forceinline__ bool grid_obstacle(const GridConst& g, const unsigned char* gt, int j, float xm, float xp, float ym, float yp, float xmi,
+                                              float xpi, float ymi, float ypi, const Exact& exact) {
+    // the box arrays live in shared memory behind the grid, or in global memory when they are too large for it; the
+    // choice is made here, on the rare path, not once per belief-step
+    const float4* boxes = g.boxes_global ? g.boxes_global : reinterpret_cast<const float4*>(gt + g.off_boxes);
     const float4 b = boxes[j];
     if ((xm >= b.z) | (xp <= b.x) | (ym >= b.w) | (yp <= b.y)) return true;
-    const float4 q = boxes[M + j];
+    const float4 q = boxes[g.M + j];
     if ((xmi < q.z) & (xpi > q.x) & (ymi < q.w) & (ypi > q.y)) return false;
-    return bm_exact_obstacle(cls[exCls[j]].A, exB + (size_t)j * 4, x, y, P0, P1, P2, P3, c);
+    return exact(j);
 }
 
 // "the belief is safe w.r.t. every obstacle" (PCCBlackmoreSVC.cpp:54-58), bit-exact.
+// SPLIT: the covariance arrives as its two summands (P = Sa + Sb, the reference's Sigma + Lambda).  The sums are formed
+// here for the fp32 broad phase and formed AGAIN (same operands, same result) where the exact path needs them, behind an
+// opaque asm so that the compiler cannot keep the first copies alive: 8 registers less across the hot loop.
+template <bool SPLIT = false>
 __device__ __forceinline__ bool grid_check(const GridConst& g, const unsigned char* gt, const unsigned char* ctab, const double* exB,
-                                           const int32_t* exCls, double c, double x, double y, double P0, double P1, double P2, double P3) {
+                                           const int32_t* exCls, double c, double x, double y, double Sa0, double Sa1, double Sa2, double Sa3,
+                                           double Sb0 = 0, double Sb1 = 0, double Sb2 = 0, double Sb3 = 0) {
     const GridConst* h = &g;
-    const float4* boxes = h->boxes_global ? h->boxes_global : reinterpret_cast<const float4*>(gt + h->off_boxes);
-    const ClassRec* cls = reinterpret_cast<const ClassRec*>(ctab + h->off_classes);   // a kernel constant: no header load per step
     const int M = h->M;
+    const double P0 = SPLIT ? Sa0 + Sb0 : Sa0, P1 = SPLIT ? Sa1 + Sb1 : Sa1, P2 = SPLIT ? Sa2 + Sb2 : Sa2, P3 = SPLIT ? Sa3 + Sb3 : Sa3;
     const float xf = __double2float_rn(x), yf = __double2float_rn(y);
     const float p0 = __double2float_rn(P0), p3 = __double2float_rn(P3);
     const float offd = __double2float_rn(fabs(P1) + fabs(P2));
     // every operand finite and far from fp32 overflow, variances non-negative (false for NaN)
     const bool fin = (fabsf(xf) + fabsf(yf)) + (p0 + p3) + offd < 1e30f && p0 >= 0.f && p3 >= 0.f;
+    // the reference's fp64 expression on obstacle j's own normals
+    auto exact = [&](int j) -> bool {
+        const ClassRec* cls = reinterpret_cast<const ClassRec*>(ctab + h->off_classes);   // a kernel constant: no header load
+        if (SPLIT) {
+            double s0 = Sa0, s1 = Sa1, s2 = Sa2, s3 = Sa3;
+            asm volatile("" : "+d"(s0), "+d"(s1), "+d"(s2), "+d"(s3));
+            return bm_exact_obstacle(cls[exCls[j]].A, exB + (size_t)j * 4, x, y, s0 + Sb0, s1 + Sb1, s2 + Sb2, s3 + Sb3, c);
+        }
+        return bm_exact_obstacle(cls[exCls[j]].A, exB + (size_t)j * 4, x, y, P0, P1, P2, P3, c);
+    };
     if (!fin) {   // rare: decide every obstacle with the reference's expression
         bool ok = true;
-        for (int j = 0; j < M && ok; ++j) ok = bm_exact_obstacle(cls[exCls[j]].A, exB + (size_t)j * 4, x, y, P0, P1, P2, P3, c);
+        for (int j = 0; j < M && ok; ++j) ok = exact(j);
         return ok;
     }
     const float ex = h->k * sqrt_approx(p0), ey = h->k * sqrt_approx(p3);
@@ -133,13 +149,13 @@ __device__ __forceinline__ bool grid_check(const GridConst& g, const unsigned ch
                 const int cell = rowbase[r] + __popcll(oc & ((1ull << cc) - 1ull));
                 const int j1 = cstart[cell + 1];
                 for (int j = cstart[cell]; j < j1 && ok; ++j)
-                    ok = grid_obstacle(boxes, M, j, xm, xp, ym, yp, xmi, xpi, ymi, ypi, cls, exB, exCls, c, x, y, P0, P1, P2, P3);
+                    ok = grid_obstacle(g, gt, j, xm, xp, ym, yp, xmi, xpi, ymi, ypi, exact);
             }
         }
     }
     // obstacles without a finite box (non-axis-aligned planes, unusable constants): box sides are +-inf
     for (int j = h->n_grid; j < M && ok; ++j)
-        ok = grid_obstacle(boxes, M, j, xm, xp, ym, yp, xmi, xpi, ymi, ypi, cls, exB, exCls, c, x, y, P0, P1, P2, P3);
+        ok = grid_obstacle(g, gt, j, xm, xp, ym, yp, xmi, xpi, ymi, ypi, exact);
     return ok;
 }
 
@@ -239,10 +255,7 @@ __global__ void __launch_bounds__(CCK_GRID_THREADS, CCK_GRID_MINB) k_rollout_lin
         cp_async8(slot + 10 * CCK_GRID_THREADS, a.ctrl + nxt);
         cp_async8(slot + 11 * CCK_GRID_THREADS, a.ctrl + a.ldc + nxt);
         cp_async4(islot, a.steps + nxt);
-        if (EXPAND) {
-            cp_async8(slot + 12 * CCK_GRID_THREADS, a.parent_cost + nxt);
-            cp_async4(islot + CCK_GRID_THREADS, a.parent_step + nxt);
-        }
+        if (EXPAND) cp_async4(islot + CCK_GRID_THREADS, a.parent_step + nxt);
         cp_async_commit();
     };
     prefetch();
@@ -250,92 +263,99 @@ __global__ void __launch_bounds__(CCK_GRID_THREADS, CCK_GRID_MINB) k_rollout_lin
 
     bool have = false;
     Lin cur;
-    double dux = 0, duy = 0, x0 = 0, y0 = 0, pcost = 0;
+    double dux = 0, duy = 0;
     int steps = 0, t = 0, pstep = 0;
     int i = 0;
     bool cons_ok = true;
     cur.mx = cur.my = 0;
 #pragma unroll
     for (int f = 0; f < 4; ++f) cur.S[f] = cur.L[f] = 0;
-    while (true) {
+    // one belief-step of a lane (A: state on entry, B: state on exit; the caller passes the same object, the step is
+    // alias-safe).  Returns true when the lane has run out of work.
+    auto step = [&](Lin& A, Lin& B) -> bool {
         while (!have && nxt >= 0) {   // take the prefetched belief, start copying the one after it
             cp_async_wait_all();
             i = nxt;
-            cur.mx = slot[0]; cur.my = slot[CCK_GRID_THREADS];
+            A.mx = slot[0]; A.my = slot[CCK_GRID_THREADS];
 #pragma unroll
-            for (int f = 0; f < 4; ++f) { cur.S[f] = slot[(2 + f) * CCK_GRID_THREADS]; cur.L[f] = slot[(6 + f) * CCK_GRID_THREADS]; }
+            for (int f = 0; f < 4; ++f) { A.S[f] = slot[(2 + f) * CCK_GRID_THREADS]; A.L[f] = slot[(6 + f) * CCK_GRID_THREADS]; }
             dux = p.dt * slot[10 * CCK_GRID_THREADS]; duy = p.dt * slot[11 * CCK_GRID_THREADS];
             steps = islot[0];
-            if (EXPAND) { pcost = slot[12 * CCK_GRID_THREADS]; pstep = islot[CCK_GRID_THREADS]; }
+            if (EXPAND) pstep = islot[CCK_GRID_THREADS];
             prefetch();
             if (steps <= 0) {         // propagateWhileValid(.., 0, ..): copy, return 0
-                a.out[i] = cur.mx; a.out[a.ldo + i] = cur.my;
+                a.out[i] = A.mx; a.out[a.ldo + i] = A.my;
 #pragma unroll
-                for (int f = 0; f < 4; ++f) { a.out[(2 + f) * a.ldo + i] = cur.S[f]; a.out[(6 + f) * a.ldo + i] = cur.L[f]; }
+                for (int f = 0; f < 4; ++f) { a.out[(2 + f) * a.ldo + i] = A.S[f]; a.out[(6 + f) * a.ldo + i] = A.L[f]; }
                 a.valid[i] = 0;
                 if (EXPAND) {
                     double gd;
-                    const bool g = goal_ok(a.goal, sp, cur.mx, cur.my, cur.S[0] + cur.L[0], cur.S[1] + cur.L[1], cur.S[2] + cur.L[2],
-                                           cur.S[3] + cur.L[3], &gd);
-                    a.cost[i] = pcost + 0.0;
+                    const bool g = goal_ok(a.goal, sp, A.mx, A.my, A.S[0] + A.L[0], A.S[1] + A.L[1], A.S[2] + A.L[2], A.S[3] + A.L[3], &gd);
+                    a.cost[i] = a.parent_cost[i] + 0.0;
                     a.goal_dist[i] = gd;
                     a.flags[i] = (uint8_t)(1 | 2 | (g ? 4 : 0));
                 }
                 continue;
             }
-            x0 = cur.mx; y0 = cur.my;
             t = 0; cons_ok = true;
             have = true;
         }
-        if (__all_sync(0xffffffffu, !have)) break;
-        if (!have) continue;
-        // stash the last valid state, advance in place
-        stash[0] = make_double2(cur.mx, cur.my);
-        stash[1] = make_double2(cur.S[0], cur.S[1]); stash[2] = make_double2(cur.S[2], cur.S[3]);
-        stash[3] = make_double2(cur.L[0], cur.L[1]); stash[4] = make_double2(cur.L[2], cur.L[3]);
-        lin_step(cur, dux, duy, p, cur);
-        const double x = cur.mx, y = cur.my;
-        const double P0 = cur.S[0] + cur.L[0], P1 = cur.S[1] + cur.L[1], P2 = cur.S[2] + cur.L[2], P3 = cur.S[3] + cur.L[3];
+        if (!have) return true;       // no belief left for this lane: it leaves the loop on its own (nothing below is warp-collective)
+        // stash the last valid state, advance A -> B
+        stash[0] = make_double2(A.mx, A.my);
+        stash[1] = make_double2(A.S[0], A.S[1]); stash[2] = make_double2(A.S[2], A.S[3]);
+        stash[3] = make_double2(A.L[0], A.L[1]); stash[4] = make_double2(A.L[2], A.L[3]);
+        lin_step(A, dux, duy, p, B);
+        const double x = B.mx, y = B.my;
         // satisfiesBounds (NaN passes): the mean rounded to fp32 strictly inside the inward-rounded bounds proves it
         // (RN is monotone: xf < bhx <= high implies x < high); otherwise the exact fp64 test decides
         const float xf = __double2float_rn(x), yf = __double2float_rn(y);
         bool ok = (xf > g.blx) & (xf < g.bhx) & (yf > g.bly) & (yf < g.bhy);
         if (!ok) ok = !(x - eps > sp.high[0] || x + eps < sp.low[0] || y - eps > sp.high[1] || y + eps < sp.low[1]);
-        if (ok && a.ftab_bytes > 0) ok = grid_check(g, gt, a.tab, a.exB, a.exCls, c, x, y, P0, P1, P2, P3);
+        if (ok && a.ftab_bytes > 0)
+            ok = grid_check<true>(g, gt, a.tab, a.exB, a.exCls, c, x, y, B.S[0], B.S[1], B.S[2], B.S[3], B.L[0], B.L[1], B.L[2], B.L[3]);
         int r = -1;                // >= 0: this rollout ends now with r valid steps
         if (!ok) {
-            r = t;                 // died: the result is the last valid state
-            const double2 s0 = stash[0], s1 = stash[1], s2 = stash[2], s3 = stash[3], s4 = stash[4];
-            cur.mx = s0.x; cur.my = s0.y; cur.S[0] = s1.x; cur.S[1] = s1.y; cur.S[2] = s2.x; cur.S[3] = s2.y;
-            cur.L[0] = s3.x; cur.L[1] = s3.y; cur.L[2] = s4.x; cur.L[3] = s4.y;
+            r = t;                 // died: the result is the last valid state (restored below, on the finish path)
         } else {
-            if (EXPAND && cons) cons_ok = cons_ok && constraints_ok_at(cons, pstep + t + 1, x, y, P0, P1, P2, P3);
+            if (EXPAND && cons) {   // Sigma + Lambda formed here, not carried across the validity check
+                double s0 = B.S[0], s1 = B.S[1], s2 = B.S[2], s3 = B.S[3];
+                asm volatile("" : "+d"(s0), "+d"(s1), "+d"(s2), "+d"(s3));
+                cons_ok = cons_ok && constraints_ok_at(cons, pstep + t + 1, x, y, s0 + B.L[0], s1 + B.L[1], s2 + B.L[2], s3 + B.L[3]);
+            }
             if (TRAJ) {
                 double* tp = a.traj + (int64_t)t * 10 * a.traj_ld + i;
-                tp[0] = cur.mx; tp[a.traj_ld] = cur.my;
+                tp[0] = B.mx; tp[a.traj_ld] = B.my;
 #pragma unroll
-                for (int f = 0; f < 4; ++f) { tp[(2 + f) * a.traj_ld] = cur.S[f]; tp[(6 + f) * a.traj_ld] = cur.L[f]; }
+                for (int f = 0; f < 4; ++f) { tp[(2 + f) * a.traj_ld] = B.S[f]; tp[(6 + f) * a.traj_ld] = B.L[f]; }
             }
             ++t;
             if (t == steps) r = steps;
         }
         if (r >= 0) {
-            a.out[i] = cur.mx; a.out[a.ldo + i] = cur.my;
+            if (!ok) {
+                const double2 s0 = stash[0], s1 = stash[1], s2 = stash[2], s3 = stash[3], s4 = stash[4];
+                B.mx = s0.x; B.my = s0.y; B.S[0] = s1.x; B.S[1] = s1.y; B.S[2] = s2.x; B.S[3] = s2.y;
+                B.L[0] = s3.x; B.L[1] = s3.y; B.L[2] = s4.x; B.L[3] = s4.y;
+            }
+            a.out[i] = B.mx; a.out[a.ldo + i] = B.my;
 #pragma unroll
-            for (int f = 0; f < 4; ++f) { a.out[(2 + f) * a.ldo + i] = cur.S[f]; a.out[(6 + f) * a.ldo + i] = cur.L[f]; }
+            for (int f = 0; f < 4; ++f) { a.out[(2 + f) * a.ldo + i] = B.S[f]; a.out[(6 + f) * a.ldo + i] = B.L[f]; }
             a.valid[i] = r;
             if (EXPAND) {
-                const double d0 = x0 - cur.mx, d1 = y0 - cur.my;
-                a.cost[i] = pcost + sqrt(d0 * d0 + d1 * d1);
+                // the rollout's start and the parent's cost are re-read here (L2 hits) instead of riding in six registers
+                const double d0 = a.bel[i] - B.mx, d1 = a.bel[a.ld + i] - B.my;
+                a.cost[i] = a.parent_cost[i] + sqrt(d0 * d0 + d1 * d1);
                 double gd;
-                const bool g = goal_ok(a.goal, sp, cur.mx, cur.my, cur.S[0] + cur.L[0], cur.S[1] + cur.L[1], cur.S[2] + cur.L[2],
-                                       cur.S[3] + cur.L[3], &gd);
+                const bool g = goal_ok(a.goal, sp, B.mx, B.my, B.S[0] + B.L[0], B.S[1] + B.L[1], B.S[2] + B.L[2], B.S[3] + B.L[3], &gd);
                 a.goal_dist[i] = gd;
                 a.flags[i] = (uint8_t)((r == steps ? 1 : 0) | (cons_ok ? 2 : 0) | (g ? 4 : 0));
             }
             have = false;
         }
-    }
+        return false;
+    };
+    while (!step(cur, cur)) {}
 }
 
 }  // namespace cck
