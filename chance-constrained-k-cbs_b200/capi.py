@@ -471,7 +471,8 @@ def belief_distance_lower(ctx, bel, dim):
 
 def build_grid_table(A, B, erf_inv_result):
     """Host-only: parse the grid table cck_set_obstacles would upload.  Returns a dict with the header scalars,
-    occ[R] (uint64), rowbase, cstart, outer / inner boxes [M, 4] = (xlo, ylo, xhi, yhi) in row order, and order[M]."""
+    dstart[R*64+1] (dense row-major CSR over the cells), outer / inner boxes [M, 4] = (xlo, ylo, xhi, yhi) in row order,
+    and order[M]."""
     A = np.ascontiguousarray(A, dtype=np.float64).reshape(-1, 4, 2)
     B = np.ascontiguousarray(B, dtype=np.float64).reshape(-1, 4)
     M = len(A)
@@ -489,10 +490,8 @@ def build_grid_table(A, B, erf_inv_result):
     hf = buf[40:72].view(np.float32)
     t = {"total_bytes": int(hi[0]), "M": int(hi[1]), "n_grid": int(hi[2]), "n_cells": int(hi[3]), "R": int(hi[4]),
          "gx0": hf[0], "gy0": hf[1], "icx": hf[2], "icy": hf[3], "SX": hf[4], "SY": hf[5], "k": hf[6], "Rm1": hf[7]}
-    off_occ, off_rb, off_cs, off_bx = int(hi[5]), int(hi[6]), int(hi[7]), int(hi[8])
-    t["occ"] = buf[off_occ:off_occ + 8 * t["R"]].view(np.uint64).copy()
-    t["rowbase"] = buf[off_rb:off_rb + 2 * t["R"]].view(np.uint16).copy()
-    t["cstart"] = buf[off_cs:off_cs + 2 * (t["n_cells"] + 1)].view(np.uint16).copy()
+    off_cs, off_bx = int(hi[7]), int(hi[8])
+    t["dstart"] = buf[off_cs:off_cs + 2 * (t["n_cells"] + 1)].view(np.uint16).copy()
     t["outer"] = buf[off_bx:off_bx + 16 * M].view(np.float32).reshape(M, 4).copy()
     t["inner"] = buf[off_bx + 16 * M:off_bx + 32 * M].view(np.float32).reshape(M, 4).copy()
     t["order"] = order[:M].copy()

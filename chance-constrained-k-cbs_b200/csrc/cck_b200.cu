@@ -423,34 +423,28 @@ static void build_grid_table(int M, const double* A, const double* B, const std:
     std::vector<Ent> ents;
     for (int o : gridded) ents.push_back({(int)grid_cellf(box[o].ylo, h.gy0, h.icy), (int)grid_cellf(box[o].xlo, h.gx0, h.icx), o});
     std::stable_sort(ents.begin(), ents.end(), [](const Ent& a, const Ent& b) { return a.cy != b.cy ? a.cy < b.cy : a.cx < b.cx; });
-    std::vector<uint64_t> occ(CCK_GRID_ROWS, 0);
-    std::vector<uint16_t> rowbase(CCK_GRID_ROWS, 0), cstart;
+    // dense CSR over the R x 64 cells in row-major order (ents are sorted the same way): the obstacles whose anchor lies in
+    // row r, columns c0..c1 are the contiguous rows dstart[r*64 + c0] .. dstart[r*64 + c1 + 1] - 1 of the box arrays
+    const int R = ents.empty() ? 0 : ents.back().cy + 1;
+    std::vector<uint16_t> dstart((size_t)R * CCK_GRID_COLS + 1, 0);
     {
-        int prev_cy = -1, prev_cx = -1;
-        for (size_t e = 0; e < ents.size(); ++e) {
-            if (ents[e].cy != prev_cy || ents[e].cx != prev_cx) {
-                cstart.push_back((uint16_t)e);
-                occ[ents[e].cy] |= 1ull << ents[e].cx;
-                prev_cy = ents[e].cy; prev_cx = ents[e].cx;
-            }
+        size_t e = 0;
+        for (int idx = 0; idx <= R * CCK_GRID_COLS; ++idx) {
+            while (e < ents.size() && ents[e].cy * CCK_GRID_COLS + ents[e].cx < idx) ++e;
+            dstart[idx] = (uint16_t)e;
         }
-        h.n_cells = (int)cstart.size();
-        cstart.push_back((uint16_t)ents.size());
-        int acc = 0;
-        for (int r = 0; r < CCK_GRID_ROWS; ++r) { rowbase[r] = (uint16_t)acc; acc += __builtin_popcountll(occ[r]); }
     }
-    h.Rm1 = (float)(CCK_GRID_ROWS - 1);
+    h.R = R;
+    h.n_cells = R * CCK_GRID_COLS;
+    h.Rm1 = (float)(R - 1);      // -1 for an empty grid: every window is empty
     auto al = [](int v, int a) { return (v + a - 1) / a * a; };
-    h.off_occ = (int)sizeof(GHeader);
-    h.off_rowbase = h.off_occ + CCK_GRID_ROWS * 8;
-    h.off_cstart = h.off_rowbase + CCK_GRID_ROWS * 2;
-    h.off_boxes = al(h.off_cstart + (int)cstart.size() * 2, 16);
+    h.off_occ = 0; h.off_rowbase = 0;
+    h.off_cstart = (int)sizeof(GHeader);
+    h.off_boxes = al(h.off_cstart + (int)dstart.size() * 2, 16);
     h.total_bytes = al(h.off_boxes + 2 * M * 16, 16);
     out.buf.assign(h.total_bytes, 0);
     std::memcpy(out.buf.data(), &h, sizeof(h));
-    std::memcpy(out.buf.data() + h.off_occ, occ.data(), occ.size() * 8);
-    std::memcpy(out.buf.data() + h.off_rowbase, rowbase.data(), rowbase.size() * 2);
-    std::memcpy(out.buf.data() + h.off_cstart, cstart.data(), cstart.size() * 2);
+    std::memcpy(out.buf.data() + h.off_cstart, dstart.data(), dstart.size() * 2);
     out.exB.assign((size_t)std::max(M, 1) * 4, 0.0);
     out.exCls.assign(std::max(M, 1), 0);
     int j = 0;
@@ -467,10 +461,10 @@ static void build_grid_table(int M, const double* A, const double* B, const std:
 }
 
 // Host-only: the serialised grid table cck_set_obstacles would upload (no GPU, no context needed), so that its
-// invariants can be tested on a CPU-only machine: layout = GHeader (80 B: int32 total_bytes, M, n_grid, n_cells, R,
-// off_occ, off_rowbase, off_cstart, off_boxes, pad; float gx0, gy0, icx, icy, SX, SY, k, Rm1; 2 x int32 pad), uint64 occ[R],
-// uint16 rowbase[R], uint16 cstart[n_cells+1], float4 outer[M], float4 inner[M] (xlo, ylo, xhi, yhi).  order[j] = index of
-// the obstacle stored in row j.
+// invariants can be tested on a CPU-only machine: layout = GHeader (80 B: int32 total_bytes, M, n_grid, n_cells = R*64, R,
+// 0, 0, off_cstart, off_boxes, pad; float gx0, gy0, icx, icy, SX, SY, k, Rm1; 2 x int32 pad), uint16 dstart[R*64+1] (dense
+// row-major CSR over the cells), float4 outer[M], float4 inner[M] (xlo, ylo, xhi, yhi).  order[j] = index of the obstacle
+// stored in row j.
 extern "C" int cck_build_grid_table(int M, const double* A, const double* B, double erf_inv_result, unsigned char* out, int64_t cap,
                                     int64_t* bytes, int32_t* order) {
     if (M < 0 || (M > 0 && (!A || !B)) || !bytes) return CCK_ERR_INVALID;
@@ -657,7 +651,7 @@ extern "C" int cck_set_obstacles(cck_ctx* c, const cck_svc_params* p, const doub
         if (M > 65535) return fail(c, CCK_ERR_INVALID, "more than 65535 obstacles");
         GHeader gh0;
         std::memcpy(&gh0, gb.buf.data(), sizeof(gh0));
-        // small tables are staged whole; for large M only the header + bitmap + cell list (<= 9 KB) go to shared memory
+        // small tables are staged whole; for large M only the header + cell CSR (<= 8.3 KB) go to shared memory
         // and the box arrays (32 B per obstacle) are read from global memory
         const bool boxes_in_smem = gb.buf.size() <= 24 * 1024;
         const int stage_bytes = boxes_in_smem ? (int)gb.buf.size() : gh0.off_boxes;
@@ -840,7 +834,7 @@ static int launch_rollout(cck_ctx* c, cudaStream_t s, const RolloutArgs& a) {
         g2.ftab = c->d_gtab; g2.ftab_bytes = c->gtab_bytes; g2.exB = c->d_gexB; g2.exCls = c->d_gexCls;
         const int rl2 = rollout_range_log2(a.n);
         const int64_t nr = (a.n + ((int64_t)1 << rl2) - 1) >> rl2;
-        const int gb = (int)std::min<int64_t>(nr, (int64_t)c->num_sms * 4);
+        const int gb = (int)std::min<int64_t>(nr, (int64_t)c->num_sms * CCK_GRID_MINB);
         const int gsmem = grid_smem_bytes(c->gtab_bytes) + (EXPAND ? a.cons_smem_bytes : 0);
         if (traj) { if ((rc = set_smem(c, (k_rollout_lin_grid<true, EXPAND>), gsmem))) return rc;
                     k_rollout_lin_grid<true, EXPAND><<<gb, CCK_GRID_THREADS, gsmem, s>>>(g2, c->lin, c->svc, c->gconst, rl2); }

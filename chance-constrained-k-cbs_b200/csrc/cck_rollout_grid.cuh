@@ -13,10 +13,11 @@
 //    whose fp32 interval [x -+ ex] x [y -+ ey] (widened by an explicit rounding margin) misses the box
 //    is PROVEN safe for the reference's fp64 inequality.  Planes that are not axis-aligned simply do
 //    not contribute a side (side = +-inf): the obstacle is then decided by the exact path.
-//  * the boxes' lower-left corners are binned into a 64-column bitmap grid in shared memory; a
-//    belief-step looks at the 3-4 bitmap rows its interval overlaps, ANDs them with a column mask and
-//    only touches the obstacles of occupied cells (a handful, usually none).  The cell function is
-//    the same monotone fp32 expression on host and device, so no margin is needed for the binning.
+//  * the boxes' lower-left corners are binned into a 64-column grid in shared memory, stored as a dense row-major CSR
+//    (u16 start per cell, the box arrays sorted in the same order): a belief-step looks at the 3-4 grid rows its interval
+//    overlaps and, per row, at ONE contiguous range of table rows (usually empty) - two nested loops, no bitmap
+//    arithmetic.  The cell function is the same monotone fp32 expression on host and device, so no margin is needed
+//    for the binning.
 //  * whatever the box test cannot prove (a real collision, the ~1e-5-wide fp32 band, non-finite
 //    operands) is decided by the reference's exact fp64 expression on the obstacle's own normals
 //    (bm_exact_obstacle).  Verdicts and first-violation steps stay bit-identical to the oracle.
@@ -27,7 +28,7 @@
 
 namespace cck {
 
-struct GHeader {                 // 80 bytes, then occ[R] (u64), rowbase[R] (u16), cstart[n_cells+1] (u16), outer boxes[M], inner boxes[M] (float4)
+struct GHeader {                 // 80 bytes, then dstart[R*64+1] (u16, dense row-major CSR over the cells), outer boxes[M], inner boxes[M] (float4)
     int32_t total_bytes, M, n_grid, n_cells;
     int32_t R, off_occ, off_rowbase, off_cstart;
     int32_t off_boxes, pad0;
@@ -135,22 +136,13 @@ __device__ __forceinline__ bool grid_check(const GridConst& g, const unsigned ch
     const float rlo = fmaxf(grid_cellf(__fsub_rd(ym, h->SY), h->gy0, h->icy), 0.f);
     const float rhi = fminf(grid_cellf(yp, h->gy0, h->icy), h->Rm1);
     if (clo <= chi && rlo <= rhi) {
-        const uint64_t* occ = reinterpret_cast<const uint64_t*>(gt + h->off_occ);
-        const uint16_t* rowbase = reinterpret_cast<const uint16_t*>(gt + h->off_rowbase);
-        const uint16_t* cstart = reinterpret_cast<const uint16_t*>(gt + h->off_cstart);
-        const int c0 = (int)clo, c1 = (int)chi, r1 = (int)rhi;
-        const uint64_t cm = (~0ull >> (63 - c1)) & (~0ull << c0);
+        // dense row-major CSR: the anchors of row r, columns c0..c1 are the contiguous table rows ds[r*64+c0] .. ds[r*64+c1+1]-1
+        const uint16_t* ds = reinterpret_cast<const uint16_t*>(gt + h->off_cstart);
+        const int c0 = (int)clo, c1 = (int)chi + 1, r1 = (int)rhi;
         for (int r = (int)rlo; r <= r1 && ok; ++r) {
-            const uint64_t oc = occ[r];
-            uint64_t m = oc & cm;
-            while (m && ok) {
-                const int cc = __ffsll((long long)m) - 1;
-                m &= m - 1;
-                const int cell = rowbase[r] + __popcll(oc & ((1ull << cc) - 1ull));
-                const int j1 = cstart[cell + 1];
-                for (int j = cstart[cell]; j < j1 && ok; ++j)
-                    ok = grid_obstacle(g, gt, j, xm, xp, ym, yp, xmi, xpi, ymi, ypi, exact);
-            }
+            int j = ds[r * CCK_GRID_COLS + c0];
+            const int j1 = ds[r * CCK_GRID_COLS + c1];
+            for (; j < j1 && ok; ++j) ok = grid_obstacle(g, gt, j, xm, xp, ym, yp, xmi, xpi, ymi, ypi, exact);
         }
     }
     // obstacles without a finite box (non-axis-aligned planes, unusable constants): box sides are +-inf
@@ -201,7 +193,9 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 
 // shared-memory carve-up: [mbarrier 16 B][grid table][work counter 16 B][stash 128 x 80 B]
 //                         [prefetch slots: 13 planes x 128 doubles][2 planes x 128 ints]
+#ifndef CCK_GRID_THREADS
 #define CCK_GRID_THREADS 128
+#endif
 #ifndef CCK_GRID_MINB
 #define CCK_GRID_MINB 4
 #endif
@@ -213,8 +207,13 @@ __host__ __device__ inline int grid_smem_bytes(int gtab_bytes) {
     return 16 + gtab_bytes + 16 + CCK_GRID_THREADS * 80 + 13 * CCK_GRID_THREADS * 8 + 2 * CCK_GRID_THREADS * 4;
 }
 
+#ifdef CCK_GRID_MAXNREG
+#define CCK_GRID_BOUNDS __maxnreg__(CCK_GRID_MAXNREG)
+#else
+#define CCK_GRID_BOUNDS __launch_bounds__(CCK_GRID_THREADS, CCK_GRID_MINB)
+#endif
 template <bool TRAJ, bool EXPAND>
-__global__ void __launch_bounds__(CCK_GRID_THREADS, CCK_GRID_MINB) k_rollout_lin_grid(const __grid_constant__ RolloutArgs a, const __grid_constant__ LinDev p,
+__global__ void CCK_GRID_BOUNDS k_rollout_lin_grid(const __grid_constant__ RolloutArgs a, const __grid_constant__ LinDev p,
                                                                           const __grid_constant__ SvcDev sp, const __grid_constant__ GridConst g,
                                                                           const int range_log2) {
     extern __shared__ __align__(128) unsigned char smem_raw[];

@@ -1,4 +1,4 @@
-"""CPU-only tests of the fp32 box + bitmap-grid broad phase of the PCCBlackmore rollout kernels
+"""CPU-only tests of the fp32 box + cell-grid broad phase of the PCCBlackmore rollout kernels
 (csrc/cck_rollout_grid.cuh): the table is built by host code (cck_build_grid_table needs no GPU), and the device's
 fp32 query is re-enacted here in numpy float32 arithmetic (IEEE round-to-nearest, like the kernel's FADD/FMUL).
 
@@ -101,16 +101,15 @@ def test_grid_table_invariants(K, W, which):
     outer, inner, order = t["outer"], t["inner"], t["order"]
     assert np.isfinite(outer[:ng]).all() and not np.isfinite(outer[ng:]).all(axis=1).any()
     assert float(t["k"]) >= np.sqrt(2.0) * c
-    # 1. binning: cell function, bitmap bit, popcount rank, CSR range
+    # 1. binning: cell function, dense row-major CSR range
     cx = _cell(outer[:ng, 0], t["gx0"], t["icx"]).astype(int)
     cy = _cell(outer[:ng, 1], t["gy0"], t["icy"]).astype(int)
     assert (cx >= 0).all() and (cx <= 63).all() and (cy >= 0).all() and (cy < t["R"]).all()
+    ds = t["dstart"].astype(int)
+    assert len(ds) == t["R"] * 64 + 1 and (np.diff(ds) >= 0).all() and ds[0] == 0 and ds[-1] == ng
     for j in range(ng):
-        occ = int(t["occ"][cy[j]])
-        assert (occ >> int(cx[j])) & 1
-        cell = int(t["rowbase"][cy[j]]) + bin(occ & ((1 << int(cx[j])) - 1)).count("1")
-        assert t["cstart"][cell] <= j < t["cstart"][cell + 1]
-    assert sum(bin(int(o)).count("1") for o in t["occ"]) == t["n_cells"] and t["cstart"][-1] == ng
+        idx = int(cy[j]) * 64 + int(cx[j])
+        assert ds[idx] <= j < ds[idx + 1]
     if ng:
         assert float(t["SX"]) >= (outer[:ng, 2].astype(np.float64) - outer[:ng, 0]).max()
         assert float(t["SY"]) >= (outer[:ng, 3].astype(np.float64) - outer[:ng, 1]).max()
@@ -194,7 +193,7 @@ def test_fp32_broad_phase_never_contradicts_the_fp64_predicate(K, W, which, sqrt
         assert proven_safe.mean() > 0.7 and proven_unsafe.any() and undecided[:, np.isfinite(outer).all(axis=1)].mean() < 0.01
     else:
         assert proven_safe.mean() > 0.9 and proven_unsafe.any() and undecided.mean() < 0.01
-    # 4. every obstacle that is not proven safe is found through the bitmap window (or sits in the always-list)
+    # 4. every obstacle that is not proven safe is found through the cell window (or sits in the always-list)
     clo = np.maximum(_cell(_sub_rd(q["xm"], t["SX"]), t["gx0"], t["icx"]), 0)
     chi = np.minimum(_cell(q["xp"], t["gx0"], t["icx"]), 63)
     rlo = np.maximum(_cell(_sub_rd(q["ym"], t["SY"]), t["gy0"], t["icy"]), 0)
@@ -205,5 +204,13 @@ def test_fp32_broad_phase_never_contradicts_the_fp64_predicate(K, W, which, sqrt
         in_window = ((cx[None, :] >= clo[:, None]) & (cx[None, :] <= chi[:, None]) &
                      (cy[None, :] >= rlo[:, None]) & (cy[None, :] <= rhi[:, None]))
         assert not (~proven_safe[:, :ng] & ~in_window).any()
+        # the kernel's enumeration (one contiguous CSR range per grid row of the window) visits exactly the window
+        ds = t["dstart"].astype(int)
+        for i in rng.choice(n, 400, replace=False):
+            got = []
+            if clo[i] <= chi[i] and rlo[i] <= rhi[i]:
+                for r in range(int(rlo[i]), int(rhi[i]) + 1):
+                    got.extend(range(ds[r * 64 + int(clo[i])], ds[r * 64 + int(chi[i]) + 1]))
+            assert sorted(got) == np.nonzero(in_window[i])[0].tolist()
         # the window is not vacuous: it skips most of the table
         assert in_window.mean() < 0.05
