@@ -398,15 +398,15 @@ static void build_grid_table(int M, const double* A, const double* B, const std:
     h.gx0 = (float)x0; h.gy0 = (float)y0;
     if ((double)h.gx0 > x0) h.gx0 = std::nextafterf(h.gx0, -HUGE_VALF);
     if ((double)h.gy0 > y0) h.gy0 = std::nextafterf(h.gy0, -HUGE_VALF);
-    // cell size: the whole anchor range must fit the bitmap, and a cell is not finer than the typical box
-    // (measured: spreading the range over all 64 columns/rows cuts false candidates 0.54 -> 0.38 per belief-step
-    // but adds bitmap rows to every query; realistic sweep 29.5 -> 28.4 G/s, so the coarser cells stay)
-    auto inv_cell = [](double range, double s, int n) {
+    // cell size.  Rows: the whole anchor range must fit 64 rows, and a row is not finer than the typical box (every grid
+    // row a query overlaps costs a CSR lookup).  Columns: always all 64 over the anchor range - within a row the
+    // candidates are ONE contiguous CSR range whatever the column width, so finer columns only trim false candidates.
+    auto inv_cell = [](double range, double s, int n, bool clamp_to_box) {
         double ic = 1.0 / std::max(s, 1e-30);
-        if (range > 0) ic = std::min(ic, (n - 0.5) / range);
+        if (range > 0) ic = clamp_to_box ? std::min(ic, (n - 0.5) / range) : (n - 0.5) / range;
         return (float)std::min(ic, 1e30);
     };
-    h.icx = inv_cell(x1 - x0, sx, CCK_GRID_COLS); h.icy = inv_cell(y1 - y0, sy, CCK_GRID_ROWS);
+    h.icx = inv_cell(x1 - x0, sx, CCK_GRID_COLS, false); h.icy = inv_cell(y1 - y0, sy, CCK_GRID_ROWS, true);
     auto fits = [&]() {
         for (int o : gridded) {
             const float cx = grid_cellf(box[o].xlo, h.gx0, h.icx), cy = grid_cellf(box[o].ylo, h.gy0, h.icy);

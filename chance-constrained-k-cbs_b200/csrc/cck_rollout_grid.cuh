@@ -77,14 +77,16 @@ __device__ __forceinline__ float sqrt_approx(float v) {
 // every plane fails with margin; +-inf for obstacles that are not one-plane-per-side boxes), else the
 // reference's fp64 expression.
 template <class Exact>
-__device__ __forceinline__ bool grid_obstacle(const GridConst& g, const unsigned char* gt, int j, float xm, float xp, float ym, float yp, float xmi,
-                                              float xpi, float ymi, float ypi, const Exact& exact) {
+__device__ __forceinline__ bool grid_obstacle(const GridConst& g, const unsigned char* gt, int j, float xm, float xp, float ym, float yp, float mx,
+                                              float my, const Exact& exact) {
     // the box arrays live in shared memory behind the grid, or in global memory when they are too large for it; the
     // choice is made here, on the rare path, not once per belief-step
     const float4* boxes = g.boxes_global ? g.boxes_global : reinterpret_cast<const float4*>(gt + g.off_boxes);
     const float4 b = boxes[j];
     if ((xm >= b.z) | (xp <= b.x) | (ym >= b.w) | (yp <= b.y)) return true;
     const float4 q = boxes[g.M + j];
+    const float mx2 = mx + mx, my2 = my + my;
+    const float xmi = xm + mx2, xpi = xp - mx2, ymi = ym + my2, ypi = yp - my2;
     if ((xmi < q.z) & (xpi > q.x) & (ymi < q.w) & (ypi > q.y)) return false;
     return exact(j);
 }
@@ -124,11 +126,12 @@ __device__ __forceinline__ bool grid_check(const GridConst& g, const unsigned ch
     // margin: 2^-18 relative covers the fp64->fp32 conversions, the fp32 sqrt/mul/add roundings (<2^-20)
     // and the fp64 roundings of the reference's expression (2^-50); 1e-17 absolute covers denormal inputs
     // (flushed by sqrt.approx.ftz: ex_true <= k * sqrt(1.2e-38) < 1e-18)
-    const float mx = (fabsf(xf) + ex) * 3.814697265625e-06f + 1e-17f;
-    const float my = (fabsf(yf) + ey) * 3.814697265625e-06f + 1e-17f;
+    const float mx = __fmaf_rn(fabsf(xf) + ex, 3.814697265625e-06f, 1e-17f);
+    const float my = __fmaf_rn(fabsf(yf) + ey, 3.814697265625e-06f, 1e-17f);
     const float dx = xf - ex, sx = xf + ex, dy = yf - ey, sy = yf + ey;
     const float xm = dx - mx, xp = sx + mx, ym = dy - my, yp = sy + my;       // outer interval (contains the true one)
-    const float xmi = dx + mx, xpi = sx - mx, ymi = dy + my, ypi = sy - my;   // inner interval (contained in the true one)
+    // the inner interval (contained in the true one) is outer -+ 2*margin, formed only for an obstacle the outer test
+    // could not skip: the two extra roundings (2^-24 relative each) are far inside the 2^-18 margin
     bool ok = true;
     // gridded obstacles: anchor (xlo, ylo) must lie in (xm - SX, xp) x (ym - SY, yp) to be unproven
     const float clo = fmaxf(grid_cellf(__fsub_rd(xm, h->SX), h->gx0, h->icx), 0.f);
@@ -142,12 +145,12 @@ __device__ __forceinline__ bool grid_check(const GridConst& g, const unsigned ch
         for (int r = (int)rlo; r <= r1 && ok; ++r) {
             int j = ds[r * CCK_GRID_COLS + c0];
             const int j1 = ds[r * CCK_GRID_COLS + c1];
-            for (; j < j1 && ok; ++j) ok = grid_obstacle(g, gt, j, xm, xp, ym, yp, xmi, xpi, ymi, ypi, exact);
+            for (; j < j1 && ok; ++j) ok = grid_obstacle(g, gt, j, xm, xp, ym, yp, mx, my, exact);
         }
     }
     // obstacles without a finite box (non-axis-aligned planes, unusable constants): box sides are +-inf
     for (int j = h->n_grid; j < M && ok; ++j)
-        ok = grid_obstacle(g, gt, j, xm, xp, ym, yp, xmi, xpi, ymi, ypi, exact);
+        ok = grid_obstacle(g, gt, j, xm, xp, ym, yp, mx, my, exact);
     return ok;
 }
 
@@ -198,6 +201,12 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 #endif
 #ifndef CCK_GRID_MINB
 #define CCK_GRID_MINB 4
+#endif
+#ifndef CCK_REFILL_MIN
+#define CCK_REFILL_MIN 6      // idle lanes of a warp that trigger a refill ...
+#endif
+#ifndef CCK_REFILL_WAIT
+#define CCK_REFILL_WAIT 4     // ... or this many loop iterations with an idle lane (power of two)
 #endif
 // the work counter hands out ranges of 2^range_log2 consecutive beliefs, round-robin over the CTAs: 256 for the
 // big sweeps (coalesced refills), 128 = one belief per lane for planner-sized batches (latency: every candidate of a
@@ -260,7 +269,7 @@ __global__ void CCK_GRID_BOUNDS k_rollout_lin_grid(const __grid_constant__ Rollo
     prefetch();
     stage_wait((uint32_t)a.ftab_bytes, bar);
 
-    bool have = false;
+    bool have = false, pending = false;
     Lin cur;
     double dux = 0, duy = 0;
     int steps = 0, t = 0, pstep = 0;
@@ -269,10 +278,33 @@ __global__ void CCK_GRID_BOUNDS k_rollout_lin_grid(const __grid_constant__ Rollo
     cur.mx = cur.my = 0;
 #pragma unroll
     for (int f = 0; f < 4; ++f) cur.S[f] = cur.L[f] = 0;
-    // one belief-step of a lane (A: state on entry, B: state on exit; the caller passes the same object, the step is
-    // alias-safe).  Returns true when the lane has run out of work.
-    auto step = [&](Lin& A, Lin& B) -> bool {
-        while (!have && nxt >= 0) {   // take the prefetched belief, start copying the one after it
+    // store the result of a finished rollout (a lane that is idle keeps its registers and its stash until then)
+    auto flush = [&](Lin& B) {
+        if (!pending) return;
+        pending = false;
+        if (t < steps) {
+            const double2 s0 = stash[0], s1 = stash[1], s2 = stash[2], s3 = stash[3], s4 = stash[4];
+            B.mx = s0.x; B.my = s0.y; B.S[0] = s1.x; B.S[1] = s1.y; B.S[2] = s2.x; B.S[3] = s2.y;
+            B.L[0] = s3.x; B.L[1] = s3.y; B.L[2] = s4.x; B.L[3] = s4.y;
+        }
+        a.out[i] = B.mx; a.out[a.ldo + i] = B.my;
+#pragma unroll
+        for (int f = 0; f < 4; ++f) { a.out[(2 + f) * a.ldo + i] = B.S[f]; a.out[(6 + f) * a.ldo + i] = B.L[f]; }
+        a.valid[i] = t;
+        if (EXPAND) {
+            // the rollout's start and the parent's cost are re-read here (L2 hits) instead of riding in six registers
+            const double d0 = a.bel[i] - B.mx, d1 = a.bel[a.ld + i] - B.my;
+            a.cost[i] = a.parent_cost[i] + sqrt(d0 * d0 + d1 * d1);
+            double gd;
+            const bool g = goal_ok(a.goal, sp, B.mx, B.my, B.S[0] + B.L[0], B.S[1] + B.L[1], B.S[2] + B.L[2], B.S[3] + B.L[3], &gd);
+            a.goal_dist[i] = gd;
+            a.flags[i] = (uint8_t)((t == steps ? 1 : 0) | (cons_ok ? 2 : 0) | (g ? 4 : 0));
+        }
+    };
+    // refill: take the prefetched belief, start copying the one after it
+    auto take = [&](Lin& A) {
+        flush(A);
+        while (!have && nxt >= 0) {
             cp_async_wait_all();
             i = nxt;
             A.mx = slot[0]; A.my = slot[CCK_GRID_THREADS];
@@ -299,7 +331,9 @@ __global__ void CCK_GRID_BOUNDS k_rollout_lin_grid(const __grid_constant__ Rollo
             t = 0; cons_ok = true;
             have = true;
         }
-        if (!have) return true;       // no belief left for this lane: it leaves the loop on its own (nothing below is warp-collective)
+    };
+    // one belief-step of a lane that has work, in place (lin_step is alias-safe)
+    auto advance = [&](Lin& A, Lin& B) {
         // stash the last valid state, advance A -> B
         stash[0] = make_double2(A.mx, A.my);
         stash[1] = make_double2(A.S[0], A.S[1]); stash[2] = make_double2(A.S[2], A.S[3]);
@@ -313,10 +347,7 @@ __global__ void CCK_GRID_BOUNDS k_rollout_lin_grid(const __grid_constant__ Rollo
         if (!ok) ok = !(x - eps > sp.high[0] || x + eps < sp.low[0] || y - eps > sp.high[1] || y + eps < sp.low[1]);
         if (ok && a.ftab_bytes > 0)
             ok = grid_check<true>(g, gt, a.tab, a.exB, a.exCls, c, x, y, B.S[0], B.S[1], B.S[2], B.S[3], B.L[0], B.L[1], B.L[2], B.L[3]);
-        int r = -1;                // >= 0: this rollout ends now with r valid steps
-        if (!ok) {
-            r = t;                 // died: the result is the last valid state (restored below, on the finish path)
-        } else {
+        if (ok) {
             if (EXPAND && cons) {   // Sigma + Lambda formed here, not carried across the validity check
                 double s0 = B.S[0], s1 = B.S[1], s2 = B.S[2], s3 = B.S[3];
                 asm volatile("" : "+d"(s0), "+d"(s1), "+d"(s2), "+d"(s3));
@@ -329,32 +360,26 @@ __global__ void CCK_GRID_BOUNDS k_rollout_lin_grid(const __grid_constant__ Rollo
                 for (int f = 0; f < 4; ++f) { tp[(2 + f) * a.traj_ld] = B.S[f]; tp[(6 + f) * a.traj_ld] = B.L[f]; }
             }
             ++t;
-            if (t == steps) r = steps;
         }
-        if (r >= 0) {
-            if (!ok) {
-                const double2 s0 = stash[0], s1 = stash[1], s2 = stash[2], s3 = stash[3], s4 = stash[4];
-                B.mx = s0.x; B.my = s0.y; B.S[0] = s1.x; B.S[1] = s1.y; B.S[2] = s2.x; B.S[3] = s2.y;
-                B.L[0] = s3.x; B.L[1] = s3.y; B.L[2] = s4.x; B.L[3] = s4.y;
-            }
-            a.out[i] = B.mx; a.out[a.ldo + i] = B.my;
-#pragma unroll
-            for (int f = 0; f < 4; ++f) { a.out[(2 + f) * a.ldo + i] = B.S[f]; a.out[(6 + f) * a.ldo + i] = B.L[f]; }
-            a.valid[i] = r;
-            if (EXPAND) {
-                // the rollout's start and the parent's cost are re-read here (L2 hits) instead of riding in six registers
-                const double d0 = a.bel[i] - B.mx, d1 = a.bel[a.ld + i] - B.my;
-                a.cost[i] = a.parent_cost[i] + sqrt(d0 * d0 + d1 * d1);
-                double gd;
-                const bool g = goal_ok(a.goal, sp, B.mx, B.my, B.S[0] + B.L[0], B.S[1] + B.L[1], B.S[2] + B.L[2], B.S[3] + B.L[3], &gd);
-                a.goal_dist[i] = gd;
-                a.flags[i] = (uint8_t)((r == steps ? 1 : 0) | (cons_ok ? 2 : 0) | (g ? 4 : 0));
-            }
-            have = false;
-        }
-        return false;
+        // the rollout ends with t valid steps: died (t < steps; the result is the last valid state, still in the stash) or
+        // complete (t == steps).  The result is stored by flush(), together with the other finished lanes of the warp.
+        if (!ok || t == steps) { have = false; pending = true; }
     };
-    while (!step(cur, cur)) {}
+    // Lanes are refilled as soon as their rollout ends, but in batches: the take / prefetch / result-store code is ~150
+    // instructions that a single finished lane would make the whole warp issue.  Idle lanes therefore wait until
+    // CCK_REFILL_MIN lanes of the warp are idle, or at most CCK_REFILL_WAIT iterations (ncu, realistic sweep: the refill
+    // path was 24 % of the issue slots at 2.1 active lanes on average).
+    int it = 0;
+    while (true) {
+        const unsigned idle = __ballot_sync(0xffffffffu, !have);
+        if (idle) {
+            if (__popc(idle) >= CCK_REFILL_MIN || (++it & (CCK_REFILL_WAIT - 1)) == 0) {
+                take(cur);
+                if (__all_sync(0xffffffffu, !have)) break;
+            }
+        }
+        if (have) advance(cur, cur);
+    }
 }
 
 }  // namespace cck

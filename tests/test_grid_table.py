@@ -67,11 +67,14 @@ def _device_query(t, x, y, P, sqrt_err=0.0):
         s0 = (np.sqrt(p0) * f32(1.0 + sqrt_err)).astype(f32)
         s3 = (np.sqrt(p3) * f32(1.0 + sqrt_err)).astype(f32)
         ex, ey = f32(t["k"]) * s0, f32(t["k"]) * s3
-        mx = (np.abs(xf) + ex) * f32(3.814697265625e-06) + f32(1e-17)
-        my = (np.abs(yf) + ey) * f32(3.814697265625e-06) + f32(1e-17)
+        # __fmaf_rn: the product of two fp32 numbers is exact in fp64; one rounding to fp32 after the add
+        mx = ((np.abs(xf) + ex).astype(np.float64) * np.float64(f32(3.814697265625e-06)) + np.float64(f32(1e-17))).astype(f32)
+        my = ((np.abs(yf) + ey).astype(np.float64) * np.float64(f32(3.814697265625e-06)) + np.float64(f32(1e-17))).astype(f32)
         dx, sx, dy, sy = xf - ex, xf + ex, yf - ey, yf + ey
-    q = {"fin": fin, "xm": dx - mx, "xp": sx + mx, "ym": dy - my, "yp": sy + my,
-         "xmi": dx + mx, "xpi": sx - mx, "ymi": dy + my, "ypi": sy - my}
+        xm, xp, ym, yp = dx - mx, sx + mx, dy - my, sy + my
+        mx2, my2 = mx + mx, my + my
+    q = {"fin": fin, "xm": xm, "xp": xp, "ym": ym, "yp": yp,
+         "xmi": xm + mx2, "xpi": xp - mx2, "ymi": ym + my2, "ypi": yp - my2}
     return q
 
 
