@@ -49,7 +49,7 @@ struct cck_ctx {
     double* d_gexB = nullptr;          // exact fp64 rows in grid-table order
     int32_t* d_gexCls = nullptr;       // class of each row
     bool uni_sparse = false;           // unicycle matrices have the reference's exact-zero pattern
-    GridConst gconst{};                // header scalars of the grid table + fp32 bounds (kernel constants)
+    GridConst gconst{0, 0, 0, 0, 0, 0, 0, -1.f};   // header scalars of the grid table + fp32 bounds (kernel constants)
     int kern = 2;                      // linear+Blackmore rollout kernel: 2 grid (default), 1 group filter, 0 generic (CCK_KERNEL)
     int M = 0;
 
@@ -644,6 +644,7 @@ extern "C" int cck_set_obstacles(cck_ctx* c, const cck_svc_params* p, const doub
     cudaFree(c->d_gtab); cudaFree(c->d_gexB); cudaFree(c->d_gexCls);
     c->d_gtab = nullptr; c->d_gexB = nullptr; c->d_gexCls = nullptr; c->gtab_bytes = 0;
     c->gconst = GridConst{};
+    c->gconst.Rm1 = -1.f;   // no grid rows: every query window is empty (M = 0 keeps the one-branch fast exit)
     c->gconst.blx = f32_up(p->low[0]); c->gconst.bhx = f32_down(p->high[0]); c->gconst.bly = f32_up(p->low[1]); c->gconst.bhy = f32_down(p->high[1]);
     if (M > 0) {
         GridBuild gb;

@@ -95,10 +95,15 @@ __device__ __forceinline__ bool grid_obstacle(const GridConst& g, const unsigned
 // SPLIT: the covariance arrives as its two summands (P = Sa + Sb, the reference's Sigma + Lambda).  The sums are formed
 // here for the fp32 broad phase and formed AGAIN (same operands, same result) where the exact path needs them, behind an
 // opaque asm so that the compiler cannot keep the first copies alive: 8 registers less across the hot loop.
-template <bool SPLIT = false>
-__device__ __forceinline__ bool grid_check(const GridConst& g, const unsigned char* gt, const unsigned char* ctab, const double* exB,
-                                           const int32_t* exCls, double c, double x, double y, double Sa0, double Sa1, double Sa2, double Sa3,
-                                           double Sb0 = 0, double Sb1 = 0, double Sb2 = 0, double Sb3 = 0) {
+// BOUNDS: the caller's fp32 bounds pre-check (`pre`) and its exact fp64 bounds test (`exact_bounds`, evaluated only
+// when pre is false) are folded in, so that the common outcome - bounds proven, operands finite, no gridded obstacle
+// near, no obstacle without a box - leaves through ONE branch (ncu: 21 of 215 instructions per warp-step were
+// BRA/BSSY/BSYNC of five separate rare-path tests).  `enabled` = there is an obstacle table at all.
+template <bool SPLIT = false, class ExactBounds>
+__device__ __forceinline__ bool grid_check_b(const GridConst& g, const unsigned char* gt, const unsigned char* ctab, const double* exB,
+                                             const int32_t* exCls, double c, bool pre, const ExactBounds& exact_bounds, bool enabled, double x, double y,
+                                             double Sa0, double Sa1, double Sa2, double Sa3, double Sb0 = 0, double Sb1 = 0, double Sb2 = 0,
+                                             double Sb3 = 0) {
     const GridConst* h = &g;
     const int M = h->M;
     const double P0 = SPLIT ? Sa0 + Sb0 : Sa0, P1 = SPLIT ? Sa1 + Sb1 : Sa1, P2 = SPLIT ? Sa2 + Sb2 : Sa2, P3 = SPLIT ? Sa3 + Sb3 : Sa3;
@@ -117,11 +122,6 @@ __device__ __forceinline__ bool grid_check(const GridConst& g, const unsigned ch
         }
         return bm_exact_obstacle(cls[exCls[j]].A, exB + (size_t)j * 4, x, y, P0, P1, P2, P3, c);
     };
-    if (!fin) {   // rare: decide every obstacle with the reference's expression
-        bool ok = true;
-        for (int j = 0; j < M && ok; ++j) ok = exact(j);
-        return ok;
-    }
     const float ex = h->k * sqrt_approx(p0), ey = h->k * sqrt_approx(p3);
     // margin: 2^-18 relative covers the fp64->fp32 conversions, the fp32 sqrt/mul/add roundings (<2^-20)
     // and the fp64 roundings of the reference's expression (2^-50); 1e-17 absolute covers denormal inputs
@@ -132,13 +132,22 @@ __device__ __forceinline__ bool grid_check(const GridConst& g, const unsigned ch
     const float xm = dx - mx, xp = sx + mx, ym = dy - my, yp = sy + my;       // outer interval (contains the true one)
     // the inner interval (contained in the true one) is outer -+ 2*margin, formed only for an obstacle the outer test
     // could not skip: the two extra roundings (2^-24 relative each) are far inside the 2^-18 margin
-    bool ok = true;
     // gridded obstacles: anchor (xlo, ylo) must lie in (xm - SX, xp) x (ym - SY, yp) to be unproven
     const float clo = fmaxf(grid_cellf(__fsub_rd(xm, h->SX), h->gx0, h->icx), 0.f);
     const float chi = fminf(grid_cellf(xp, h->gx0, h->icx), (float)(CCK_GRID_COLS - 1));
     const float rlo = fmaxf(grid_cellf(__fsub_rd(ym, h->SY), h->gy0, h->icy), 0.f);
     const float rhi = fminf(grid_cellf(yp, h->gy0, h->icy), h->Rm1);
-    if (clo <= chi && rlo <= rhi) {
+    const bool window = (clo <= chi) & (rlo <= rhi);
+    // everything above is branch-free (garbage in, garbage out for non-finite operands: `fin` is then false)
+    if (pre & fin & !window & (h->n_grid == M)) return true;
+    if (!pre && !exact_bounds()) return false;
+    if (!enabled) return true;
+    bool ok = true;
+    if (!fin) {   // rare: decide every obstacle with the reference's expression
+        for (int j = 0; j < M && ok; ++j) ok = exact(j);
+        return ok;
+    }
+    if (window) {
         // dense row-major CSR: the anchors of row r, columns c0..c1 are the contiguous table rows ds[r*64+c0] .. ds[r*64+c1+1]-1
         const uint16_t* ds = reinterpret_cast<const uint16_t*>(gt + h->off_cstart);
         const int c0 = (int)clo, c1 = (int)chi + 1, r1 = (int)rhi;
@@ -152,6 +161,13 @@ __device__ __forceinline__ bool grid_check(const GridConst& g, const unsigned ch
     for (int j = h->n_grid; j < M && ok; ++j)
         ok = grid_obstacle(g, gt, j, xm, xp, ym, yp, mx, my, exact);
     return ok;
+}
+
+template <bool SPLIT = false>
+__device__ __forceinline__ bool grid_check(const GridConst& g, const unsigned char* gt, const unsigned char* ctab, const double* exB,
+                                           const int32_t* exCls, double c, double x, double y, double Sa0, double Sa1, double Sa2, double Sa3,
+                                           double Sb0 = 0, double Sb1 = 0, double Sb2 = 0, double Sb3 = 0) {
+    return grid_check_b<SPLIT>(g, gt, ctab, exB, exCls, c, true, [] { return true; }, true, x, y, Sa0, Sa1, Sa2, Sa3, Sb0, Sb1, Sb2, Sb3);
 }
 
 // PCCBlackmoreSVC::isValid, batched (row a4), through the same broad phase: bounds, then grid_check.
@@ -343,10 +359,11 @@ __global__ void CCK_GRID_BOUNDS k_rollout_lin_grid(const __grid_constant__ Rollo
         // satisfiesBounds (NaN passes): the mean rounded to fp32 strictly inside the inward-rounded bounds proves it
         // (RN is monotone: xf < bhx <= high implies x < high); otherwise the exact fp64 test decides
         const float xf = __double2float_rn(x), yf = __double2float_rn(y);
-        bool ok = (xf > g.blx) & (xf < g.bhx) & (yf > g.bly) & (yf < g.bhy);
-        if (!ok) ok = !(x - eps > sp.high[0] || x + eps < sp.low[0] || y - eps > sp.high[1] || y + eps < sp.low[1]);
-        if (ok && a.ftab_bytes > 0)
-            ok = grid_check<true>(g, gt, a.tab, a.exB, a.exCls, c, x, y, B.S[0], B.S[1], B.S[2], B.S[3], B.L[0], B.L[1], B.L[2], B.L[3]);
+        const bool pre = (xf > g.blx) & (xf < g.bhx) & (yf > g.bly) & (yf < g.bhy);
+        const bool ok = grid_check_b<true>(
+            g, gt, a.tab, a.exB, a.exCls, c, pre,
+            [&] { return !(x - eps > sp.high[0] || x + eps < sp.low[0] || y - eps > sp.high[1] || y + eps < sp.low[1]); }, a.ftab_bytes > 0, x, y,
+            B.S[0], B.S[1], B.S[2], B.S[3], B.L[0], B.L[1], B.L[2], B.L[3]);
         if (ok) {
             if (EXPAND && cons) {   // Sigma + Lambda formed here, not carried across the validity check
                 double s0 = B.S[0], s1 = B.S[1], s2 = B.S[2], s3 = B.S[3];
