@@ -667,7 +667,7 @@ extern "C" int cck_set_obstacles(cck_ctx* c, const cck_svc_params* p, const doub
         const GHeader& gh = gh0;
         const GridConst keep = c->gconst;
         c->gconst = GridConst{gh.k, gh.SX, gh.SY, gh.gx0, gh.gy0, gh.icx, gh.icy, gh.Rm1, gh.M, gh.n_grid, gh.off_occ, gh.off_rowbase, gh.off_cstart, gh.off_boxes,
-                              keep.blx, keep.bhx, keep.bly, keep.bhy, (int32_t)sizeof(TabHeader), 0,
+                              keep.blx, keep.bhx, keep.bly, keep.bhy, (int32_t)sizeof(TabHeader), gh.Rm1 + 1.f,
                               boxes_in_smem ? nullptr : reinterpret_cast<const float4*>(c->d_gtab + gh.off_boxes)};
     }
 

@@ -46,7 +46,8 @@ struct GridConst {
     float k, SX, SY, gx0, gy0, icx, icy, Rm1;
     int32_t M, n_grid, off_occ, off_rowbase, off_cstart, off_boxes;
     float blx, bhx, bly, bhy;
-    int32_t off_classes, pad;   // byte offset of the ClassRec array inside the (global) class table
+    int32_t off_classes;        // byte offset of the ClassRec array inside the (global) class table
+    float Rf;                   // (float)R = Rm1 + 1
     const float4* boxes_global; // non-null: the box arrays are too large for shared memory and are read from global (L1/L2)
 };
 
@@ -95,10 +96,11 @@ __device__ __forceinline__ bool grid_obstacle(const GridConst& g, const unsigned
 // SPLIT: the covariance arrives as its two summands (P = Sa + Sb, the reference's Sigma + Lambda).  The sums are formed
 // here for the fp32 broad phase and formed AGAIN (same operands, same result) where the exact path needs them, behind an
 // opaque asm so that the compiler cannot keep the first copies alive: 8 registers less across the hot loop.
-// BOUNDS: the caller's fp32 bounds pre-check (`pre`) and its exact fp64 bounds test (`exact_bounds`, evaluated only
-// when pre is false) are folded in, so that the common outcome - bounds proven, operands finite, no gridded obstacle
-// near, no obstacle without a box - leaves through ONE branch (ncu: 21 of 215 instructions per warp-step were
-// BRA/BSSY/BSYNC of five separate rare-path tests).  `enabled` = there is an obstacle table at all.
+// The caller's fp32 bounds pre-check (`pre`, which must imply a FINITE mean: 0 * NaN poisons every plane of the
+// reference's expression) and its exact fp64 bounds test (`exact_bounds`, evaluated only when pre is false) are folded
+// in, so that the common outcome - bounds proven, operands finite, no gridded obstacle near, no obstacle without a box -
+// leaves through ONE branch (ncu: 21 of 215 instructions per warp-step were BRA/BSSY/BSYNC of five separate rare-path
+// tests).  `enabled` = there is an obstacle table at all.
 template <bool SPLIT = false, class ExactBounds>
 __device__ __forceinline__ bool grid_check_b(const GridConst& g, const unsigned char* gt, const unsigned char* ctab, const double* exB,
                                              const int32_t* exCls, double c, bool pre, const ExactBounds& exact_bounds, bool enabled, double x, double y,
@@ -109,9 +111,6 @@ __device__ __forceinline__ bool grid_check_b(const GridConst& g, const unsigned 
     const double P0 = SPLIT ? Sa0 + Sb0 : Sa0, P1 = SPLIT ? Sa1 + Sb1 : Sa1, P2 = SPLIT ? Sa2 + Sb2 : Sa2, P3 = SPLIT ? Sa3 + Sb3 : Sa3;
     const float xf = __double2float_rn(x), yf = __double2float_rn(y);
     const float p0 = __double2float_rn(P0), p3 = __double2float_rn(P3);
-    const float offd = __double2float_rn(fabs(P1) + fabs(P2));
-    // every operand finite and far from fp32 overflow, variances non-negative (false for NaN)
-    const bool fin = (fabsf(xf) + fabsf(yf)) + (p0 + p3) + offd < 1e30f && p0 >= 0.f && p3 >= 0.f;
     // the reference's fp64 expression on obstacle j's own normals
     auto exact = [&](int j) -> bool {
         const ClassRec* cls = reinterpret_cast<const ClassRec*>(ctab + h->off_classes);   // a kernel constant: no header load
@@ -133,21 +132,33 @@ __device__ __forceinline__ bool grid_check_b(const GridConst& g, const unsigned 
     // the inner interval (contained in the true one) is outer -+ 2*margin, formed only for an obstacle the outer test
     // could not skip: the two extra roundings (2^-24 relative each) are far inside the 2^-18 margin
     // gridded obstacles: anchor (xlo, ylo) must lie in (xm - SX, xp) x (ym - SY, yp) to be unproven
-    const float clo = fmaxf(grid_cellf(__fsub_rd(xm, h->SX), h->gx0, h->icx), 0.f);
-    const float chi = fminf(grid_cellf(xp, h->gx0, h->icx), (float)(CCK_GRID_COLS - 1));
-    const float rlo = fmaxf(grid_cellf(__fsub_rd(ym, h->SY), h->gy0, h->icy), 0.f);
-    const float rhi = fminf(grid_cellf(yp, h->gy0, h->icy), h->Rm1);
-    const bool window = (clo <= chi) & (rlo <= rhi);
-    // everything above is branch-free (garbage in, garbage out for non-finite operands: `fin` is then false)
-    if (pre & fin & !window & (h->n_grid == M)) return true;
+    // un-floored cell coordinates of the window's corners (grid_cellf before its floorf)
+    const float uclo = __fmul_rn(__fsub_rn(__fsub_rd(xm, h->SX), h->gx0), h->icx), uchi = __fmul_rn(__fsub_rn(xp, h->gx0), h->icx);
+    const float urlo = __fmul_rn(__fsub_rn(__fsub_rd(ym, h->SY), h->gy0), h->icy), urhi = __fmul_rn(__fsub_rn(yp, h->gy0), h->icy);
+    // the window misses the grid <=> floor(uchi) < 0 or floor(uclo) > 63 or floor(urhi) < 0 or floor(urlo) > R - 1
+    // (floor(v) < 0 <=> v < 0, floor(v) > n <=> v >= n + 1); every comparison is false for NaN: not proven empty
+    const bool empty = (uchi < 0.f) | (uclo >= (float)CCK_GRID_COLS) | (urhi < 0.f) | (urlo >= h->Rf);
+    // covariance entries finite, non-negative on the diagonal and below 2^100, by their high words (sign bit or NaN
+    // exponent compare as huge unsigned numbers): with `pre` (mean strictly inside the fp32 bounds) this is all the fast
+    // exit needs - a non-finite or overflowing fp32 intermediate above can only make the window look NON-empty
+    const unsigned T = 0x46300000u;
+    const bool cov_ok = ((unsigned)__double2hiint(P0) < T) & ((unsigned)__double2hiint(P3) < T) &
+                        ((unsigned)__double2hiint(fabs(P1) + fabs(P2)) < T);
+    // everything above is branch-free
+    if (pre & cov_ok & empty & (h->n_grid == M)) return true;
     if (!pre && !exact_bounds()) return false;
     if (!enabled) return true;
+    const float offd = __double2float_rn(fabs(P1) + fabs(P2));
+    // every operand finite and far from fp32 overflow, variances non-negative (false for NaN)
+    const bool fin = (fabsf(xf) + fabsf(yf)) + (p0 + p3) + offd < 1e30f && p0 >= 0.f && p3 >= 0.f;
     bool ok = true;
     if (!fin) {   // rare: decide every obstacle with the reference's expression
         for (int j = 0; j < M && ok; ++j) ok = exact(j);
         return ok;
     }
-    if (window) {
+    const float clo = fmaxf(floorf(uclo), 0.f), chi = fminf(floorf(uchi), (float)(CCK_GRID_COLS - 1));
+    const float rlo = fmaxf(floorf(urlo), 0.f), rhi = fminf(floorf(urhi), h->Rm1);
+    if ((clo <= chi) & (rlo <= rhi)) {
         // dense row-major CSR: the anchors of row r, columns c0..c1 are the contiguous table rows ds[r*64+c0] .. ds[r*64+c1+1]-1
         const uint16_t* ds = reinterpret_cast<const uint16_t*>(gt + h->off_cstart);
         const int c0 = (int)clo, c1 = (int)chi + 1, r1 = (int)rhi;
@@ -167,7 +178,10 @@ template <bool SPLIT = false>
 __device__ __forceinline__ bool grid_check(const GridConst& g, const unsigned char* gt, const unsigned char* ctab, const double* exB,
                                            const int32_t* exCls, double c, double x, double y, double Sa0, double Sa1, double Sa2, double Sa3,
                                            double Sb0 = 0, double Sb1 = 0, double Sb2 = 0, double Sb3 = 0) {
-    return grid_check_b<SPLIT>(g, gt, ctab, exB, exCls, c, true, [] { return true; }, true, x, y, Sa0, Sa1, Sa2, Sa3, Sb0, Sb1, Sb2, Sb3);
+    // the caller has done the bounds test, which a NaN mean passes (and 0 * NaN poisons every plane of the reference's
+    // expression): the fast exit needs a finite mean
+    const bool pre = fabs(x) + fabs(y) < 1e30;
+    return grid_check_b<SPLIT>(g, gt, ctab, exB, exCls, c, pre, [] { return true; }, true, x, y, Sa0, Sa1, Sa2, Sa3, Sb0, Sb1, Sb2, Sb3);
 }
 
 // PCCBlackmoreSVC::isValid, batched (row a4), through the same broad phase: bounds, then grid_check.

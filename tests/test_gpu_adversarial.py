@@ -78,11 +78,14 @@ def test_blackmore_threshold_ulp_sweep(K, O, W, ctx):
     assert ((g.min(axis=1) == 0) & (g.max(axis=1) == 1)).sum() >= 100
 
 
-def test_blackmore_nonfinite_and_degenerate_beliefs(K, O, W, ctx):
-    world, svc = oracle_synth(O, W, 256, "realistic", 0, 2)
+@pytest.mark.parametrize("variant", ["realistic", "all_survive"])
+def test_blackmore_nonfinite_and_degenerate_beliefs(K, O, W, ctx, variant):
+    """all_survive: the obstacle field is far away, so every query window misses the grid and the kernel's one-branch
+    fast exit decides - it must not call a belief safe whose covariance poisons the reference's expression (0 * inf)."""
+    world, svc = oracle_synth(O, W, 256, variant, 0, 2)
     install_from_oracle_svc(K, ctx, svc, K.MODEL_LINEAR2D)
     n = 6000
-    bel, ctrl = W.synthetic_beliefs(n, "linear", seed=123)
+    bel, ctrl = W.synthetic_beliefs(n, "linear", seed=123, variant=variant)
     rng = np.random.default_rng(9)
     specials = [np.nan, np.inf, -np.inf, 0.0, -0.0, 1e300, -1e300, 1e30, 1e39, 3.5e38, 1e-300, 5e-324, -1e-3, 1e-45, 1e-38]
     for j in range(n):
@@ -103,6 +106,8 @@ def test_blackmore_nonfinite_and_degenerate_beliefs(K, O, W, ctx):
     assert np.array_equal(valid, ref_valid)
     assert np.array_equal(out, ref_out, equal_nan=True)
     assert 0.05 < (ref_valid == steps).mean() < 0.95
+    if variant == "all_survive":   # the untouched beliefs all survive; a good part of the poisoned ones must not
+        assert (ref_valid == steps)[342::6].all() and (ref_valid < steps).mean() > 0.2   # 342 = first untouched index past the special rows
 
 
 def _random_tables(rng, M, mode, size=1.0):
@@ -217,4 +222,34 @@ def test_unicycle_sparse_step_degenerate_inputs(K, O, W, ctx, kind):
     assert len(mism) <= 2, f"{len(mism)} verdict mismatches"
     ok = np.ones(n, bool); ok[mism] = False
     assert np.array_equal(out[ok][:, 4:], ref_out[ok][:, 4:], equal_nan=True)          # Sigma, Lambda: no transcendental
+    assert np.allclose(out[ok][:, :4], ref_out[ok][:, :4], rtol=1e-9, atol=1e-12, equal_nan=True)
+
+
+def test_unicycle_far_field_nonfinite(K, O, W, ctx):
+    """Unicycle + PCCBlackmore with the obstacle field far away: every window misses the grid, so the one-branch fast
+    exit of grid_check decides.  NaN means pass the reference's bounds test and then poison every plane (0 * NaN);
+    non-finite covariance entries do the same - none of them may be called safe."""
+    world, svc = oracle_synth(O, W, 64, "all_survive", 0, 4, seed=31)
+    install_from_oracle_svc(K, ctx, svc, K.MODEL_UNICYCLE)
+    n = 3000
+    bel, ctrl = W.synthetic_beliefs(n, "unicycle", seed=67, variant="all_survive")
+    bel[4:, :] *= 0.02
+    rng = np.random.default_rng(17)
+    specials = [np.nan, np.inf, -np.inf, 0.0, -0.0, 1e200, -1e200, 1e30, -1e-3, 1e-300]
+    for j in range(0, n, 2):
+        bel[rng.integers(0, 36), j] = specials[rng.integers(len(specials))]
+    with np.errstate(all="ignore"):
+        got_v = ctx.is_valid(bel)
+        ref_v = svc.is_valid(K.soa_to_aos(bel))[0]
+    assert np.array_equal(got_v, ref_v)
+    assert ref_v[1::2].all() and 0.1 < (~ref_v[0::2]).mean() < 0.9
+    steps = rng.integers(1, 4, size=n).astype(np.int32)
+    with np.errstate(all="ignore"):
+        out, valid = ctx.propagate_while_valid(bel, ctrl, steps)
+        ref_out, ref_valid, _ = svc.rollout(K.soa_to_aos(bel), K.soa_to_aos(ctrl), steps, nthreads=8)
+    out = K.soa_to_aos(out)
+    mism = np.nonzero(valid != ref_valid)[0]
+    assert len(mism) <= 2, f"{len(mism)} verdict mismatches"
+    ok = np.ones(n, bool); ok[mism] = False
+    assert np.array_equal(out[ok][:, 4:], ref_out[ok][:, 4:], equal_nan=True)
     assert np.allclose(out[ok][:, :4], ref_out[ok][:, :4], rtol=1e-9, atol=1e-12, equal_nan=True)
