@@ -466,12 +466,14 @@ def run_ours(args):
         except Exception:
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
-        # executed-work view: what must stay fp64 for bit-exact results is the Kalman recursion + bounds test
-        # (linear: 95 FP64-pipe instructions per belief-step = ncu's FP64-pipe-active cycles x 64 lanes x SMs /
-        # belief-steps, profiles/r1i_*; the SASS hot path holds 99 DADD/DMUL/DFMA of which the reciprocal's slow
-        # path is rarely taken.  No FMA contraction is allowed, so the attainable rate is the FP64 ISSUE rate =
-        # DFMA peak / 2 flop); the chance check itself runs in the fp32 broad phase
-        inst_per_step = 95.0 if dim == 2 else 880.0   # unicycle: ncu FP64-pipe-active x issue peak x time / belief-steps (profiles/r1g_unicycle_ncu_summary.csv)
+        # executed-work view: what must stay fp64 for bit-exact results is the Kalman recursion + the covariance sums
+        # (linear: 75 FP64-pipe instructions per belief-step on the hot path - 70 of lin_step_diag, which skips the exact
+        # zeros of the reference's diagonal Q, R, A_cl, plus Sigma+Lambda and |P01|+|P10|; counted from the ncu source
+        # view, profiles/r1o_*.  The dense step of the reference's accumulation order is 95.)  No FMA contraction is
+        # allowed, so the attainable rate is the FP64 ISSUE rate = DFMA peak / 2 flop; the chance check itself runs in
+        # the fp32 broad phase
+        lin_dense = os.environ.get("CCK_LIN_DENSE", "") == "1"
+        inst_per_step = (95.0 if lin_dense else 75.0) if dim == 2 else 880.0   # unicycle: ncu FP64-pipe-active x issue peak x time / belief-steps (profiles/r1g_unicycle_ncu_summary.csv)
         exec_tinst = per_launch_units * inst_per_step / (kern_ms * 1e-3) / 1e12
         inst_peak = fp64_peak / 2.0      # one DFMA = 2 flop = 1 FP64-pipe instruction per lane
         # ---- second half of BASELINE.json's metric: CCK-CBS solve time, short live sample (full distribution:

@@ -305,6 +305,15 @@ extern "C" int cck_set_model(cck_ctx* c, const cck_model_params* p) {
     c->lin.dt = p->dt;
     std::memcpy(c->lin.Q, p->lin_Q, sizeof(c->lin.Q)); std::memcpy(c->lin.R, p->lin_R, sizeof(c->lin.R));
     std::memcpy(c->lin.Acl, p->lin_Acl, sizeof(c->lin.Acl));
+    {   // lin_step_diag: off-diagonals exactly +0.0 (bit pattern), |A_cl| <= 1; CCK_LIN_DENSE=1 forces the dense step
+        const double z = 0.0;
+        auto pz = [&](double v) { return std::memcmp(&v, &z, 8) == 0; };
+        const double* q = c->lin.Q; const double* r = c->lin.R; const double* a = c->lin.Acl;
+        const char* e = std::getenv("CCK_LIN_DENSE");
+        c->lin.diag = (pz(q[1]) && pz(q[2]) && pz(r[1]) && pz(r[2]) && pz(a[1]) && pz(a[2]) && std::fabs(a[0]) <= 1.0 && std::fabs(a[3]) <= 1.0 &&
+                       std::isfinite(q[0]) && std::isfinite(q[3]) && std::isfinite(r[0]) && std::isfinite(r[3]) && !(e && e[0] == '1')) ? 1 : 0;
+        c->lin.pad = 0;
+    }
     std::memcpy(c->uni.F, p->uni_F, sizeof(c->uni.F)); std::memcpy(c->uni.Acl, p->uni_Acl, sizeof(c->uni.Acl));
     std::memcpy(c->uni.Q, p->uni_Q, sizeof(c->uni.Q)); std::memcpy(c->uni.R, p->uni_R, sizeof(c->uni.R));
     std::memcpy(c->uni.gains, p->uni_gains, sizeof(c->uni.gains));

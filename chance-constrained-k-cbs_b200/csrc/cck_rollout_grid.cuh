@@ -105,7 +105,7 @@ template <bool SPLIT = false, class ExactBounds>
 __device__ __forceinline__ bool grid_check_b(const GridConst& g, const unsigned char* gt, const unsigned char* ctab, const double* exB,
                                              const int32_t* exCls, double c, bool pre, const ExactBounds& exact_bounds, bool enabled, double x, double y,
                                              double Sa0, double Sa1, double Sa2, double Sa3, double Sb0 = 0, double Sb1 = 0, double Sb2 = 0,
-                                             double Sb3 = 0) {
+                                             double Sb3 = 0, bool* cov_small_out = nullptr) {
     const GridConst* h = &g;
     const int M = h->M;
     const double P0 = SPLIT ? Sa0 + Sb0 : Sa0, P1 = SPLIT ? Sa1 + Sb1 : Sa1, P2 = SPLIT ? Sa2 + Sb2 : Sa2, P3 = SPLIT ? Sa3 + Sb3 : Sa3;
@@ -141,9 +141,8 @@ __device__ __forceinline__ bool grid_check_b(const GridConst& g, const unsigned 
     // covariance entries finite, non-negative on the diagonal and below 2^100, by their high words (sign bit or NaN
     // exponent compare as huge unsigned numbers): with `pre` (mean strictly inside the fp32 bounds) this is all the fast
     // exit needs - a non-finite or overflowing fp32 intermediate above can only make the window look NON-empty
-    const unsigned T = 0x46300000u;
-    const bool cov_ok = ((unsigned)__double2hiint(P0) < T) & ((unsigned)__double2hiint(P3) < T) &
-                        ((unsigned)__double2hiint(fabs(P1) + fabs(P2)) < T);
+    const bool cov_ok = cov_small(P0, P1, P2, P3);
+    if (cov_small_out) *cov_small_out = cov_ok;
     // everything above is branch-free
     if (pre & cov_ok & empty & (h->n_grid == M)) return true;
     if (!pre && !exact_bounds()) return false;
@@ -300,6 +299,7 @@ __global__ void CCK_GRID_BOUNDS k_rollout_lin_grid(const __grid_constant__ Rollo
     stage_wait((uint32_t)a.ftab_bytes, bar);
 
     bool have = false, pending = false;
+    bool dense = true;             // this lane's next step must be the dense lin_step (see lin_step_diag's preconditions)
     Lin cur;
     double dux = 0, duy = 0;
     int steps = 0, t = 0, pstep = 0;
@@ -359,6 +359,7 @@ __global__ void CCK_GRID_BOUNDS k_rollout_lin_grid(const __grid_constant__ Rollo
                 continue;
             }
             t = 0; cons_ok = true;
+            dense = !p.diag || !cov_small(A.S[0] + A.L[0], A.S[1] + A.L[1], A.S[2] + A.L[2], A.S[3] + A.L[3]);
             have = true;
         }
     };
@@ -368,16 +369,18 @@ __global__ void CCK_GRID_BOUNDS k_rollout_lin_grid(const __grid_constant__ Rollo
         stash[0] = make_double2(A.mx, A.my);
         stash[1] = make_double2(A.S[0], A.S[1]); stash[2] = make_double2(A.S[2], A.S[3]);
         stash[3] = make_double2(A.L[0], A.L[1]); stash[4] = make_double2(A.L[2], A.L[3]);
-        lin_step(A, dux, duy, p, B);
+        if (dense) lin_step(A, dux, duy, p, B); else lin_step_diag(A, dux, duy, p, B);
         const double x = B.mx, y = B.my;
         // satisfiesBounds (NaN passes): the mean rounded to fp32 strictly inside the inward-rounded bounds proves it
         // (RN is monotone: xf < bhx <= high implies x < high); otherwise the exact fp64 test decides
         const float xf = __double2float_rn(x), yf = __double2float_rn(y);
         const bool pre = (xf > g.blx) & (xf < g.bhx) & (yf > g.bly) & (yf < g.bhy);
+        bool small;
         const bool ok = grid_check_b<true>(
             g, gt, a.tab, a.exB, a.exCls, c, pre,
             [&] { return !(x - eps > sp.high[0] || x + eps < sp.low[0] || y - eps > sp.high[1] || y + eps < sp.low[1]); }, a.ftab_bytes > 0, x, y,
-            B.S[0], B.S[1], B.S[2], B.S[3], B.L[0], B.L[1], B.L[2], B.L[3]);
+            B.S[0], B.S[1], B.S[2], B.S[3], B.L[0], B.L[1], B.L[2], B.L[3], &small);
+        dense = !p.diag || !small;   // the new covariance is finite: the next step may skip the exact-zero terms
         if (ok) {
             if (EXPAND && cons) {   // Sigma + Lambda formed here, not carried across the validity check
                 double s0 = B.S[0], s1 = B.S[1], s2 = B.S[2], s3 = B.S[3];

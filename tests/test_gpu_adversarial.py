@@ -253,3 +253,39 @@ def test_unicycle_far_field_nonfinite(K, O, W, ctx):
     ok = np.ones(n, bool); ok[mism] = False
     assert np.array_equal(out[ok][:, 4:], ref_out[ok][:, 4:], equal_nan=True)
     assert np.allclose(out[ok][:, :4], ref_out[ok][:, :4], rtol=1e-9, atol=1e-12, equal_nan=True)
+
+
+@pytest.mark.parametrize("M", [0, 256])
+def test_linear_diagonal_step_equals_dense_step(K, W, ctx, M, monkeypatch):
+    """The rollout kernel skips the exact-zero terms of the reference's diagonal Q, R, A_cl (lin_step_diag) for beliefs
+    whose covariance is finite; CCK_LIN_DENSE=1 forces the reference's dense accumulation.  Both must give the same
+    values (at most the sign of an exact zero may differ), also for beliefs that carry inf / NaN / huge entries - with
+    M = 0 those survive the (bounds-only) check and keep being propagated."""
+    import os
+    n = 20000
+    bel, ctrl = W.synthetic_beliefs(n, "linear", seed=321, variant="all_survive")
+    rng = np.random.default_rng(23)
+    specials = [np.nan, np.inf, -np.inf, 0.0, -0.0, 1e300, -1e300, 1e200, 1e30, 1e-300, 5e-324, -1e-3]
+    for j in range(0, n, 4):
+        bel[rng.integers(2, 10), j] = specials[rng.integers(len(specials))]
+    bel[2:, 1:2000:4] = 0.0                               # all-zero covariances
+    bel[[3, 4, 7, 8], 2:4000:4] = 0.0                     # diagonal Sigma / Lambda (exact zeros stay exact zeros)
+    steps = rng.integers(0, 12, size=n).astype(np.int32)
+    W.install_synthetic(ctx, "linear", M, variant="all_survive")
+    with np.errstate(all="ignore"):
+        out_a, valid_a = ctx.propagate_while_valid(bel, ctrl, steps)
+    dense = K.Context(0)
+    try:
+        monkeypatch.setenv("CCK_LIN_DENSE", "1")
+        W.install_synthetic(dense, "linear", M, variant="all_survive")
+        monkeypatch.delenv("CCK_LIN_DENSE")
+        with np.errstate(all="ignore"):
+            out_b, valid_b = dense.propagate_while_valid(bel, ctrl, steps)
+    finally:
+        dense.close()
+    assert np.array_equal(valid_a, valid_b)
+    assert np.array_equal(out_a, out_b, equal_nan=True)
+    # bit patterns: identical except NaN payloads and the sign of exact zeros
+    diff = out_a.view(np.uint64) != out_b.view(np.uint64)
+    assert (np.isnan(out_a[diff]) | (out_a[diff] == 0.0)).all()
+    assert (valid_a == steps).mean() > 0.5
