@@ -313,6 +313,7 @@ extern "C" int cck_set_model(cck_ctx* c, const cck_model_params* p) {
         c->lin.diag = (pz(q[1]) && pz(q[2]) && pz(r[1]) && pz(r[2]) && pz(a[1]) && pz(a[2]) && std::fabs(a[0]) <= 1.0 && std::fabs(a[3]) <= 1.0 &&
                        std::isfinite(q[0]) && std::isfinite(q[3]) && std::isfinite(r[0]) && std::isfinite(r[3]) && !(e && e[0] == '1')) ? 1 : 0;
         c->lin.pad = 0;
+        c->lin.dg[0] = q[0]; c->lin.dg[1] = q[3]; c->lin.dg[2] = r[0]; c->lin.dg[3] = r[3]; c->lin.dg[4] = a[0]; c->lin.dg[5] = a[3];
     }
     std::memcpy(c->uni.F, p->uni_F, sizeof(c->uni.F)); std::memcpy(c->uni.Acl, p->uni_Acl, sizeof(c->uni.Acl));
     std::memcpy(c->uni.Q, p->uni_Q, sizeof(c->uni.Q)); std::memcpy(c->uni.R, p->uni_R, sizeof(c->uni.R));

@@ -50,7 +50,7 @@ struct SvcDev {
     double dec_cos[10], dec_sin[10];   // decagon directions cos/sin(-i*2pi/10), accumulated as Boost does
 };
 
-struct LinDev { double dt; double Q[4], R[4], Acl[4]; int diag, pad; };   // diag: Q, R, A_cl are diagonal with |A_cl| <= 1 (lin_step_diag is usable)
+struct LinDev { double dt; double Q[4], R[4], Acl[4]; int diag, pad; double dg[6]; };   // diag: Q, R, A_cl are diagonal with |A_cl| <= 1 (lin_step_diag is usable); dg = {Q00, Q11, R00, R11, A00, A11} packed for three 16-byte constant loads
 struct UniDev { double F[16], Acl[16], Q[16], R[16], gains[8], acc_lo, acc_hi, turn_lo, turn_hi; };
 
 // ---------------------------------------------------------------------------
@@ -140,15 +140,16 @@ __device__ __forceinline__ void lin_step_diag(const Lin& s, double dux, double d
     o.mx = s.mx + dux;
     o.my = s.my + duy;
     double sp[4], S[4], Si[4], K[4], lp[4], ImK[4], KP[4];
-    sp[0] = s.S[0] + p.Q[0]; sp[1] = s.S[1]; sp[2] = s.S[2]; sp[3] = s.S[3] + p.Q[3];
-    S[0] = sp[0] + p.R[0]; S[1] = sp[1]; S[2] = sp[2]; S[3] = sp[3] + p.R[3];
+    const double q0 = p.dg[0], q3 = p.dg[1], r0 = p.dg[2], r3 = p.dg[3], a0 = p.dg[4], a3 = p.dg[5];
+    sp[0] = s.S[0] + q0; sp[1] = s.S[1]; sp[2] = s.S[2]; sp[3] = s.S[3] + q3;
+    S[0] = sp[0] + r0; S[1] = sp[1]; S[2] = sp[2]; S[3] = sp[3] + r3;
     const double det = S[0] * S[3] - S[2] * S[1];
     const double invdet = 1.0 / det;
     Si[0] = S[3] * invdet; Si[2] = -S[2] * invdet; Si[1] = -S[1] * invdet; Si[3] = S[0] * invdet;
     mm2(sp, Si, K);
     // (A_cl L) A_cl with A_cl = diag(a0, a3): entry (i, j) = (a_i * L_ij) * a_j
-    lp[0] = (p.Acl[0] * s.L[0]) * p.Acl[0]; lp[1] = (p.Acl[0] * s.L[1]) * p.Acl[3];
-    lp[2] = (p.Acl[3] * s.L[2]) * p.Acl[0]; lp[3] = (p.Acl[3] * s.L[3]) * p.Acl[3];
+    lp[0] = (a0 * s.L[0]) * a0; lp[1] = (a0 * s.L[1]) * a3;
+    lp[2] = (a3 * s.L[2]) * a0; lp[3] = (a3 * s.L[3]) * a3;
     ImK[0] = 1.0 - K[0]; ImK[1] = 0.0 - K[1]; ImK[2] = 0.0 - K[2]; ImK[3] = 1.0 - K[3];
     mm2(ImK, sp, o.S);
     mm2(K, sp, KP);

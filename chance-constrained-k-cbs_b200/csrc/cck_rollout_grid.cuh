@@ -127,8 +127,8 @@ __device__ __forceinline__ bool grid_check_b(const GridConst& g, const unsigned 
     // (flushed by sqrt.approx.ftz: ex_true <= k * sqrt(1.2e-38) < 1e-18)
     const float mx = __fmaf_rn(fabsf(xf) + ex, 3.814697265625e-06f, 1e-17f);
     const float my = __fmaf_rn(fabsf(yf) + ey, 3.814697265625e-06f, 1e-17f);
-    const float dx = xf - ex, sx = xf + ex, dy = yf - ey, sy = yf + ey;
-    const float xm = dx - mx, xp = sx + mx, ym = dy - my, yp = sy + my;       // outer interval (contains the true one)
+    const float wx = ex + mx, wy = ey + my;
+    const float xm = xf - wx, xp = xf + wx, ym = yf - wy, yp = yf + wy;       // outer interval (contains the true one)
     // the inner interval (contained in the true one) is outer -+ 2*margin, formed only for an obstacle the outer test
     // could not skip: the two extra roundings (2^-24 relative each) are far inside the 2^-18 margin
     // gridded obstacles: anchor (xlo, ylo) must lie in (xm - SX, xp) x (ym - SY, yp) to be unproven

@@ -70,8 +70,8 @@ def _device_query(t, x, y, P, sqrt_err=0.0):
         # __fmaf_rn: the product of two fp32 numbers is exact in fp64; one rounding to fp32 after the add
         mx = ((np.abs(xf) + ex).astype(np.float64) * np.float64(f32(3.814697265625e-06)) + np.float64(f32(1e-17))).astype(f32)
         my = ((np.abs(yf) + ey).astype(np.float64) * np.float64(f32(3.814697265625e-06)) + np.float64(f32(1e-17))).astype(f32)
-        dx, sx, dy, sy = xf - ex, xf + ex, yf - ey, yf + ey
-        xm, xp, ym, yp = dx - mx, sx + mx, dy - my, sy + my
+        wx, wy = ex + mx, ey + my
+        xm, xp, ym, yp = xf - wx, xf + wx, yf - wy, yf + wy
         mx2, my2 = mx + mx, my + my
     q = {"fin": fin, "xm": xm, "xp": xp, "ym": ym, "yp": yp,
          "xmi": xm + mx2, "xpi": xp - mx2, "ymi": ym + my2, "ypi": yp - my2}
