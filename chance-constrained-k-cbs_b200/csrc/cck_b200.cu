@@ -666,7 +666,7 @@ extern "C" int cck_set_obstacles(cck_ctx* c, const cck_svc_params* p, const doub
         // and the box arrays (32 B per obstacle) are read from global memory
         const bool boxes_in_smem = gb.buf.size() <= 24 * 1024;
         const int stage_bytes = boxes_in_smem ? (int)gb.buf.size() : gh0.off_boxes;
-        if (grid_smem_bytes(stage_bytes) > c->max_smem_optin) return fail(c, CCK_ERR_INVALID, "grid table exceeds shared memory");
+        if (grid_smem_bytes(stage_bytes, CCK_GRID_THREADS) > c->max_smem_optin) return fail(c, CCK_ERR_INVALID, "grid table exceeds shared memory");
         CK(c, cudaMalloc(&c->d_gtab, gb.buf.size()));
         CK(c, cudaMalloc(&c->d_gexB, gb.exB.size() * 8));
         CK(c, cudaMalloc(&c->d_gexCls, gb.exCls.size() * 4));
@@ -845,12 +845,12 @@ static int launch_rollout(cck_ctx* c, cudaStream_t s, const RolloutArgs& a) {
         g2.ftab = c->d_gtab; g2.ftab_bytes = c->gtab_bytes; g2.exB = c->d_gexB; g2.exCls = c->d_gexCls;
         const int rl2 = rollout_range_log2(a.n);
         const int64_t nr = (a.n + ((int64_t)1 << rl2) - 1) >> rl2;
-        const int gb = (int)std::min<int64_t>(nr, (int64_t)c->num_sms * CCK_GRID_MINB);
-        const int gsmem = grid_smem_bytes(c->gtab_bytes) + (EXPAND ? a.cons_smem_bytes : 0);
+        const int gb = (int)std::min<int64_t>(nr, (int64_t)c->num_sms * grid_minb(EXPAND));
+        const int gsmem = grid_smem_bytes(c->gtab_bytes, grid_threads(EXPAND)) + (EXPAND ? a.cons_smem_bytes : 0);
         if (traj) { if ((rc = set_smem(c, (k_rollout_lin_grid<true, EXPAND>), gsmem))) return rc;
-                    k_rollout_lin_grid<true, EXPAND><<<gb, CCK_GRID_THREADS, gsmem, s>>>(g2, c->lin, c->svc, c->gconst, rl2); }
+                    k_rollout_lin_grid<true, EXPAND><<<gb, grid_threads(EXPAND), gsmem, s>>>(g2, c->lin, c->svc, c->gconst, rl2); }
         else { if ((rc = set_smem(c, (k_rollout_lin_grid<false, EXPAND>), gsmem))) return rc;
-               k_rollout_lin_grid<false, EXPAND><<<gb, CCK_GRID_THREADS, gsmem, s>>>(g2, c->lin, c->svc, c->gconst, rl2); }
+               k_rollout_lin_grid<false, EXPAND><<<gb, grid_threads(EXPAND), gsmem, s>>>(g2, c->lin, c->svc, c->gconst, rl2); }
     } else if (c->model.model == CCK_MODEL_LINEAR2D && c->svc.kind == CCK_SVC_BLACKMORE && c->kern == 1 && c->bpt > 0) {
         // second generation: threshold (group filter) kernel, BPT beliefs per thread
         if (c->M > 0 && c->ftab_bytes == 0) return fail(c, CCK_ERR_INVALID, "group-filter table exceeds shared memory; use the default kernel");

@@ -223,14 +223,19 @@ __device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-// shared-memory carve-up: [mbarrier 16 B][grid table][work counter 16 B][stash 128 x 80 B]
-//                         [prefetch slots: 13 planes x 128 doubles][2 planes x 128 ints]
+// shared-memory carve-up (T = CCK_GRID_THREADS): [mbarrier 16 B][grid table][work counter 16 B][stash T x 80 B]
+//                         [prefetch slots: 13 planes x T doubles][2 planes x T ints]
+// Sweeps (EXPAND = false): 5 warps x 4 CTAs = 20 warps per SM at <= 96 registers (measured: +4 % on the realistic sweep
+// over 4 x 128 threads).  The expansion kernel carries the constraint and goal tests: 128 threads x 3 CTAs leaves it 168
+// registers (no spills); its launches are planner-sized and latency-bound.
 #ifndef CCK_GRID_THREADS
-#define CCK_GRID_THREADS 128
+#define CCK_GRID_THREADS 160
 #endif
 #ifndef CCK_GRID_MINB
 #define CCK_GRID_MINB 4
 #endif
+__host__ __device__ constexpr int grid_threads(bool expand) { return expand ? 128 : CCK_GRID_THREADS; }
+__host__ __device__ constexpr int grid_minb(bool expand) { return expand ? 3 : CCK_GRID_MINB; }
 #ifndef CCK_REFILL_MIN
 #define CCK_REFILL_MIN 6      // idle lanes of a warp that trigger a refill ...
 #endif
@@ -241,33 +246,29 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // big sweeps (coalesced refills), 128 = one belief per lane for planner-sized batches (latency: every candidate of a
 // K <= 75k launch starts immediately on its own lane)
 __host__ inline int rollout_range_log2(int64_t n) { return n >= ((int64_t)1 << 22) ? 8 : 7; }
-__host__ __device__ inline int grid_smem_bytes(int gtab_bytes) {
-    return 16 + gtab_bytes + 16 + CCK_GRID_THREADS * 80 + 13 * CCK_GRID_THREADS * 8 + 2 * CCK_GRID_THREADS * 4;
+__host__ __device__ inline int grid_smem_bytes(int gtab_bytes, int threads) {
+    return 16 + gtab_bytes + 16 + threads * 80 + 13 * threads * 8 + 2 * threads * 4;
 }
 
-#ifdef CCK_GRID_MAXNREG
-#define CCK_GRID_BOUNDS __maxnreg__(CCK_GRID_MAXNREG)
-#else
-#define CCK_GRID_BOUNDS __launch_bounds__(CCK_GRID_THREADS, CCK_GRID_MINB)
-#endif
 template <bool TRAJ, bool EXPAND>
-__global__ void CCK_GRID_BOUNDS k_rollout_lin_grid(const __grid_constant__ RolloutArgs a, const __grid_constant__ LinDev p,
+__global__ void __launch_bounds__(grid_threads(EXPAND), grid_minb(EXPAND)) k_rollout_lin_grid(const __grid_constant__ RolloutArgs a, const __grid_constant__ LinDev p,
                                                                           const __grid_constant__ SvcDev sp, const __grid_constant__ GridConst g,
                                                                           const int range_log2) {
+    constexpr int T = grid_threads(EXPAND);
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
     unsigned char* gt = smem_raw + 16;
     int* next_k = reinterpret_cast<int*>(smem_raw + 16 + a.ftab_bytes);
     double2* stash = reinterpret_cast<double2*>(smem_raw + 16 + a.ftab_bytes + 16) + threadIdx.x * 5;   // 80 B per thread, conflict-free STS.128
-    double* slot = reinterpret_cast<double*>(smem_raw + 16 + a.ftab_bytes + 16 + CCK_GRID_THREADS * 80) + threadIdx.x;   // plane f at slot[f*128]
-    int* islot = reinterpret_cast<int*>(smem_raw + 16 + a.ftab_bytes + 16 + CCK_GRID_THREADS * 80 + 13 * CCK_GRID_THREADS * 8) + threadIdx.x;
+    double* slot = reinterpret_cast<double*>(smem_raw + 16 + a.ftab_bytes + 16 + T * 80) + threadIdx.x;   // plane f at slot[f*T]
+    int* islot = reinterpret_cast<int*>(smem_raw + 16 + a.ftab_bytes + 16 + T * 80 + 13 * T * 8) + threadIdx.x;
     if (threadIdx.x == 0) *next_k = 0;
     // EXPAND: a small constraint table is copied behind the prefetch slots (a dependent global load per step and
     // candidate is what a planner-sized launch would otherwise wait for)
     const unsigned char* cons = a.cons;
     if (EXPAND && a.cons_smem_bytes > 0) {
-        unsigned char* sc = smem_raw + grid_smem_bytes(a.ftab_bytes);
-        for (int o = threadIdx.x * 16; o < a.cons_smem_bytes; o += CCK_GRID_THREADS * 16)
+        unsigned char* sc = smem_raw + grid_smem_bytes(a.ftab_bytes, T);
+        for (int o = threadIdx.x * 16; o < a.cons_smem_bytes; o += T * 16)
             *reinterpret_cast<uint4*>(sc + o) = *reinterpret_cast<const uint4*>(a.cons + o);
         cons = sc;
     }
@@ -288,11 +289,11 @@ __global__ void CCK_GRID_BOUNDS k_rollout_lin_grid(const __grid_constant__ Rollo
             if (idx < a.n) { nxt = (int)idx; break; }
         }
 #pragma unroll
-        for (int f = 0; f < 10; ++f) cp_async8(slot + f * CCK_GRID_THREADS, a.bel + f * a.ld + nxt);
-        cp_async8(slot + 10 * CCK_GRID_THREADS, a.ctrl + nxt);
-        cp_async8(slot + 11 * CCK_GRID_THREADS, a.ctrl + a.ldc + nxt);
+        for (int f = 0; f < 10; ++f) cp_async8(slot + f * T, a.bel + f * a.ld + nxt);
+        cp_async8(slot + 10 * T, a.ctrl + nxt);
+        cp_async8(slot + 11 * T, a.ctrl + a.ldc + nxt);
         cp_async4(islot, a.steps + nxt);
-        if (EXPAND) cp_async4(islot + CCK_GRID_THREADS, a.parent_step + nxt);
+        if (EXPAND) cp_async4(islot + T, a.parent_step + nxt);
         cp_async_commit();
     };
     prefetch();
@@ -337,12 +338,12 @@ __global__ void CCK_GRID_BOUNDS k_rollout_lin_grid(const __grid_constant__ Rollo
         while (!have && nxt >= 0) {
             cp_async_wait_all();
             i = nxt;
-            A.mx = slot[0]; A.my = slot[CCK_GRID_THREADS];
+            A.mx = slot[0]; A.my = slot[T];
 #pragma unroll
-            for (int f = 0; f < 4; ++f) { A.S[f] = slot[(2 + f) * CCK_GRID_THREADS]; A.L[f] = slot[(6 + f) * CCK_GRID_THREADS]; }
-            dux = p.dt * slot[10 * CCK_GRID_THREADS]; duy = p.dt * slot[11 * CCK_GRID_THREADS];
+            for (int f = 0; f < 4; ++f) { A.S[f] = slot[(2 + f) * T]; A.L[f] = slot[(6 + f) * T]; }
+            dux = p.dt * slot[10 * T]; duy = p.dt * slot[11 * T];
             steps = islot[0];
-            if (EXPAND) pstep = islot[CCK_GRID_THREADS];
+            if (EXPAND) pstep = islot[T];
             prefetch();
             if (steps <= 0) {         // propagateWhileValid(.., 0, ..): copy, return 0
                 a.out[i] = A.mx; a.out[a.ldo + i] = A.my;
