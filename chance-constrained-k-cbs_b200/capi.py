@@ -67,7 +67,7 @@ SYMBOLS = [
     "cck_set_constraints", "cck_satisfies_constraints", "cck_satisfies_constraints_dev",
     "cck_expand_batch", "cck_expand_batch_dev", "cck_rollout_summary_dev", "cck_select_winner_dev", "cck_measure_fp64_peak",
     "cck_tree_create", "cck_tree_destroy", "cck_tree_clear", "cck_tree_size", "cck_tree_append", "cck_tree_update",
-    "cck_tree_select", "cck_tree_nearest", "cck_belief_distance", "cck_belief_distance_lower", "cck_belief_distance_cols", "cck_build_grid_table",
+    "cck_tree_select", "cck_tree_nearest", "cck_belief_distance", "cck_belief_distance_lower", "cck_belief_distance_cols", "cck_belief_distance_cols_near", "cck_build_grid_table",
 ]
 
 
@@ -150,6 +150,7 @@ def lib():
     L.cck_build_grid_table.argtypes = [C.c_int, vp, vp, C.c_double, vp, i64, C.POINTER(i64), vp]
     L.cck_belief_distance_lower.argtypes = [vp, C.c_int, i64, vp, i64, vp]
     L.cck_belief_distance_cols.argtypes = [vp, C.c_int, i64, vp, i64, C.c_int32, vp, vp]
+    L.cck_belief_distance_cols_near.argtypes = [vp, C.c_int, i64, vp, i64, C.c_int32, vp, vp, C.c_int32, vp, vp, vp]
     _lib = L
     return L
 
@@ -508,6 +509,20 @@ def belief_distance_cols(ctx, bel, dim, cols):
     out = out[:, :nf]
     out[np.arange(n)[:, None] <= cols[None, :]] = 0.0
     return out
+
+
+def belief_distance_cols_near(ctx, bel, dim, cols, limit, cap=16):
+    """Sparse form of belief_distance_cols: per row q the pairs (a, distance(b_cols[a], b_q)) with cols[a] < q and
+    distance < limit[q], in increasing a.  Returns (count[n], idx[n, cap], dist[n, cap]); count may exceed cap."""
+    bel = np.ascontiguousarray(bel, dtype=np.float64)
+    cols = np.ascontiguousarray(cols, dtype=np.int32)
+    limit = np.ascontiguousarray(limit, dtype=np.float64)
+    n, nf = bel.shape[1], len(cols)
+    idx = np.full((n, cap), -1, dtype=np.int32)
+    dist = np.zeros((n, cap))
+    cnt = np.zeros(n, dtype=np.int32)
+    ctx._ck(ctx.L.cck_belief_distance_cols_near(ctx.h, dim, n, _ptr(bel), n, nf, _ptr(cols), _ptr(limit), cap, _ptr(idx), _ptr(dist), _ptr(cnt)))
+    return cnt, idx, dist
 
 
 def aos_to_soa(b):

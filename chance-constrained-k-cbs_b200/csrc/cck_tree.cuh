@@ -39,7 +39,13 @@ __host__ __device__ inline void sym_sqrt(const double* Ain, double* out) {
 #pragma unroll
             for (int j = 0; j < DIM; ++j)
                 if (j < i) off += A[i * DIM + j] * A[i * DIM + j];
-        if (off < 1e-300) break;
+        // converged: the off-diagonal is at the rounding floor (<= 1e-15 of the diagonal in norm).  Rounding leaves a residue
+        // of ~1e-17 there that never reaches the absolute 1e-300 test, so that test alone ran all 60 sweeps every time
+        // (ncu: 9000 instructions per warp for one 2x2 distance) - ten times the work of the converged iteration.
+        double dg = 0;
+#pragma unroll
+        for (int i = 0; i < DIM; ++i) dg += A[i * DIM + i] * A[i * DIM + i];
+        if (off < 1e-300 || off <= 1e-30 * dg) break;
 #pragma unroll
         for (int p = 0; p < DIM; ++p)
 #pragma unroll
@@ -274,6 +280,62 @@ __global__ void __launch_bounds__(128) k_distance_cols(int64_t n, const double* 
         }
         out[q * nf + a] = dist;
     }
+}
+
+// The same matrix, but only the entries the sequential witness replay can use: for row q the pairs (a, distance) with
+// cols[a] < q and distance < limit[q], in increasing a, at most `cap` of them (count[q] is the full number, so the
+// caller sees an overflow).  One CTA of 128 threads per row (a distance is a long dependent chain of fp64 div/sqrt, so
+// the columns of a row are spread over as many threads as possible); ordered compaction with ballot + popc per warp
+// and a 4-entry prefix over the warps.  cols must be ascending.
+template <int DIM>
+__global__ void __launch_bounds__(128) k_distance_cols_near(int64_t n, const double* __restrict__ bel, int64_t ld, int nf,
+                                                            const int32_t* __restrict__ cols, const double* __restrict__ limit, int cap,
+                                                            int32_t* __restrict__ out_idx, double* __restrict__ out_dist, int32_t* __restrict__ count) {
+    __shared__ int wcnt[4];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t q = blockIdx.x;
+    double qm[DIM], qC[DIM * DIM], qS[DIM * DIM];
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) qm[d] = bel[d * ld + q];
+#pragma unroll
+    for (int f = 0; f < DIM * DIM; ++f) qC[f] = bel[(DIM + f) * ld + q] + bel[(DIM + DIM * DIM + f) * ld + q];
+    sym_sqrt<DIM, false>(qC, qS);
+    const double lim = limit[q];
+    int base = 0;
+    for (int a0 = 0; a0 < nf; a0 += 128) {
+        if (cols[a0] >= q) break;                      // ascending: nothing further is below q (CTA-uniform)
+        const int a = a0 + threadIdx.x;
+        bool keep = false;
+        double dist = 0;
+        if (a < nf) {
+            const int64_t i = cols[a];
+            if (i < q) {
+                double d2 = 0;
+#pragma unroll
+                for (int d = 0; d < DIM; ++d) { const double e = bel[d * ld + i] - qm[d]; d2 += e * e; }
+                if (d2 != 0) {
+                    double C[DIM * DIM];
+#pragma unroll
+                    for (int f = 0; f < DIM * DIM; ++f) C[f] = bel[(DIM + f) * ld + i] + bel[(DIM + DIM * DIM + f) * ld + i];
+                    dist = fabs(d2 + cov_term<DIM>(C, qC, qS));
+                }
+                keep = dist < lim;
+            }
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) wcnt[warp] = __popc(m);
+        __syncthreads();
+        int before = base, total = 0;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) { if (w < warp) before += wcnt[w]; total += wcnt[w]; }
+        if (keep) {
+            const int pos = before + __popc(m & ((1u << lane) - 1u));
+            if (pos < cap) { out_idx[q * cap + pos] = a; out_dist[q * cap + pos] = dist; }
+        }
+        base += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) count[q] = base;
 }
 
 // plain batched distance(a_i, b_i) (second argument's sqrt, as RealVectorBeliefSpace::distance(state1, state2))

@@ -71,7 +71,9 @@ struct SegmentPath {
     std::vector<double> durations;               // n durations (seconds)
 };
 
-struct PlannerStats { int64_t launches = 0, candidates = 0, accepted = 0, nodes = 0; double seconds = 0; };
+struct PlannerStats { int64_t launches = 0, candidates = 0, accepted = 0, nodes = 0; double seconds = 0;
+                      double t_sample = 0, t_select = 0, t_expand = 0, t_commit = 0, t_extract = 0;
+                      double c_nearest = 0, c_cols = 0, c_replay = 0, c_mirror = 0; int64_t c_surv = 0, c_fresh = 0; };   // where solve() spends its time
 
 // One robot's low-level planning problem (what set_up_ConstraintBSST_MP_Problems wires per robot,
 // OmplSetUp.cpp:183-353): belief space + bounds, control bounds, SVC, propagator, start, goal.
@@ -157,6 +159,7 @@ public:
         int solution = -1;
         while (solution < 0) {
             if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > seconds) break;
+            const auto ta = std::chrono::steady_clock::now();
             // ---- sample K (state, control, duration) triples (ConstraintRespectingBSST.cpp:226-247) ----
             std::fill(samples.begin(), samples.end(), 0.0);
             for (int j = 0; j < K; ++j) {
@@ -171,6 +174,7 @@ public:
                 for (int d = 0; d < dim_; ++d) ctrl[(size_t)d * K + j] = uni(cbounds_.low[d], cbounds_.high[d]);
                 steps[j] = prm_.min_steps + (int)(rng_() % (uint64_t)(prm_.max_steps - prm_.min_steps + 1));
             }
+            const auto tb = std::chrono::steady_clock::now();
             // ---- ONE launch: selectNode for all K samples (:119-148) ----
             nodes_dev_->select(K, samples.data(), K, prm_.selection_radius, parent.data());
             stats_.launches++;
@@ -179,18 +183,26 @@ public:
                 for (int f = 0; f < W_; ++f) bel[(size_t)f * K + j] = m.state[f];
                 pstep[j] = m.depth; pcost[j] = m.accCost;
             }
+            const auto tc = std::chrono::steady_clock::now();
             // ---- ONE launch: K x (<=10 steps) propagate + check (+ constraints, cost, goal) ----
             gpu_->check(cck_expand_batch(gpu_->get(), K, bel.data(), K, ctrl.data(), K, steps.data(), pstep.data(), pcost.data(), &goal_, out.data(), K,
                                          valid.data(), cost.data(), gdist.data(), flags.data()), "cck_expand_batch");
             stats_.launches++; stats_.candidates += K;
+            const auto td = std::chrono::steady_clock::now();
             // ---- commit in sample order with the reference's witness rules (:250-326) ----
             solution = commit(K, out, ctrl, steps, parent, cost, flags);
+            const auto te = std::chrono::steady_clock::now();
+            auto sec = [](auto a, auto b) { return std::chrono::duration<double>(b - a).count(); };
+            stats_.t_sample += sec(ta, tb); stats_.t_select += sec(tb, tc); stats_.t_expand += sec(tc, td); stats_.t_commit += sec(td, te);
         }
         stats_.nodes = (int64_t)motions_.size();
         stats_.seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         if (solution < 0) return {};
         if (cost_out) *cost_out = motions_[solution].accCost;
-        return extract(solution);
+        const auto tx = std::chrono::steady_clock::now();
+        Trajectory traj = extract(solution);
+        stats_.t_extract += std::chrono::duration<double>(std::chrono::steady_clock::now() - tx).count();
+        return traj;
     }
 
 private:
@@ -212,7 +224,11 @@ private:
             for (int s = 0; s < S; ++s) { const int j = surv[c0 + s]; for (int f = 0; f < W_; ++f) q[(size_t)f * S + s] = out[(size_t)f * K + j]; qcost[s] = cost[j]; }
             std::vector<int32_t> widx(S);
             std::vector<double> wdist(S);
+            auto now = [] { return std::chrono::steady_clock::now(); };
+            auto secs = [](auto a, auto b) { return std::chrono::duration<double>(b - a).count(); };
+            const auto t1 = now();
             wit_dev_->nearest(S, q.data(), S, widx.data(), wdist.data());
+            const auto t2 = now();
             stats_.launches++;
             // only survivors farther than the pruning radius from every existing witness can become witnesses:
             // their columns of the batch's distance matrix are all the sequential replay needs
@@ -220,11 +236,28 @@ private:
             std::vector<int> col_of(S, -1);
             for (int s = 0; s < S; ++s) if (widx[s] < 0 || wdist[s] > prm_.pruning_radius) { col_of[s] = (int)cols.size(); cols.push_back(s); }
             const int nf = (int)cols.size();
-            std::vector<double> dcols((size_t)S * std::max(nf, 1));
+            // A survivor adopts a same-launch witness only if that one is nearer than its nearest existing witness AND
+            // within the pruning radius (a farther one leaves "new witness" / "existing witness" unchanged), so only
+            // those entries of the S x nf distance matrix are fetched: a few pairs per row instead of S x nf doubles.
+            int cap = 32;
+            near_cnt_.assign(S, 0);
             if (nf > 0) {
-                gpu_->check(cck_belief_distance_cols(gpu_->get(), dim_, S, q.data(), S, nf, cols.data(), dcols.data()), "cck_belief_distance_cols");
-                stats_.launches++;
+                std::vector<double> lim(S);
+                const double pr_up = std::nextafter(prm_.pruning_radius, std::numeric_limits<double>::infinity());
+                for (int s = 0; s < S; ++s) lim[s] = std::min(widx[s] >= 0 ? wdist[s] : std::numeric_limits<double>::infinity(), pr_up);
+                for (int attempt = 0; attempt < 2; ++attempt) {
+                    near_idx_.resize((size_t)S * cap); near_dist_.resize((size_t)S * cap);
+                    gpu_->check(cck_belief_distance_cols_near(gpu_->get(), dim_, S, q.data(), S, nf, cols.data(), lim.data(), cap, near_idx_.data(),
+                                                              near_dist_.data(), near_cnt_.data()), "cck_belief_distance_cols_near");
+                    stats_.launches++;
+                    int mx = 0;
+                    for (int s = 0; s < S; ++s) mx = std::max(mx, near_cnt_[s]);
+                    if (mx <= cap) break;
+                    cap = mx;     // a row overflowed (many survivors inside one pruning ball): once more with room for the fullest row
+                }
             }
+            std::vector<int> fresh_of_col(std::max(nf, 1), -1);      // column a -> index into `fresh` once cols[a] became a witness
+            const auto t3 = now();
             std::vector<std::pair<int, int>> fresh;       // (survivor s, witness index) of witnesses created in this chunk
             std::vector<int32_t> deact;
             std::vector<int> new_nodes;                   // survivors appended to the tree, in order
@@ -233,14 +266,21 @@ private:
                 const int j = surv[c0 + s];
                 int w = widx[s];
                 double cd = w >= 0 ? wdist[s] : std::numeric_limits<double>::infinity();
-                for (const auto& fw : fresh) { const double d = dcols[(size_t)s * nf + col_of[fw.first]]; if (d < cd) { cd = d; w = fw.second; } }
+                // the reference's scan over the witnesses created so far, restricted to the fetched pairs, in the same
+                // order (columns ascend with creation order)
+                for (int e = 0; e < near_cnt_[s]; ++e) {
+                    const int fi = fresh_of_col[near_idx_[(size_t)s * cap + e]];
+                    if (fi < 0) continue;
+                    const double d = near_dist_[(size_t)s * cap + e];
+                    if (d < cd) { cd = d; w = fresh[fi].second; }
+                }
                 const int idx = (int)motions_.size();
                 bool is_new = false;
-                if (w < 0 || cd > prm_.pruning_radius) { witnesses_.push_back(Witness{idx}); w = (int)witnesses_.size() - 1; fresh.emplace_back(s, w); is_new = true; }
+                if (w < 0 || cd > prm_.pruning_radius) { witnesses_.push_back(Witness{idx}); w = (int)witnesses_.size() - 1; fresh.emplace_back(s, w); fresh_of_col[col_of[s]] = (int)fresh.size() - 1; is_new = true; }
                 Witness& wit = witnesses_[w];
                 if (!(is_new || cost[j] < motions_[wit.rep].accCost)) continue;
                 if (!constraints_.empty() && !(flags[j] & 2)) {                 // satisfiesConstraints failed (:300)
-                    if (is_new) { witnesses_.pop_back(); fresh.pop_back(); }
+                    if (is_new) { witnesses_.pop_back(); fresh.pop_back(); fresh_of_col[col_of[s]] = -1; }
                     continue;
                 }
                 Motion m;
@@ -257,6 +297,7 @@ private:
                 if (c00 > max_eig_) max_eig_ = c00; else if (c11 > max_eig_) max_eig_ = c11;     // :313-320
                 if (flags[j] & 4) solution = idx;                                // goal->isSatisfied (:326)
             }
+            const auto t4 = now();
             // mirror the chunk's changes on the device: new nodes, new witnesses, deactivated representatives
             if (!new_nodes.empty()) {
                 const int n = (int)new_nodes.size();
@@ -271,6 +312,9 @@ private:
                 wit_dev_->append(n, wb.data(), n, wc.data());
             }
             nodes_dev_->deactivate(deact);
+            const auto t5 = now();
+            stats_.c_nearest += secs(t1, t2); stats_.c_cols += secs(t2, t3); stats_.c_replay += secs(t3, t4); stats_.c_mirror += secs(t4, t5);
+            stats_.c_surv += S; stats_.c_fresh += (int64_t)fresh.size();
         }
         return solution;
     }
@@ -345,6 +389,8 @@ private:
     double max_eig_ = 10.0;                                            // :221
     PlannerStats stats_;
     SegmentPath last_path_;
+    std::vector<int32_t> near_idx_, near_cnt_;      // commit(): sparse same-launch distances (kept across launches)
+    std::vector<double> near_dist_;
 };
 
 // ---------------------------------------------------------------------------
@@ -352,7 +398,8 @@ private:
 // conflict spawns two children, one per involved agent, each re-planned under the union of that
 // agent's constraints along the branch.  (The merge block is unimplemented in the reference.)
 // ---------------------------------------------------------------------------
-struct KCBSResult { bool solved = false; Plan plan; std::vector<SegmentPath> paths; double cost = 0, seconds = 0; int nodes_expanded = 0, replans = 0; };
+struct KCBSResult { bool solved = false; Plan plan; std::vector<SegmentPath> paths; double cost = 0, seconds = 0; int nodes_expanded = 0, replans = 0;
+                    double t_root = 0, t_validate = 0; };
 
 class KCBS {
 public:
@@ -373,10 +420,24 @@ public:
         const int k = (int)planners_.size();
         auto root = std::make_shared<Node>();
         root->cost = 0;
-        for (int r = 0; r < k; ++r) {                                   // :213-228
+        // :213-228.  The k root plans are independent (one planner, context, stream and device tree per robot, own
+        // random stream), so they are computed concurrently; results are consumed in robot order.
+        std::vector<std::future<Trajectory>> roots;
+        for (int r = 0; r < k; ++r) {
             planners_[r]->updateConstraints({});
-            Trajectory t;
-            while (t.empty() && elapsed() < seconds) t = planners_[r]->solve(ll_seconds_);
+            BatchedBSST* pl = planners_[r].get();
+            const double secs = ll_seconds_;
+            roots.push_back(std::async(k > 1 ? std::launch::async : std::launch::deferred, [pl, secs, seconds, &elapsed] {
+                Trajectory t;
+                while (t.empty() && elapsed() < seconds) t = pl->solve(secs);
+                return t;
+            }));
+        }
+        std::vector<Trajectory> root_traj;
+        for (int r = 0; r < k; ++r) root_traj.push_back(roots[r].get());      // join every task before any early return
+        res.t_root = elapsed();
+        for (int r = 0; r < k; ++r) {
+            Trajectory& t = root_traj[r];
             if (t.empty()) { res.seconds = elapsed(); return res; }
             root->cost += 0.2 * (double)(t.size() - 1);                 // sum of control durations (KCBSNode::updatePlanAndCost)
             root->plan.push_back(std::move(t));
@@ -387,7 +448,9 @@ public:
         while (!pq.empty() && elapsed() < seconds) {
             auto cur = pq.top(); pq.pop();
             res.nodes_expanded++;
+            const double tv = elapsed();
             const std::vector<ConflictPtr> confs = pv->validatePlan(cur->plan);      // :289
+            res.t_validate += elapsed() - tv;
             if (confs.empty()) { res.solved = true; res.plan = cur->plan; res.paths = cur->paths; res.cost = cur->cost; break; }
             const int agents[2] = {confs.front()->agent1Idx_, confs.front()->agent2Idx_};
             // :389-467: the two child replans are independent (different agents, each planner owns its context,

@@ -259,6 +259,13 @@ int cck_belief_distance_lower(cck_ctx* ctx, int dim, int64_t n, const double* be
 /* the same matrix restricted to nf columns: out[q*nf + a] = distance(b_cols[a], b_q) for cols[a] < q.  Only candidates farther
  * than the pruning radius from every existing witness can become witnesses, so the planner asks for those columns only */
 int cck_belief_distance_cols(cck_ctx* ctx, int dim, int64_t n, const double* bel, int64_t ld, int32_t nf, const int32_t* cols, double* out);
+/* the part of that matrix the sequential witness rules (ConstraintRespectingBSST.cpp:150-178, :250-326) can use: for row q
+ * the pairs (a, distance(b_cols[a], b_q)) with cols[a] < q and distance < limit[q], in increasing a.  out_count[q] is the
+ * full number of such pairs; the first min(out_count[q], cap) are stored at out_idx / out_dist [q*cap ...].  cols must be
+ * ascending.  A candidate only ever adopts a same-launch witness that is nearer than its nearest existing witness and
+ * within the pruning radius, so limit[q] = min(that distance, nextafter(pruning radius)) makes the rows nearly empty. */
+int cck_belief_distance_cols_near(cck_ctx* ctx, int dim, int64_t n, const double* bel, int64_t ld, int32_t nf, const int32_t* cols,
+                                  const double* limit, int32_t cap, int32_t* out_idx, double* out_dist, int32_t* out_count);
 
 
 #ifdef __cplusplus

@@ -467,7 +467,9 @@ inline void sym_operator_sqrt(const double* Ain, int n, double* out) {
     for (int sweep = 0; sweep < 60; ++sweep) {
         double off = 0;
         for (int i = 0; i < n; ++i) for (int j = 0; j < i; ++j) off += A[i * n + j] * A[i * n + j];
-        if (off < 1e-300) break;
+        double dg = 0;                                    // same convergence test as the kernel (csrc/cck_tree.cuh)
+        for (int i = 0; i < n; ++i) dg += A[i * n + i] * A[i * n + i];
+        if (off < 1e-300 || off <= 1e-30 * dg) break;
         for (int p = 0; p < n; ++p)
             for (int q = p + 1; q < n; ++q) {
                 if (std::fabs(A[p * n + q]) < 1e-300) continue;

@@ -104,6 +104,22 @@ def test_gpu_distance_lower_matrix(K, O, ctx, dim):
     sub = K.belief_distance_cols(ctx, K.aos_to_soa(b), dim, cols)
     assert np.array_equal(sub, got[:, cols])
     assert K.belief_distance_cols(ctx, K.aos_to_soa(b), dim, np.zeros(0, dtype=np.int32)).shape == (300, 0)
+    # the sparse form the planner uses: per row the pairs below a per-row limit, in column order, count beyond the cap
+    cols = np.sort(rng.choice(300, size=140, replace=False)).astype(np.int32)
+    full = got[:, cols]
+    lim = np.where(rng.random(300) < 0.3, np.inf, rng.uniform(0.5, 6.0, 300))
+    lim[5] = 0.0
+    for cap in (4, 64):
+        cnt, idx, dist = K.capi.belief_distance_cols_near(ctx, K.aos_to_soa(b), dim, cols, lim, cap=cap)
+        for q in range(300):
+            want = [a for a in range(len(cols)) if cols[a] < q and full[q, a] < lim[q]]
+            assert cnt[q] == len(want)
+            m = min(len(want), cap)
+            assert idx[q, :m].tolist() == want[:m]
+            assert np.array_equal(dist[q, :m], full[q, want[:m]])
+        assert (cnt > 4).any()
+    cnt, _, _ = K.capi.belief_distance_cols_near(ctx, K.aos_to_soa(b), dim, np.zeros(0, dtype=np.int32), lim)
+    assert (cnt == 0).all()
 
 
 @pytest.mark.gpu

@@ -75,6 +75,10 @@ def main():
                           "launches_median": float(np.median([r["launches"] for r in ok])) if ok else None,
                           "candidates_median": float(np.median([r["candidates"] for r in ok])) if ok else None,
                           "cbs_nodes_median": float(np.median([r["cbs_nodes"] for r in ok])) if ok else None}
+            if ok and "phase_seconds" in ok[0]:      # where the wall clock goes (medians; planner phases are summed over robots)
+                res[label]["root_seconds_median"] = float(np.median([r["root_seconds"] for r in ok]))
+                res[label]["validate_seconds_median"] = float(np.median([r["validate_seconds"] for r in ok]))
+                res[label]["phase_seconds_median"] = {k2: float(np.median([r["phase_seconds"][k2] for r in ok])) for k2 in ok[0]["phase_seconds"]}
             print(label, json.dumps(res[label]), flush=True)
     if a.out:
         json.dump(res, open(a.out, "w"), indent=1)
