@@ -1485,9 +1485,9 @@ extern "C" int cck_belief_distance_cols(cck_ctx* c, int dim, int64_t n, const do
 extern "C" int cck_belief_distance_cols_near(cck_ctx* c, int dim, int64_t n, const double* bel, int64_t ld, int32_t nf, const int32_t* cols,
                                              const double* limit, int32_t cap, int32_t* out_idx, double* out_dist, int32_t* out_count) {
     if (!c) return CCK_ERR_INVALID;
-    if ((dim != 2 && dim != 4) || n < 0 || ld < n || nf < 0 || n > 65536 || cap < 1 || cap > 1024 ||
+    if ((dim != 2 && dim != 4) || n < 0 || ld < n || nf < 0 || n > 65536 || cap < 1 || cap > 65536 ||
         (n > 0 && (!out_count || (nf > 0 && (!bel || !cols || !limit || !out_idx || !out_dist)))))
-        return fail(c, CCK_ERR_INVALID, "bad near-distance-columns arguments (n <= 65536, 1 <= cap <= 1024)");
+        return fail(c, CCK_ERR_INVALID, "bad near-distance-columns arguments (n <= 65536, 1 <= cap <= 65536)");
     if (n == 0) return CCK_OK;
     if (nf == 0) { std::memset(out_count, 0, (size_t)n * 4); return CCK_OK; }
     for (int a = 0; a < nf; ++a)

@@ -126,6 +126,33 @@ public:
         for (int i = 0; i < dim_; ++i) { start_[dim_ + i * dim_ + i] = 0.01; start_[dim_ + dim_ * dim_ + i * dim_ + i] = 0.01; }
         goal_.gx = r.getGoalLocation().x_; goal_.gy = r.getGoalLocation().y_;
         goal_.threshold = prm_.goal_threshold; goal_.sc = cck_chi2_quantile_2dof(prm_.goal_p_safe);
+        warmup();
+    }
+
+    // Part of the setup, like the reference's planner->setup(): one throw-away iteration at full batch size on constant
+    // data (the random stream is untouched).  It loads the kernels (CUDA loads a module's functions lazily, ~ms each)
+    // and sizes the device scratch and pinned staging buffers, so that solve() does not pay for them.
+    void warmup() {
+        const int K = prm_.K;
+        std::vector<double> bel((size_t)W_ * K), ctrl((size_t)dim_ * K, 0.0), out((size_t)W_ * K), pcost(K, 0.0), cost(K), gdist(K), dist(K), lim(K, 1.0);
+        for (int j = 0; j < K; ++j) for (int f = 0; f < W_; ++f) bel[(size_t)f * K + j] = start_[f];
+        std::vector<int32_t> steps(K, 1), pstep(K, 0), valid(K), idx(K), cols(K / 2), cnt(K), nidx((size_t)K * 32);
+        std::vector<double> ndist((size_t)K * 32);
+        std::vector<uint8_t> flags(K);
+        for (int a = 0; a < K / 2; ++a) cols[a] = a;
+        const double zero = 0.0;
+        pvc_->installConstraints({});
+        nodes_dev_->append(1, start_.data(), 1, &zero);
+        wit_dev_->append(1, start_.data(), 1, &zero);
+        nodes_dev_->select(K, bel.data(), K, prm_.selection_radius, idx.data());
+        gpu_->check(cck_expand_batch(gpu_->get(), K, bel.data(), K, ctrl.data(), K, steps.data(), pstep.data(), pcost.data(), &goal_, out.data(), K,
+                                     valid.data(), cost.data(), gdist.data(), flags.data()), "cck_expand_batch (warm-up)");
+        wit_dev_->nearest(K, bel.data(), K, idx.data(), dist.data());
+        if (K >= 2)
+            gpu_->check(cck_belief_distance_cols_near(gpu_->get(), dim_, K, bel.data(), K, K / 2, cols.data(), lim.data(), 32, nidx.data(), ndist.data(),
+                                                      cnt.data()), "cck_belief_distance_cols_near (warm-up)");
+        nodes_dev_->deactivate({0});
+        clear();
     }
 
     const oc::SpaceInformationPtr& getSpaceInformation() const { return si_; }
