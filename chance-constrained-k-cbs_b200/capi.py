@@ -67,7 +67,7 @@ SYMBOLS = [
     "cck_set_constraints", "cck_satisfies_constraints", "cck_satisfies_constraints_dev",
     "cck_expand_batch", "cck_expand_batch_dev", "cck_rollout_summary_dev", "cck_select_winner_dev", "cck_measure_fp64_peak",
     "cck_tree_create", "cck_tree_destroy", "cck_tree_clear", "cck_tree_size", "cck_tree_append", "cck_tree_update",
-    "cck_tree_select", "cck_tree_nearest", "cck_belief_distance", "cck_belief_distance_lower", "cck_belief_distance_cols", "cck_belief_distance_cols_near", "cck_build_grid_table",
+    "cck_tree_select", "cck_tree_nearest", "cck_tree_witness_batch", "cck_belief_distance", "cck_belief_distance_lower", "cck_belief_distance_cols", "cck_belief_distance_cols_near", "cck_build_grid_table",
 ]
 
 
@@ -146,6 +146,7 @@ def lib():
     L.cck_tree_update.argtypes = [vp, i64, vp, vp, vp]
     L.cck_tree_select.argtypes = [vp, i64, vp, i64, C.c_double, vp, vp]
     L.cck_tree_nearest.argtypes = [vp, i64, vp, i64, vp, vp]
+    L.cck_tree_witness_batch.argtypes = [vp, i64, vp, i64, C.c_double, vp, vp, vp, vp, vp, vp]
     L.cck_belief_distance.argtypes = [vp, C.c_int, i64, vp, i64, vp, i64, vp]
     L.cck_build_grid_table.argtypes = [C.c_int, vp, vp, C.c_double, vp, i64, C.POINTER(i64), vp]
     L.cck_belief_distance_lower.argtypes = [vp, C.c_int, i64, vp, i64, vp]
@@ -436,6 +437,19 @@ class Tree:
         cost = None if cost is None else np.ascontiguousarray(cost, dtype=np.float64)
         active = None if active is None else np.ascontiguousarray(active, dtype=np.uint8)
         self.ctx._ck(self.ctx.L.cck_tree_update(self.h, len(idx), _ptr(idx), _ptr(cost), _ptr(active)))
+
+    def witness_batch(self, queries, pruning_radius, eligible=None):
+        """The witness rules of one launch for n <= 1024 survivors [W, n] against this tree (= the existing witnesses):
+        (widx, wdist, near, near_dist, fresh), see cck_tree_witness_batch in include/cck_b200.h."""
+        q = np.ascontiguousarray(queries, dtype=np.float64)
+        n = q.shape[1]
+        widx, near = np.zeros(n, dtype=np.int32), np.zeros(n, dtype=np.int32)
+        wdist, ndist = np.zeros(n), np.zeros(n)
+        fresh = np.zeros(n, dtype=np.uint8)
+        el = None if eligible is None else np.ascontiguousarray(eligible, dtype=np.uint8)
+        self.ctx._ck(self.ctx.L.cck_tree_witness_batch(self.h, n, _ptr(q), n, float(pruning_radius), None if el is None else _ptr(el),
+                                                       _ptr(widx), _ptr(wdist), _ptr(near), _ptr(ndist), _ptr(fresh)))
+        return widx, wdist, near, ndist, fresh.astype(bool)
 
     def select(self, samples, radius=0.2):
         q = np.ascontiguousarray(samples, dtype=np.float64)

@@ -742,7 +742,11 @@ static cudaStream_t pick(cck_ctx* c, void* stream) { return stream ? (cudaStream
 
 template <typename K>
 static int set_smem(cck_ctx* c, K kernel, int bytes) {
-    if (bytes > 48 * 1024) CK(c, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    // The opt-in limit is a per-function attribute shared by every thread of the process, and contexts of different robots
+    // launch the same kernels concurrently with different sizes: always raise it to the device maximum, never to this
+    // call's size (a smaller value set by another thread would fail this thread's launch).
+    if (bytes > c->max_smem_optin) return fail(c, CCK_ERR_INVALID, "kernel needs more shared memory than the device offers");
+    if (bytes > 48 * 1024) CK(c, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin));
     return CCK_OK;
 }
 
@@ -1433,6 +1437,70 @@ extern "C" int cck_tree_select(cck_tree* t, int64_t K, const double* samples, in
 }
 extern "C" int cck_tree_nearest(cck_tree* t, int64_t K, const double* queries, int64_t ldq, int32_t* out_idx, double* out_dist) {
     return tree_query(t, 1, K, queries, ldq, 0.0, out_idx, out_dist);
+}
+
+extern "C" int cck_tree_witness_batch(cck_tree* t, int64_t n, const double* q, int64_t ldq, double pruning_radius, const uint8_t* eligible,
+                                      int32_t* out_widx, double* out_wdist, int32_t* out_near, double* out_near_dist, uint8_t* out_fresh) {
+    if (!t) return CCK_ERR_INVALID;
+    cck_ctx* c = t->c;
+    if (n < 0 || ldq < n || n > CCK_WIT_MAX || !(pruning_radius >= 0) ||
+        (n > 0 && (!q || !out_widx || !out_wdist || !out_near || !out_near_dist || !out_fresh)))
+        return fail(c, CCK_ERR_INVALID, "bad witness-batch arguments (n <= 1024)");
+    if (n == 0) return CCK_OK;
+    CK(c, cudaSetDevice(c->device));
+    int rc;
+    const int W = t->dim + 2 * t->dim * t->dim, N = (int)n, nw = CCK_WIT_MAX / 32;
+    // scratch: inputs and intermediates, then ONE result block [widx][near][wdist][near_dist][fresh] for a single D2H
+    const size_t b_q = al256((size_t)n * W * 8), b_el = al256((size_t)n), b_flag = al256((size_t)n), b_lim = al256((size_t)n * 8),
+                 b_D = al256((size_t)n * n * 8), b_adj = al256((size_t)n * nw * 4), b_fw = al256((size_t)nw * 4);
+    const size_t r_i = al256((size_t)n * 4), r_d = al256((size_t)n * 8), r_f = al256((size_t)n), r_all = 2 * r_i + 2 * r_d + r_f;
+    if ((rc = tree_scratch(t, b_q + b_el + 2 * b_flag + b_lim + b_D + b_adj + b_fw + r_all))) return rc;
+    if (c->h_stage_cap < r_all) {
+        if (c->h_stage) cudaFreeHost(c->h_stage);
+        c->h_stage = nullptr; c->h_stage_cap = 0;
+        if (cudaHostAlloc((void**)&c->h_stage, r_all * 2, cudaHostAllocDefault) != cudaSuccess) return fail(c, CCK_ERR_NOMEM, "cudaHostAlloc staging");
+        c->h_stage_cap = r_all * 2;
+    }
+    unsigned char* p = (unsigned char*)t->scratch;
+    double* d_q = (double*)p; p += b_q;
+    uint8_t* d_el = (uint8_t*)p; p += b_el;
+    uint8_t* d_iscol = (uint8_t*)p; p += b_flag;
+    uint8_t* d_cand = (uint8_t*)p; p += b_flag;
+    double* d_lim = (double*)p; p += b_lim;
+    double* d_D = (double*)p; p += b_D;
+    uint32_t* d_adj = (uint32_t*)p; p += b_adj;
+    uint32_t* d_fw = (uint32_t*)p; p += b_fw;
+    unsigned char* d_r = p;
+    int32_t* d_widx = (int32_t*)d_r; int32_t* d_near = (int32_t*)(d_r + r_i);
+    double* d_wdist = (double*)(d_r + 2 * r_i); double* d_ndist = (double*)(d_r + 2 * r_i + r_d);
+    uint8_t* d_fresh = d_r + 2 * r_i + 2 * r_d;
+    cudaStream_t s = c->stream;
+    CK(c, h2d_planes(d_q, q, 8, n, ldq, W, s));
+    if (eligible) CK(c, cudaMemcpyAsync(d_el, eligible, (size_t)n, cudaMemcpyHostToDevice, s));
+    TreeDev td{t->planes, t->active, t->cap};
+    const double r_up = std::nextafter(pruning_radius, HUGE_VAL);
+    const size_t gsm = (size_t)n * nw * 4;
+    if (t->dim == 2) {
+        k_tree_query<2, 1><<<N, 128, 0, s>>>(td, t->n, d_q, n, 0.0, d_widx, d_wdist);
+        k_wit_prep<<<(N + 127) / 128, 128, 0, s>>>(N, d_widx, d_wdist, pruning_radius, r_up, eligible ? d_el : nullptr, d_iscol, d_cand, d_lim);
+        k_wit_rows<2><<<N, 128, 0, s>>>(N, d_q, n, d_cand, pruning_radius, d_D, d_adj);
+    } else {
+        k_tree_query<4, 1><<<N, 128, 0, s>>>(td, t->n, d_q, n, 0.0, d_widx, d_wdist);
+        k_wit_prep<<<(N + 127) / 128, 128, 0, s>>>(N, d_widx, d_wdist, pruning_radius, r_up, eligible ? d_el : nullptr, d_iscol, d_cand, d_lim);
+        k_wit_rows<4><<<N, 128, 0, s>>>(N, d_q, n, d_cand, pruning_radius, d_D, d_adj);
+    }
+    if ((rc = set_smem(c, k_wit_greedy, (int)gsm))) return rc;
+    k_wit_greedy<<<1, 1024, gsm, s>>>(N, d_cand, d_adj, d_fw, d_fresh);
+    k_wit_rowmin<<<(N + 3) / 4, 128, 0, s>>>(N, d_D, d_fw, d_lim, d_near, d_ndist);
+    c->launches += 5;
+    CK(c, cudaGetLastError());
+    unsigned char* h = c->h_stage;
+    CK(c, cudaMemcpyAsync(h, d_r, r_all, cudaMemcpyDeviceToHost, s));
+    CK(c, cudaStreamSynchronize(s));
+    std::memcpy(out_widx, h, (size_t)n * 4); std::memcpy(out_near, h + r_i, (size_t)n * 4);
+    std::memcpy(out_wdist, h + 2 * r_i, (size_t)n * 8); std::memcpy(out_near_dist, h + 2 * r_i + r_d, (size_t)n * 8);
+    std::memcpy(out_fresh, h + 2 * r_i + 2 * r_d, (size_t)n);
+    return CCK_OK;
 }
 
 extern "C" int cck_belief_distance_lower(cck_ctx* c, int dim, int64_t n, const double* bel, int64_t ld, double* out) {

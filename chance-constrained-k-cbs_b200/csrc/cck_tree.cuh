@@ -338,6 +338,124 @@ __global__ void __launch_bounds__(128) k_distance_cols_near(int64_t n, const dou
     if (threadIdx.x == 0) count[q] = base;
 }
 
+// ---------------------------------------------------------------------------
+// The witness rules of one launch, resolved on the device (ConstraintRespectingBSST.cpp:150-178 and :250-326).
+// The reference handles the survivors one at a time; survivor s becomes a NEW witness iff no witness - existing or created
+// by an earlier survivor of the same launch - lies within the pruning radius.  With the nearest EXISTING witness known
+// (k_tree_query MODE 1), the same-launch part is a greedy scan over the "potential" survivors (no existing witness within
+// the radius, and allowed to persist: `eligible`, i.e. not rejected by the constraints) in order:
+//   fresh[t] = potential[t] && no fresh f < t with distance(f, t) <= radius.
+// k_wit_rows forms the lower-triangular distances to potential columns and their "<= radius" bit rows, k_wit_greedy runs
+// the scan from shared memory (one warp, one word of the fresh set per lane, n <= 1024), k_wit_rowmin gives every survivor
+// its nearest fresh predecessor below its limit.  The host replays the remaining bookkeeping with O(1) work per survivor.
+// ---------------------------------------------------------------------------
+#define CCK_WIT_MAX 1024
+__global__ void k_wit_prep(int n, const int32_t* __restrict__ widx, const double* __restrict__ wdist, double radius, double radius_up,
+                           const uint8_t* __restrict__ eligible, uint8_t* __restrict__ iscol, uint8_t* __restrict__ cand, double* __restrict__ lim) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const bool far = widx[s] < 0 || wdist[s] > radius;
+    iscol[s] = far ? 1 : 0;                                    // would be a new witness if no same-launch witness is near
+    cand[s] = (far && (!eligible || eligible[s])) ? 1 : 0;     // ... and would persist
+    const double w = widx[s] < 0 ? HUGE_VAL : wdist[s];
+    lim[s] = w < radius_up ? w : radius_up;                    // only a same-launch witness nearer than this can matter
+}
+
+// one CTA (128 threads) per survivor s: D[s][t] = distance(t, s) for candidate columns t < s (the survivor's own sqrt, like
+// findClosestWitness), adj[s][t/32] bit t%32 = D[s][t] <= radius.  Words at and beyond s are written as zero.
+template <int DIM>
+__global__ void __launch_bounds__(128) k_wit_rows(int n, const double* __restrict__ bel, int64_t ld, const uint8_t* __restrict__ cand, double radius,
+                                                  double* __restrict__ D, uint32_t* __restrict__ adj) {
+    __shared__ double sq[DIM * DIM];
+    const int s = blockIdx.x, lane = threadIdx.x & 31;
+    double qm[DIM], qC[DIM * DIM], qS[DIM * DIM];
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) qm[d] = bel[d * ld + s];
+#pragma unroll
+    for (int f = 0; f < DIM * DIM; ++f) qC[f] = bel[(DIM + f) * ld + s] + bel[(DIM + DIM * DIM + f) * ld + s];
+    if (threadIdx.x == 0) {          // the row's own square root once, not once per thread
+        sym_sqrt<DIM, false>(qC, qS);
+#pragma unroll
+        for (int f = 0; f < DIM * DIM; ++f) sq[f] = qS[f];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int f = 0; f < DIM * DIM; ++f) qS[f] = sq[f];
+    const int nw = CCK_WIT_MAX / 32;
+    for (int t0 = 0; t0 < nw * 32; t0 += 128) {
+        const int t = t0 + threadIdx.x;
+        bool near = false;
+        if (t < s && cand[t]) {
+            double d2 = 0;
+#pragma unroll
+            for (int d = 0; d < DIM; ++d) { const double e = bel[d * ld + t] - qm[d]; d2 += e * e; }
+            double dist = 0;
+            if (d2 != 0) {
+                double C[DIM * DIM];
+#pragma unroll
+                for (int f = 0; f < DIM * DIM; ++f) C[f] = bel[(DIM + f) * ld + t] + bel[(DIM + DIM * DIM + f) * ld + t];
+                dist = fabs(d2 + cov_term<DIM>(C, qC, qS));
+            }
+            D[(size_t)s * n + t] = dist;
+            near = dist <= radius;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, near);
+        if (lane == 0) adj[(size_t)s * nw + (t >> 5)] = m;
+    }
+}
+
+// one CTA: the bit rows go to shared memory (128 KB for 1024 survivors), warp 0 runs the sequential scan
+__global__ void __launch_bounds__(1024) k_wit_greedy(int n, const uint8_t* __restrict__ cand, const uint32_t* __restrict__ adj, uint32_t* __restrict__ fresh_words,
+                                                     uint8_t* __restrict__ fresh) {
+    extern __shared__ uint32_t sadj[];
+    const int nw = CCK_WIT_MAX / 32;
+    for (int i = threadIdx.x; i < n * nw; i += blockDim.x) sadj[i] = adj[i];
+    __syncthreads();
+    if (threadIdx.x >= 32) return;
+    const int lane = threadIdx.x;
+    uint32_t mine = 0;                       // word `lane` of the fresh set
+    for (int w = 0; w < (n + 31) / 32; ++w) {
+        const int t_me = w * 32 + lane;
+        uint32_t cw = __ballot_sync(0xffffffffu, t_me < n && cand[t_me]);
+        while (cw) {
+            const int b = __ffs(cw) - 1;
+            cw &= cw - 1;
+            const int t = w * 32 + b;
+            const bool hit = (sadj[t * nw + lane] & mine) != 0;
+            if (!__any_sync(0xffffffffu, hit) && lane == w) mine |= 1u << b;
+        }
+    }
+    fresh_words[lane] = mine;
+    for (int w = 0; w < nw; ++w) {
+        const uint32_t word = __shfl_sync(0xffffffffu, mine, w);
+        const int t = w * 32 + lane;
+        if (t < n) fresh[t] = (word >> lane) & 1u;
+    }
+}
+
+// one warp per survivor: nearest fresh predecessor with distance < lim[s]; ties resolve to the lowest index (the
+// sequential scan keeps the first strict minimum)
+__global__ void __launch_bounds__(128) k_wit_rowmin(int n, const double* __restrict__ D, const uint32_t* __restrict__ fresh_words, const double* __restrict__ lim,
+                                                    int32_t* __restrict__ near_col, double* __restrict__ near_dist) {
+    const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (s >= n) return;
+    const double l = lim[s];
+    double bd = HUGE_VAL;
+    int bt = -1;
+    for (int t = lane; t < s; t += 32) {
+        if (!((fresh_words[t >> 5] >> (t & 31)) & 1u)) continue;
+        const double d = D[(size_t)s * n + t];
+        if (d < l && d < bd) { bd = d; bt = t; }          // t ascends per lane: strict < keeps the lowest index
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double od = __shfl_down_sync(0xffffffffu, bd, o);
+        const int ot = __shfl_down_sync(0xffffffffu, bt, o);
+        if (ot >= 0 && (bt < 0 || od < bd || (od == bd && ot < bt))) { bd = od; bt = ot; }
+    }
+    if (lane == 0) { near_col[s] = bt; near_dist[s] = bt >= 0 ? bd : 0.0; }
+}
+
 // plain batched distance(a_i, b_i) (second argument's sqrt, as RealVectorBeliefSpace::distance(state1, state2))
 template <int DIM>
 __global__ void __launch_bounds__(128) k_belief_distance(int64_t n, const double* __restrict__ a, int64_t lda, const double* __restrict__ b,

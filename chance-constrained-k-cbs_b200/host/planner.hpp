@@ -40,6 +40,7 @@ public:
     DeviceTree(const DeviceTree&) = delete;
     DeviceTree& operator=(const DeviceTree&) = delete;
     void clear() { gpu_->check(cck_tree_clear(t_), "cck_tree_clear"); }
+    cck_tree* get() const { return t_; }
     int64_t size() const { return cck_tree_size(t_); }
     void append(int64_t n, const double* bel_soa, int64_t ld, const double* cost) { gpu_->check(cck_tree_append(t_, n, bel_soa, ld, cost, nullptr), "cck_tree_append"); }
     void deactivate(const std::vector<int32_t>& idx) {
@@ -134,12 +135,10 @@ public:
     // and sizes the device scratch and pinned staging buffers, so that solve() does not pay for them.
     void warmup() {
         const int K = prm_.K;
-        std::vector<double> bel((size_t)W_ * K), ctrl((size_t)dim_ * K, 0.0), out((size_t)W_ * K), pcost(K, 0.0), cost(K), gdist(K), dist(K), lim(K, 1.0);
+        std::vector<double> bel((size_t)W_ * K), ctrl((size_t)dim_ * K, 0.0), out((size_t)W_ * K), pcost(K, 0.0), cost(K), gdist(K), dist(K);
         for (int j = 0; j < K; ++j) for (int f = 0; f < W_; ++f) bel[(size_t)f * K + j] = start_[f];
-        std::vector<int32_t> steps(K, 1), pstep(K, 0), valid(K), idx(K), cols(K / 2), cnt(K), nidx((size_t)K * 32);
-        std::vector<double> ndist((size_t)K * 32);
+        std::vector<int32_t> steps(K, 1), pstep(K, 0), valid(K), idx(K);
         std::vector<uint8_t> flags(K);
-        for (int a = 0; a < K / 2; ++a) cols[a] = a;
         const double zero = 0.0;
         pvc_->installConstraints({});
         nodes_dev_->append(1, start_.data(), 1, &zero);
@@ -147,10 +146,14 @@ public:
         nodes_dev_->select(K, bel.data(), K, prm_.selection_radius, idx.data());
         gpu_->check(cck_expand_batch(gpu_->get(), K, bel.data(), K, ctrl.data(), K, steps.data(), pstep.data(), pcost.data(), &goal_, out.data(), K,
                                      valid.data(), cost.data(), gdist.data(), flags.data()), "cck_expand_batch (warm-up)");
-        wit_dev_->nearest(K, bel.data(), K, idx.data(), dist.data());
-        if (K >= 2)
-            gpu_->check(cck_belief_distance_cols_near(gpu_->get(), dim_, K, bel.data(), K, K / 2, cols.data(), lim.data(), 32, nidx.data(), ndist.data(),
-                                                      cnt.data()), "cck_belief_distance_cols_near (warm-up)");
+        {
+            const int S = std::min(K, 1024);
+            std::vector<int32_t> near(S);
+            std::vector<double> nd(S);
+            std::vector<uint8_t> fr(S);
+            gpu_->check(cck_tree_witness_batch(wit_dev_->get(), S, bel.data(), K, prm_.pruning_radius, nullptr, idx.data(), dist.data(), near.data(), nd.data(),
+                                               fr.data()), "cck_tree_witness_batch (warm-up)");
+        }
         nodes_dev_->deactivate({0});
         clear();
     }
@@ -237,53 +240,34 @@ private:
 
     // Commit the survivors of one launch.  The reference handles one candidate at a time: findClosestWitness
     // (:150-178) sees every witness created so far, including those of earlier candidates of the same batch.
-    // Here: one launch finds each survivor's nearest PRE-BATCH witness, one more the lower-triangular distance
-    // matrix among the survivors; the loop below then replays the sequential rules with table look-ups only.
+    // Here: cck_tree_witness_batch finds each survivor's nearest PRE-BATCH witness, runs the greedy new-witness scan on the
+    // device and returns each survivor's nearest same-launch witness; the loop below replays the remaining bookkeeping
+    // (representatives, pruning, tree growth) with O(1) work per survivor.
     int commit(int K, const std::vector<double>& out, const std::vector<double>& ctrl, const std::vector<int32_t>& steps,
                const std::vector<int32_t>& parent, const std::vector<double>& cost, const std::vector<uint8_t>& flags) {
         std::vector<int> surv;
         for (int j = 0; j < K; ++j) if (flags[j] & 1) surv.push_back(j);          // propCd == cd
         int solution = -1;
-        const int kMaxChunk = 2048;
+        const int kMaxChunk = 1024;      // cck_tree_witness_batch resolves up to 1024 survivors per call
         for (size_t c0 = 0; c0 < surv.size() && solution < 0; c0 += kMaxChunk) {
             const int S = (int)std::min<size_t>(kMaxChunk, surv.size() - c0);
             std::vector<double> q((size_t)W_ * S), qcost(S);
             for (int s = 0; s < S; ++s) { const int j = surv[c0 + s]; for (int f = 0; f < W_; ++f) q[(size_t)f * S + s] = out[(size_t)f * K + j]; qcost[s] = cost[j]; }
-            std::vector<int32_t> widx(S);
-            std::vector<double> wdist(S);
             auto now = [] { return std::chrono::steady_clock::now(); };
             auto secs = [](auto a, auto b) { return std::chrono::duration<double>(b - a).count(); };
             const auto t1 = now();
-            wit_dev_->nearest(S, q.data(), S, widx.data(), wdist.data());
+            // ONE call: nearest existing witness of every survivor, which survivors become new witnesses (greedy in sample
+            // order, on the device) and each survivor's nearest new witness among its predecessors.  A survivor the
+            // constraints reject creates a witness only to drop it again (:300-306), so it is not eligible.
+            std::vector<int32_t> widx(S), near(S);
+            std::vector<double> wdist(S), near_dist(S);
+            std::vector<uint8_t> fresh_dev(S), elig(S, 1);
+            if (!constraints_.empty()) for (int s = 0; s < S; ++s) elig[s] = (flags[surv[c0 + s]] & 2) ? 1 : 0;
+            gpu_->check(cck_tree_witness_batch(wit_dev_->get(), S, q.data(), S, prm_.pruning_radius, constraints_.empty() ? nullptr : elig.data(),
+                                               widx.data(), wdist.data(), near.data(), near_dist.data(), fresh_dev.data()), "cck_tree_witness_batch");
+            stats_.launches += 5;
             const auto t2 = now();
-            stats_.launches++;
-            // only survivors farther than the pruning radius from every existing witness can become witnesses:
-            // their columns of the batch's distance matrix are all the sequential replay needs
-            std::vector<int32_t> cols;
-            std::vector<int> col_of(S, -1);
-            for (int s = 0; s < S; ++s) if (widx[s] < 0 || wdist[s] > prm_.pruning_radius) { col_of[s] = (int)cols.size(); cols.push_back(s); }
-            const int nf = (int)cols.size();
-            // A survivor adopts a same-launch witness only if that one is nearer than its nearest existing witness AND
-            // within the pruning radius (a farther one leaves "new witness" / "existing witness" unchanged), so only
-            // those entries of the S x nf distance matrix are fetched: a few pairs per row instead of S x nf doubles.
-            int cap = 32;
-            near_cnt_.assign(S, 0);
-            if (nf > 0) {
-                std::vector<double> lim(S);
-                const double pr_up = std::nextafter(prm_.pruning_radius, std::numeric_limits<double>::infinity());
-                for (int s = 0; s < S; ++s) lim[s] = std::min(widx[s] >= 0 ? wdist[s] : std::numeric_limits<double>::infinity(), pr_up);
-                for (int attempt = 0; attempt < 2; ++attempt) {
-                    near_idx_.resize((size_t)S * cap); near_dist_.resize((size_t)S * cap);
-                    gpu_->check(cck_belief_distance_cols_near(gpu_->get(), dim_, S, q.data(), S, nf, cols.data(), lim.data(), cap, near_idx_.data(),
-                                                              near_dist_.data(), near_cnt_.data()), "cck_belief_distance_cols_near");
-                    stats_.launches++;
-                    int mx = 0;
-                    for (int s = 0; s < S; ++s) mx = std::max(mx, near_cnt_[s]);
-                    if (mx <= cap) break;
-                    cap = mx;     // a row overflowed (many survivors inside one pruning ball): once more with room for the fullest row
-                }
-            }
-            std::vector<int> fresh_of_col(std::max(nf, 1), -1);      // column a -> index into `fresh` once cols[a] became a witness
+            std::vector<int> wit_of(S, -1);               // survivor -> index of the witness it created in this chunk
             const auto t3 = now();
             std::vector<std::pair<int, int>> fresh;       // (survivor s, witness index) of witnesses created in this chunk
             std::vector<int32_t> deact;
@@ -293,21 +277,17 @@ private:
                 const int j = surv[c0 + s];
                 int w = widx[s];
                 double cd = w >= 0 ? wdist[s] : std::numeric_limits<double>::infinity();
-                // the reference's scan over the witnesses created so far, restricted to the fetched pairs, in the same
-                // order (columns ascend with creation order)
-                for (int e = 0; e < near_cnt_[s]; ++e) {
-                    const int fi = fresh_of_col[near_idx_[(size_t)s * cap + e]];
-                    if (fi < 0) continue;
-                    const double d = near_dist_[(size_t)s * cap + e];
-                    if (d < cd) { cd = d; w = fresh[fi].second; }
-                }
+                // the reference's scan over the witnesses created so far: the device found the first nearest one below
+                // min(cd, radius), which is the only one that can change (w, cd) or the new-witness decision
+                if (near[s] >= 0 && wit_of[near[s]] >= 0 && near_dist[s] < cd) { cd = near_dist[s]; w = wit_of[near[s]]; }
                 const int idx = (int)motions_.size();
                 bool is_new = false;
-                if (w < 0 || cd > prm_.pruning_radius) { witnesses_.push_back(Witness{idx}); w = (int)witnesses_.size() - 1; fresh.emplace_back(s, w); fresh_of_col[col_of[s]] = (int)fresh.size() - 1; is_new = true; }
+                if (w < 0 || cd > prm_.pruning_radius) { witnesses_.push_back(Witness{idx}); w = (int)witnesses_.size() - 1; fresh.emplace_back(s, w); wit_of[s] = w; is_new = true; }
+                if (elig[s] && is_new != (fresh_dev[s] != 0)) throw std::logic_error("witness batch: device and host disagree on a new witness");
                 Witness& wit = witnesses_[w];
                 if (!(is_new || cost[j] < motions_[wit.rep].accCost)) continue;
                 if (!constraints_.empty() && !(flags[j] & 2)) {                 // satisfiesConstraints failed (:300)
-                    if (is_new) { witnesses_.pop_back(); fresh.pop_back(); fresh_of_col[col_of[s]] = -1; }
+                    if (is_new) { witnesses_.pop_back(); fresh.pop_back(); wit_of[s] = -1; }
                     continue;
                 }
                 Motion m;
@@ -416,8 +396,6 @@ private:
     double max_eig_ = 10.0;                                            // :221
     PlannerStats stats_;
     SegmentPath last_path_;
-    std::vector<int32_t> near_idx_, near_cnt_;      // commit(): sparse same-launch distances (kept across launches)
-    std::vector<double> near_dist_;
 };
 
 // ---------------------------------------------------------------------------

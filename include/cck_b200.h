@@ -251,6 +251,15 @@ int cck_tree_update(cck_tree* tree, int64_t n, const int32_t* idx, const double*
 int cck_tree_select(cck_tree* tree, int64_t K, const double* samples, int64_t lds, double selection_radius, int32_t* out_idx,
                     double* out_dist /* or NULL */);
 int cck_tree_nearest(cck_tree* tree, int64_t K, const double* queries, int64_t ldq, int32_t* out_idx, double* out_dist /* or NULL */);
+/* The witness rules of one launch (ConstraintRespectingBSST.cpp:150-178, :250-326) for n <= 1024 survivors in sample order,
+ * against `tree` = the existing witnesses.  out_widx / out_wdist: nearest existing witness (findClosestWitness; -1 if none).
+ * A survivor with no existing witness within the pruning radius, and eligible[s] != 0 (NULL = all: not rejected by the
+ * constraints), becomes a new witness unless an earlier NEW witness of the same launch is within the radius: out_fresh.
+ * out_near / out_near_dist: the nearest new witness created by an EARLIER survivor whose distance is below
+ * min(out_wdist, radius) (first one on ties; -1 if none) - what the sequential scan would have found.  One upload, five
+ * kernels, one download. */
+int cck_tree_witness_batch(cck_tree* tree, int64_t n, const double* queries, int64_t ldq, double pruning_radius, const uint8_t* eligible /* or NULL */,
+                           int32_t* out_widx, double* out_wdist, int32_t* out_near, double* out_near_dist, uint8_t* out_fresh);
 /* distance(a_i, b_i) for n pairs (RealVectorBeliefSpace::distance(state1 = a, state2 = b)) */
 int cck_belief_distance(cck_ctx* ctx, int dim, int64_t n, const double* a, int64_t lda, const double* b, int64_t ldb, double* out);
 /* out[q*n + i] = distance(b_i, b_q) for i < q (n <= 8192; other entries unspecified): the witness tests between

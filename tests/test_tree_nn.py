@@ -155,3 +155,46 @@ def test_gpu_select_and_nearest_bitexact(K, O, ctx, dim):
     tree.clear()
     assert len(tree) == 0
     tree.close(); t2.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dim", [2, 4])
+@pytest.mark.parametrize("with_eligibility", [False, True])
+def test_gpu_witness_batch_replays_the_sequential_rules(K, O, ctx, dim, with_eligibility):
+    """cck_tree_witness_batch against a plain sequential replay of ConstraintRespectingBSST.cpp:150-178 / :250-326 built
+    from the oracle's distances: survivor by survivor, every witness created so far is scanned in creation order."""
+    rng = np.random.default_rng(50 + dim)
+    wit = _beliefs(rng, 60, dim, spread=25.0)
+    n = 700
+    b = _beliefs(rng, n, dim, spread=25.0)
+    b[100:140] = b[99]                                     # identical survivors (distance 0)
+    b[200:260, :dim] = b[199, :dim] + rng.normal(0, 0.05, (60, dim))   # a tight cluster
+    pr = 2.0
+    elig = (rng.random(n) < 0.7) if with_eligibility else None
+    tree = K.Tree(ctx, dim)
+    tree.append(K.aos_to_soa(wit), np.zeros(len(wit)))
+    widx, wdist, near, ndist, fresh = tree.witness_batch(K.aos_to_soa(b), pr, elig)
+    ridx, rdist = O.nearest_witness(wit, b, dim)
+    assert np.array_equal(widx, ridx) and np.array_equal(wdist, rdist)
+    created = []                                           # survivors that became (persisting) witnesses, in order
+    n_new = n_adopt = 0
+    for s in range(n):
+        cd, best = rdist[s], -1
+        if created:
+            d = O.belief_distance(b[created], np.repeat(b[s:s + 1], len(created), axis=0), dim)   # distance(witness, node)
+            for f, df in zip(created, d):
+                if df < cd:
+                    cd, best = df, f
+        is_new = cd > pr
+        keeps = is_new and (elig is None or elig[s])
+        assert bool(fresh[s]) == keeps, s
+        if best >= 0 and cd <= pr:                         # the scan found a same-launch witness that matters
+            assert near[s] == best and ndist[s] == cd, s
+            n_adopt += 1
+        else:
+            assert near[s] == -1, s
+        if keeps:
+            created.append(s)
+            n_new += 1
+    assert n_new > 50 and n_adopt > 50, (n_new, n_adopt)
+    tree.close()

@@ -61,12 +61,15 @@ def main():
             runs = []
             nseeds = max(1, int(round(a.seeds * scale)))
             for seed in range(1, nseeds + 1):
+                out = None
                 try:
                     out = subprocess.run([os.path.join(HOST, "cck_plan"), "-m", mp, "-s", sc, "-k", str(k), "-t", str(a.time), "--K", str(a.K),
                                           "--seed", str(seed), "--lltime", str(min(a.time, 20.0))], capture_output=True, text=True, timeout=a.time + 60)
                     runs.append(json.loads(out.stdout.strip().splitlines()[-1]))
                 except Exception as e:  # noqa: BLE001
-                    runs.append({"solved": False, "seconds": a.time, "error": str(e)[:200]})
+                    err = (out.stderr if "out" in dir() and out is not None else "")[-300:]
+                    runs.append({"solved": False, "seconds": a.time, "error": str(e)[:200], "stderr": err})
+                    print(f"  seed {seed}: failed: {str(e)[:80]} | {err.strip()[-200:]}", flush=True)
             ok = [r for r in runs if r.get("solved")]
             t = np.array([r["seconds"] for r in ok]) if ok else np.array([np.nan])
             res[label] = {"seeds": nseeds, "solved": len(ok), "time_limit_s": a.time, "K": a.K,
