@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(CCK_UNI_THREADS, 2) k_rollout_uni2(const __gri
     const double c = sp.erf_inv_result;
     const bool has_obstacles = reinterpret_cast<const TabHeader*>(a.tab)->M > 0;
 
-    bool have = false, done = false, dense = false;
+    bool have = false, done = false, dense = false, pending = false;
     double v[4], u[4], S[16], L[16], v0[4];
     double sr = 0, cr = 1, pcost = 0;
     int steps = 0, t = 0, pstep = 0;
@@ -147,8 +147,22 @@ __global__ void __launch_bounds__(CCK_UNI_THREADS, 2) k_rollout_uni2(const __gri
         }
     };
 
-    while (true) {
-        while (!have && !done) {   // the CTA owns ranges blockIdx, blockIdx+gridDim, ... of 256 beliefs
+    // store the result of a finished rollout: a lane that is idle keeps its registers and its stash until then
+    auto flush = [&]() {
+        if (!pending) return;
+        pending = false;
+        if (t < steps) {           // died: the result is the last valid state
+#pragma unroll
+            for (int f = 0; f < 4; ++f) v[f] = stash[f * CCK_UNI_THREADS];
+#pragma unroll
+            for (int f = 0; f < 16; ++f) { S[f] = stash[(4 + f) * CCK_UNI_THREADS]; L[f] = stash[(20 + f) * CCK_UNI_THREADS]; }
+        }
+        finish(t);
+    };
+    // refill: the CTA owns ranges blockIdx, blockIdx+gridDim, ... of 2^range_log2 beliefs
+    auto take = [&]() {
+        flush();
+        while (!have && !done) {
             const int kk = atomicAdd(next_k, 1);
             const int rg = kk >> range_log2;
             const int64_t base = ((int64_t)blockIdx.x + (int64_t)rg * gridDim.x) << range_log2;
@@ -173,7 +187,18 @@ __global__ void __launch_bounds__(CCK_UNI_THREADS, 2) k_rollout_uni2(const __gri
             t = 0;
             have = true;
         }
-        if (__all_sync(0xffffffffu, !have)) break;
+    };
+    // Finished lanes are served in batches (see k_rollout_lin_grid): the result store (36 planes) and the reload are
+    // ~400 instructions that one finished lane would make the whole warp issue.
+    int it = 0;
+    while (true) {
+        const unsigned idle = __ballot_sync(0xffffffffu, !have);
+        if (idle) {
+            if (__popc(idle) >= CCK_REFILL_MIN || (++it & (CCK_REFILL_WAIT - 1)) == 0) {
+                take();
+                if (__all_sync(0xffffffffu, !have)) break;
+            }
+        }
         if (!have) continue;
         // stash the last valid state, advance in place
 #pragma unroll
@@ -203,13 +228,8 @@ __global__ void __launch_bounds__(CCK_UNI_THREADS, 2) k_rollout_uni2(const __gri
             else if (KIND == CCK_SVC_ADAPTIVE) ok = halfplane_check<true>(tab, v[0], v[1], P0, P1, P2, P3, adaptive_c(sp, tab, v[0], v[1]));
             else ok = chisq_check(sp, tab, v[0], v[1], P0, P1, P2, P3);
         }
-        int r = -1;
         if (!ok) {
-            r = t;
-#pragma unroll
-            for (int f = 0; f < 4; ++f) v[f] = stash[f * CCK_UNI_THREADS];
-#pragma unroll
-            for (int f = 0; f < 16; ++f) { S[f] = stash[(4 + f) * CCK_UNI_THREADS]; L[f] = stash[(20 + f) * CCK_UNI_THREADS]; }
+            have = false; pending = true;      // died with t valid steps; flush() restores the last valid state from the stash
         } else {
             if (EXPAND && cons) {
                 // getDistribution_ picks entries (0,0),(0,2),(2,0),(2,2) (BeliefPVC.cpp:94-97)
@@ -223,9 +243,8 @@ __global__ void __launch_bounds__(CCK_UNI_THREADS, 2) k_rollout_uni2(const __gri
                 for (int f = 0; f < 16; ++f) { tp[(4 + f) * a.traj_ld] = S[f]; tp[(20 + f) * a.traj_ld] = L[f]; }
             }
             ++t;
-            if (t == steps) r = steps;
+            if (t == steps) { have = false; pending = true; }
         }
-        if (r >= 0) { finish(r); have = false; }
     }
 }
 
