@@ -44,7 +44,7 @@ struct cck_ctx {
     int ftab_bytes = 0;
     double* d_exB = nullptr;           // exact fp64 rows in filter-table order
     int32_t* d_exCls = nullptr;        // class of each row (-1: padding)
-    unsigned char* d_gtab = nullptr;   // fp32 box + bitmap-grid table (Blackmore broad phase, cck_rollout_grid.cuh)
+    unsigned char* d_gtab = nullptr;   // fp32 box + cell-grid table (Blackmore broad phase, cck_rollout_grid.cuh)
     int gtab_bytes = 0;
     double* d_gexB = nullptr;          // exact fp64 rows in grid-table order
     int32_t* d_gexCls = nullptr;       // class of each row
@@ -340,7 +340,7 @@ extern "C" int cck_set_model(cck_ctx* c, const cck_model_params* p) {
 
 
 // ---------------------------------------------------------------------------
-// fp32 box + bitmap-grid table of the Blackmore broad phase (cck_rollout_grid.cuh).
+// fp32 box + cell-grid table of the Blackmore broad phase (cck_rollout_grid.cuh).
 // Box sides are rounded OUTWARD and bumped one more ulp, so "interval misses box" in fp32
 // implies the reference's fp64 inequality for that half-plane.
 // ---------------------------------------------------------------------------
@@ -383,7 +383,7 @@ static void build_grid_table(int M, const double* A, const double* B, const std:
         }
         if (!pure || sides != 15) q = Box{HUGE_VALF, HUGE_VALF, -HUGE_VALF, -HUGE_VALF};
         // sides beyond the magnitudes the broad phase accepts (|x|, P < 1e30) become infinite, so that one far-away
-        // plane cannot stretch the bitmap grid: towards "never proven" from 1e30 on (always allowed), towards "always
+        // plane cannot stretch the cell grid: towards "never proven" from 1e30 on (always allowed), towards "always
         // proven" only beyond 1e31 (x -+ ex stays below 1.01e30 for every belief that passes the finiteness guard)
         auto clamp_hi = [](float v) { return v > 1e30f ? HUGE_VALF : (v < -1e31f ? -HUGE_VALF : v); };   // proven if x - ex >= v
         auto clamp_lo = [](float v) { return v < -1e30f ? -HUGE_VALF : (v > 1e31f ? HUGE_VALF : v); };   // proven if x + ex <= v
@@ -650,7 +650,7 @@ extern "C" int cck_set_obstacles(cck_ctx* c, const cck_svc_params* p, const doub
         c->ftab_bytes = fh.total_bytes;
         }
     }
-    // ---- fp32 box + bitmap-grid table (the default broad phase) ----
+    // ---- fp32 box + cell-grid table (the default broad phase) ----
     cudaFree(c->d_gtab); cudaFree(c->d_gexB); cudaFree(c->d_gexCls);
     c->d_gtab = nullptr; c->d_gexB = nullptr; c->d_gexCls = nullptr; c->gtab_bytes = 0;
     c->gconst = GridConst{};
@@ -796,7 +796,7 @@ extern "C" int cck_is_valid_dev(cck_ctx* c, void* stream, int64_t n, const doubl
     CK(c, cudaSetDevice(c->device));
     cudaStream_t s = pick(c, stream);
     const int dim = c->model.dim;
-    if (c->svc.kind == CCK_SVC_BLACKMORE && c->kern >= 2) {   // fp32 box/bitmap-grid broad phase + exact decision
+    if (c->svc.kind == CCK_SVC_BLACKMORE && c->kern >= 2) {   // fp32 box/cell-grid broad phase + exact decision
         const int gsm = 16 + c->gtab_bytes;
         if ((rc = set_smem(c, k_is_valid_grid, gsm))) return rc;
         k_is_valid_grid<<<grid_for(c, n, 256, 4), 256, gsm, s>>>(n, dim, bel, ld, valid, c->d_gtab, c->gtab_bytes, c->d_tab, c->d_gexB, c->d_gexCls, c->svc, c->gconst);
@@ -843,7 +843,7 @@ static int launch_rollout(cck_ctx* c, cudaStream_t s, const RolloutArgs& a) {
         else LAUNCH_R((NAME<CCK_SVC_CHISQUARED, TRAJ, EXPAND>), PAR);                                               \
     } while (0)
     if (c->model.model == CCK_MODEL_LINEAR2D && c->svc.kind == CCK_SVC_BLACKMORE && c->kern == 2) {
-        // default configuration: fp32 box/bitmap-grid broad phase + exact fp64 decision, lane refill
+        // default configuration: fp32 box/cell-grid broad phase + exact fp64 decision, lane refill
         if (a.n > (int64_t)INT_MAX) return fail(c, CCK_ERR_INVALID, "more than 2^31-1 beliefs in one launch");
         RolloutArgs g2 = a;
         g2.ftab = c->d_gtab; g2.ftab_bytes = c->gtab_bytes; g2.exB = c->d_gexB; g2.exCls = c->d_gexCls;

@@ -3,7 +3,7 @@
 //
 // The first version (k_rollout_uni) spent ~2000 FP64 instructions per belief-step in the generic
 // per-obstacle test and ~1100 in dense 4x4 algebra at 255 registers with spills.  This one
-//  * checks PCCBlackmore obstacles with the conservative fp32 box/bitmap-grid broad phase of
+//  * checks PCCBlackmore obstacles with the conservative fp32 box/cell-grid broad phase of
 //    cck_rollout_grid.cuh (exact fp64 decision for whatever is not proven: verdicts unchanged),
 //  * exploits the EXACT zeros of the model matrices (F = I + dt(e0e1^T + e2e3^T), A_cl_d block
 //    diagonal, Q/R diagonal).  A skipped term is 0*x, which is an exact zero for finite x, and

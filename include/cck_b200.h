@@ -225,7 +225,7 @@ int cck_select_winner_dev(cck_ctx* ctx, void* stream, int64_t n, const double* c
  * FP64 entry). */
 int cck_measure_fp64_peak(cck_ctx* ctx, double* tflops);
 
-/* Host-only (no GPU, no context): the serialised fp32 box + bitmap-grid table that cck_set_obstacles builds for the
+/* Host-only (no GPU, no context): the serialised fp32 box + cell-grid table that cck_set_obstacles builds for the
  * PCCBlackmoreSVC broad phase (PCCBlackmoreSVC.cpp:54-75 is what it must never contradict).  Exposed so that the
  * table's invariants — every obstacle binned into its own cell, boxes rounded outward / inward by at least one ulp —
  * can be tested without a device.  `out` may be NULL to query `*bytes`; order[j] = obstacle stored in row j. */
