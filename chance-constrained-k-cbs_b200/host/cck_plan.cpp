@@ -45,20 +45,20 @@ int main(int argc, char** argv) {
         KCBS kcbs(inst, svc, pvc, prm, lltime, devices);
         KCBSResult r = kcbs.solve(time_s);
         int64_t launches = 0, cands = 0, nodes = 0;
-        double ts = 0, tsel = 0, tex = 0, tcm = 0, txt = 0, tll = 0, cn = 0, cc = 0, cr = 0, cmi = 0; long long csurv = 0, cfresh = 0;
+        double ts = 0, tsel = 0, tex = 0, tcm = 0, txt = 0, tll = 0, cn = 0, cr = 0, cmi = 0; long long csurv = 0, cfresh = 0;
         for (int i = 0; i < k; ++i) {
             const PlannerStats& st = kcbs.planner(i).stats();
             launches += st.launches; cands += st.candidates; nodes += st.nodes;
             ts += st.t_sample; tsel += st.t_select; tex += st.t_expand; tcm += st.t_commit; txt += st.t_extract; tll += st.seconds;
-            cn += st.c_nearest; cc += st.c_cols; cr += st.c_replay; cmi += st.c_mirror; csurv += st.c_surv; cfresh += st.c_fresh;
+            cn += st.c_witness; cr += st.c_replay; cmi += st.c_mirror; csurv += st.c_surv; cfresh += st.c_fresh;
         }
         // phase_seconds: summed over the robots' planners (which run concurrently, so they can exceed the wall clock)
         std::printf("{\"solved\": %s, \"seconds\": %.6f, \"cost\": %.6f, \"cbs_nodes\": %d, \"replans\": %d, \"launches\": %lld, \"candidates\": %lld, "
                     "\"tree_nodes\": %lld, \"obstacles\": %zu, \"agents\": %d, \"K\": %d, \"root_seconds\": %.6f, \"validate_seconds\": %.6f, "
                     "\"phase_seconds\": {\"low_level\": %.6f, \"sample\": %.6f, \"select\": %.6f, \"expand\": %.6f, \"commit\": %.6f, \"extract\": %.6f, "
-                    "\"commit_nearest\": %.6f, \"commit_cols\": %.6f, \"commit_replay\": %.6f, \"commit_mirror\": %.6f, \"survivors\": %lld, \"new_witnesses\": %lld}}\n",
+                    "\"commit_witness_batch\": %.6f, \"commit_replay\": %.6f, \"commit_mirror\": %.6f, \"survivors\": %lld, \"new_witnesses\": %lld}}\n",
                     r.solved ? "true" : "false", r.seconds, r.cost, r.nodes_expanded, r.replans, (long long)launches, (long long)cands, (long long)nodes,
-                    inst->getObstacles().size(), k, K, r.t_root, r.t_validate, tll, ts, tsel, tex, tcm, txt, cn, cc, cr, cmi, csurv, cfresh);
+                    inst->getObstacles().size(), k, K, r.t_root, r.t_validate, tll, ts, tsel, tex, tcm, txt, cn, cr, cmi, csurv, cfresh);
         if (!export_dir.empty() && r.solved) exportBeliefPlan(r.paths, export_dir);
         if (!output.empty() && r.solved) {
             FILE* f = std::fopen(output.c_str(), "w");

@@ -74,7 +74,7 @@ struct SegmentPath {
 
 struct PlannerStats { int64_t launches = 0, candidates = 0, accepted = 0, nodes = 0; double seconds = 0;
                       double t_sample = 0, t_select = 0, t_expand = 0, t_commit = 0, t_extract = 0;
-                      double c_nearest = 0, c_cols = 0, c_replay = 0, c_mirror = 0; int64_t c_surv = 0, c_fresh = 0; };   // where solve() spends its time
+                      double c_witness = 0, c_replay = 0, c_mirror = 0; int64_t c_surv = 0, c_fresh = 0; };   // where solve() spends its time
 
 // One robot's low-level planning problem (what set_up_ConstraintBSST_MP_Problems wires per robot,
 // OmplSetUp.cpp:183-353): belief space + bounds, control bounds, SVC, propagator, start, goal.
@@ -268,7 +268,6 @@ private:
             stats_.launches += 5;
             const auto t2 = now();
             std::vector<int> wit_of(S, -1);               // survivor -> index of the witness it created in this chunk
-            const auto t3 = now();
             std::vector<std::pair<int, int>> fresh;       // (survivor s, witness index) of witnesses created in this chunk
             std::vector<int32_t> deact;
             std::vector<int> new_nodes;                   // survivors appended to the tree, in order
@@ -320,7 +319,7 @@ private:
             }
             nodes_dev_->deactivate(deact);
             const auto t5 = now();
-            stats_.c_nearest += secs(t1, t2); stats_.c_cols += secs(t2, t3); stats_.c_replay += secs(t3, t4); stats_.c_mirror += secs(t4, t5);
+            stats_.c_witness += secs(t1, t2); stats_.c_replay += secs(t2, t4); stats_.c_mirror += secs(t4, t5);
             stats_.c_surv += S; stats_.c_fresh += (int64_t)fresh.size();
         }
         return solution;
