@@ -1452,9 +1452,9 @@ extern "C" int cck_tree_witness_batch(cck_tree* t, int64_t n, const double* q, i
     const int W = t->dim + 2 * t->dim * t->dim, N = (int)n, nw = CCK_WIT_MAX / 32;
     // scratch: inputs and intermediates, then ONE result block [widx][near][wdist][near_dist][fresh] for a single D2H
     const size_t b_q = al256((size_t)n * W * 8), b_el = al256((size_t)n), b_flag = al256((size_t)n), b_lim = al256((size_t)n * 8),
-                 b_D = al256((size_t)n * n * 8), b_adj = al256((size_t)n * nw * 4), b_fw = al256((size_t)nw * 4);
+                 b_D = al256((size_t)n * n * 8), b_adj = al256((size_t)n * nw * 4), b_fw = al256((size_t)nw * 4), b_cw = al256((size_t)nw * 4);
     const size_t r_i = al256((size_t)n * 4), r_d = al256((size_t)n * 8), r_f = al256((size_t)n), r_all = 2 * r_i + 2 * r_d + r_f;
-    if ((rc = tree_scratch(t, b_q + b_el + 2 * b_flag + b_lim + b_D + b_adj + b_fw + r_all))) return rc;
+    if ((rc = tree_scratch(t, b_q + b_el + 2 * b_flag + b_lim + b_D + b_adj + b_fw + b_cw + r_all))) return rc;
     if (c->h_stage_cap < r_all) {
         if (c->h_stage) cudaFreeHost(c->h_stage);
         c->h_stage = nullptr; c->h_stage_cap = 0;
@@ -1470,6 +1470,7 @@ extern "C" int cck_tree_witness_batch(cck_tree* t, int64_t n, const double* q, i
     double* d_D = (double*)p; p += b_D;
     uint32_t* d_adj = (uint32_t*)p; p += b_adj;
     uint32_t* d_fw = (uint32_t*)p; p += b_fw;
+    uint32_t* d_cw = (uint32_t*)p; p += b_cw;
     unsigned char* d_r = p;
     int32_t* d_widx = (int32_t*)d_r; int32_t* d_near = (int32_t*)(d_r + r_i);
     double* d_wdist = (double*)(d_r + 2 * r_i); double* d_ndist = (double*)(d_r + 2 * r_i + r_d);
@@ -1482,15 +1483,15 @@ extern "C" int cck_tree_witness_batch(cck_tree* t, int64_t n, const double* q, i
     const size_t gsm = (size_t)n * nw * 4;
     if (t->dim == 2) {
         k_tree_query<2, 1><<<N, 128, 0, s>>>(td, t->n, d_q, n, 0.0, d_widx, d_wdist);
-        k_wit_prep<<<(N + 127) / 128, 128, 0, s>>>(N, d_widx, d_wdist, pruning_radius, r_up, eligible ? d_el : nullptr, d_iscol, d_cand, d_lim);
+        k_wit_prep<<<CCK_WIT_MAX / 128, 128, 0, s>>>(N, d_widx, d_wdist, pruning_radius, r_up, eligible ? d_el : nullptr, d_iscol, d_cand, d_cw, d_lim);
         k_wit_rows<2><<<N, 128, 0, s>>>(N, d_q, n, d_cand, pruning_radius, d_D, d_adj);
     } else {
         k_tree_query<4, 1><<<N, 128, 0, s>>>(td, t->n, d_q, n, 0.0, d_widx, d_wdist);
-        k_wit_prep<<<(N + 127) / 128, 128, 0, s>>>(N, d_widx, d_wdist, pruning_radius, r_up, eligible ? d_el : nullptr, d_iscol, d_cand, d_lim);
+        k_wit_prep<<<CCK_WIT_MAX / 128, 128, 0, s>>>(N, d_widx, d_wdist, pruning_radius, r_up, eligible ? d_el : nullptr, d_iscol, d_cand, d_cw, d_lim);
         k_wit_rows<4><<<N, 128, 0, s>>>(N, d_q, n, d_cand, pruning_radius, d_D, d_adj);
     }
     if ((rc = set_smem(c, k_wit_greedy, (int)gsm))) return rc;
-    k_wit_greedy<<<1, 1024, gsm, s>>>(N, d_cand, d_adj, d_fw, d_fresh);
+    k_wit_greedy<<<1, 1024, gsm, s>>>(N, d_cw, d_adj, d_fw, d_fresh);
     k_wit_rowmin<<<(N + 3) / 4, 128, 0, s>>>(N, d_D, d_fw, d_lim, d_near, d_ndist);
     c->launches += 5;
     CK(c, cudaGetLastError());

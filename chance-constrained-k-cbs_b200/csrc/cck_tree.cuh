@@ -351,14 +351,20 @@ __global__ void __launch_bounds__(128) k_distance_cols_near(int64_t n, const dou
 // ---------------------------------------------------------------------------
 #define CCK_WIT_MAX 1024
 __global__ void k_wit_prep(int n, const int32_t* __restrict__ widx, const double* __restrict__ wdist, double radius, double radius_up,
-                           const uint8_t* __restrict__ eligible, uint8_t* __restrict__ iscol, uint8_t* __restrict__ cand, double* __restrict__ lim) {
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n) return;
-    const bool far = widx[s] < 0 || wdist[s] > radius;
-    iscol[s] = far ? 1 : 0;                                    // would be a new witness if no same-launch witness is near
-    cand[s] = (far && (!eligible || eligible[s])) ? 1 : 0;     // ... and would persist
-    const double w = widx[s] < 0 ? HUGE_VAL : wdist[s];
-    lim[s] = w < radius_up ? w : radius_up;                    // only a same-launch witness nearer than this can matter
+                           const uint8_t* __restrict__ eligible, uint8_t* __restrict__ iscol, uint8_t* __restrict__ cand, uint32_t* __restrict__ cand_words,
+                           double* __restrict__ lim) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;     // grid covers CCK_WIT_MAX: every word of cand_words is written
+    bool is_cand = false;
+    if (s < n) {
+        const bool far = widx[s] < 0 || wdist[s] > radius;
+        iscol[s] = far ? 1 : 0;                                    // would be a new witness if no same-launch witness is near
+        is_cand = far && (!eligible || eligible[s]);               // ... and would persist
+        cand[s] = is_cand ? 1 : 0;
+        const double w = widx[s] < 0 ? HUGE_VAL : wdist[s];
+        lim[s] = w < radius_up ? w : radius_up;                    // only a same-launch witness nearer than this can matter
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, is_cand);
+    if ((threadIdx.x & 31) == 0) cand_words[s >> 5] = m;
 }
 
 // one CTA (128 threads) per survivor s: D[s][t] = distance(t, s) for candidate columns t < s (the survivor's own sqrt, like
@@ -405,24 +411,28 @@ __global__ void __launch_bounds__(128) k_wit_rows(int n, const double* __restric
 }
 
 // one CTA: the bit rows go to shared memory (128 KB for 1024 survivors), warp 0 runs the sequential scan
-__global__ void __launch_bounds__(1024) k_wit_greedy(int n, const uint8_t* __restrict__ cand, const uint32_t* __restrict__ adj, uint32_t* __restrict__ fresh_words,
-                                                     uint8_t* __restrict__ fresh) {
+__global__ void __launch_bounds__(1024) k_wit_greedy(int n, const uint32_t* __restrict__ cand_words, const uint32_t* __restrict__ adj,
+                                                     uint32_t* __restrict__ fresh_words, uint8_t* __restrict__ fresh) {
     extern __shared__ uint32_t sadj[];
     const int nw = CCK_WIT_MAX / 32;
     for (int i = threadIdx.x; i < n * nw; i += blockDim.x) sadj[i] = adj[i];
     __syncthreads();
     if (threadIdx.x >= 32) return;
     const int lane = threadIdx.x;
-    uint32_t mine = 0;                       // word `lane` of the fresh set
+    const uint32_t my_cand = cand_words[lane];   // word `lane` of the candidate set
+    uint32_t mine = 0;                           // word `lane` of the fresh set
     for (int w = 0; w < (n + 31) / 32; ++w) {
-        const int t_me = w * 32 + lane;
-        uint32_t cw = __ballot_sync(0xffffffffu, t_me < n && cand[t_me]);
-        while (cw) {
-            const int b = __ffs(cw) - 1;
+        uint32_t cw = __shfl_sync(0xffffffffu, my_cand, w);
+        if (!cw) continue;
+        int b = __ffs(cw) - 1;
+        uint32_t row = sadj[(w * 32 + b) * nw + lane];
+        while (true) {
             cw &= cw - 1;
-            const int t = w * 32 + b;
-            const bool hit = (sadj[t * nw + lane] & mine) != 0;
-            if (!__any_sync(0xffffffffu, hit) && lane == w) mine |= 1u << b;
+            const int bn = cw ? __ffs(cw) - 1 : b;
+            const uint32_t row_next = sadj[(w * 32 + bn) * nw + lane];     // the next row is read before this one is voted on
+            if (!__any_sync(0xffffffffu, (row & mine) != 0) && lane == w) mine |= 1u << b;
+            if (!cw) break;
+            b = bn; row = row_next;
         }
     }
     fresh_words[lane] = mine;
