@@ -473,7 +473,8 @@ def run_ours(args):
         # allowed, so the attainable rate is the FP64 ISSUE rate = DFMA peak / 2 flop; the chance check itself runs in
         # the fp32 broad phase
         lin_dense = os.environ.get("CCK_LIN_DENSE", "") == "1"
-        inst_per_step = (95.0 if lin_dense else 75.0) if dim == 2 else 880.0   # unicycle: ncu FP64-pipe-active x issue peak x time / belief-steps (profiles/r1g_unicycle_ncu_summary.csv)
+        # unicycle: 316 DMUL + 251 DADD + 32 DFMA + 10 DSETP per warp-step in the ncu source view of k_rollout_uni2 (gpurun r1g capture)
+        inst_per_step = (95.0 if lin_dense else 75.0) if dim == 2 else 609.0
         exec_tinst = per_launch_units * inst_per_step / (kern_ms * 1e-3) / 1e12
         inst_peak = fp64_peak / 2.0      # one DFMA = 2 flop = 1 FP64-pipe instruction per lane
         # ---- second half of BASELINE.json's metric: CCK-CBS solve time, short live sample (full distribution:
