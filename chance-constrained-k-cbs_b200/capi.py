@@ -6,6 +6,7 @@ CPU oracle; when the shared library is missing or no sm_100 GPU is present every
 raises (there is no fallback).
 """
 import ctypes as C
+import weakref
 import os
 import subprocess
 
@@ -229,9 +230,12 @@ class Context:
         self.h = h
         self.dim, self.dt, self.model = None, 0.2, None
         self._keep = []
+        self._trees = weakref.WeakSet()   # cck_tree handles dereference the context: they must go first
 
     def close(self):
         if getattr(self, "h", None):
+            for t in list(self._trees):
+                t.close()
             self.L.cck_ctx_destroy(self.h)
             self.h = None
 
@@ -406,11 +410,13 @@ class Tree:
         h = C.c_void_p()
         ctx._ck(ctx.L.cck_tree_create(ctx.h, dim, C.byref(h)))
         self.h = h
+        ctx._trees.add(self)
 
     def close(self):
-        if self.h:
+        # a no-op once the owning context is gone (Context.close destroys its trees before itself)
+        if getattr(self, "h", None) and getattr(self.ctx, "h", None):
             self.ctx.L.cck_tree_destroy(self.h)
-            self.h = None
+        self.h = None
 
     def __del__(self):
         try:
@@ -581,10 +587,9 @@ def constraint_entries(k, dim, constrained, constraints):
     ent_step, pair_ab, mu, cov = [], [], [], []
     for other, steps, states in constraints:
         st = np.asarray(states, dtype=np.float64).reshape(len(steps), -1)
-        lo, hi = min(constrained, other), max(constrained, other)
         for s, b in zip(steps, st):
             ent_step.append(int(s))
-            pair_ab.append(lo * k + hi)
+            pair_ab.append(constrained * k + other)      # planning robot first (cck_b200.h)
             mu.append(b[:2])
             S, L = b[dim:dim + dim * dim], b[dim + dim * dim:]
             if dim == 4:   # BeliefPVC::getDistribution_ picks (0,0),(0,2),(2,0),(2,2)

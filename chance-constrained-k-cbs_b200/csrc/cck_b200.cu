@@ -28,8 +28,6 @@ struct cck_ctx {
     cudaStream_t pipe[CCK_SLOTS] = {};
     std::string err;
     int64_t launches = 0;
-    bool refill = true;   // lane-refill rollout kernel (CCK_REFILL=0: static assignment)
-    int bpt = 1;   // beliefs per thread of the linear+Blackmore rollout kernel (CCK_BPT=0 selects the generic kernel)
 
     bool has_model = false;
     cck_model_params model{};
@@ -40,17 +38,12 @@ struct cck_ctx {
     SvcDev svc{};
     unsigned char* d_tab = nullptr;
     int tab_bytes = 0;
-    unsigned char* d_ftab = nullptr;   // fp32 filter table (Blackmore fast path)
-    int ftab_bytes = 0;
-    double* d_exB = nullptr;           // exact fp64 rows in filter-table order
-    int32_t* d_exCls = nullptr;        // class of each row (-1: padding)
     unsigned char* d_gtab = nullptr;   // fp32 box + cell-grid table (Blackmore broad phase, cck_rollout_grid.cuh)
     int gtab_bytes = 0;
     double* d_gexB = nullptr;          // exact fp64 rows in grid-table order
     int32_t* d_gexCls = nullptr;       // class of each row
     bool uni_sparse = false;           // unicycle matrices have the reference's exact-zero pattern
     GridConst gconst{0, 0, 0, 0, 0, 0, 0, -1.f};   // header scalars of the grid table + fp32 bounds (kernel constants)
-    int kern = 2;                      // linear+Blackmore rollout kernel: 2 grid (default), 1 group filter, 0 generic (CCK_KERNEL)
     int M = 0;
 
     bool has_pvc = false;
@@ -121,10 +114,7 @@ extern "C" int cck_ctx_create(int device, cck_ctx** out) {
     c->device = device;
     c->num_sms = prop.multiProcessorCount;
     c->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
-    if (const char* e3 = getenv("CCK_REFILL")) c->refill = atoi(e3) != 0;
     if (const char* e5 = getenv("CCK_CHUNK_LOG2")) { const int v = atoi(e5); if (v >= 10 && v <= 26) kChunk = (int64_t)1 << v; }
-    if (const char* e4 = getenv("CCK_KERNEL")) { const int v = atoi(e4); if (v >= 0 && v <= 2) c->kern = v; }
-    if (const char* e2 = getenv("CCK_BPT")) { const int v = atoi(e2); if (v == 0 || v == 1 || v == 2 || v == 4) c->bpt = v; }
     if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = create_pipe_streams(c)) != cudaSuccess ||
         (e = cudaMalloc(&c->d_key, sizeof(unsigned long long))) != cudaSuccess || (e = cudaMalloc(&c->d_run, sizeof(cck_conflict_run))) != cudaSuccess) {
@@ -142,7 +132,7 @@ extern "C" int cck_ctx_destroy(cck_ctx* c) {
     cudaStreamSynchronize(c->stream);
     cudaFreeHost(c->h_stage);
     for (int i = 0; i < CCK_SLOTS; ++i) { if (c->pipe[i]) { cudaStreamSynchronize(c->pipe[i]); cudaStreamDestroy(c->pipe[i]); } cudaFree(c->d_scratch[i]); }
-    cudaFree(c->d_ftab); cudaFree(c->d_exB); cudaFree(c->d_exCls); cudaFree(c->d_gtab); cudaFree(c->d_gexB); cudaFree(c->d_gexCls);
+    cudaFree(c->d_gtab); cudaFree(c->d_gexB); cudaFree(c->d_gexCls);
     cudaFree(c->d_tab); cudaFree(c->d_pvc_A); cudaFree(c->d_pvc_B); cudaFree(c->d_pvc_radii); cudaFree(c->d_pvc_order);
     cudaFree(c->d_key); cudaFree(c->d_run); cudaFree(c->d_cons);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -333,6 +323,7 @@ extern "C" int cck_set_model(cck_ctx* c, const cck_model_params* p) {
             if (!std::isfinite(F[i]) || !std::isfinite(A[i]) || !std::isfinite(c->uni.Q[i]) || !std::isfinite(c->uni.R[i])) ok = false;
         }
         c->uni_sparse = ok;
+        c->uni.sparse = ok ? 1 : 0; c->uni.pad = 0;
     }
     c->has_model = true;
     return CCK_OK;
@@ -498,6 +489,7 @@ extern "C" int cck_set_obstacles(cck_ctx* c, const cck_svc_params* p, const doub
     if (p->kind == CCK_SVC_ADAPTIVE && M > 0 && !centres) return fail(c, CCK_ERR_INVALID, "Adaptive SVC needs obstacle centres");
     if (p->kind == CCK_SVC_CHISQUARED && M > 0 && !rects) return fail(c, CCK_ERR_INVALID, "ChiSquared SVC needs inflated rectangles");
     if (p->kind < 0 || p->kind > 2 || p->dim < 1 || p->dim > 4) return fail(c, CCK_ERR_INVALID, "bad svc params");
+    if (M > 65535) return fail(c, CCK_ERR_INVALID, "more than 65535 obstacles");   // uint16 cell CSR of the grid table
     CK(c, cudaSetDevice(c->device));
 
     struct Key { uint64_t w[8]; bool operator<(const Key& o) const { return std::memcmp(w, o.w, sizeof(w)) < 0; } };
@@ -542,114 +534,29 @@ extern "C" int cck_set_obstacles(cck_ctx* c, const cck_svc_params* p, const doub
     if (centres && M) std::memcpy(buf.data() + h.off_centres, centres, (size_t)M * 16);   // original order (sum order, eta_list[0])
     if (rects && M) std::memcpy(buf.data() + h.off_rects, rects, (size_t)M * 32);
 
+    // the grid table is built (host only) and checked against the shared-memory budget BEFORE any context state changes:
+    // a refused call leaves the previous tables installed and usable
+    GridBuild gb;
+    GHeader gh0{};
+    bool boxes_in_smem = true;
+    int stage_bytes = 0;
+    if (M > 0) {
+        build_grid_table(M, A, B, cls_idx, p->erf_inv_result, gb);
+        std::memcpy(&gh0, gb.buf.data(), sizeof(gh0));
+        // small tables are staged whole; for large M only the header + cell CSR (<= 8.3 KB) go to shared memory
+        // and the box arrays (32 B per obstacle) are read from global memory
+        boxes_in_smem = gb.buf.size() <= 24 * 1024;
+        stage_bytes = boxes_in_smem ? (int)gb.buf.size() : gh0.off_boxes;
+        if (grid_smem_bytes(stage_bytes, CCK_GRID_THREADS) > c->max_smem_optin) return fail(c, CCK_ERR_INVALID, "grid table exceeds shared memory");
+    }
     CK(c, cudaStreamSynchronize(c->stream));
+    c->has_svc = false;   // until every table below is in place: a CUDA failure half-way must not leave a usable-looking checker
     cudaFree(c->d_tab); c->d_tab = nullptr;
     CK(c, cudaMalloc(&c->d_tab, h.total_bytes));
     CK(c, cudaMemcpy(c->d_tab, buf.data(), h.total_bytes, cudaMemcpyHostToDevice));
     c->tab_bytes = h.total_bytes;
     c->M = M;
 
-    // ---- fp32 filter table: super-classes of normals that agree to 1e-14 relative ----
-    cudaFree(c->d_ftab); cudaFree(c->d_exB); cudaFree(c->d_exCls);
-    c->d_ftab = nullptr; c->d_exB = nullptr; c->d_exCls = nullptr; c->ftab_bytes = 0;
-    if (M > 0) {
-        std::vector<std::vector<int>> supers;          // class indices per super-class
-        for (int k = 0; k < nc; ++k) {
-            double Ak[8]; std::memcpy(Ak, keys[k].w, 64);
-            int found = -1;
-            for (size_t sidx = 0; sidx < supers.size() && found < 0; ++sidx) {
-                double Ar[8]; std::memcpy(Ar, keys[supers[sidx][0]].w, 64);
-                double scale = 0, diff = 0;
-                for (int i = 0; i < 8; ++i) { scale = std::max(scale, std::fabs(Ar[i])); diff = std::max(diff, std::fabs(Ar[i] - Ak[i])); }
-                if (std::isfinite(scale) && diff <= 1e-14 * scale) found = (int)sidx;
-            }
-            if (found < 0) { supers.emplace_back(); found = (int)supers.size() - 1; }
-            supers[found].push_back(k);
-        }
-        const int nsup = (int)supers.size();
-        int frows = 0, fgroups = 0;
-        std::vector<int> sup_rows(nsup);
-        std::vector<std::vector<std::pair<int, int>>> sup_members(nsup);   // (obstacle, class), Morton-sorted
-        for (int sidx = 0; sidx < nsup; ++sidx) {
-            auto& mem = sup_members[sidx];
-            for (int k : supers[sidx]) for (int o : members[k]) mem.emplace_back(o, k);
-            // spatial order: Morton code of the (B_1, B_2) offsets quantised to 16 bits
-            double lo1 = HUGE_VAL, hi1 = -HUGE_VAL, lo2 = HUGE_VAL, hi2 = -HUGE_VAL;
-            for (auto& m : mem) {
-                const double b1 = B[4 * m.first + 1], b2 = B[4 * m.first + 2];
-                if (std::isfinite(b1)) { lo1 = std::min(lo1, b1); hi1 = std::max(hi1, b1); }
-                if (std::isfinite(b2)) { lo2 = std::min(lo2, b2); hi2 = std::max(hi2, b2); }
-            }
-            auto quant = [](double v, double lo, double hi) -> uint32_t {
-                if (!std::isfinite(v) || !(hi > lo)) return 0u;
-                return (uint32_t)std::min(65535.0, std::max(0.0, (v - lo) / (hi - lo) * 65535.0));
-            };
-            auto spread = [](uint32_t v) { uint32_t x = v & 0xffff; x = (x | (x << 8)) & 0x00ff00ff; x = (x | (x << 4)) & 0x0f0f0f0f;
-                                           x = (x | (x << 2)) & 0x33333333; x = (x | (x << 1)) & 0x55555555; return x; };
-            auto key = [&](const std::pair<int, int>& m) { return spread(quant(B[4 * m.first + 1], lo1, hi1)) | (spread(quant(B[4 * m.first + 2], lo2, hi2)) << 1); };
-            std::stable_sort(mem.begin(), mem.end(), [&](const std::pair<int, int>& x, const std::pair<int, int>& y) { return key(x) < key(y); });
-            sup_rows[sidx] = ((int)mem.size() + CCK_GROUP - 1) / CCK_GROUP * CCK_GROUP;
-            frows += sup_rows[sidx];
-            fgroups += sup_rows[sidx] / CCK_GROUP;
-        }
-        FHeader fh{};
-        fh.n_super = nsup; fh.rows_total = frows; fh.groups_total = fgroups;
-        fh.off_super = sizeof(FHeader);
-        fh.off_rows = fh.off_super + nsup * (int)sizeof(SuperRec);
-        fh.off_groups = fh.off_rows + frows * 16;
-        fh.total_bytes = (fh.off_groups + fgroups * 16 + 15) & ~15;
-        const bool filter_fits = fh.total_bytes + 16 <= c->max_smem_optin;   // else: CCK_KERNEL=1 is refused at launch
-        if (filter_fits) {
-        std::vector<unsigned char> fbuf(fh.total_bytes, 0);
-        std::vector<double> exB((size_t)frows * 4, -HUGE_VAL);
-        std::vector<int32_t> exCls(frows, -1);
-        std::memcpy(fbuf.data(), &fh, sizeof(fh));
-        float* frow = reinterpret_cast<float*>(fbuf.data() + fh.off_rows);
-        float* fgrp = reinterpret_cast<float*>(fbuf.data() + fh.off_groups);
-        int rpos = 0, gpos = 0;
-        for (int sidx = 0; sidx < nsup; ++sidx) {
-            SuperRec sr{};
-            std::memcpy(sr.A, keys[supers[sidx][0]].w, 64);
-            sr.first_row = rpos; sr.n_rows_pad = sup_rows[sidx]; sr.first_group = gpos; sr.n_groups = sup_rows[sidx] / CCK_GROUP;
-            std::memcpy(fbuf.data() + fh.off_super + sidx * sizeof(SuperRec), &sr, sizeof(sr));
-            // member rows are stored TRANSPOSED: member q of group g at first_row + q*n_groups + g, so lanes
-            // scanning different groups in the per-lane second level hit consecutive 16-byte words (no bank conflicts)
-            const int ngr = sr.n_groups;
-            auto slot = [&](int w) { return rpos + (w % CCK_GROUP) * ngr + (w / CCK_GROUP); };
-            int written = 0;
-            for (auto& m : sup_members[sidx]) {
-                const int o = m.first, at = slot(written);
-                for (int i = 0; i < 4; ++i) {
-                    const double bv = B[4 * o + i];
-                    float bf = (float)bv;                       // round to nearest, then force UP
-                    if ((double)bf < bv) bf = std::nextafterf(bf, HUGE_VALF);
-                    if (std::isnan(bv)) bf = HUGE_VALF;         // never "proven" by the filter
-                    frow[(size_t)at * 4 + i] = bf;
-                    exB[(size_t)at * 4 + i] = bv;
-                }
-                exCls[at] = m.second;
-                ++written;
-            }
-            for (; written < sup_rows[sidx]; ++written)
-                for (int i = 0; i < 4; ++i) frow[(size_t)slot(written) * 4 + i] = -HUGE_VALF;
-            for (int g = 0; g < ngr; ++g)
-                for (int i = 0; i < 4; ++i) {
-                    float mx = -HUGE_VALF;
-                    for (int q = 0; q < CCK_GROUP; ++q) mx = std::max(mx, frow[(size_t)(rpos + q * ngr + g) * 4 + i]);
-                    fgrp[(size_t)(gpos + g) * 4 + i] = mx;
-                }
-            rpos += sup_rows[sidx];
-            gpos += sr.n_groups;
-        }
-        CK(c, cudaMalloc(&c->d_ftab, fh.total_bytes));
-        CK(c, cudaMalloc(&c->d_exB, exB.size() * 8));
-        CK(c, cudaMalloc(&c->d_exCls, exCls.size() * 4));
-        CK(c, cudaMemcpy(c->d_ftab, fbuf.data(), fh.total_bytes, cudaMemcpyHostToDevice));
-        CK(c, cudaMemcpy(c->d_exB, exB.data(), exB.size() * 8, cudaMemcpyHostToDevice));
-        CK(c, cudaMemcpy(c->d_exCls, exCls.data(), exCls.size() * 4, cudaMemcpyHostToDevice));
-        c->ftab_bytes = fh.total_bytes;
-        }
-    }
     // ---- fp32 box + cell-grid table (the default broad phase) ----
     cudaFree(c->d_gtab); cudaFree(c->d_gexB); cudaFree(c->d_gexCls);
     c->d_gtab = nullptr; c->d_gexB = nullptr; c->d_gexCls = nullptr; c->gtab_bytes = 0;
@@ -657,16 +564,6 @@ extern "C" int cck_set_obstacles(cck_ctx* c, const cck_svc_params* p, const doub
     c->gconst.Rm1 = -1.f;   // no grid rows: every query window is empty (M = 0 keeps the one-branch fast exit)
     c->gconst.blx = f32_up(p->low[0]); c->gconst.bhx = f32_down(p->high[0]); c->gconst.bly = f32_up(p->low[1]); c->gconst.bhy = f32_down(p->high[1]);
     if (M > 0) {
-        GridBuild gb;
-        build_grid_table(M, A, B, cls_idx, p->erf_inv_result, gb);
-        if (M > 65535) return fail(c, CCK_ERR_INVALID, "more than 65535 obstacles");
-        GHeader gh0;
-        std::memcpy(&gh0, gb.buf.data(), sizeof(gh0));
-        // small tables are staged whole; for large M only the header + cell CSR (<= 8.3 KB) go to shared memory
-        // and the box arrays (32 B per obstacle) are read from global memory
-        const bool boxes_in_smem = gb.buf.size() <= 24 * 1024;
-        const int stage_bytes = boxes_in_smem ? (int)gb.buf.size() : gh0.off_boxes;
-        if (grid_smem_bytes(stage_bytes, CCK_GRID_THREADS) > c->max_smem_optin) return fail(c, CCK_ERR_INVALID, "grid table exceeds shared memory");
         CK(c, cudaMalloc(&c->d_gtab, gb.buf.size()));
         CK(c, cudaMalloc(&c->d_gexB, gb.exB.size() * 8));
         CK(c, cudaMalloc(&c->d_gexCls, gb.exCls.size() * 4));
@@ -796,7 +693,7 @@ extern "C" int cck_is_valid_dev(cck_ctx* c, void* stream, int64_t n, const doubl
     CK(c, cudaSetDevice(c->device));
     cudaStream_t s = pick(c, stream);
     const int dim = c->model.dim;
-    if (c->svc.kind == CCK_SVC_BLACKMORE && c->kern >= 2) {   // fp32 box/cell-grid broad phase + exact decision
+    if (c->svc.kind == CCK_SVC_BLACKMORE) {   // fp32 box/cell-grid broad phase + exact decision
         const int gsm = 16 + c->gtab_bytes;
         if ((rc = set_smem(c, k_is_valid_grid, gsm))) return rc;
         k_is_valid_grid<<<grid_for(c, n, 256, 4), 256, gsm, s>>>(n, dim, bel, ld, valid, c->d_gtab, c->gtab_bytes, c->d_tab, c->d_gexB, c->d_gexCls, c->svc, c->gconst);
@@ -812,8 +709,7 @@ extern "C" int cck_is_valid_dev(cck_ctx* c, void* stream, int64_t n, const doubl
         if ((rc = set_smem(c, k_is_valid<KIND>, smem))) return rc;                                \
         k_is_valid<KIND><<<g, 256, smem, s>>>(n, dim, bel, ld, valid, c->d_tab, c->tab_bytes, c->svc); \
     } while (0)
-    if (c->svc.kind == CCK_SVC_BLACKMORE) LAUNCH_VALID(CCK_SVC_BLACKMORE);
-    else if (c->svc.kind == CCK_SVC_ADAPTIVE) LAUNCH_VALID(CCK_SVC_ADAPTIVE);
+    if (c->svc.kind == CCK_SVC_ADAPTIVE) LAUNCH_VALID(CCK_SVC_ADAPTIVE);
     else LAUNCH_VALID(CCK_SVC_CHISQUARED);
 #undef LAUNCH_VALID
     c->launches++;
@@ -838,11 +734,10 @@ static int launch_rollout(cck_ctx* c, cudaStream_t s, const RolloutArgs& a) {
     } while (0)
 #define DISPATCH_KIND(NAME, PAR, TRAJ)                                                                              \
     do {                                                                                                            \
-        if (c->svc.kind == CCK_SVC_BLACKMORE) LAUNCH_R((NAME<CCK_SVC_BLACKMORE, TRAJ, EXPAND>), PAR);              \
-        else if (c->svc.kind == CCK_SVC_ADAPTIVE) LAUNCH_R((NAME<CCK_SVC_ADAPTIVE, TRAJ, EXPAND>), PAR);           \
+        if (c->svc.kind == CCK_SVC_ADAPTIVE) LAUNCH_R((NAME<CCK_SVC_ADAPTIVE, TRAJ, EXPAND>), PAR);           \
         else LAUNCH_R((NAME<CCK_SVC_CHISQUARED, TRAJ, EXPAND>), PAR);                                               \
     } while (0)
-    if (c->model.model == CCK_MODEL_LINEAR2D && c->svc.kind == CCK_SVC_BLACKMORE && c->kern == 2) {
+    if (c->model.model == CCK_MODEL_LINEAR2D && c->svc.kind == CCK_SVC_BLACKMORE) {
         // default configuration: fp32 box/cell-grid broad phase + exact fp64 decision, lane refill
         if (a.n > (int64_t)INT_MAX) return fail(c, CCK_ERR_INVALID, "more than 2^31-1 beliefs in one launch");
         RolloutArgs g2 = a;
@@ -855,36 +750,13 @@ static int launch_rollout(cck_ctx* c, cudaStream_t s, const RolloutArgs& a) {
                     k_rollout_lin_grid<true, EXPAND><<<gb, grid_threads(EXPAND), gsmem, s>>>(g2, c->lin, c->svc, c->gconst, rl2); }
         else { if ((rc = set_smem(c, (k_rollout_lin_grid<false, EXPAND>), gsmem))) return rc;
                k_rollout_lin_grid<false, EXPAND><<<gb, grid_threads(EXPAND), gsmem, s>>>(g2, c->lin, c->svc, c->gconst, rl2); }
-    } else if (c->model.model == CCK_MODEL_LINEAR2D && c->svc.kind == CCK_SVC_BLACKMORE && c->kern == 1 && c->bpt > 0) {
-        // second generation: threshold (group filter) kernel, BPT beliefs per thread
-        if (c->M > 0 && c->ftab_bytes == 0) return fail(c, CCK_ERR_INVALID, "group-filter table exceeds shared memory; use the default kernel");
-#define LAUNCH_BM(BPT, TRAJ)                                                                             \
-    do {                                                                                                 \
-        const int gb = grid_for(c, (a.n + BPT - 1) / BPT, threads, 8);                                   \
-        const int fsmem = 16 + c->ftab_bytes;                                                            \
-        if ((rc = set_smem(c, (k_rollout_lin_bm<BPT, TRAJ, EXPAND>), fsmem))) return rc;                 \
-        k_rollout_lin_bm<BPT, TRAJ, EXPAND><<<gb, threads, fsmem, s>>>(a, c->lin, c->svc);               \
-    } while (0)
-        if (c->bpt == 1 && c->refill) {
-            // lane-refill kernel: each CTA owns a contiguous range and hands beliefs to idle lanes
-            const int64_t per_cta = 1024;
-            int64_t nb = (a.n + per_cta - 1) / per_cta;
-            const int gb = (int)std::min<int64_t>(nb, (int64_t)c->num_sms * 64);
-            const int fsmem = 16 + c->ftab_bytes;
-            if (traj) { if ((rc = set_smem(c, (k_rollout_lin_refill<true, EXPAND>), fsmem))) return rc;
-                        k_rollout_lin_refill<true, EXPAND><<<gb, threads, fsmem, s>>>(a, c->lin, c->svc, per_cta); }
-            else { if ((rc = set_smem(c, (k_rollout_lin_refill<false, EXPAND>), fsmem))) return rc;
-                   k_rollout_lin_refill<false, EXPAND><<<gb, threads, fsmem, s>>>(a, c->lin, c->svc, per_cta); }
-        }
-        else if (c->bpt == 1) { if (traj) LAUNCH_BM(1, true); else LAUNCH_BM(1, false); }
-        else if (c->bpt == 2) { if (traj) LAUNCH_BM(2, true); else LAUNCH_BM(2, false); }
-        else { if (traj) LAUNCH_BM(4, true); else LAUNCH_BM(4, false); }
-#undef LAUNCH_BM
     } else if (c->model.model == CCK_MODEL_LINEAR2D) {
+        // adaptive / chi-squared checkers: generic kernel over the staged class table
         if ((rc = check_tab_fits(c))) return rc;
         if (traj) DISPATCH_KIND(k_rollout_lin, c->lin, true); else DISPATCH_KIND(k_rollout_lin, c->lin, false);
-    } else if (c->uni_sparse && c->kern >= 2) {
-        // unicycle, second generation: sparse covariance step, grid broad phase for Blackmore, lane refill
+    } else {
+        // unicycle: sparse covariance step where the model has the reference's exact-zero pattern (UniDev::sparse, else the
+        // dense step), grid broad phase for Blackmore, lane refill
         RolloutArgs g2 = a;
         if (c->svc.kind == CCK_SVC_BLACKMORE) { g2.ftab = c->d_gtab; g2.ftab_bytes = c->gtab_bytes; g2.exB = c->d_gexB; g2.exCls = c->d_gexCls; }
         else { if ((rc = check_tab_fits(c))) return rc; g2.ftab = c->d_tab; g2.ftab_bytes = c->tab_bytes; }
@@ -902,9 +774,6 @@ static int launch_rollout(cck_ctx* c, cudaStream_t s, const RolloutArgs& a) {
         else if (c->svc.kind == CCK_SVC_ADAPTIVE) { if (traj) LAUNCH_U2(CCK_SVC_ADAPTIVE, true); else LAUNCH_U2(CCK_SVC_ADAPTIVE, false); }
         else { if (traj) LAUNCH_U2(CCK_SVC_CHISQUARED, true); else LAUNCH_U2(CCK_SVC_CHISQUARED, false); }
 #undef LAUNCH_U2
-    } else {
-        if ((rc = check_tab_fits(c))) return rc;
-        if (traj) DISPATCH_KIND(k_rollout_uni, c->uni, true); else DISPATCH_KIND(k_rollout_uni, c->uni, false);
     }
 #undef DISPATCH_KIND
 #undef LAUNCH_R
@@ -919,12 +788,12 @@ extern "C" int cck_propagate_while_valid_dev(cck_ctx* c, void* stream, int64_t n
     int rc = check_ready(c, true);
     if (rc) return rc;
     if (n < 0 || ld < n || ldc < n || ldo < n || (traj && traj_ld < n)) return fail(c, CCK_ERR_INVALID, "bad n/ld");
+    if (traj && traj_T < 1) return fail(c, CCK_ERR_INVALID, "traj_T must be >= 1 when a trajectory buffer is given");
     if (n == 0) return CCK_OK;
     CK(c, cudaSetDevice(c->device));
     RolloutArgs a{};
     a.n = n; a.bel = bel; a.ld = ld; a.ctrl = ctrl; a.ldc = ldc; a.steps = steps; a.out = out; a.ldo = ldo; a.valid = valid_steps;
     a.traj = traj; a.traj_ld = traj_ld; a.traj_T = traj_T; a.tab = c->d_tab; a.tab_bytes = c->tab_bytes; a.duration = c->model.dt;
-    a.ftab = c->d_ftab; a.ftab_bytes = c->ftab_bytes; a.exB = c->d_exB; a.exCls = c->d_exCls;
     return launch_rollout<false>(c, pick(c, stream), a);
 }
 
@@ -944,7 +813,6 @@ extern "C" int cck_expand_batch_dev(cck_ctx* c, void* stream, int64_t n, const d
     a.parent_step = parent_step; a.parent_cost = parent_cost; a.cost = cost; a.goal_dist = goal_dist; a.flags = flags;
     a.goal = *goal; a.cons = c->d_cons;
     a.cons_smem_bytes = (c->d_cons && c->cons_bytes <= CCK_CONS_SMEM_MAX) ? c->cons_bytes : 0;   // small tables are copied into shared memory by each CTA
-    a.ftab = c->d_ftab; a.ftab_bytes = c->ftab_bytes; a.exB = c->d_exB; a.exCls = c->d_exCls;
     return launch_rollout<true>(c, pick(c, stream), a);
 }
 
@@ -988,6 +856,7 @@ extern "C" int cck_set_constraints(cck_ctx* c, int n_entries, const int32_t* ent
     for (int e = 0; e < n_entries; ++e) {
         if (ent_step[e] < 0) return fail(c, CCK_ERR_INVALID, "negative constraint step");
         if (pair_ab[e] < 0 || pair_ab[e] >= c->pvc.k * c->pvc.k) return fail(c, CCK_ERR_INVALID, "pair index out of range");
+        if (pair_ab[e] / c->pvc.k == pair_ab[e] % c->pvc.k) return fail(c, CCK_ERR_INVALID, "a robot cannot constrain itself");
         max_step = std::max(max_step, ent_step[e]);
     }
     std::vector<int> order(n_entries);
@@ -998,7 +867,7 @@ extern "C" int cck_set_constraints(cck_ctx* c, int n_entries, const int32_t* ent
     h.off_first = sizeof(ConsHeader);
     h.off_entries = (h.off_first + (max_step + 2) * 4 + 15) & ~15;
     h.pvc_kind = c->pvc.kind; h.dim = c->pvc.dim; h.k = c->pvc.k;
-    h.c_pair = c->pvc.c_pair; h.p_coll_agnts = c->pvc.p_coll_agnts;
+    h.c_pair = c->pvc.c_pair; h.p_coll_agnts = c->pvc.p_coll_agnts; h.sc = c->pvc.sc;
     const size_t total = h.off_entries + (size_t)n_entries * sizeof(ConsEntry);
     std::vector<unsigned char> buf(total, 0);
     std::memcpy(buf.data(), &h, sizeof(h));
@@ -1013,8 +882,12 @@ extern "C" int cck_set_constraints(cck_ctx* c, int n_entries, const int32_t* ent
         const int src = order[i];
         std::memcpy(ent[i].mu, mu2 + 2 * src, 16);
         std::memcpy(ent[i].cov, cov4 + 4 * src, 32);
-        std::memcpy(ent[i].A, c->pvc_A.data() + (size_t)pair_ab[src] * 8, 64);
-        std::memcpy(ent[i].B, c->pvc_B.data() + (size_t)pair_ab[src] * 4, 32);
+        // pair_ab = constrained * k + constraining; the half-planes belong to the unordered pair (stored at [lo*k + hi])
+        const int k = c->pvc.k, ra = pair_ab[src] / k, rb = pair_ab[src] % k;
+        const size_t hp = (size_t)std::min(ra, rb) * k + std::max(ra, rb);
+        std::memcpy(ent[i].A, c->pvc_A.data() + hp * 8, 64);
+        std::memcpy(ent[i].B, c->pvc_B.data() + hp * 4, 32);
+        ent[i].rad[0] = c->pvc_radii[ra]; ent[i].rad[1] = c->pvc_radii[rb];
     }
     if (total > c->cons_cap) {
         cudaFree(c->d_cons); c->d_cons = nullptr; c->cons_cap = 0;
@@ -1175,6 +1048,11 @@ static int rollout_host(cck_ctx* c, bool expand, int64_t n, const double* bel, i
     if (rc) return rc;
     if (n < 0 || ld < n || ldc < n || ldo < n || (traj && (traj_ld < n || traj_T < 1))) return fail(c, CCK_ERR_INVALID, "bad n/ld");
     if (!bel || !ctrl || !steps || !out || !valid_steps) return fail(c, CCK_ERR_INVALID, "null argument");
+    if (traj) {   // the trajectory buffer holds traj_T steps per belief: a longer rollout would write past it
+        int32_t mx = 0;
+        for (int64_t i = 0; i < n; ++i) mx = std::max(mx, steps[i]);
+        if (mx > traj_T) return fail(c, CCK_ERR_INVALID, "max(steps) = " + std::to_string(mx) + " exceeds traj_T = " + std::to_string(traj_T));
+    }
     CK(c, cudaSetDevice(c->device));
     if (n > 0 && n <= 16384 && !traj)
         return rollout_host_small(c, expand, n, bel, ld, ctrl, ldc, steps, parent_step, parent_cost, goal, out, ldo, valid_steps, cost, goal_dist, flags);

@@ -34,15 +34,6 @@ struct ClassRec {
 static_assert(sizeof(TabHeader) == 32, "header");
 static_assert(sizeof(ClassRec) == 80, "class record");
 
-// Filter table (Blackmore fast path): obstacles grouped into SUPER-classes whose normals agree to
-// 1e-14 relative (the reference's tables: one super-class), rows = B rounded UP to fp32.
-// Rows are sorted along a Morton curve of (B_1, B_2) and cut into GROUPS of 8; a group row holds the
-// component-wise max of its members, so one proven group row proves all 8 obstacles.
-struct FHeader { int32_t n_super, rows_total, off_super, off_rows, total_bytes, off_groups, groups_total, pad; };
-struct SuperRec { double A[8]; int32_t first_row, n_rows_pad, first_group, n_groups; };
-#define CCK_GROUP 8
-static_assert(sizeof(FHeader) == 32 && sizeof(SuperRec) == 80, "filter table records");
-
 struct SvcDev {
     int32_t kind, dim;
     double low[4], high[4];
@@ -51,7 +42,7 @@ struct SvcDev {
 };
 
 struct LinDev { double dt; double Q[4], R[4], Acl[4]; int diag, pad; double dg[6]; };   // diag: Q, R, A_cl are diagonal with |A_cl| <= 1 (lin_step_diag is usable); dg = {Q00, Q11, R00, R11, A00, A11} packed for three 16-byte constant loads
-struct UniDev { double F[16], Acl[16], Q[16], R[16], gains[8], acc_lo, acc_hi, turn_lo, turn_hi; };
+struct UniDev { double F[16], Acl[16], Q[16], R[16], gains[8], acc_lo, acc_hi, turn_lo, turn_hi; int sparse, pad; };   // sparse: F, A_cl_d, Q, R have the reference's exact-zero pattern (uni_cov_step_sparse is usable)
 
 // ---------------------------------------------------------------------------
 // PTX helpers: mbarrier + TMA 1-D bulk copy (cp.async.bulk -> SASS UBLKCP)

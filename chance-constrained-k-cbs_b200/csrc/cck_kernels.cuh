@@ -27,7 +27,8 @@ struct RolloutArgs {
     cck_goal_params goal;
     const unsigned char* cons;   // constraint table (global memory)
     int32_t cons_smem_bytes;     // > 0: the table is small, every CTA copies it into shared memory first (multiple of 16)
-    // Blackmore fast path: fp32 filter table (staged to smem) + exact rows (global, slow path only)
+    // staged table: the fp32 box/cell-grid table (Blackmore; exact rows exB/exCls stay in global memory for the rare
+    // exact decision) or the class table (other checkers, unicycle kernel)
     const unsigned char* ftab; int32_t ftab_bytes;
     const double* exB; const int32_t* exCls;
 };
@@ -40,11 +41,14 @@ struct ConsHeader {
     int32_t off_first, off_entries;    // byte offsets: int32 first[max_step+2]; ConsEntry entries[n]
     int32_t pvc_kind, dim, k, pad;
     double c_pair, p_coll_agnts;
+    double sc, pad2;                   // ChiSquaredBoundaryPVC: chi2_2 quantile (ChiSquaredBoundaryPVC.cpp:19)
 };
 struct ConsEntry {
-    double mu[2], cov[4];
-    double A[8], B[4];
+    double mu[2], cov[4];              // the constraining robot's getDistribution_ at this step
+    double A[8], B[4];                 // half-planes of the unordered robot pair
+    double rad[2];                     // bounding radii: [0] constrained (planning) robot, [1] constraining robot
 };
+static_assert(sizeof(ConsHeader) == 64 && sizeof(ConsEntry) == 160, "constraint table records");
 
 __device__ __forceinline__ bool pair_safe_halfplanes(const double* A, const double* B, double mx, double my, double S0,
                                                      double S1, double S2, double S3, double c) {
@@ -73,6 +77,15 @@ __device__ __forceinline__ bool constraints_ok_at(const unsigned char* cons, int
     for (int e = first[s]; e < first[s + 1] && ok; ++e) {
         const double dx = mx - ent[e].mu[0], dy = my - ent[e].mu[1];
         const double S0 = C0 + ent[e].cov[0], S1 = C1 + ent[e].cov[1], S2 = C2 + ent[e].cov[2], S3 = C3 + ent[e].cov[3];
+        if (h->pvc_kind == CCK_PVC_CHISQUARED) {
+            // ChiSquaredBoundaryPVC::satisfiesConstraints (ChiSquaredBoundaryPVC.cpp:54-87) -> isSafe_ (:139-168):
+            // belief_a = the planning robot's state, belief_b = the stored state of the constraining robot
+            const double la = max_eig_real_2x2(C0, C1, C2, C3), lb = max_eig_real_2x2(ent[e].cov[0], ent[e].cov[1], ent[e].cov[2], ent[e].cov[3]);
+            const double dist = sqrt(dx * dx + dy * dy);
+            const double boundary = (la * h->sc + ent[e].rad[0]) + (lb * h->sc + ent[e].rad[1]);
+            ok = dist > boundary;
+            continue;
+        }
         double c = h->c_pair;
         if (h->pvc_kind == CCK_PVC_ADAPTIVE_BLACKMORE || h->pvc_kind == CCK_PVC_ADAPTIVE_BOUNDINGBOX) {
             // states_map holds only the two robots (AdaptiveRiskBlackmorePVC.cpp:92-101)
@@ -222,7 +235,7 @@ __global__ void __launch_bounds__(128) k_rollout_lin(const __grid_constant__ Rol
             if (!svc_valid<KIND>(sp, tab, v, P0, P1, P2, P3)) { r = t; break; }
             cur = nxt;
             if (EXPAND && a.cons) cons_ok = cons_ok && constraints_ok_at(a.cons, pstep + t + 1, nxt.mx, nxt.my, P0, P1, P2, P3);
-            if (TRAJ) {
+            if (TRAJ && t < a.traj_T) {   // device-pointer callers: steps beyond the buffer are not recorded
                 double* tp = a.traj + (int64_t)t * 10 * a.traj_ld + i;
                 tp[0] = nxt.mx; tp[a.traj_ld] = nxt.my;
 #pragma unroll
@@ -240,70 +253,6 @@ __global__ void __launch_bounds__(128) k_rollout_lin(const __grid_constant__ Rol
             double gd;
             const bool g = goal_ok(a.goal, sp, cur.mx, cur.my, cur.S[0] + cur.L[0], cur.S[1] + cur.L[1], cur.S[2] + cur.L[2],
                                    cur.S[3] + cur.L[3], &gd);
-            a.goal_dist[i] = gd;
-            a.flags[i] = (uint8_t)((r == steps ? 1 : 0) | (cons_ok ? 2 : 0) | (g ? 4 : 0));
-        }
-    }
-    if (!waited) stage_wait((uint32_t)a.tab_bytes, bar);
-}
-
-// unicycle rollout.  The covariance recursion is independent of the mean, so (Sigma, Lambda)
-// advance in place; the previous step's copy needed for "last valid state" lives in local memory.
-template <int KIND, bool TRAJ, bool EXPAND>
-__global__ void __launch_bounds__(128) k_rollout_uni(const __grid_constant__ RolloutArgs a, const __grid_constant__ UniDev p,
-                                                     const __grid_constant__ SvcDev sp) {
-    CCK_SMEM_PROLOGUE(a)
-    bool waited = false;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * blockDim.x) {
-        double v[4], u[4], S[16], L[16];
-#pragma unroll
-        for (int f = 0; f < 4; ++f) { v[f] = a.bel[f * a.ld + i]; u[f] = a.ctrl[f * a.ldc + i]; }
-#pragma unroll
-        for (int f = 0; f < 16; ++f) { S[f] = a.bel[(4 + f) * a.ld + i]; L[f] = a.bel[(20 + f) * a.ld + i]; }
-        double sr, cr;
-        sincos(u[2], &sr, &cr);
-        const int steps = a.steps[i];
-        const double v0[4] = {v[0], v[1], v[2], v[3]};
-        int pstep = 0;
-        bool cons_ok = true;
-        if (EXPAND) pstep = a.parent_step[i];
-        if (!waited) { stage_wait((uint32_t)a.tab_bytes, bar); waited = true; }
-        int r = steps > 0 ? steps : 0;
-        for (int t = 0; t < steps; ++t) {
-            double vn[4], Sn[16], Ln[16];
-            uni_mean_step(v, u, cr, sr, a.duration, p, vn);
-            uni_cov_step(S, L, p, Sn, Ln);
-            const double P0 = Sn[0] + Ln[0], P1 = Sn[1] + Ln[1], P2 = Sn[4] + Ln[4], P3 = Sn[5] + Ln[5];   // (x, xdot) block, quirk 2
-            if (!svc_valid<KIND>(sp, tab, vn, P0, P1, P2, P3)) { r = t; break; }
-#pragma unroll
-            for (int f = 0; f < 4; ++f) v[f] = vn[f];
-#pragma unroll
-            for (int f = 0; f < 16; ++f) { S[f] = Sn[f]; L[f] = Ln[f]; }
-            if (EXPAND && a.cons) {
-                // getDistribution_ picks entries (0,0),(0,2),(2,0),(2,2) (BeliefPVC.cpp:94-97)
-                cons_ok = cons_ok && constraints_ok_at(a.cons, pstep + t + 1, vn[0], vn[1], Sn[0] + Ln[0], Sn[2] + Ln[2],
-                                                       Sn[8] + Ln[8], Sn[10] + Ln[10]);
-            }
-            if (TRAJ) {
-                double* tp = a.traj + (int64_t)t * 36 * a.traj_ld + i;
-#pragma unroll
-                for (int f = 0; f < 4; ++f) tp[f * a.traj_ld] = vn[f];
-#pragma unroll
-                for (int f = 0; f < 16; ++f) { tp[(4 + f) * a.traj_ld] = Sn[f]; tp[(20 + f) * a.traj_ld] = Ln[f]; }
-            }
-        }
-#pragma unroll
-        for (int f = 0; f < 4; ++f) a.out[f * a.ldo + i] = v[f];
-#pragma unroll
-        for (int f = 0; f < 16; ++f) { a.out[(4 + f) * a.ldo + i] = S[f]; a.out[(20 + f) * a.ldo + i] = L[f]; }
-        a.valid[i] = r;
-        if (EXPAND) {
-            double acc = 0;
-#pragma unroll
-            for (int f = 0; f < 4; ++f) { const double d = v0[f] - v[f]; acc = acc + d * d; }
-            a.cost[i] = a.parent_cost[i] + sqrt(acc);
-            double gd;
-            const bool g = goal_ok(a.goal, sp, v[0], v[1], S[0] + L[0], S[1] + L[1], S[4] + L[4], S[5] + L[5], &gd);
             a.goal_dist[i] = gd;
             a.flags[i] = (uint8_t)((r == steps ? 1 : 0) | (cons_ok ? 2 : 0) | (g ? 4 : 0));
         }
@@ -461,7 +410,6 @@ __global__ void __launch_bounds__(128) k_constraints(int64_t n_paths, int dim, c
     const ConsHeader* h = reinterpret_cast<const ConsHeader*>(cons);
     const int W = dim + 2 * dim * dim;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_paths; i += (int64_t)gridDim.x * blockDim.x) {
-        if (h->pvc_kind == CCK_PVC_CHISQUARED) { ok[i] = 0; continue; }   // ChiSquaredBoundaryPVC.cpp:54-61 returns false
         bool good = true;
         const int len = path_len[i], s0 = step0[i];
         for (int t = 0; t < len && good; ++t) {

@@ -28,9 +28,26 @@
 //    Q, R, A_cl (lin_step_diag) while the lane's covariance is known finite.  171 instructions per warp-step, 75 of
 //    them FP64 (profiles/r1o_*).
 #pragma once
-#include "cck_rollout_bm.cuh"
+#include "cck_kernels.cuh"
 
 namespace cck {
+
+// exact reference test of one obstacle (rare path; PCCBlackmoreSVC.cpp:63-75)
+__device__ __noinline__ bool bm_exact_obstacle(const double* A8, const double* B, double x, double y, double P0, double P1,
+                                               double P2, double P3, double c) {
+    bool safe = false;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const double a0 = A8[2 * i], a1 = A8[2 * i + 1];
+        const double t0 = a0 * P0 + a1 * P2;
+        const double t1 = a0 * P1 + a1 * P3;
+        const double tmp = t0 * a0 + t1 * a1;
+        const double PV = sqrt(tmp);
+        const double bb = 1.4142135623730951 * PV * c;
+        safe = safe | (x * a0 + y * a1 >= B[i] + bb);
+    }
+    return safe;
+}
 
 struct GHeader {                 // 80 bytes, then dstart[R*64+1] (u16, dense row-major CSR over the cells), outer boxes[M], inner boxes[M] (float4)
     int32_t total_bytes, M, n_grid, n_cells;
@@ -392,7 +409,7 @@ __global__ void __launch_bounds__(grid_threads(EXPAND), grid_minb(EXPAND)) k_rol
                 asm volatile("" : "+d"(s0), "+d"(s1), "+d"(s2), "+d"(s3));
                 cons_ok = cons_ok && constraints_ok_at(cons, pstep + t + 1, x, y, s0 + B.L[0], s1 + B.L[1], s2 + B.L[2], s3 + B.L[3]);
             }
-            if (TRAJ) {
+            if (TRAJ && t < a.traj_T) {
                 double* tp = a.traj + (int64_t)t * 10 * a.traj_ld + i;
                 tp[0] = B.mx; tp[a.traj_ld] = B.my;
 #pragma unroll

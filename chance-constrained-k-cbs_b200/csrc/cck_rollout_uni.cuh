@@ -1,8 +1,8 @@
 // cck_rollout_uni.cuh — second generation of the fused propagateWhileValid kernel for the
 // Uncertain-Unicycle model (UncertainUnicycleSP.cpp:146-227).
 //
-// The first version (k_rollout_uni) spent ~2000 FP64 instructions per belief-step in the generic
-// per-obstacle test and ~1100 in dense 4x4 algebra at 255 registers with spills.  This one
+// The first version (one thread per belief, static assignment, generic per-obstacle test, dense 4x4 algebra: git
+// history) spent ~2000 + ~1100 FP64 instructions per belief-step at 255 registers with spills.  This one
 //  * checks PCCBlackmore obstacles with the conservative fp32 box/cell-grid broad phase of
 //    cck_rollout_grid.cuh (exact fp64 decision for whatever is not proven: verdicts unchanged),
 //  * exploits the EXACT zeros of the model matrices (F = I + dt(e0e1^T + e2e3^T), A_cl_d block
@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(CCK_UNI_THREADS, 2) k_rollout_uni2(const __gri
             double mag = 0;
 #pragma unroll
             for (int f = 0; f < 16; ++f) mag = mag + (fabs(S[f]) + fabs(L[f]));
-            dense = !(mag < 1e300);      // non-finite (or absurd) covariance: 0*x is not an exact zero any more
+            dense = !p.sparse || !(mag < 1e300);      // non-reference sparsity, or a non-finite (or absurd) covariance: 0*x is not an exact zero any more
             t = 0;
             have = true;
         }
@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(CCK_UNI_THREADS, 2) k_rollout_uni2(const __gri
                 // getDistribution_ picks entries (0,0),(0,2),(2,0),(2,2) (BeliefPVC.cpp:94-97)
                 cons_ok = cons_ok && constraints_ok_at(cons, pstep + t + 1, v[0], v[1], S[0] + L[0], S[2] + L[2], S[8] + L[8], S[10] + L[10]);
             }
-            if (TRAJ) {
+            if (TRAJ && t < a.traj_T) {
                 double* tp = a.traj + (int64_t)t * 36 * a.traj_ld + i;
 #pragma unroll
                 for (int f = 0; f < 4; ++f) tp[f * a.traj_ld] = v[f];

@@ -381,7 +381,7 @@ public:
         std::vector<int32_t> ent_step, pair_ab;
         std::vector<double> mu, cov;
         for (const auto& c : constraints) {
-            const int a = std::min(c->getConstrainedAgent(), c->getConstrainingAgent()), b = std::max(c->getConstrainedAgent(), c->getConstrainingAgent());
+            const int a = c->getConstrainedAgent(), b = c->getConstrainingAgent();   // planning robot first (cck_b200.h)
             for (size_t i = 0; i < c->getSteps().size(); ++i) {
                 const std::vector<double>& s = c->getStates()[i].v;
                 ent_step.push_back(c->getSteps()[i]);

@@ -173,7 +173,10 @@ int cck_validate_plan_dev(cck_ctx* ctx, void* stream, int k, const int32_t* lens
  * Constraints (BeliefConstraint, include/Constraints/BeliefConstraint.h:8-16) are
  * flattened into entries: entry e applies at absolute step ent_step[e] and carries the
  * constraining robot's belief as (mu[2], cov[4]) = getDistribution_ of the stored state,
- * plus the robot-pair index pair_ab[e] = a*k+b (a<b) selecting the half-planes.
+ * plus pair_ab[e] = constrained*k + constraining (the planning robot first; the half-planes of the
+ * unordered pair are used, the bounding radii pair up with the two beliefs as in
+ * ChiSquaredBoundaryPVC.cpp:81).  Every PVC kind checks its own isSafe_ at the constraint times,
+ * ChiSquaredBoundaryPVC included (ChiSquaredBoundaryPVC.cpp:54-87).
  * Paths: n_paths candidate paths in one SoA trajectory buffer (plane f of step t of
  * path i at path[(t*W+f)*ld + i]); path i has path_len[i] states and its first state
  * sits at absolute step path_step0[i].  ok[i] = 1 iff every entry whose step falls on

@@ -975,13 +975,12 @@ inline BeliefConstraint<D> create_constraint(const std::vector<std::vector<Belie
     return c;
 }
 
-// satisfiesConstraints (MinkowskiSumBlackmorePVC.cpp:64-104; Adaptive :61-107).
-// ChiSquaredBoundaryPVC::satisfiesConstraints returns false unconditionally
-// (ChiSquaredBoundaryPVC.cpp:54-61).
+// satisfiesConstraints (MinkowskiSumBlackmorePVC.cpp:64-104; Adaptive :61-107;
+// ChiSquaredBoundaryPVC.cpp:54-87: the chi-squared isSafe_ of the planning robot's state
+// against the stored state of the constraining robot, radii paired with their beliefs :81).
 template <int D>
 inline bool satisfies_constraints(const Pvc& p, const std::vector<Belief<D>>& path, double step_size,
                                   const std::vector<BeliefConstraint<D>>& constraints, Counters* cnt = nullptr) {
-    if (p.kind == PVC_CHISQUARED) return false;
     double current_time = 0.0;
     for (size_t s = 0; s < path.size(); ++s) {
         for (const auto& c : constraints) {
@@ -992,6 +991,10 @@ inline bool satisfies_constraints(const Pvc& p, const std::vector<Belief<D>>& pa
             const int a = c.constrained, b = c.constraining;
             const Dist2 da = get_distribution<D>(path[s]);
             const Dist2 db = get_distribution<D>(c.states[idx]);
+            if (p.kind == PVC_CHISQUARED) {
+                if (!pair_is_safe_chisq(da, p.radii[a], db, p.radii[b], p.sc)) return false;
+                continue;
+            }
             const double mu_ab[2] = {da.mu[0] - db.mu[0], da.mu[1] - db.mu[1]};
             double S_ab[4];
             for (int i = 0; i < 4; ++i) S_ab[i] = da.cov[i] + db.cov[i];

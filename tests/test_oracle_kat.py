@@ -201,8 +201,6 @@ def test_validate_plan_and_constraints(O):
         assert all(c[:2] == (0, 1) for c in conf)
         # head-on robots meet around x=8: |dx| = 12 - 0.4 t  => first conflict before t=30
         assert 20 <= s0 <= 30
-        if kind == O.PVC_CHISQUARED:
-            continue
         # constraint for robot 0 = robot 1's states over the run; robot 0's own path violates it ...
         steps = [c[2] for c in conf]
         states = np.array([trajs[1][min(s, len(trajs[1]) - 1)] for s in steps])
