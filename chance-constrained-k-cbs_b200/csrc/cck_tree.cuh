@@ -20,7 +20,7 @@
 
 namespace cck {
 
-// symmetric square root of the lower-triangle-symmetrised A (DIM x DIM): out = V diag(sqrt(max(l,0))) V^T.
+// symmetric square root of the lower-triangle-symmetrised A (DIM x DIM): out = V diag(sqrt(l)) V^T (NaN for an indefinite input, as Eigen's SelfAdjointEigenSolver::operatorSqrt).
 // DIAG_ONLY: only out[i*DIM+i] is produced (that is all the trace needs).
 template <int DIM, bool DIAG_ONLY>
 __host__ __device__ inline void sym_sqrt(const double* Ain, double* out) {
@@ -65,7 +65,7 @@ __host__ __device__ inline void sym_sqrt(const double* Ain, double* out) {
     }
     double sq[DIM];
 #pragma unroll
-    for (int k = 0; k < DIM; ++k) sq[k] = sqrt(A[k * DIM + k] > 0.0 ? A[k * DIM + k] : 0.0);
+    for (int k = 0; k < DIM; ++k) sq[k] = sqrt(A[k * DIM + k]);   // Eigen's operatorSqrt is eigenvalues().cwiseSqrt(): a negative eigenvalue (indefinite lower triangle) gives NaN, not 0
 #pragma unroll
     for (int i = 0; i < DIM; ++i)
 #pragma unroll

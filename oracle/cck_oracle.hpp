@@ -482,7 +482,7 @@ inline void sym_operator_sqrt(const double* Ain, int n, double* out) {
             }
     }
     double sq[4];
-    for (int k = 0; k < n; ++k) sq[k] = std::sqrt(A[k * n + k] > 0.0 ? A[k * n + k] : 0.0);
+    for (int k = 0; k < n; ++k) sq[k] = std::sqrt(A[k * n + k]);   // m_eivalues.cwiseSqrt(): NaN for a negative eigenvalue, exactly as Eigen (pinned by tests/test_ref_pin2.py)
     for (int i = 0; i < n; ++i)
         for (int j = 0; j < n; ++j) {
             double acc = 0;

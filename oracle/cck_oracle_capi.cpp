@@ -146,6 +146,8 @@ void orc_svc_info(void* s, double* out) {
     const Svc& v = ((SvcH*)s)->svc;
     out[0] = v.erf_inv_result; out[1] = v.p_collision; out[2] = v.sc; out[3] = v.max_rad;
 }
+// test hook: the robot bounding radius the chi-squared checker adds to lambda_max * sc (band tests shift it by +-1e-6)
+void orc_svc_set_max_rad(void* s, double r) { ((SvcH*)s)->svc.max_rad = r; }
 // A[M][4][2], B[M][4], centres[M][2], rects[M][4] = (xlo, ylo, xhi, yhi) of the inflated ring
 void orc_svc_tables(void* s, double* A, double* B, double* centres, double* rects) {
     const Svc& v = ((SvcH*)s)->svc;

@@ -64,6 +64,7 @@ def lib():
         L.orc_svc_info.argtypes = [vp, dp]
         L.orc_svc_tables.argtypes = [vp, dp, dp, dp, dp]
         L.orc_svc_override_tables.argtypes = [vp, C.c_int, dp, dp, C.c_double]
+        L.orc_svc_set_max_rad.argtypes = [vp, C.c_double]
         L.orc_propagate.argtypes = [C.c_int, C.c_double, C.c_double, C.c_long, dp, dp, dp]
         L.orc_is_valid.argtypes = [vp, C.c_int, C.c_long, dp, u8p, u64p]
         L.orc_rollout.argtypes = [vp, C.c_int, C.c_double, C.c_long, dp, dp, ip, dp, ip, dp, C.c_int, u64p, C.c_int]
@@ -212,6 +213,11 @@ class Svc:
         self.centres, self.rects = np.zeros((M, 2)), np.zeros((M, 4))
         self.erf_inv_result = float(erf_inv_result)
         lib().orc_svc_override_tables(self.h, M, _dp(self.A), _dp(self.B), self.erf_inv_result)
+
+    def set_max_rad(self, r):
+        """Test hook: the robot bounding radius of the chi-squared checker (band tests shift it by +-1e-6)."""
+        self.max_rad = float(r)
+        lib().orc_svc_set_max_rad(self.h, self.max_rad)
 
     def is_valid(self, beliefs):
         b = _f64(beliefs)

@@ -5,8 +5,8 @@
 //   src/StateValidityCheckers/PCCBlackmoreSVC.cpp                 (Minkowski sums, half-planes, erf_inv constant, isValid)
 // against the stand-in headers of oracle/shim/ (Eigen / Boost / OMPL subsets, see the notes there: every matrix
 // product on this path has inner dimension 2, so the shim's evaluation order cannot differ from Eigen's).
-// RealVectorBeliefSpace.cpp is NOT compiled (its distance() needs Eigen's eigen-solver); its five one-line
-// members are defined below following src/Spaces/RealVectorBeliefSpace.cpp:7-14,64-76.
+// src/Spaces/RealVectorBeliefSpace.cpp is compiled in place too (round 2; the entry points over it, the unicycle
+// propagator, the goal and the chi-squared checkers are in ref_capi2.cpp).
 // propagateWhileValid is OMPL's (SpaceInformation.cpp), restated here around the reference's two virtuals.
 #include <algorithm>
 #include <any>
@@ -31,27 +31,6 @@
 #include "StateValidityCheckers/AdaptiveRiskBlackmoreSVC.h"
 #undef private
 #include "StatePropogators/UncertainLinearSP.h"
-
-// ---- RealVectorBeliefSpace members (src/Spaces/RealVectorBeliefSpace.cpp:7-14, 64-76) ----
-ompl::base::State* RealVectorBeliefSpace::allocState(void) const {
-    StateType* rstate = new StateType();
-    rstate->values = new double[dimension_];
-    rstate->sigma_ = 0.01 * Eigen::MatrixXd::Identity(dimension_, dimension_);
-    rstate->lambda_ = 0.01 * Eigen::MatrixXd::Identity(dimension_, dimension_);
-    return rstate;
-}
-void RealVectorBeliefSpace::copyState(State* destination, const State* source) const {
-    RealVectorStateSpace::copyState(destination, source);
-    destination->as<StateType>()->sigma_ = source->as<StateType>()->sigma_;
-    destination->as<StateType>()->lambda_ = source->as<StateType>()->lambda_;
-}
-void RealVectorBeliefSpace::freeState(State* state) const {
-    StateType* s = state->as<StateType>();
-    delete[] s->values;
-    delete s;
-}
-double RealVectorBeliefSpace::distance(const State*, const State*) const { return 0.0; }   // not on the pinned path
-void RealVectorBeliefSpace::printState(const State*, std::ostream&) const {}
 
 namespace {
 struct RefWorld { InstancePtr inst; };

@@ -51,6 +51,7 @@ public:
     virtual double distance(const State*, const State*) const = 0;
     virtual void printState(const State*, std::ostream&) const {}
     virtual bool satisfiesBounds(const State*) const = 0;
+    virtual unsigned getDimension() const = 0;
 protected:
     int type_ = STATE_SPACE_UNKNOWN;
     std::string name_ = "Space";
@@ -64,7 +65,7 @@ public:
         double* values = nullptr;
     };
     explicit RealVectorStateSpace(unsigned dim = 0) : dimension_(dim), bounds_(dim) {}
-    unsigned getDimension() const { return dimension_; }
+    unsigned getDimension() const override { return dimension_; }
     void setBounds(const RealVectorBounds& b) { bounds_ = b; }
     const RealVectorBounds& getBounds() const { return bounds_; }
     State* allocState() const override { auto* s = new StateType(); s->values = new double[dimension_]; return s; }
@@ -104,6 +105,17 @@ protected:
     StateSpacePtr space_;
 };
 using SpaceInformationPtr = std::shared_ptr<SpaceInformation>;
+
+// base::Goal: what ChanceConstrainedGoal overrides (ompl/base/Goal.h)
+class Goal {
+public:
+    explicit Goal(const SpaceInformationPtr& si) : si_(si) {}
+    virtual ~Goal() = default;
+    virtual bool isSatisfied(const State*) const = 0;
+    virtual bool isSatisfied(const State* st, double* distance) const { if (distance) *distance = std::numeric_limits<double>::max(); return isSatisfied(st); }
+protected:
+    SpaceInformationPtr si_;
+};
 
 class StateValidityChecker {
 public:

@@ -8,6 +8,7 @@ import numpy as np
 import pytest
 
 from conftest import GOLDEN
+from helpers import assert_rollout_mismatches_in_band
 
 pytestmark = pytest.mark.gpu
 
@@ -188,9 +189,9 @@ def test_expand_batch_vs_oracle(K, O, W, ctx, model):
     out, valid, cost, gd, fl = ctx.expand_batch(bel, ctrl, steps, pstep, pcost, goal)
     aos_b, aos_c = K.soa_to_aos(bel), K.soa_to_aos(ctrl)
     ref_out, ref_valid, _, traj = svc.rollout(aos_b, aos_c, steps, traj_stride=10)
-    mism = valid != ref_valid
-    assert mism.sum() <= (0 if dim == 2 else 3)
-    good = ~mism
+    if dim == 2:
+        assert np.array_equal(valid, ref_valid)
+    good = assert_rollout_mismatches_in_band(O, svc, aos_b, aos_c, valid, ref_valid)
     if dim == 2:
         assert np.array_equal(K.soa_to_aos(out), ref_out)
     else:
@@ -199,7 +200,15 @@ def test_expand_batch_vs_oracle(K, O, W, ctx, model):
     assert np.allclose(cost[good], ref_cost[good], rtol=1e-12)
     g_ok, g_d = O.goal(ref_out, dim, goal[0], goal[1])
     assert np.allclose(gd[good], g_d[good], rtol=1e-12, atol=1e-12)
-    assert (((fl & K.FLAG_GOAL) != 0)[good] == g_ok[good]).sum() >= good.sum() - 2 and g_ok.any()
+    # goal flags: exact, except where the goal test itself is inside the band (the goal decagon's radius moved by +-1e-6
+    # flips the oracle's verdict) - the unicycle's final mean carries the device sincos ulps
+    g_bad = (((fl & K.FLAG_GOAL) != 0) != g_ok) & good
+    if g_bad.any():
+        flips = np.zeros(n, dtype=bool)
+        for thr in (2.0 - 1e-6, 2.0 + 1e-6):
+            flips |= O.goal(ref_out, dim, goal[0], goal[1], threshold=thr)[0] != g_ok
+        assert not (g_bad & ~flips).any()
+    assert g_ok.any() and (dim == 4 or not g_bad.any())
     assert np.array_equal(((fl & K.FLAG_FULL) != 0)[good], (ref_valid == steps)[good])
     # constraints on the new segment: states at absolute steps pstep+1 .. pstep+valid
     ref_c = np.ones(n, bool)

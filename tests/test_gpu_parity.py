@@ -7,7 +7,7 @@ checkers (device erfinv vs Boost-style erf_inv) exact outside the band.
 import numpy as np
 import pytest
 
-from helpers import band_mask_halfplane, install_from_oracle_svc, oracle_synth
+from helpers import assert_rollout_mismatches_in_band, band_mask_halfplane, install_from_oracle_svc, oracle_synth
 
 pytestmark = pytest.mark.gpu
 
@@ -140,12 +140,12 @@ def test_rollout_linear_other_checkers(K, O, W, ctx, kind):
     steps = np.full(n, 12, dtype=np.int32)
     out, valid = ctx.propagate_while_valid(bel, ctrl, steps)
     ref_out, ref_valid, _ = svc.rollout(K.soa_to_aos(bel), K.soa_to_aos(ctrl), steps, nthreads=8)
-    mism = np.nonzero(valid != ref_valid)[0]
     if kind == 2:
-        assert len(mism) == 0 and np.array_equal(K.soa_to_aos(out), ref_out)
+        assert np.array_equal(valid, ref_valid) and np.array_equal(K.soa_to_aos(out), ref_out)
     else:
-        assert len(mism) <= 3   # adaptive: device erfinv, exact outside the band
-        ok = np.ones(n, bool); ok[mism] = False
+        # adaptive: device erfinv differs from the oracle's erf_inv in the last ulps - a verdict may differ only where the
+        # deciding state is inside the +-1e-6 band, which is asserted state by state
+        ok = assert_rollout_mismatches_in_band(O, svc, K.soa_to_aos(bel), K.soa_to_aos(ctrl), valid, ref_valid)
         assert np.array_equal(K.soa_to_aos(out)[ok], ref_out[ok])
 
 
@@ -160,9 +160,8 @@ def test_rollout_unicycle(K, O, W, ctx, kind):
     steps = rng.integers(1, 11, size=n).astype(np.int32)
     out, valid = ctx.propagate_while_valid(bel, ctrl, steps)
     ref_out, ref_valid, _ = svc.rollout(K.soa_to_aos(bel), K.soa_to_aos(ctrl), steps, nthreads=8)
-    mism = np.nonzero(valid != ref_valid)[0]
-    assert len(mism) <= max(2, n // 2000), f"{len(mism)} verdict mismatches"
-    ok = np.ones(n, bool); ok[mism] = False
+    # device sincos differs from libm in the last ulps: verdicts exact outside the +-1e-6 band, asserted state by state
+    ok = assert_rollout_mismatches_in_band(O, svc, K.soa_to_aos(bel), K.soa_to_aos(ctrl), valid, ref_valid)
     assert np.allclose(K.soa_to_aos(out)[ok], ref_out[ok], rtol=RTOL, atol=1e-12)
     assert 0.02 < (ref_valid == steps).mean() < 0.98
 

@@ -17,6 +17,7 @@ import numpy as np
 import pytest
 
 from conftest import GOLDEN
+from helpers import svc_band
 
 FILES = sorted(glob.glob(os.path.join(GOLDEN, "ref_*.npz")))
 IDS = [os.path.basename(f)[:-4] for f in FILES]
@@ -175,9 +176,39 @@ def test_oracle_matches_live_reference_build(O):
     assert checked >= 8
 
 
+def _adaptive_pvc_plan_in_band(O, K, g, trajs, kind, band=1e-6):
+    """True if SOME adaptive pair test of the plan (any step, any pair, either eta map: all active robots or the pair alone,
+    AdaptiveRiskBlackmorePVC.cpp:179-206 / :92-101) has a half-plane inequality within `band` of equality."""
+    k = len(trajs)
+    rad = K.rect_robot_bounding_radius()
+    A, B = K.build_pair_halfplanes(rad, rad, kind == K.PVC_ADAPTIVE_BOUNDINGBOX)
+    p_coll = 1 - float(g["p_safe_agents"])
+    T = max(len(t) for t in trajs)
+    for t in range(T + 1):
+        st = [tr[min(t, len(tr) - 1)] for tr in trajs]
+        mu = np.array([s_[:2] for s_ in st]); cov = np.array([s_[2:6] + s_[6:10] for s_ in st])
+        for a in range(k):
+            for b in range(k):
+                if a == b:
+                    continue
+                d = np.sqrt(((mu[a] - mu) ** 2).sum(axis=1))
+                for others in ([j for j in range(k) if j != a], [b]):
+                    alpha = 1 / sum(1 / d[j] for j in others)
+                    c = O.erf_inv(1 - 2 * ((alpha / d[b]) * p_coll))
+                    S = cov[a] + cov[b]
+                    dm = mu[a] - mu[b]
+                    for i in range(4):
+                        a0, a1 = A[i]
+                        q = a0 * (a0 * S[0] + a1 * S[2]) + a1 * (a0 * S[1] + a1 * S[3])
+                        if abs(a0 * dm[0] + a1 * dm[1] - B[i] - np.sqrt(2) * np.sqrt(max(q, 0)) * c) < band or not np.isfinite(c):
+                            return True
+    return False
+
+
 @pytest.mark.gpu
-def test_cuda_adaptive_checkers_match_reference_vectors(K, ctx):
-    """Device erfinv vs the reference build's erf_inv: verdicts equal outside the +-1e-6 band (<= 1 % mismatches)."""
+def test_cuda_adaptive_checkers_match_reference_vectors(K, O, ctx):
+    """Device erfinv vs the reference build's erf_inv: verdicts equal outside the +-1e-6 band - every mismatch is shown
+    to sit inside it (helpers.svc_band on the oracle's tables, which test_oracle_* prove equal to the reference's)."""
     g = np.load(os.path.join(GOLDEN, "ref_config2_random32_10_k4.npz"))
     k, M = int(g["k"]), int(g["n_obstacles"])
     ctx.set_model(K.MODEL_LINEAR2D)
@@ -188,18 +219,20 @@ def test_cuda_adaptive_checkers_match_reference_vectors(K, ctx):
                       erf_inv_result=0.0, p_collision=p_coll)
     ref = g["adaptive_is_valid"]
     got = ctx.is_valid(K.aos_to_soa(g["beliefs"][:len(ref)]))
-    assert (got != ref).sum() <= max(2, len(ref) // 100)
+    bad = np.nonzero(got != ref)[0]
+    if len(bad):
+        osvc = O.Svc(O.World.synthetic(g["centres"], float(g["x_max"]), float(g["y_max"]), k, float(g["p_safe"])), O.SVC_ADAPTIVE, 2)
+        assert svc_band(O, osvc, g["beliefs"][bad]).all(), bad
     plans = _plans(g)
     for kind, tag in ((K.PVC_ADAPTIVE_BLACKMORE, "amink"), (K.PVC_ADAPTIVE_BOUNDINGBOX, "abbox")):
         K.install_pvc(ctx, kind, 2, [rad] * k, float(g["p_safe_agents"]))
         ref_c = g[f"{tag}_conflicts"]
-        bad = 0
         for i in range(25):
             exp = ref_c[ref_c[:, 0] == i]
             run = ctx.validate_plan([K.aos_to_soa(t) for t in plans[i]])
             want = None if len(exp) == 0 else (int(exp[0, 1]), int(exp[0, 2]), int(exp[0, 3]), len(exp))
-            bad += (run != want)
-        assert bad <= 1, (tag, bad)
+            if run != want:      # allowed only if some pair test of this plan is inside the band
+                assert _adaptive_pvc_plan_in_band(O, K, g, plans[i], kind), (tag, i, run, want)
 
 
 @pytest.mark.gpu
