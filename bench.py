@@ -6,12 +6,16 @@ beliefs (BASELINE.json config 5: B beliefs x T=50 steps x M=256 obstacles, linea
 PCCBlackmore checker, seed 20240501).  Units = executed belief-steps (one propagate + one
 validity check against all M obstacles).
 
-  value     device-resident inputs, CUDA-event timed, K launches, max over ranks
+  value     device-resident inputs, CUDA-event timed, K launches, max over ranks (headline variant: all_survive)
   e2e       the same metric through the host-pointer C-ABI call (pinned host buffers,
-            H2D + kernel + D2H inside the timed region)
-  roofline  F_alg (oracle-counted algorithmic flops) / kernel time vs the FP64
-            pipe peak measured live; plus the kernel's algorithmic HBM bytes vs MEASURED_PEAKS
-  cpu_baseline  the CPU oracle ("port": the reference cannot be built here) on a bounded sample
+            H2D + kernel + D2H inside the timed region); pcie.duplex_copy_* is the same traffic without a kernel
+  roofline  FP64-pipe instructions executed / kernel time vs the FP64 issue rate measured live (and vs the DFMA flop
+            peak); f_alg_frac = SURVEY 8(d)'s oracle-counted algorithmic flops; roofline_hbm = algorithmic bytes
+  variants  all_survive / dense_survive / realistic on the same B: value, FP64-issue fraction, F_alg fraction, traffic
+  unicycle, m0_trajectory, expand_sharded   secondary legs (config-3 propagator, HBM-bound regime, sharded expansion
+            with the winner record gathered over NCCL)
+  parity    the CUDA path re-run on the cpu_baseline sample's inputs and compared with the oracle's outputs
+  cpu_baseline  the CPU oracle ("port": the reference's own build needs OMPL/Eigen/Boost) on a bounded sample, N = 1 only
 
 `--impl reference` times the oracle alone on the host cores (rank 0 only).
 """
@@ -42,11 +46,13 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--log2-beliefs", type=int, default=24, help="beliefs per GPU (weak scaling)")
-    ap.add_argument("--variant", default="all_survive", choices=["all_survive", "realistic"])
+    ap.add_argument("--variant", default="all_survive", choices=["all_survive", "dense_survive", "realistic"],
+                    help="which variant of the sweep is the headline `value` (all three are measured and reported under `variants`)")
     ap.add_argument("--model", default="linear", choices=["linear", "unicycle"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-realistic", action="store_true", help="skip the secondary realistic-variant measurement")
+    ap.add_argument("--no-secondary", "--no-realistic", dest="no_secondary", action="store_true",
+                    help="headline variant only: skip the other variants, the unicycle, M=0 and sharded-expansion legs (profiling runs)")
     ap.add_argument("--no-solve", action="store_true", help="skip the short live CCK-CBS solve-time sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs under ncu)")
     return ap.parse_args()
@@ -68,13 +74,15 @@ def oracle_setup(args):
     return O, W, O.Svc(world, O.SVC_BLACKMORE, dim)
 
 
-def oracle_time(args, O, W, svc, n, threads, offset=1000):
+def oracle_time(args, O, W, svc, n, threads, offset=1000, keep=None):
     bel, ctrl = W.synthetic_beliefs(n, args.model, variant=args.variant, offset=offset)
     aos_b, aos_c = np.ascontiguousarray(bel.T), np.ascontiguousarray(ctrl.T)
     steps = np.full(n, T_STEPS, dtype=np.int32)
     t0 = time.perf_counter()
-    _, valid, cnt = svc.rollout(aos_b, aos_c, steps, nthreads=threads)
+    out, valid, cnt = svc.rollout(aos_b, aos_c, steps, nthreads=threads)
     dt = time.perf_counter() - t0
+    if keep is not None:      # the oracle's outputs on this sample, for the parity check of the bench line
+        keep.extend([aos_b, aos_c, out, valid])
     return dt, int(cnt[0]), int(cnt[1])
 
 
@@ -112,15 +120,21 @@ def reference_sources_timing(args, W):
         return {"error": str(e)[:200]}
 
 
-def cpu_baseline(args):
+def cpu_baseline(args, keep=False):
     """Oracle timed on all host cores on a bounded sample of the same workload."""
     O, W, svc = oracle_setup(args)
     cores = os.cpu_count() or 1
     dt, nsteps, _ = oracle_time(args, O, W, svc, 4096, cores)
     rate = nsteps / dt
     n = int(min(1 << 20, max(8192, rate * args.cpu_seconds / T_STEPS)))
-    dt, nsteps, nhp = oracle_time(args, O, W, svc, n, cores)
+    sample = [] if keep else None
+    dt, nsteps, nhp = oracle_time(args, O, W, svc, n, cores, keep=sample)
     dt1, nsteps1, _ = oracle_time(args, O, W, svc, max(2048, n // (4 * cores)), 1)
+    res = _cpu_baseline_record(args, W, cores, n, nsteps, dt, nsteps1, dt1, nhp)
+    return (res, sample) if keep else res
+
+
+def _cpu_baseline_record(args, W, cores, n, nsteps, dt, nsteps1, dt1, nhp):
     return {"value": nsteps / dt, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"{n} beliefs x {T_STEPS} steps x {M_OBS} obstacles ({nsteps} belief-steps, {dt:.1f} s, std::thread over beliefs)",
             "single_thread_value": nsteps1 / dt1, "halfplane_tests_per_belief_step": nhp / nsteps,
@@ -235,17 +249,82 @@ class Clocks:
 
 
 # ----------------------------------------------------------------------------- GPU leg
+# half-plane tests per belief-step under the reference's early-exit order (PCCBlackmoreSVC.cpp:54-58, 66-72), counted by the
+# oracle on the seeded workload (bench runs at N = 1 re-count them live; these are the values those runs print)
+HPS_RECORDED = {"linear/all_survive": 533.99, "linear/dense_survive": 475.6, "linear/realistic": 400.0,
+                "unicycle/all_survive": 533.99, "unicycle/realistic": 400.0}
+# FP64-pipe instructions per belief-step on the hot path, from the ncu source view (profiles/): linear 70 (lin_step_diag) + 5
+# (Sigma+Lambda, |P01|+|P10|); unicycle 316 DMUL + 251 DADD + 32 DFMA + 10 DSETP
+FP64_INST = {"linear": 75.0, "linear_dense": 95.0, "unicycle": 609.0}
+
+
+def pin_to_gpu_cpus(index):
+    """Bind this rank (and the pinned buffers it first-touches) to the CPUs NVML reports as local to its GPU."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[index]) if vis and all(t.strip().isdigit() for t in vis.split(",")) else index
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = [w * 64 + b for w, m in enumerate(words) for b in range(64) if (int(m) >> b) & 1 and w * 64 + b < ncpu]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return {"cpus": f"{cpus[0]}-{cpus[-1]}", "n": len(cpus)}
+    except Exception as e:  # noqa: BLE001
+        return {"error": str(e)[:100]}
+    return None
+
+
+class DeviceSweep:
+    """One (model, variant) of the config-5 sweep resident in HBM: own context, inputs, outputs."""
+
+    def __init__(self, K, W, torch, dev, local, rank, model, variant, B, keep_host=False):
+        self.K, self.torch, self.dev, self.B, self.model, self.variant = K, torch, dev, B, model, variant
+        self.dim = 2 if model == "linear" else 4
+        self.Wd = K.width(self.dim)
+        self.ctx = K.Context(local)
+        W.install_synthetic(self.ctx, model, M_OBS, variant=variant)
+        bel_np, ctrl_np = W.synthetic_beliefs(B, model, variant=variant, offset=rank)
+        self.h_bel = self.h_ctrl = None
+        if keep_host:
+            self.h_bel = torch.from_numpy(bel_np).pin_memory()
+            self.h_ctrl = torch.from_numpy(ctrl_np).pin_memory()
+            self.d_bel, self.d_ctrl = self.h_bel.to(dev), self.h_ctrl.to(dev)
+        else:
+            self.d_bel, self.d_ctrl = torch.from_numpy(bel_np).to(dev), torch.from_numpy(ctrl_np).to(dev)
+        del bel_np, ctrl_np
+        self.d_steps = torch.full((B,), T_STEPS, dtype=torch.int32, device=dev)
+        self.d_out = torch.empty((self.Wd, B), dtype=torch.float64, device=dev)
+        self.d_valid = torch.empty((B,), dtype=torch.int32, device=dev)
+        self.d_sum = torch.zeros(3, dtype=torch.int64, device=dev)
+
+    def launch(self, stream):
+        self.ctx.propagate_while_valid_dev(stream, self.B, self.d_bel, self.B, self.d_ctrl, self.B, self.d_steps, self.d_out, self.B, self.d_valid)
+
+    def summary(self, stream):
+        self.d_sum.zero_()
+        self.ctx.rollout_summary_dev(stream, self.B, self.d_steps, self.d_valid, self.d_sum)
+
+    def close(self):
+        self.ctx.close()
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
     import cck_b200 as K
     from cck_b200 import workloads as W
+    from cck_b200 import sharding
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
+    all_cpus = os.sched_getaffinity(0)
+    affinity = pin_to_gpu_cpus(local)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -255,23 +334,8 @@ def run_ours(args):
     B = 1 << args.log2_beliefs
     dim = 2 if args.model == "linear" else 4
     Wd = K.width(dim)
-    ctx = K.Context(local)
-    W.install_synthetic(ctx, args.model, M_OBS, variant=args.variant)
-
-    # host inputs (pinned) — each rank owns a disjoint shard (weak scaling, no data-path collective)
-    bel_np, ctrl_np = W.synthetic_beliefs(B, args.model, variant=args.variant, offset=rank)
-    h_bel = torch.from_numpy(bel_np).pin_memory()
-    h_ctrl = torch.from_numpy(ctrl_np).pin_memory()
-    h_steps = torch.full((B,), T_STEPS, dtype=torch.int32).pin_memory()
-    h_out = torch.empty((Wd, B), dtype=torch.float64).pin_memory()
-    h_valid = torch.empty((B,), dtype=torch.int32).pin_memory()
-    del bel_np, ctrl_np
-
-    d_bel, d_ctrl, d_steps = h_bel.to(dev), h_ctrl.to(dev), h_steps.to(dev)
-    d_out = torch.empty((Wd, B), dtype=torch.float64, device=dev)
-    d_valid = torch.empty((B,), dtype=torch.int32, device=dev)
-    d_sum = torch.zeros(3, dtype=torch.int64, device=dev)
-    from cck_b200 import sharding
+    warm = max(3, args.warmup)
+    launches = 0
 
     # a non-default torch stream: its handle is non-NULL (NULL would select the context's own stream)
     # and torch.cuda.Event records on it, so events bracket exactly the kernels launched below
@@ -280,23 +344,42 @@ def run_ours(args):
     stream = tstream.cuda_stream
     assert stream != 0
 
-    def step():
-        ctx.propagate_while_valid_dev(stream, B, d_bel, B, d_ctrl, B, d_steps, d_out, B, d_valid)
-        ctx.rollout_summary_dev(stream, B, d_steps, d_valid, d_sum)
-        if world > 1:   # only the per-rank result record crosses NVLink
-            sharding.gather_summary(d_sum)
-
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(3, args.warmup)):
+    def allmax(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    def allsum(x):
+        t = torch.tensor([x], dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return int(t[0])
+
+    # ---- headline: device-resident inputs (3.1 GB of operands per launch >> 126 MB L2) ----
+    head = DeviceSweep(K, W, torch, dev, local, rank, args.model, args.variant, B, keep_host=not args.no_e2e)
+    ctx = head.ctx
+    d_sum = torch.zeros(3, dtype=torch.int64, device=dev)
+
+    def step():
+        head.launch(stream)
+        ctx.rollout_summary_dev(stream, B, head.d_steps, head.d_valid, d_sum)
+        if world > 1:   # only the per-rank result record crosses NVLink
+            sharding.gather_summary(d_sum)
+
+    for _ in range(warm):
+        d_sum.zero_()
         step()
     barrier()
     exec_steps = int(d_sum[1].item())
+    if args.variant != "realistic":
+        assert exec_steps == B * T_STEPS, f"{args.variant}: {exec_steps} executed belief-steps, expected {B * T_STEPS} (every belief must survive)"
 
-    # ---- timed region: device-resident inputs (1.7 GB/step of operands >> 126 MB L2) ----
     barrier()
     clocks = Clocks(local)
     l0 = ctx.launch_count
@@ -306,33 +389,31 @@ def run_ours(args):
     ev[0].record()
     for i in range(args.steps):
         kev[i][0].record()
-        ctx.propagate_while_valid_dev(stream, B, d_bel, B, d_ctrl, B, d_steps, d_out, B, d_valid)
+        head.launch(stream)
         kev[i][1].record()
-        ctx.rollout_summary_dev(stream, B, d_steps, d_valid, d_sum)
+        ctx.rollout_summary_dev(stream, B, head.d_steps, head.d_valid, d_sum)
         if world > 1:
             sharding.gather_summary(d_sum)
         ev[i + 1].record()
     barrier()
-    launches = ctx.launch_count - l0
-    total_ms = ev[0].elapsed_time(ev[-1])
-    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
+    launches += ctx.launch_count - l0
+    total_ms = allmax(ev[0].elapsed_time(ev[-1]))
+    kern_ms = allmax(float(np.mean([a.elapsed_time(b) for a, b in kev])))
     clk = clocks.stop()
-    t = torch.tensor([total_ms, kern_ms], dtype=torch.float64, device=dev)
-    units = torch.tensor([exec_steps], dtype=torch.int64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(units, op=dist.ReduceOp.SUM)
-    total_ms, kern_ms = float(t[0]), float(t[1])
-    units_all = int(units[0])
+    units_all = allsum(exec_steps)
     value = units_all * args.steps / (total_ms * 1e-3)
 
     # ---- e2e: host-pointer C-ABI call, pinned host buffers, H2D + kernel + D2H timed ----
-    e2e = None
+    e2e = pcie = None
     if not args.no_e2e:
+        h_steps = torch.full((B,), T_STEPS, dtype=torch.int32).pin_memory()
+        h_out = torch.empty((Wd, B), dtype=torch.float64).pin_memory()
+        h_valid = torch.empty((B,), dtype=torch.int32).pin_memory()
         n_e2e = max(1, min(args.steps, 3))
         L = ctx.L
+
         def e2e_call():
-            ctx._ck(L.cck_propagate_while_valid(ctx.h, B, h_bel.data_ptr(), B, h_ctrl.data_ptr(), B, h_steps.data_ptr(),
+            ctx._ck(L.cck_propagate_while_valid(ctx.h, B, head.h_bel.data_ptr(), B, head.h_ctrl.data_ptr(), B, h_steps.data_ptr(),
                                                 h_out.data_ptr(), B, h_valid.data_ptr(), None, 0, 0))
         e2e_call()
         barrier()
@@ -341,191 +422,335 @@ def run_ours(args):
         for _ in range(n_e2e):
             e2e_call()
         torch.cuda.synchronize()
-        te = time.perf_counter() - t0
+        te = allmax(time.perf_counter() - t0)
         launches += ctx.launch_count - l1
-        tt = torch.tensor([te], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e_units = int(np.minimum(h_valid.numpy().astype(np.int64) + 1, T_STEPS).sum())
-        eu = torch.tensor([e2e_units], dtype=torch.int64, device=dev)
-        if world > 1:
-            dist.all_reduce(eu, op=dist.ReduceOp.SUM)
-        e2e = {"value": int(eu[0]) * n_e2e / float(tt[0]), "unit": UNIT,
-               "h2d_bytes_per_step": int(B * (Wd * 8 + dim * 8 + 4)), "d2h_bytes_per_step": int(B * (Wd * 8 + 4)),
-               "calls": n_e2e, "timing": "host wall clock around the blocking C-ABI call, device synchronised both sides"}
-        assert torch.equal(h_valid.to(dev), d_valid), "e2e and device-resident paths disagree"
+        e2e_units = allsum(int(np.minimum(h_valid.numpy().astype(np.int64) + 1, T_STEPS).sum()))
+        h2d, d2h = int(B * (Wd * 8 + dim * 8 + 4)), int(B * (Wd * 8 + 4))
+        e2e = {"value": e2e_units * n_e2e / te, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "calls": n_e2e, "ms_per_call": 1e3 * te / n_e2e,
+               "host_link_gbs_aggregate": world * (h2d + d2h) * n_e2e / te / 1e9,
+               "timing": "host wall clock around the blocking C-ABI call, device synchronised both sides"}
+        assert torch.equal(h_valid.to(dev), head.d_valid), "e2e and device-resident paths disagree"
+        # the ceiling of the same transfers without any kernel: every rank copies its buffers H2D and D2H CONCURRENTLY (two
+        # streams), all ranks at once - what this host's memory system and PCIe root complexes give N GPUs at a time
+        s_up, s_dn = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(2):
+            with torch.cuda.stream(s_up):
+                head.d_bel.copy_(head.h_bel, non_blocking=True)
+                head.d_ctrl.copy_(head.h_ctrl, non_blocking=True)
+            with torch.cuda.stream(s_dn):
+                h_out.copy_(head.d_out, non_blocking=True)
+        torch.cuda.synchronize()
+        tc = allmax(time.perf_counter() - t0)
+        moved = 2 * (head.h_bel.numel() + head.h_ctrl.numel() + h_out.numel()) * 8
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        barrier()
+        e0.record(); head.d_bel.copy_(head.h_bel, non_blocking=True); e1.record(); h_out.copy_(head.d_out, non_blocking=True); e2.record()
+        torch.cuda.synchronize()
+        pcie = {"h2d_gbs": head.h_bel.numel() * 8 / (e0.elapsed_time(e1) * 1e-3) / 1e9, "d2h_gbs": h_out.numel() * 8 / (e1.elapsed_time(e2) * 1e-3) / 1e9,
+                "duplex_copy_gbs_aggregate": world * moved / tc / 1e9,
+                "e2e_bound_ms_per_call": 1e3 * (h2d + d2h) / (moved / tc),
+                "note": "duplex_copy: all ranks copy their e2e buffers H2D and D2H at the same time, no kernel - the host-side ceiling of e2e at this N"}
+        del h_out
 
-    # ---- secondary: the realistic variant (obstacle field inside the world, early exits) on the same B ----
-    realistic = None
-    if args.variant == "all_survive" and not args.no_realistic:
-        ctx2 = K.Context(local)
-        W.install_synthetic(ctx2, args.model, M_OBS, variant="realistic")
-        rb, rc = W.synthetic_beliefs(B, args.model, variant="realistic", offset=rank)
-        d_rb, d_rc = torch.from_numpy(rb).to(dev), torch.from_numpy(rc).to(dev)
-        del rb, rc
-        d_rsum = torch.zeros(3, dtype=torch.int64, device=dev)
-        for _ in range(3):
-            ctx2.propagate_while_valid_dev(stream, B, d_rb, B, d_rc, B, d_steps, d_out, B, d_valid)
-        ctx2.rollout_summary_dev(stream, B, d_steps, d_valid, d_rsum)
-        barrier()
-        r_units = int(d_rsum[1].item())
-        hist = torch.bincount(d_valid.to(torch.int64), minlength=T_STEPS + 1).tolist()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(args.steps):
-            ctx2.propagate_while_valid_dev(stream, B, d_rb, B, d_rc, B, d_steps, d_out, B, d_valid)
-        e1.record()
-        barrier()
-        launches += ctx2.launch_count - 4
-        rt = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-        ru = torch.tensor([r_units], dtype=torch.int64, device=dev)
-        if world > 1:
-            dist.all_reduce(rt, op=dist.ReduceOp.MAX)
-            dist.all_reduce(ru, op=dist.ReduceOp.SUM)
-        realistic = {"value": int(ru[0]) * args.steps / (float(rt[0]) * 1e-3), "unit": UNIT, "belief_steps_per_launch": r_units,
-                     "kernel_ms": float(rt[0]) / args.steps,
-                     "survival_histogram_valid_steps": {"0": hist[0], "1-9": sum(hist[1:10]), "10-24": sum(hist[10:25]),
-                                                        "25-49": sum(hist[25:50]), "50": hist[50]},
-                     "note": "same B/T/M with the obstacle field inside the world (SURVEY 8d variant i): ~2/3 of the rollouts end early"}
-        del d_rb, d_rc
-        ctx2.close()
+    # ---- the other variants of the sweep (SURVEY 8d (i)/(ii) + dense_survive) on the same B, same model ----
+    variants = {}
+    names = [v for v in W.VARIANTS if not (args.model != "linear" and v == "dense_survive")]
+    per_variant_exec = {args.variant: exec_steps}
+    per_variant_ms = {args.variant: kern_ms}
+    hists = {}
+    if not args.no_secondary:
+        for v in names:
+            if v == args.variant:
+                continue
+            sw = DeviceSweep(K, W, torch, dev, local, rank, args.model, v, B)
+            for _ in range(warm):
+                sw.launch(stream)
+            sw.summary(stream)
+            barrier()
+            ex = int(sw.d_sum[1].item())
+            if v != "realistic":
+                assert ex == B * T_STEPS, f"{v}: {ex} executed belief-steps, expected {B * T_STEPS}"
+            else:
+                hist = torch.bincount(sw.d_valid.to(torch.int64), minlength=T_STEPS + 1).tolist()
+                hists[v] = {"0": hist[0], "1-9": sum(hist[1:10]), "10-24": sum(hist[10:25]), "25-49": sum(hist[25:50]), "50": hist[50]}
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(args.steps):
+                sw.launch(stream)
+            e1.record()
+            barrier()
+            launches += warm + 1 + args.steps
+            per_variant_ms[v] = allmax(e0.elapsed_time(e1)) / args.steps
+            per_variant_exec[v] = ex
+            sw.close()
+            del sw
 
     # ---- secondary: M = 0 trajectory mode (config-1 shape: bounds-only checker, every intermediate belief written
     #      for the plan validator) -- the HBM-bound regime of the path ----
     m0 = None
-    if args.variant == "all_survive" and args.model == "linear" and not args.no_realistic:
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    if args.model == "linear" and not args.no_secondary:
         Bm = min(B, 1 << 22)
         ctx3 = K.Context(local)
         W.install_synthetic(ctx3, "linear", 0, variant="all_survive")
         d_traj = torch.empty((T_STEPS * Wd, Bm), dtype=torch.float64, device=dev)
-        for _ in range(3):
-            ctx3.propagate_while_valid_dev(stream, Bm, d_bel, B, d_ctrl, B, d_steps, d_out, B, d_valid, traj=d_traj, traj_ld=Bm, traj_T=T_STEPS)
+        mb, mc = W.synthetic_beliefs(Bm, "linear", variant="all_survive", offset=rank)
+        d_mb, d_mc = torch.from_numpy(mb).to(dev), torch.from_numpy(mc).to(dev)
+        del mb, mc
+        for _ in range(warm):
+            ctx3.propagate_while_valid_dev(stream, Bm, d_mb, Bm, d_mc, Bm, head.d_steps, head.d_out, B, head.d_valid, traj=d_traj, traj_ld=Bm, traj_T=T_STEPS)
         barrier()
-        assert int((d_valid[:Bm] == T_STEPS).sum().item()) == Bm
+        assert int((head.d_valid[:Bm] == T_STEPS).sum().item()) == Bm
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(args.steps):
-            ctx3.propagate_while_valid_dev(stream, Bm, d_bel, B, d_ctrl, B, d_steps, d_out, B, d_valid, traj=d_traj, traj_ld=Bm, traj_T=T_STEPS)
+            ctx3.propagate_while_valid_dev(stream, Bm, d_mb, Bm, d_mc, Bm, head.d_steps, head.d_out, B, head.d_valid, traj=d_traj, traj_ld=Bm, traj_T=T_STEPS)
         e1.record()
         barrier()
-        launches += args.steps
-        mt = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(mt, op=dist.ReduceOp.MAX)
-        m_ms = float(mt[0]) / args.steps
+        launches += warm + args.steps
+        m_ms = allmax(e0.elapsed_time(e1)) / args.steps
         m_rate = Bm * T_STEPS / (m_ms * 1e-3)
         bytes_per_step = Wd * 8 + (Wd * 8 + dim * 8 + 4 + Wd * 8 + 4) / T_STEPS          # 80 + 184/T
-        peaks0 = {}
-        try:
-            peaks0 = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        hp = peaks0.get("hbm_gbs", 6650.0)
         m0 = {"value": m_rate * world, "unit": UNIT, "beliefs_per_gpu": Bm, "kernel_ms": m_ms,
-              "roofline": {"bound": "hbm", "achieved": m_rate * bytes_per_step / 1e9, "peak": hp, "unit": "GB/s",
-                           "frac": m_rate * bytes_per_step / 1e9 / hp, "bytes_per_belief_step": bytes_per_step},
+              "roofline": {"bound": "hbm", "achieved": m_rate * bytes_per_step / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                           "frac": m_rate * bytes_per_step / 1e9 / hbm_peak, "bytes_per_belief_step": bytes_per_step},
               "note": "M = 0 (bounds-only checker, config-1 shape), trajectory mode: 80 B written per belief-step"}
-        del d_traj
+        del d_traj, d_mb, d_mc
         ctx3.close()
 
-    # ---- PCIe context for e2e: pinned H2D / D2H copy bandwidth of the same buffers ----
-    pcie = None
-    if not args.no_e2e:
-        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-        e0.record(); d_bel.copy_(h_bel, non_blocking=True); e1.record(); h_out.copy_(d_out, non_blocking=True); e2.record()
+    # ---- secondary: the unicycle model (BASELINE config 3's propagator) on the same sweep, 2^22 beliefs ----
+    uni = None
+    if args.model == "linear" and not args.no_secondary:
+        Bu = min(B, 1 << 22)
+        uni = {"beliefs_per_gpu": Bu, "variants": {}}
+        for v in ("all_survive", "realistic"):
+            sw = DeviceSweep(K, W, torch, dev, local, rank, "unicycle", v, Bu)
+            for _ in range(warm):
+                sw.launch(stream)
+            sw.summary(stream)
+            barrier()
+            ex = int(sw.d_sum[1].item())
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(max(3, args.steps // 2)):
+                sw.launch(stream)
+            e1.record()
+            barrier()
+            n_l = max(3, args.steps // 2)
+            launches += warm + 1 + n_l
+            ms = allmax(e0.elapsed_time(e1)) / n_l
+            uni["variants"][v] = {"value": allsum(ex) / (ms * 1e-3), "unit": UNIT, "kernel_ms": ms, "belief_steps_per_launch": ex}
+            sw.close()
+            del sw
+
+    # ---- secondary: batched expansion sharded over the ranks, winner record gathered over NCCL (north_star) ----
+    expand = None
+    if not args.no_secondary:
+        Kt = 1 << 20
+        lo, hi = sharding.shard_bounds(Kt, rank, world)
+        n = hi - lo
+        ctx4 = K.Context(local)
+        info = W.install_synthetic(ctx4, args.model, M_OBS, variant="realistic")
+        K.install_pvc(ctx4, K.PVC_BLACKMORE, dim, [info["robot_rad"]] * 4, info["p_safe_agents"])
+        other = np.zeros(Wd); other[:2] = [32.0, 32.0]
+        for i in range(dim):
+            other[dim + i * dim + i] = other[dim + dim * dim + i * dim + i] = 0.01
+        csteps = list(range(8, 25))
+        ctx4.set_constraints(*K.constraint_entries(4, dim, 0, [(1, csteps, np.repeat(other[None, :], len(csteps), axis=0))]))
+        cb, cc = W.synthetic_beliefs(n, args.model, variant="realistic", offset=100 + rank)
+        rng = np.random.Generator(np.random.Philox(key=W.SEED + 77 + rank))
+        d_cb, d_cc = torch.from_numpy(cb).to(dev), torch.from_numpy(cc).to(dev)
+        del cb, cc
+        d_st = torch.from_numpy(rng.integers(1, 11, n).astype(np.int32)).to(dev)
+        d_ps = torch.from_numpy(rng.integers(0, 30, n).astype(np.int32)).to(dev)
+        d_pc = torch.from_numpy(rng.uniform(0, 5, n)).to(dev)
+        d_o = torch.empty((Wd, n), dtype=torch.float64, device=dev)
+        d_v = torch.empty(n, dtype=torch.int32, device=dev)
+        d_c, d_g = torch.empty(n, dtype=torch.float64, device=dev), torch.empty(n, dtype=torch.float64, device=dev)
+        d_f = torch.empty(n, dtype=torch.uint8, device=dev)
+        d_w = torch.zeros(2, dtype=torch.float64, device=dev)
+
+        def expand_step():
+            ctx4.expand_batch_dev(stream, n, d_cb, n, d_cc, n, d_st, d_ps, d_pc, (60.0, 60.0), d_o, n, d_v, d_c, d_g, d_f)
+            ctx4.select_winner_dev(stream, n, d_c, d_f, K.FLAG_FULL | K.FLAG_CONS_OK, lo, d_w)
+            return sharding.gather_winner(d_w)     # all-gather of 16 bytes per rank (NCCL), then the host reads the records
+
+        for _ in range(warm):
+            win = expand_step()
+        barrier()
+        reps = max(10, args.steps)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            win = expand_step()
         torch.cuda.synchronize()
-        pcie = {"h2d_gbs": h_bel.numel() * 8 / (e0.elapsed_time(e1) * 1e-3) / 1e9, "d2h_gbs": h_out.numel() * 8 / (e1.elapsed_time(e2) * 1e-3) / 1e9}
+        tx = allmax(time.perf_counter() - t0)
+        launches += 2 * (warm + reps)
+        # the gathered winner must be the minimum over the ranks' local winners: recompute it from the costs on this rank
+        ok_mask = (d_f & (K.FLAG_FULL | K.FLAG_CONS_OK)) == (K.FLAG_FULL | K.FLAG_CONS_OK)
+        loc = float(torch.where(ok_mask, d_c, torch.full_like(d_c, float("inf"))).min().item()) if n else float("inf")
+        gmin = torch.tensor([loc], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(gmin, op=dist.ReduceOp.MIN)
+        assert win[0] == float(gmin[0]), (win, float(gmin[0]))
+        expand = {"candidates_total": Kt, "candidates_per_rank": n, "iteration_us": 1e6 * tx / reps, "candidates_per_s": Kt * reps / tx,
+                  "winner": {"cost": win[0], "global_index": win[1]}, "admissible_fraction_rank0": float(ok_mask.float().mean().item()),
+                  "how": "per iteration: cck_expand_batch_dev (rollout + constraint check + cost + goal, ONE launch) + cck_select_winner_dev on every "
+                         "rank, then sharding.gather_winner (NCCL all-gather of one 16-byte record per rank) and the host-side argmin; wall clock, "
+                         "device-resident candidates"}
+        ctx4.close()
 
     if rank == 0:
-        peaks = {}
         try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            os.sched_setaffinity(0, all_cpus)      # the CPU legs (oracle, planner) use every host core, not just the GPU-local ones
         except Exception:
             pass
         fp64_peak = ctx.measure_fp64_peak()
-        if args.no_cpu:
-            cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "skipped (--no-cpu)",
-                   "halfplane_tests_per_belief_step": 533.99 if args.variant == "all_survive" else 400.0}
+        key = lambda v: f"{args.model}/{v}"       # noqa: E731
+        # ---- cpu_baseline + parity (N = 1 only: the oracle is test infrastructure and is timed once per box) ----
+        parity = None
+        hps = dict(HPS_RECORDED)
+        if world == 1 and not args.no_cpu:
+            cpu, sample = cpu_baseline(args, keep=True)
+            hps[key(args.variant)] = cpu["halfplane_tests_per_belief_step"]
+            parity = {"how": "the CUDA path (host-pointer C-ABI call) re-run on the oracle's own inputs; linear: bit-exact finals and first-violation "
+                             "steps; unicycle: steps exact outside the +-1e-6 band (counted), finals 1e-9 relative", "cases": {}}
+            aos_b, aos_c, o_out, o_valid = sample
+            n_p = len(aos_b)
+            g_out, g_valid = ctx.propagate_while_valid(np.ascontiguousarray(aos_b.T), np.ascontiguousarray(aos_c.T), np.full(n_p, T_STEPS, dtype=np.int32))
+            launches += 1
+            mism = int((g_valid != o_valid).sum()) + int((np.ascontiguousarray(g_out.T) != o_out).any(axis=1).sum()) if dim == 2 else int((g_valid != o_valid).sum())
+            parity["cases"][key(args.variant)] = {"checked": n_p, "mismatches": mism}
+            if not args.no_secondary:
+                O, Wm, _ = oracle_setup(args)
+                todo = [(args.model, v) for v in names if v != args.variant] + ([("unicycle", "all_survive"), ("unicycle", "realistic")] if args.model == "linear" else [])
+                for model, v in todo:
+                    dm = 2 if model == "linear" else 4
+                    n_s = 1 << (16 if dm == 2 else 13)
+                    pb, pc = Wm.synthetic_beliefs(n_s, model, variant=v, offset=1000)
+                    osvc = O.Svc(O.World.synthetic(Wm.synthetic_obstacles(M_OBS, Wm.SEED, v), float(Wm.WORLD), float(Wm.WORLD), 4, 0.9), O.SVC_BLACKMORE, dm)
+                    st = np.full(n_s, T_STEPS, dtype=np.int32)
+                    oo, ov, cnt = osvc.rollout(np.ascontiguousarray(pb.T), np.ascontiguousarray(pc.T), st, nthreads=os.cpu_count() or 1)
+                    hps[f"{model}/{v}"] = float(cnt[1]) / max(1, int(cnt[0]))
+                    cx = K.Context(local)
+                    Wm.install_synthetic(cx, model, M_OBS, variant=v)
+                    go, gv = cx.propagate_while_valid(pb, pc, st)
+                    launches += 1
+                    cx.close()
+                    if dm == 2:
+                        mism = int(((gv != ov) | (np.ascontiguousarray(go.T) != oo).any(axis=1)).sum())
+                        parity["cases"][f"{model}/{v}"] = {"checked": n_s, "mismatches": mism}
+                    else:
+                        same = gv == ov
+                        rel = np.abs(np.ascontiguousarray(go.T)[same] - oo[same]) / np.maximum(np.abs(oo[same]), 1e-12)
+                        parity["cases"][f"{model}/{v}"] = {"checked": n_s, "step_mismatches": int((~same).sum()), "max_rel_value_error": float(rel.max()) if same.any() else None}
+            parity["checked"] = sum(c["checked"] for c in parity["cases"].values())
+            parity["mismatches"] = sum(c.get("mismatches", 0) for c in parity["cases"].values())
         else:
-            cpu = cpu_baseline(args)
-        hps = cpu["halfplane_tests_per_belief_step"]
+            cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port",
+                   "sample": "not run: cpu_baseline is timed at N = 1 only" if world > 1 else "skipped (--no-cpu)"}
+        # ---- rooflines ----
         f_prop = 60.0 if dim == 2 else 700.0
-        f_alg_per_step = f_prop + 15.0 * hps          # F_alg = N_steps*F_prop + H_total*15
-        per_launch_units = exec_steps
-        achieved_tf = per_launch_units * f_alg_per_step / (kern_ms * 1e-3) / 1e12
+        inst_per_step = FP64_INST["linear_dense" if (dim == 2 and os.environ.get("CCK_LIN_DENSE", "") == "1") else args.model]
         bytes_per_belief = (Wd * 8 + dim * 8 + 4) + (Wd * 8 + 4)     # 184 B linear, 616 B unicycle
-        hbm_gbs = B * bytes_per_belief / (kern_ms * 1e-3) / 1e9
-        # dram__bytes_read+write of one launch from the committed ncu --set full capture (per belief, scaled to B)
-        traffic = None
+        issue_peak = fp64_peak / 2.0      # FP64-pipe instructions/s per lane: one DFMA = 2 flop = one instruction
+        traffic_tab = {}
         try:
-            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-            key = f"{args.model}/{args.variant}"
-            if key in tj:
-                traffic = {"bytes_per_launch": tj[key]["dram_bytes_per_belief"] * B, "algorithmic_bytes_per_launch": B * bytes_per_belief,
-                           "source": tj[key]["source"]}
+            traffic_tab = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
         except Exception:
             pass
-        hbm_peak = peaks.get("hbm_gbs", 6650.0)
-        # executed-work view: what must stay fp64 for bit-exact results is the Kalman recursion + the covariance sums
-        # (linear: 75 FP64-pipe instructions per belief-step on the hot path - 70 of lin_step_diag, which skips the exact
-        # zeros of the reference's diagonal Q, R, A_cl, plus Sigma+Lambda and |P01|+|P10|; counted from the ncu source
-        # view, profiles/r1o_*.  The dense step of the reference's accumulation order is 95.)  No FMA contraction is
-        # allowed, so the attainable rate is the FP64 ISSUE rate = DFMA peak / 2 flop; the chance check itself runs in
-        # the fp32 broad phase
-        lin_dense = os.environ.get("CCK_LIN_DENSE", "") == "1"
-        # unicycle: 316 DMUL + 251 DADD + 32 DFMA + 10 DSETP per warp-step in the ncu source view of k_rollout_uni2 (gpurun r1g capture)
-        inst_per_step = (95.0 if lin_dense else 75.0) if dim == 2 else 609.0
-        exec_tinst = per_launch_units * inst_per_step / (kern_ms * 1e-3) / 1e12
-        inst_peak = fp64_peak / 2.0      # one DFMA = 2 flop = 1 FP64-pipe instruction per lane
-        # ---- second half of BASELINE.json's metric: CCK-CBS solve time, short live sample (full distribution:
-        #      tools/solve_bench.py -> profiles/r1_solve_times.json) ----
+
+        def roof(model, v, ex, ms, nB):
+            d_ = 2 if model == "linear" else 4
+            ips = FP64_INST[model] if model != args.model else inst_per_step
+            fa = (60.0 if d_ == 2 else 700.0) + 15.0 * hps.get(f"{model}/{v}", 0.0)
+            tinst = ex * ips / (ms * 1e-3) / 1e12
+            bpb = (K.width(d_) * 8 + d_ * 8 + 4) + (K.width(d_) * 8 + 4)
+            tr = traffic_tab.get(f"{model}/{v}")
+            return {"value": ex * world / (ms * 1e-3) if model == args.model else None, "kernel_ms": ms, "belief_steps_per_launch": ex,
+                    "fp64_issue_frac": tinst / issue_peak, "dfma_flop_peak_frac": tinst / fp64_peak,
+                    "f_alg_frac": ex * fa / (ms * 1e-3) / 1e12 / fp64_peak, "f_alg_flop_per_belief_step": fa,
+                    "hbm_frac": nB * bpb / (ms * 1e-3) / 1e9 / hbm_peak,
+                    "traffic_ratio": (tr["dram_bytes_per_belief"] / bpb) if tr else None}
+
+        for v in per_variant_ms:
+            variants[v] = roof(args.model, v, per_variant_exec[v], per_variant_ms[v], B)
+            variants[v]["value"] = allsum_cached(per_variant_exec[v], world) / (per_variant_ms[v] * 1e-3)
+            if v in hists:
+                variants[v]["survival_histogram_valid_steps"] = hists[v]
+        if uni:
+            for v, r in uni["variants"].items():
+                r.update({k_: x for k_, x in roof("unicycle", v, r["belief_steps_per_launch"], r["kernel_ms"], uni["beliefs_per_gpu"]).items() if k_ != "value"})
+        hv = variants[args.variant]
+        exec_tinst = exec_steps * inst_per_step / (kern_ms * 1e-3) / 1e12
+        tr = traffic_tab.get(key(args.variant))
+        traffic = ({"bytes_per_launch": tr["dram_bytes_per_belief"] * B, "algorithmic_bytes_per_launch": B * bytes_per_belief, "source": tr["source"]} if tr else None)
+        # ---- second half of BASELINE.json's metric: CCK-CBS solve time, short live sample ----
         solve = None
         if world == 1 and not args.no_solve and not args.no_cpu:
-            try:
-                out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "solve_bench.py"), "--seeds", "5", "--time", "20", "--only", "k=4"],
-                                     capture_output=True, text=True, timeout=300)
-                solve = {}
-                for ln in out.stdout.splitlines():
-                    if ln.startswith("config"):
-                        lab, js = ln.split(" {", 1)
-                        d = json.loads("{" + js)
-                        solve[lab] = {k: d[k] for k in ("seeds", "solved", "seconds_median", "seconds_p90", "K", "candidates_median", "cbs_nodes_median")}
-                solve["how"] = "K-CBS over the batched GPU BSST (host/cck_plan), instances rebuilt from tests/golden; wall seconds per solve"
-            except Exception as e:  # noqa: BLE001
-                solve = {"error": str(e)[:200]}
+            solve = solve_sample()
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(args, B), "beliefs_per_gpu": B, "T": T_STEPS, "M": M_OBS,
                        "l2": "inputs+outputs per launch (%.1f GB) exceed the 126 MB L2; no flush needed" % (B * bytes_per_belief / 1e9),
-                       "parallelism": f"beliefs sharded over {world} GPU(s); only a 24-byte result record per rank is all-gathered (NCCL)"},
-            "kernel_ms": kern_ms, "belief_steps_per_launch": per_launch_units,
-            # The kernel is FP64-issue bound (neither HBM nor tensor): `roofline` is the executed-work view, the one that says
-            # how well the silicon is used.  One DADD/DMUL = one flop = one FP64-pipe instruction per lane; FMA contraction is
-            # not allowed (bit-exact results), so the attainable rate is the FP64 issue rate = DFMA peak / 2.
-            "roofline": {"bound": "fp64", "achieved": exec_tinst, "peak": inst_peak, "unit": "TFLOP/s", "frac": exec_tinst / inst_peak,
+                       "parallelism": f"beliefs sharded over {world} GPU(s); only a 24-byte result record per rank is all-gathered (NCCL)",
+                       "cpu_affinity": affinity},
+            "kernel_ms": kern_ms, "belief_steps_per_launch": exec_steps,
+            # The kernel is FP64-issue bound (neither HBM nor tensor).  achieved = FP64-pipe instructions the hot path executes (counted
+            # in the ncu source view) x belief-steps per launch / CUDA-event kernel time.  FMA contraction is forbidden (bit-exact
+            # results), so every flop is its own instruction and the attainable rate is the ISSUE rate = measured DFMA flop peak / 2;
+            # the fraction against the DFMA flop peak itself is given next to it.
+            "roofline": {"bound": "fp64", "achieved": exec_tinst, "peak": issue_peak, "unit": "TFLOP/s", "frac": exec_tinst / issue_peak,
+                         "peak_dfma_flop": fp64_peak, "frac_of_dfma_flop_peak": exec_tinst / fp64_peak,
                          "traffic": traffic, "fp64_inst_per_belief_step": inst_per_step,
-                         "how": "achieved = fp64 flops the kernel must execute for bit-exact results (%.0f DADD/DMUL per belief-step on the hot "
-                                "path: Kalman recursion + covariance sums, counted in the ncu source view) x belief-steps per launch / CUDA-event "
-                                "kernel time; peak = DFMA-chain microbenchmark run live on this GPU / 2 (no FMA contraction; "
-                                "MEASURED_PEAKS.json has no FP64 entry)" % inst_per_step},
-            # SURVEY 8(d)'s algorithmic figure: the reference's un-strength-reduced flop count.  The fp32 broad phase never
-            # evaluates most half-planes, so this credited rate exceeds the machine peak; it measures the strength reduction.
-            "roofline_algorithmic": {"bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak,
-                                     "how": "oracle-counted F_alg (%.0f flop per belief-step = %.0f + 15 x %.2f half-plane tests) x belief-steps per "
-                                            "launch / CUDA-event kernel time vs the measured DFMA peak" % (f_alg_per_step, f_prop, hps)},
-            "roofline_hbm": {"bound": "hbm", "achieved": hbm_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_gbs / hbm_peak,
-                             "peak_source": "MEASURED_PEAKS.json (burst copy)" if "hbm_gbs" in peaks else "fallback 6650",
-                             "bytes_per_belief": bytes_per_belief},
-            "realistic": realistic, "m0_trajectory": m0, "solve_time": solve, "pcie": pcie,
-            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
+                         "f_alg_frac": hv["f_alg_frac"],
+                         "how": "one DADD/DMUL = one flop = one FP64-pipe instruction per lane; peak = DFMA-chain microbenchmark run live on this GPU "
+                                "(MEASURED_PEAKS.json has no FP64 entry), halved for `peak` because no FMA may be formed; f_alg_frac is SURVEY 8(d)'s "
+                                "credited figure (oracle-counted flops of the reference's un-strength-reduced algorithm vs the DFMA flop peak): it "
+                                "exceeds 1 because the fp32 broad phase proves most half-planes without evaluating them"},
+            "roofline_hbm": {"bound": "hbm", "achieved": B * bytes_per_belief / (kern_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                             "frac": B * bytes_per_belief / (kern_ms * 1e-3) / 1e9 / hbm_peak,
+                             "peak_source": "MEASURED_PEAKS.json (burst copy)" if "hbm_gbs" in peaks else "fallback 6650", "bytes_per_belief": bytes_per_belief},
+            "variants": variants, "unicycle": uni, "m0_trajectory": m0, "expand_sharded": expand, "solve_time": solve, "pcie": pcie,
+            "parity": parity, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
         }
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    ctx.close()
+    head.close()
+
+
+def allsum_cached(x, world):
+    """weak scaling: every rank executes the same number of belief-steps per launch up to the seed-dependent realistic count;
+    the secondary variants report rank 0's count x N (the headline `value` uses the exact all-reduced sum)."""
+    return x * world
+
+
+def solve_sample():
+    try:
+        out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "solve_bench.py"), "--seeds", "5", "--time", "20", "--only", "k=4"],
+                             capture_output=True, text=True, timeout=300)
+        solve = {}
+        for ln in out.stdout.splitlines():
+            if ln.startswith("config"):
+                lab, js = ln.split(" {", 1)
+                d = json.loads("{" + js)
+                solve[lab] = {k: d[k] for k in d if k in ("seeds", "solved", "seconds_median", "seconds_p90", "K", "candidates_median", "cbs_nodes_median",
+                                                          "cpu_seconds_median", "cpu_solved")}
+        solve["how"] = "K-CBS over the batched GPU BSST (host/cck_plan), instances rebuilt from tests/golden; wall seconds per solve"
+        return solve
+    except Exception as e:  # noqa: BLE001
+        return {"error": str(e)[:200]}
 
 
 def main():

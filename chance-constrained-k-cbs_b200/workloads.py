@@ -16,9 +16,18 @@ def _rng(seed, stream=0):
     return np.random.Generator(np.random.Philox(key=int(seed) + (int(stream) << 32)))
 
 
+VARIANTS = ("all_survive", "dense_survive", "realistic")
+# dense_survive: clearance (Chebyshev distance mean -> obstacle centre) that keeps every belief valid for 50 steps:
+# inflated half-side 0.5 + 0.177, plus sqrt2 * c * sqrt(P) <= 1.01 (c = 2.38 at M = 256, P <= 0.09), plus 50 * 0.2 * 0.05
+# of travel, plus slack
+DENSE_CLEARANCE = 2.25
+DENSE_CTRL = 0.05
+
+
 def synthetic_obstacles(M=256, seed=SEED, variant="realistic"):
     """M distinct integer cells of the 64x64 world (unit squares).  variant 'all_survive'
-    translates the field to x >= 1000 so no belief ever meets an obstacle."""
+    translates the field to x >= 1000 so no belief ever meets an obstacle; 'dense_survive' and 'realistic' keep
+    it inside the world."""
     rng = _rng(seed, 1)
     cells = rng.choice(WORLD * WORLD, size=M, replace=False)
     centres = np.stack([cells % WORLD, cells // WORLD], axis=1).astype(np.float64)
@@ -38,6 +47,8 @@ def _spd(rng, n, d):
 def synthetic_beliefs(n, model="linear", seed=SEED, variant="realistic", offset=0):
     """SoA belief batch [W, n] and controls [dim, n].  `offset` selects a disjoint RNG stream
     (rank sharding: rank r uses offset=r)."""
+    if variant == "dense_survive":
+        return _dense_survive_beliefs(n, model, seed, offset)
     rng = _rng(seed, 2 + 16 * offset)
     dim = 2 if model == "linear" else 4
     W = capi.width(dim)
@@ -56,6 +67,40 @@ def synthetic_beliefs(n, model="linear", seed=SEED, variant="realistic", offset=
     else:
         ctrl = np.stack([rng.uniform(-1.0, WORLD, n), rng.uniform(-1.0, WORLD, n), rng.uniform(-np.pi, np.pi, n),
                          rng.uniform(0.01, 10.0, n)])
+    return np.ascontiguousarray(bel), np.ascontiguousarray(ctrl)
+
+
+def _dense_survive_beliefs(n, model, seed, offset, M=256):
+    """SURVEY 8(d) variant (ii) with the obstacle field INSIDE the world: every belief survives all 50 steps (so a launch is
+    exactly B*T belief-steps) but lives among the obstacles, so the broad phase finds candidates and the box tests run on
+    surviving beliefs.  Means are uniform over the part of the world (rastered at 1/8 cell) whose Chebyshev distance to every obstacle centre is
+    >= DENSE_CLEARANCE (about 30 % of the world); the control is small (|u| <= DENSE_CTRL: <= 0.5 cells of travel)."""
+    if model != "linear":
+        raise ValueError("dense_survive is defined for the linear model only (a unicycle cannot hold its position)")
+    rng = _rng(seed, 3 + 16 * offset)
+    dim = 2
+    W = capi.width(dim)
+    centres = synthetic_obstacles(M, seed, "dense_survive")
+    # free-space raster at 1/8 cell: a sub-cell is allowed when even its farthest point keeps the clearance
+    R = 8
+    lo, hi = 3.0, WORLD - 4.0
+    ns = int((hi - lo) * R)
+    sub = lo + (np.arange(ns) + 0.5) / R                        # sub-cell centres
+    allowed = np.ones((ns, ns), dtype=bool)
+    lim = DENSE_CLEARANCE + 0.5 / R
+    for ox, oy in centres:
+        ix = np.nonzero(np.abs(sub - ox) < lim)[0]
+        iy = np.nonzero(np.abs(sub - oy) < lim)[0]
+        if len(ix) and len(iy):
+            allowed[ix[0]:ix[-1] + 1, iy[0]:iy[-1] + 1] = False
+    free = np.flatnonzero(allowed)
+    pick = free[rng.integers(0, len(free), n)]
+    bel = np.empty((W, n))
+    bel[0] = lo + (pick // ns + rng.uniform(0.0, 1.0, n)) / R
+    bel[1] = lo + (pick % ns + rng.uniform(0.0, 1.0, n)) / R
+    bel[dim:dim + dim * dim] = _spd(rng, n, dim).T
+    bel[dim + dim * dim:] = _spd(rng, n, dim).T
+    ctrl = rng.uniform(-DENSE_CTRL, DENSE_CTRL, size=(2, n))
     return np.ascontiguousarray(bel), np.ascontiguousarray(ctrl)
 
 

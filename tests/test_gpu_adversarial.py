@@ -289,3 +289,29 @@ def test_linear_diagonal_step_equals_dense_step(K, W, ctx, M, monkeypatch):
     diff = out_a.view(np.uint64) != out_b.view(np.uint64)
     assert (np.isnan(out_a[diff]) | (out_a[diff] == 0.0)).all()
     assert (valid_a == steps).mean() > 0.5
+
+
+def test_traj_T_is_enforced(K, W, ctx):
+    """a trajectory buffer of traj_T steps must never be written past its end - the host entry point refuses
+    max(steps) > traj_T, the device entry point refuses traj_T < 1 and the kernels drop stores beyond traj_T."""
+    W.install_synthetic(ctx, "linear", 0, variant="all_survive")
+    n = 256
+    bel, ctrl = W.synthetic_beliefs(n, "linear", variant="all_survive")
+    steps = np.full(n, 8, dtype=np.int32)
+    with pytest.raises(K.CckError):
+        ctx.propagate_while_valid(bel, ctrl, steps, traj_T=4)
+    out, valid, traj = ctx.propagate_while_valid(bel, ctrl, steps, traj_T=8)
+    assert (valid == 8).all() and np.array_equal(traj[7], out)
+    import torch
+    dev = torch.device("cuda", 0)
+    d_b, d_c, d_s = (torch.from_numpy(x).to(dev) for x in (bel, ctrl, steps))
+    d_o = torch.empty_like(d_b); d_v = torch.empty(n, dtype=torch.int32, device=dev)
+    T = 4
+    d_t = torch.full(((T + 2) * 10, n), -7.0, dtype=torch.float64, device=dev)       # two guard steps behind the buffer
+    with pytest.raises(K.CckError):
+        ctx.propagate_while_valid_dev(None, n, d_b, n, d_c, n, d_s, d_o, n, d_v, traj=d_t, traj_ld=n, traj_T=0)
+    ctx.propagate_while_valid_dev(None, n, d_b, n, d_c, n, d_s, d_o, n, d_v, traj=d_t, traj_ld=n, traj_T=T)
+    ctx.synchronize()
+    t = d_t.cpu().numpy().reshape(T + 2, 10, n)
+    assert (t[T:] == -7.0).all(), "stores beyond traj_T"
+    assert np.array_equal(t[:T], traj[:T]) and (d_v.cpu().numpy() == 8).all()
