@@ -65,7 +65,7 @@ SYMBOLS = [
     "cck_propagate", "cck_propagate_dev", "cck_is_valid", "cck_is_valid_dev",
     "cck_propagate_while_valid", "cck_propagate_while_valid_dev",
     "cck_validate_plan", "cck_validate_plan_dev",
-    "cck_set_constraints", "cck_satisfies_constraints", "cck_satisfies_constraints_dev",
+    "cck_set_constraints", "cck_satisfies_constraints", "cck_satisfies_constraints_dev", "cck_build_clearance_field",
     "cck_expand_batch", "cck_expand_batch_dev", "cck_rollout_summary_dev", "cck_select_winner_dev", "cck_measure_fp64_peak",
     "cck_tree_create", "cck_tree_destroy", "cck_tree_clear", "cck_tree_size", "cck_tree_append", "cck_tree_update",
     "cck_tree_select", "cck_tree_nearest", "cck_tree_witness_batch", "cck_belief_distance", "cck_belief_distance_lower", "cck_belief_distance_cols", "cck_belief_distance_cols_near", "cck_build_grid_table",
@@ -150,6 +150,7 @@ def lib():
     L.cck_tree_witness_batch.argtypes = [vp, i64, vp, i64, C.c_double, vp, vp, vp, vp, vp, vp]
     L.cck_belief_distance.argtypes = [vp, C.c_int, i64, vp, i64, vp, i64, vp]
     L.cck_build_grid_table.argtypes = [C.c_int, vp, vp, C.c_double, vp, i64, C.POINTER(i64), vp]
+    L.cck_build_clearance_field.argtypes = [C.c_int, vp, vp, C.c_double, vp, vp, vp, vp, C.POINTER(C.c_int)]
     L.cck_belief_distance_lower.argtypes = [vp, C.c_int, i64, vp, i64, vp]
     L.cck_belief_distance_cols.argtypes = [vp, C.c_int, i64, vp, i64, C.c_int32, vp, vp]
     L.cck_belief_distance_cols_near.argtypes = [vp, C.c_int, i64, vp, i64, C.c_int32, vp, vp, C.c_int32, vp, vp, vp]
@@ -470,6 +471,24 @@ class Tree:
         idx, dist = np.zeros(K, dtype=np.int32), np.zeros(K)
         self.ctx._ck(self.ctx.L.cck_tree_nearest(self.h, K, _ptr(q), K, _ptr(idx), _ptr(dist)))
         return idx, dist
+
+
+DF_N = 128       # CCK_DF_N
+
+
+def build_clearance_field(A, B, erf_inv_result, low, high):
+    """Host-only: the clearance field of the PCCBlackmore broad phase (cck_build_clearance_field) -> dict or None."""
+    A = np.ascontiguousarray(A, dtype=np.float64); B = np.ascontiguousarray(B, dtype=np.float64)
+    low = np.ascontiguousarray(low, dtype=np.float64); high = np.ascontiguousarray(high, dtype=np.float64)
+    q = np.zeros((DF_N, DF_N), dtype=np.uint8)
+    par = np.zeros(3, dtype=np.float32)
+    has = C.c_int(0)
+    rc = lib().cck_build_clearance_field(len(A), _ptr(A), _ptr(B), float(erf_inv_result), _ptr(low), _ptr(high), _ptr(q), _ptr(par), C.byref(has))
+    if rc:
+        raise CckError(rc, "cck_build_clearance_field")
+    if not has.value:
+        return None
+    return {"q": q, "icx": par[0], "icy": par[1], "k2": par[2]}
 
 
 def belief_distance(ctx, a, b, dim):

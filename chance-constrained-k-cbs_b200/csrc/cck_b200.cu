@@ -38,12 +38,13 @@ struct cck_ctx {
     SvcDev svc{};
     unsigned char* d_tab = nullptr;
     int tab_bytes = 0;
+    unsigned char* d_df = nullptr;     // clearance field (first test of a belief-step, cck_rollout_grid.cuh), CCK_DF_N^2 bytes
     unsigned char* d_gtab = nullptr;   // fp32 box + cell-grid table (Blackmore broad phase, cck_rollout_grid.cuh)
     int gtab_bytes = 0;
     double* d_gexB = nullptr;          // exact fp64 rows in grid-table order
     int32_t* d_gexCls = nullptr;       // class of each row
     bool uni_sparse = false;           // unicycle matrices have the reference's exact-zero pattern
-    GridConst gconst{0, 0, 0, 0, 0, 0, 0, -1.f};   // header scalars of the grid table + fp32 bounds (kernel constants)
+    GridConst gconst{0, 0, 0, 0, 0, 0, 0, -1.f};   // value-initialised tail: no clearance field   // header scalars of the grid table + fp32 bounds (kernel constants)
     int M = 0;
 
     bool has_pvc = false;
@@ -132,7 +133,7 @@ extern "C" int cck_ctx_destroy(cck_ctx* c) {
     cudaStreamSynchronize(c->stream);
     cudaFreeHost(c->h_stage);
     for (int i = 0; i < CCK_SLOTS; ++i) { if (c->pipe[i]) { cudaStreamSynchronize(c->pipe[i]); cudaStreamDestroy(c->pipe[i]); } cudaFree(c->d_scratch[i]); }
-    cudaFree(c->d_gtab); cudaFree(c->d_gexB); cudaFree(c->d_gexCls);
+    cudaFree(c->d_df); cudaFree(c->d_gtab); cudaFree(c->d_gexB); cudaFree(c->d_gexCls);
     cudaFree(c->d_tab); cudaFree(c->d_pvc_A); cudaFree(c->d_pvc_B); cudaFree(c->d_pvc_radii); cudaFree(c->d_pvc_order);
     cudaFree(c->d_key); cudaFree(c->d_run); cudaFree(c->d_cons);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -461,6 +462,79 @@ static void build_grid_table(int M, const double* A, const double* B, const std:
     for (int o : always) put(o);
 }
 
+// ---------------------------------------------------------------------------
+// Clearance field: CCK_DF_N x CCK_DF_N cells over the fp32 (inward-rounded) state bounds.  Cell value = floor(16 * D) (0..255),
+// D = a LOWER bound of the Chebyshev clearance between any mean the device maps to the cell and every obstacle's OUTER box:
+//   D_cell = min_o max(dx_o, dy_o),  dx_o / dy_o = gap between the (padded) cell interval and the box interval per axis.
+// A belief with max(ex, ey) <= D (ex = sqrt2 c sqrt(P00), ...) has x - ex >= xhi or x + ex <= xlo or the same in y for
+// EVERY box, which is what the box test proves obstacle by obstacle.  The cell is padded by `pad` per side for the fp32
+// roundings of the device's cell function and of the mean itself; the field is built only when every obstacle has a finite
+// outer box (n_grid == M) and the bounds are usable.  Returns false when there is no field.
+// ---------------------------------------------------------------------------
+static bool build_clearance_field(const GridBuild& gb, double c, float blx, float bhx, float bly, float bhy, std::vector<unsigned char>& q,
+                                  float& icx, float& icy, float& k2) {
+    GHeader h;
+    std::memcpy(&h, gb.buf.data(), sizeof(h));
+    const int M = h.M, N = CCK_DF_N;
+    const bool c_ok = std::isfinite(c) && c >= 0.0 && c < 1e6;
+    if (M <= 0 || h.n_grid != M || !c_ok) return false;
+    const double rx = (double)bhx - (double)blx, ry = (double)bhy - (double)bly;
+    const double mag = std::max(std::max(std::fabs((double)blx), std::fabs((double)bhx)), std::max(std::fabs((double)bly), std::fabs((double)bhy)));
+    if (!(rx > 0 && ry > 0) || !std::isfinite(rx) || !std::isfinite(ry) || !(mag < 1e6) || !(rx > 1e-3 && ry > 1e-3)) return false;
+    // cells per unit, shrunk by 2^-18 and rounded down: (xf - blx) * icx < N for every float xf < bhx
+    icx = f32_down((double)N / rx * (1.0 - 1.0 / 262144.0));
+    icy = f32_down((double)N / ry * (1.0 - 1.0 / 262144.0));
+    k2 = f32_up(CCK_DF_SCALE * CCK_DF_SCALE * 2.0 * c * c * (1.0 + 1.0 / 262144.0) * (1.0 + 1e-12));
+    const double wx = 1.0 / (double)icx, wy = 1.0 / (double)icy;          // cell size in world units
+    const double padx = wx / 1024.0 + (std::max(mag, 1.0) + rx) / 1048576.0, pady = wy / 1024.0 + (std::max(mag, 1.0) + ry) / 1048576.0;
+    const float* boxes = reinterpret_cast<const float*>(gb.buf.data() + h.off_boxes);
+    std::vector<float> D((size_t)N * N, HUGE_VALF);
+    const double reach = 256.0 / CCK_DF_SCALE;      // clearances beyond 255/16 saturate
+    for (int o = 0; o < M; ++o) {
+        const double xlo = boxes[4 * o], ylo = boxes[4 * o + 1], xhi = boxes[4 * o + 2], yhi = boxes[4 * o + 3];
+        // only cells within `reach` of the box can get a value below saturation from it
+        const int i0 = std::max(0, (int)std::floor((xlo - reach - blx) / wx) - 1), i1 = std::min(N - 1, (int)std::floor((xhi + reach - blx) / wx) + 1);
+        const int j0 = std::max(0, (int)std::floor((ylo - reach - bly) / wy) - 1), j1 = std::min(N - 1, (int)std::floor((yhi + reach - bly) / wy) + 1);
+        for (int j = j0; j <= j1; ++j) {
+            const double cy0 = (double)bly + j * wy - pady, cy1 = (double)bly + (j + 1) * wy + pady;
+            const double dy = std::max(ylo - cy1, cy0 - yhi);
+            for (int i = i0; i <= i1; ++i) {
+                const double cx0 = (double)blx + i * wx - padx, cx1 = (double)blx + (i + 1) * wx + padx;
+                const double dx = std::max(xlo - cx1, cx0 - xhi);
+                const float d = (float)std::max(0.0, std::max(dx, dy));
+                float& cell = D[(size_t)j * N + i];
+                if (d < cell) cell = d;
+            }
+        }
+    }
+    q.assign((size_t)N * N, 0);
+    for (size_t i = 0; i < q.size(); ++i) {
+        const double v = std::floor(std::min((double)D[i], reach) * CCK_DF_SCALE * (1.0 - 1e-6));
+        q[i] = (unsigned char)std::max(0.0, std::min(255.0, v));
+    }
+    return true;
+}
+
+// Host-only (no GPU, no context): the clearance field cck_set_obstacles builds next to the grid table, for CPU tests of its
+// invariant (a cell's value never exceeds 16 x the true Chebyshev clearance of any point mapped to it).  out: CCK_DF_N^2 bytes
+// (row-major, y-major); params[0..2] = icx, icy, k2.  Returns CCK_OK with *has = 0 when no field is built.
+extern "C" int cck_build_clearance_field(int M, const double* A, const double* B, double erf_inv_result, const double* low, const double* high,
+                                         unsigned char* out, float* params, int* has) {
+    if (M < 0 || (M > 0 && (!A || !B)) || !low || !high || !out || !params || !has) return CCK_ERR_INVALID;
+    *has = 0;
+    if (M == 0) return CCK_OK;
+    GridBuild gb;
+    std::vector<int> cls_idx(M, 0);
+    build_grid_table(M, A, B, cls_idx, erf_inv_result, gb);
+    std::vector<unsigned char> q;
+    float icx, icy, k2;
+    if (!build_clearance_field(gb, erf_inv_result, f32_up(low[0]), f32_down(high[0]), f32_up(low[1]), f32_down(high[1]), q, icx, icy, k2)) return CCK_OK;
+    std::memcpy(out, q.data(), q.size());
+    params[0] = icx; params[1] = icy; params[2] = k2;
+    *has = 1;
+    return CCK_OK;
+}
+
 // Host-only: the serialised grid table cck_set_obstacles would upload (no GPU, no context needed), so that its
 // invariants can be tested on a CPU-only machine: layout = GHeader (80 B: int32 total_bytes, M, n_grid, n_cells = R*64, R,
 // 0, 0, off_cstart, off_boxes, pad; float gx0, gy0, icx, icy, SX, SY, k, Rm1; 2 x int32 pad), uint16 dstart[R*64+1] (dense
@@ -558,6 +632,7 @@ extern "C" int cck_set_obstacles(cck_ctx* c, const cck_svc_params* p, const doub
     c->M = M;
 
     // ---- fp32 box + cell-grid table (the default broad phase) ----
+    cudaFree(c->d_df); c->d_df = nullptr;
     cudaFree(c->d_gtab); cudaFree(c->d_gexB); cudaFree(c->d_gexCls);
     c->d_gtab = nullptr; c->d_gexB = nullptr; c->d_gexCls = nullptr; c->gtab_bytes = 0;
     c->gconst = GridConst{};
@@ -575,7 +650,15 @@ extern "C" int cck_set_obstacles(cck_ctx* c, const cck_svc_params* p, const doub
         const GridConst keep = c->gconst;
         c->gconst = GridConst{gh.k, gh.SX, gh.SY, gh.gx0, gh.gy0, gh.icx, gh.icy, gh.Rm1, gh.M, gh.n_grid, gh.off_occ, gh.off_rowbase, gh.off_cstart, gh.off_boxes,
                               keep.blx, keep.bhx, keep.bly, keep.bhy, (int32_t)sizeof(TabHeader), gh.Rm1 + 1.f,
-                              boxes_in_smem ? nullptr : reinterpret_cast<const float4*>(c->d_gtab + gh.off_boxes)};
+                              boxes_in_smem ? nullptr : reinterpret_cast<const float4*>(c->d_gtab + gh.off_boxes),
+                              nullptr, 0.f, 0.f, 0.f};
+        std::vector<unsigned char> dfq;
+        float dicx = 0, dicy = 0, dk2 = 0;
+        if (!std::getenv("CCK_NO_DF") && build_clearance_field(gb, p->erf_inv_result, keep.blx, keep.bhx, keep.bly, keep.bhy, dfq, dicx, dicy, dk2)) {
+            CK(c, cudaMalloc(&c->d_df, dfq.size()));
+            CK(c, cudaMemcpy(c->d_df, dfq.data(), dfq.size(), cudaMemcpyHostToDevice));
+            c->gconst.df = c->d_df; c->gconst.df_icx = dicx; c->gconst.df_icy = dicy; c->gconst.df_k2 = dk2;
+        }
     }
 
     SvcDev& s = c->svc;

@@ -141,7 +141,9 @@ __device__ __forceinline__ void lin_step_diag(const Lin& s, double dux, double d
     // (A_cl L) A_cl with A_cl = diag(a0, a3): entry (i, j) = (a_i * L_ij) * a_j
     lp[0] = (a0 * s.L[0]) * a0; lp[1] = (a0 * s.L[1]) * a3;
     lp[2] = (a3 * s.L[2]) * a0; lp[3] = (a3 * s.L[3]) * a3;
-    ImK[0] = 1.0 - K[0]; ImK[1] = 0.0 - K[1]; ImK[2] = 0.0 - K[2]; ImK[3] = 1.0 - K[3];
+    // 0 - K_ij is a sign flip (a free operand modifier instead of a DADD) except for K_ij = +0, where 0 - (+0) = +0 but
+    // -(+0) = -0: again only the sign of an exact zero can differ (see above)
+    ImK[0] = 1.0 - K[0]; ImK[1] = -K[1]; ImK[2] = -K[2]; ImK[3] = 1.0 - K[3];
     mm2(ImK, sp, o.S);
     mm2(K, sp, KP);
 #pragma unroll

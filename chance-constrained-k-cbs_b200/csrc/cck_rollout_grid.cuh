@@ -70,7 +70,14 @@ struct GridConst {
     int32_t off_classes;        // byte offset of the ClassRec array inside the (global) class table
     float Rf;                   // (float)R = Rm1 + 1
     const float4* boxes_global; // non-null: the box arrays are too large for shared memory and are read from global (L1/L2)
+    // clearance field (first test of a belief-step): CCK_DF_N x CCK_DF_N cells over the fp32 state bounds, one byte per cell =
+    // floor(16 * Chebyshev clearance of the cell to the nearest obstacle box), global memory (16 KB: L1-resident)
+    const unsigned char* df;    // null: no field (no obstacles, an obstacle without a box, unusable bounds)
+    float df_icx, df_icy;       // cells per unit, shrunk so that a mean strictly inside the bounds lands in [0, CCK_DF_N)
+    float df_k2;                // >= 256 * 2 c^2 (1 + 2^-18): variance -> (16 * sqrt2 c sqrt(P))^2, rounded up
 };
+#define CCK_DF_N 128
+#define CCK_DF_SCALE 16.0
 
 #define CCK_GRID_COLS 64
 #define CCK_GRID_ROWS 64
@@ -122,16 +129,37 @@ __device__ __forceinline__ bool grid_obstacle(const GridConst& g, const unsigned
 // in, so that the common outcome - bounds proven, operands finite, no gridded obstacle near, no obstacle without a box -
 // leaves through ONE branch (ncu: 21 of 215 instructions per warp-step were BRA/BSSY/BSYNC of five separate rare-path
 // tests).  `enabled` = there is an obstacle table at all.
+// Clearance field lookup for a mean the caller has PROVEN strictly inside the fp32 bounds (`pre`): the squared clearance of
+// its cell in units of 1/16, or 0 when there is no field / the mean is not proven inside.  Issued right after the mean
+// update so that the load overlaps the covariance recursion.
+__device__ __forceinline__ float df_lookup(const GridConst& g, bool pre, float xf, float yf) {
+    if (!g.df || !pre) return 0.f;
+    const int cx = __float2int_rz(__fmul_rn(__fsub_rn(xf, g.blx), g.df_icx));
+    const int cy = __float2int_rz(__fmul_rn(__fsub_rn(yf, g.bly), g.df_icy));
+    const float q = (float)__ldg(g.df + (cy * CCK_DF_N + cx));
+    return q * q;
+}
+
+// `q2` (optional): df_lookup's result for this mean.  If (16 * sqrt2 c sqrt(max(P00, P11)))^2 < q2, the belief's interval
+// stays clear of EVERY obstacle box by Chebyshev distance: proven safe with one compare, before any window arithmetic.
 template <bool SPLIT = false, class ExactBounds>
 __device__ __forceinline__ bool grid_check_b(const GridConst& g, const unsigned char* gt, const unsigned char* ctab, const double* exB,
                                              const int32_t* exCls, double c, bool pre, const ExactBounds& exact_bounds, bool enabled, double x, double y,
                                              double Sa0, double Sa1, double Sa2, double Sa3, double Sb0 = 0, double Sb1 = 0, double Sb2 = 0,
-                                             double Sb3 = 0, bool* cov_small_out = nullptr) {
+                                             double Sb3 = 0, bool* cov_small_out = nullptr, float q2 = 0.f) {
     const GridConst* h = &g;
     const int M = h->M;
     const double P0 = SPLIT ? Sa0 + Sb0 : Sa0, P1 = SPLIT ? Sa1 + Sb1 : Sa1, P2 = SPLIT ? Sa2 + Sb2 : Sa2, P3 = SPLIT ? Sa3 + Sb3 : Sa3;
-    const float xf = __double2float_rn(x), yf = __double2float_rn(y);
     const float p0 = __double2float_rn(P0), p3 = __double2float_rn(P3);
+    {
+        // covariance entries finite, non-negative on the diagonal and below 2^100, by their high words (sign bit or NaN
+        // exponent compare as huge unsigned numbers)
+        const bool cov_ok0 = cov_small(P0, P1, P2, P3);
+        if (cov_small_out) *cov_small_out = cov_ok0;
+        // q2 > 0 implies `pre` (df_lookup): bounds proven, mean finite.  NaN variances compare false.
+        if (cov_ok0 & (__fmul_rn(fmaxf(p0, p3), h->df_k2) < q2)) return true;
+    }
+    const float xf = __double2float_rn(x), yf = __double2float_rn(y);
     // the reference's fp64 expression on obstacle j's own normals
     auto exact = [&](int j) -> bool {
         const ClassRec* cls = reinterpret_cast<const ClassRec*>(ctab + h->off_classes);   // a kernel constant: no header load
@@ -159,12 +187,9 @@ __device__ __forceinline__ bool grid_check_b(const GridConst& g, const unsigned 
     // the window misses the grid <=> floor(uchi) < 0 or floor(uclo) > 63 or floor(urhi) < 0 or floor(urlo) > R - 1
     // (floor(v) < 0 <=> v < 0, floor(v) > n <=> v >= n + 1); every comparison is false for NaN: not proven empty
     const bool empty = (uchi < 0.f) | (uclo >= (float)CCK_GRID_COLS) | (urhi < 0.f) | (urlo >= h->Rf);
-    // covariance entries finite, non-negative on the diagonal and below 2^100, by their high words (sign bit or NaN
-    // exponent compare as huge unsigned numbers): with `pre` (mean strictly inside the fp32 bounds) this is all the fast
-    // exit needs - a non-finite or overflowing fp32 intermediate above can only make the window look NON-empty
+    // with `pre` (mean strictly inside the fp32 bounds) and a small finite covariance this is all the second fast exit needs -
+    // a non-finite or overflowing fp32 intermediate above can only make the window look NON-empty
     const bool cov_ok = cov_small(P0, P1, P2, P3);
-    if (cov_small_out) *cov_small_out = cov_ok;
-    // everything above is branch-free
     if (pre & cov_ok & empty & (h->n_grid == M)) return true;
     if (!pre && !exact_bounds()) return false;
     if (!enabled) return true;
@@ -201,7 +226,10 @@ __device__ __forceinline__ bool grid_check(const GridConst& g, const unsigned ch
     // the caller has done the bounds test, which a NaN mean passes (and 0 * NaN poisons every plane of the reference's
     // expression): the fast exit needs a finite mean
     const bool pre = fabs(x) + fabs(y) < 1e30;
-    return grid_check_b<SPLIT>(g, gt, ctab, exB, exCls, c, pre, [] { return true; }, true, x, y, Sa0, Sa1, Sa2, Sa3, Sb0, Sb1, Sb2, Sb3);
+    // the clearance field needs the mean strictly inside the fp32 bounds it was built over
+    const float xf = __double2float_rn(x), yf = __double2float_rn(y);
+    const float q2 = df_lookup(g, (xf > g.blx) & (xf < g.bhx) & (yf > g.bly) & (yf < g.bhy), xf, yf);
+    return grid_check_b<SPLIT>(g, gt, ctab, exB, exCls, c, pre, [] { return true; }, true, x, y, Sa0, Sa1, Sa2, Sa3, Sb0, Sb1, Sb2, Sb3, nullptr, q2);
 }
 
 // PCCBlackmoreSVC::isValid, batched (row a4), through the same broad phase: bounds, then grid_check.
@@ -298,17 +326,27 @@ __global__ void __launch_bounds__(grid_threads(EXPAND), grid_minb(EXPAND)) k_rol
     const double c = sp.erf_inv_result;
 
     int nxt = -1;                  // belief indices fit 32 bits (the launcher refuses n >= 2^31)
-    // claim the next belief of this CTA (ranges blockIdx, blockIdx+gridDim, ... of 256 beliefs) and start copying it
-    auto prefetch = [&]() {
+    // Claim the next beliefs of this CTA (ranges blockIdx, blockIdx+gridDim, ... of 2^range_log2 beliefs) for the lanes that
+    // `want` one and start copying them.  WARP-SYNCHRONOUS (every lane of the warp calls it): ONE atomicAdd per warp hands
+    // out consecutive beliefs to the wanting lanes in lane order, so their 8-byte copies of a plane are contiguous - four
+    // lanes fill one 32-byte sector (ncu, round 1: one atomicAdd per lane and 1.58x the algorithmic DRAM traffic on the
+    // realistic sweep, because a sector fetched for one lane was evicted before its neighbours asked for the rest).
+    const unsigned lane = threadIdx.x & 31u;
+    auto prefetch = [&](bool want) {
+        const unsigned mw = __ballot_sync(0xffffffffu, want);
+        if (mw == 0) return;
+        const int cnt = __popc(mw);
+        int base = 0;
+        if (lane == (unsigned)(__ffs(mw) - 1)) base = atomicAdd(next_k, cnt);
+        base = __shfl_sync(0xffffffffu, base, __ffs(mw) - 1);
+        if (!want) return;
         nxt = -1;
-        while (true) {
-            const int kk = atomicAdd(next_k, 1);
-            const int rg = kk >> range_log2;
-            const int64_t base = ((int64_t)blockIdx.x + (int64_t)rg * gridDim.x) << range_log2;
-            if (base >= a.n) return;
-            const int64_t idx = base + (kk & ((1 << range_log2) - 1));
-            if (idx < a.n) { nxt = (int)idx; break; }
-        }
+        const int kk = base + __popc(mw & ((1u << lane) - 1u));
+        const int rg = kk >> range_log2;
+        const int64_t rbase = ((int64_t)blockIdx.x + (int64_t)rg * gridDim.x) << range_log2;
+        const int64_t idx = rbase + (kk & ((1 << range_log2) - 1));
+        if (idx >= a.n) return;          // past the end of the batch (later ranges start even further out)
+        nxt = (int)idx;
 #pragma unroll
         for (int f = 0; f < 10; ++f) cp_async8(slot + f * T, a.bel + f * a.ld + nxt);
         cp_async8(slot + 10 * T, a.ctrl + nxt);
@@ -317,7 +355,7 @@ __global__ void __launch_bounds__(grid_threads(EXPAND), grid_minb(EXPAND)) k_rol
         if (EXPAND) cp_async4(islot + T, a.parent_step + nxt);
         cp_async_commit();
     };
-    prefetch();
+    prefetch(true);
     stage_wait((uint32_t)a.ftab_bytes, bar);
 
     bool have = false, pending = false;
@@ -353,10 +391,17 @@ __global__ void __launch_bounds__(grid_threads(EXPAND), grid_minb(EXPAND)) k_rol
             a.flags[i] = (uint8_t)((t == steps ? 1 : 0) | (cons_ok ? 2 : 0) | (g ? 4 : 0));
         }
     };
-    // refill: take the prefetched belief, start copying the one after it
+    // refill (warp-synchronous): idle lanes take their prefetched belief and the warp claims the ones after them.  When four
+    // or more lanes are served, whole quads only (the rest waits for the next round): four consecutive beliefs = one sector
+    // per plane.  A belief with steps <= 0 is answered on the spot; its lane picks up real work in the next round.
     auto take = [&](Lin& A) {
         flush(A);
-        while (!have && nxt >= 0) {
+        const bool cand = !have && nxt >= 0;
+        const unsigned mc = __ballot_sync(0xffffffffu, cand);
+        int nserve = __popc(mc);
+        if (nserve >= 4) nserve &= ~3;
+        const bool serve = cand && __popc(mc & ((1u << lane) - 1u)) < nserve;
+        if (serve) {
             cp_async_wait_all();
             i = nxt;
             A.mx = slot[0]; A.my = slot[T];
@@ -365,7 +410,9 @@ __global__ void __launch_bounds__(grid_threads(EXPAND), grid_minb(EXPAND)) k_rol
             dux = p.dt * slot[10 * T]; duy = p.dt * slot[11 * T];
             steps = islot[0];
             if (EXPAND) pstep = islot[T];
-            prefetch();
+        }
+        prefetch(serve);
+        if (serve) {
             if (steps <= 0) {         // propagateWhileValid(.., 0, ..): copy, return 0
                 a.out[i] = A.mx; a.out[a.ldo + i] = A.my;
 #pragma unroll
@@ -378,11 +425,11 @@ __global__ void __launch_bounds__(grid_threads(EXPAND), grid_minb(EXPAND)) k_rol
                     a.goal_dist[i] = gd;
                     a.flags[i] = (uint8_t)(1 | 2 | (g ? 4 : 0));
                 }
-                continue;
+            } else {
+                t = 0; cons_ok = true;
+                dense = !p.diag || !cov_small(A.S[0] + A.L[0], A.S[1] + A.L[1], A.S[2] + A.L[2], A.S[3] + A.L[3]);
+                have = true;
             }
-            t = 0; cons_ok = true;
-            dense = !p.diag || !cov_small(A.S[0] + A.L[0], A.S[1] + A.L[1], A.S[2] + A.L[2], A.S[3] + A.L[3]);
-            have = true;
         }
     };
     // one belief-step of a lane that has work, in place (lin_step is alias-safe)
@@ -391,17 +438,20 @@ __global__ void __launch_bounds__(grid_threads(EXPAND), grid_minb(EXPAND)) k_rol
         stash[0] = make_double2(A.mx, A.my);
         stash[1] = make_double2(A.S[0], A.S[1]); stash[2] = make_double2(A.S[2], A.S[3]);
         stash[3] = make_double2(A.L[0], A.L[1]); stash[4] = make_double2(A.L[2], A.L[3]);
-        if (dense) lin_step(A, dux, duy, p, B); else lin_step_diag(A, dux, duy, p, B);
-        const double x = B.mx, y = B.my;
+        // the new mean first (UncertainLinearSP.cpp:92-93; the step functions below form the same sums): its clearance-field
+        // cell is looked up NOW so that the load is in flight during the covariance recursion
+        const double x = A.mx + dux, y = A.my + duy;
         // satisfiesBounds (NaN passes): the mean rounded to fp32 strictly inside the inward-rounded bounds proves it
         // (RN is monotone: xf < bhx <= high implies x < high); otherwise the exact fp64 test decides
         const float xf = __double2float_rn(x), yf = __double2float_rn(y);
         const bool pre = (xf > g.blx) & (xf < g.bhx) & (yf > g.bly) & (yf < g.bhy);
+        const float q2 = df_lookup(g, pre, xf, yf);
+        if (dense) lin_step(A, dux, duy, p, B); else lin_step_diag(A, dux, duy, p, B);
         bool small;
         const bool ok = grid_check_b<true>(
             g, gt, a.tab, a.exB, a.exCls, c, pre,
             [&] { return !(x - eps > sp.high[0] || x + eps < sp.low[0] || y - eps > sp.high[1] || y + eps < sp.low[1]); }, a.ftab_bytes > 0, x, y,
-            B.S[0], B.S[1], B.S[2], B.S[3], B.L[0], B.L[1], B.L[2], B.L[3], &small);
+            B.S[0], B.S[1], B.S[2], B.S[3], B.L[0], B.L[1], B.L[2], B.L[3], &small, q2);
         dense = !p.diag || !small;   // the new covariance is finite: the next step may skip the exact-zero terms
         if (ok) {
             if (EXPAND && cons) {   // Sigma + Lambda formed here, not carried across the validity check
@@ -431,7 +481,7 @@ __global__ void __launch_bounds__(grid_threads(EXPAND), grid_minb(EXPAND)) k_rol
         if (idle) {
             if (__popc(idle) >= CCK_REFILL_MIN || (++it & (CCK_REFILL_WAIT - 1)) == 0) {
                 take(cur);
-                if (__all_sync(0xffffffffu, !have)) break;
+                if (__all_sync(0xffffffffu, !have && nxt < 0)) break;   // nothing running and nothing prefetched (a lane the quad rule skipped is served next round)
             }
         }
         if (have) advance(cur, cur);

@@ -235,6 +235,16 @@ int cck_measure_fp64_peak(cck_ctx* ctx, double* tflops);
 int cck_build_grid_table(int M, const double* A, const double* B, double erf_inv_result, unsigned char* out, int64_t cap,
                          int64_t* bytes, int32_t* order);
 
+/* Host-only: the clearance field built next to the grid table - CCK_DF_N x CCK_DF_N (128 x 128) bytes over the fp32 state
+ * bounds, value = floor(16 x a lower bound of the Chebyshev clearance between any mean mapped to the cell and every
+ * obstacle's outer box).  It is the FIRST test of a belief-step (one byte load + one compare proves "safe w.r.t. every
+ * obstacle" for a belief whose sqrt2 c sqrt(P) interval is smaller than the clearance); everything it cannot prove goes on to
+ * the cell-grid broad phase and the exact decision.  params[0..2] = cells per unit in x, in y, and the factor that turns a
+ * variance into the squared 1/16-unit interval half-width.  *has = 0: no field (M = 0, an obstacle without an axis-aligned
+ * box, unusable bounds).  For CPU tests of the invariant. */
+int cck_build_clearance_field(int M, const double* A, const double* B, double erf_inv_result, const double* low, const double* high,
+                              unsigned char* out, float* params, int* has);
+
 /* ---- belief-space nearest neighbours over a device-resident tree ----
  * RealVectorBeliefSpace::distance (src/Spaces/RealVectorBeliefSpace.cpp:16-62):
  *   | ||mu1-mu2||^2 + trace(C1 + C2 - 2 (C2^1/2 C1 C2^1/2)^1/2) |, 0 when the means coincide, C = Sigma + Lambda.

@@ -217,3 +217,53 @@ def test_fp32_broad_phase_never_contradicts_the_fp64_predicate(K, W, which, sqrt
             assert sorted(got) == np.nonzero(in_window[i])[0].tolist()
         # the window is not vacuous: it skips most of the table
         assert in_window.mean() < 0.05
+
+
+@pytest.mark.parametrize("which", ["synthetic", "far", "dense32"])
+def test_clearance_field_never_contradicts_the_fp64_predicate(K, W, which):
+    """The FIRST test of a belief-step: one byte of the clearance field proves "safe w.r.t. every obstacle" when
+    (16 sqrt2 c sqrt(max(P00, P11)))^2 < q^2.  Re-enacted in numpy float32: whatever it proves must be true for the reference's
+    fp64 predicate, and it must not be vacuous."""
+    rng = np.random.default_rng(17)
+    A, B = _tables(K, W, which, rng)
+    c = 2.378449440526247
+    span = 64.0 if which != "dense32" else 32.0
+    low, high = np.array([-1.0, -1.0]), np.array([span, span])
+    df = K.capi.build_clearance_field(A, B, c, low, high)
+    assert df is not None
+    q, icx, icy, k2 = df["q"], f32(df["icx"]), f32(df["icy"]), f32(df["k2"])
+    n = 60000
+    x, y = rng.uniform(-1.0, span, n), rng.uniform(-1.0, span, n)
+    Lc = rng.uniform(0.01, 0.3, (n, 3))
+    P = np.stack([Lc[:, 0] ** 2, Lc[:, 0] * Lc[:, 1], Lc[:, 0] * Lc[:, 1], Lc[:, 1] ** 2 + Lc[:, 2] ** 2], axis=1)
+    P[::3] *= 0.05
+    # adversarial: means a few fp32 ulps from cell borders, covariances a hair from the cell's threshold
+    blx = np.nextafter(f32(low[0]), f32(np.inf)); bly = np.nextafter(f32(low[1]), f32(np.inf))
+    k = np.arange(0, n, 4)
+    x[k] = np.float64(blx) + rng.integers(1, K.capi.DF_N, len(k)) / np.float64(icx) + rng.uniform(-2e-5, 2e-5, len(k))
+    xf, yf = x.astype(f32), y.astype(f32)
+    bhx, bhy = np.nextafter(f32(high[0]), f32(-np.inf)), np.nextafter(f32(high[1]), f32(-np.inf))
+    pre = (xf > blx) & (xf < bhx) & (yf > bly) & (yf < bhy)
+    with np.errstate(all="ignore"):
+        cx = ((xf - blx) * icx).astype(f32).astype(np.int64)
+        cy = ((yf - bly) * icy).astype(f32).astype(np.int64)
+    assert (cx[pre] >= 0).all() and (cx[pre] < K.capi.DF_N).all() and (cy[pre] >= 0).all() and (cy[pre] < K.capi.DF_N).all()
+    qq = np.where(pre, q[np.clip(cy, 0, 127), np.clip(cx, 0, 127)], 0).astype(f32)
+    j = np.arange(1, n, 4)                                   # variance right at the threshold of its cell (+- 1e-5 relative)
+    thr = (qq[j].astype(np.float64) ** 2) / np.float64(k2)
+    s = thr / np.maximum(np.maximum(P[j, 0], P[j, 3]), 1e-300) * rng.uniform(1 - 1e-5, 1 + 1e-5, len(j))
+    P[j] *= np.where(thr > 0, s, 1.0)[:, None]
+    p0, p3 = P[:, 0].astype(f32), P[:, 3].astype(f32)
+    proven = pre & ((np.maximum(p0, p3) * k2).astype(f32) < qq * qq)
+    exact = _exact_safe(A, B, x, y, P, c).all(axis=1)
+    assert not (proven & ~exact).any()
+    if which == "far":
+        rest = pre.copy(); rest[j] = False         # (the threshold-hugging quarter fails half of the time by construction)
+        assert proven[rest].mean() > 0.99          # obstacles beyond the saturation distance: everything is proven at once
+    else:
+        assert proven.mean() > 0.1 and (exact & ~proven).any()
+    # no field: rotated obstacle, no obstacles
+    A2, B2 = A.copy(), B.copy()
+    A2[0] = [[0.3, -0.4], [0.4, 0.3], [-0.3, 0.4], [-0.4, -0.3]]
+    assert K.capi.build_clearance_field(A2, B2, c, low, high) is None
+    assert K.capi.build_clearance_field(A[:0], B[:0], c, low, high) is None
