@@ -53,6 +53,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-secondary", "--no-realistic", dest="no_secondary", action="store_true",
                     help="headline variant only: skip the other variants, the unicycle, M=0 and sharded-expansion legs (profiling runs)")
+    ap.add_argument("--no-extra", action="store_true", help="keep the three sweep variants, skip the unicycle / M=0 / sharded-expansion legs (kernel tuning)")
     ap.add_argument("--no-solve", action="store_true", help="skip the short live CCK-CBS solve-time sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs under ncu)")
     return ap.parse_args()
@@ -497,7 +498,7 @@ def run_ours(args):
     except Exception:
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
-    if args.model == "linear" and not args.no_secondary:
+    if args.model == "linear" and not args.no_secondary and not args.no_extra:
         Bm = min(B, 1 << 22)
         ctx3 = K.Context(local)
         W.install_synthetic(ctx3, "linear", 0, variant="all_survive")
@@ -528,7 +529,7 @@ def run_ours(args):
 
     # ---- secondary: the unicycle model (BASELINE config 3's propagator) on the same sweep, 2^22 beliefs ----
     uni = None
-    if args.model == "linear" and not args.no_secondary:
+    if args.model == "linear" and not args.no_secondary and not args.no_extra:
         Bu = min(B, 1 << 22)
         uni = {"beliefs_per_gpu": Bu, "variants": {}}
         for v in ("all_survive", "realistic"):
@@ -553,7 +554,7 @@ def run_ours(args):
 
     # ---- secondary: batched expansion sharded over the ranks, winner record gathered over NCCL (north_star) ----
     expand = None
-    if not args.no_secondary:
+    if not args.no_secondary and not args.no_extra:
         Kt = 1 << 20
         lo, hi = sharding.shard_bounds(Kt, rank, world)
         n = hi - lo

@@ -65,7 +65,7 @@ SYMBOLS = [
     "cck_propagate", "cck_propagate_dev", "cck_is_valid", "cck_is_valid_dev",
     "cck_propagate_while_valid", "cck_propagate_while_valid_dev",
     "cck_validate_plan", "cck_validate_plan_dev",
-    "cck_set_constraints", "cck_satisfies_constraints", "cck_satisfies_constraints_dev", "cck_build_clearance_field",
+    "cck_set_constraints", "cck_satisfies_constraints", "cck_satisfies_constraints_dev", "cck_build_clearance_field", "cck_measure_fp64_rates",
     "cck_expand_batch", "cck_expand_batch_dev", "cck_rollout_summary_dev", "cck_select_winner_dev", "cck_measure_fp64_peak",
     "cck_tree_create", "cck_tree_destroy", "cck_tree_clear", "cck_tree_size", "cck_tree_append", "cck_tree_update",
     "cck_tree_select", "cck_tree_nearest", "cck_tree_witness_batch", "cck_belief_distance", "cck_belief_distance_lower", "cck_belief_distance_cols", "cck_belief_distance_cols_near", "cck_build_grid_table",
@@ -138,6 +138,7 @@ def lib():
     L.cck_rollout_summary_dev.argtypes = [vp, vp, i64, vp, vp, vp]
     L.cck_select_winner_dev.argtypes = [vp, vp, i64, vp, vp, C.c_int, i64, vp]
     L.cck_measure_fp64_peak.argtypes = [vp, dp]
+    L.cck_measure_fp64_rates.argtypes = [vp, dp]
     L.cck_tree_create.argtypes = [vp, C.c_int, C.POINTER(vp)]
     L.cck_tree_destroy.argtypes = [vp]
     L.cck_tree_clear.argtypes = [vp]
@@ -397,6 +398,12 @@ class Context:
         self._ck(self.L.cck_expand_batch_dev(self.h, stream, n, _ptr(bel), ld, _ptr(ctrl), ldc, _ptr(steps), _ptr(parent_step), _ptr(parent_cost),
                                              C.byref(g), _ptr(out), ldo, _ptr(valid), _ptr(cost), _ptr(goal_dist), _ptr(flags)))
 
+    def measure_fp64_rates(self):
+        out = (C.c_double * 6)()
+        self._ck(self.L.cck_measure_fp64_rates(self.h, out))
+        return {"dmul_dadd": out[0], "dadd": out[1], "dmul": out[2], "with_1_fp32_per_fp64": out[3], "with_2_fp32_per_fp64": out[4],
+                "with_3_fp32_per_fp64": out[5]}
+
     def measure_fp64_peak(self):
         t = C.c_double()
         self._ck(self.L.cck_measure_fp64_peak(self.h, C.byref(t)))
@@ -480,7 +487,7 @@ def build_clearance_field(A, B, erf_inv_result, low, high):
     """Host-only: the clearance field of the PCCBlackmore broad phase (cck_build_clearance_field) -> dict or None."""
     A = np.ascontiguousarray(A, dtype=np.float64); B = np.ascontiguousarray(B, dtype=np.float64)
     low = np.ascontiguousarray(low, dtype=np.float64); high = np.ascontiguousarray(high, dtype=np.float64)
-    q = np.zeros((DF_N, DF_N), dtype=np.uint8)
+    q = np.zeros((DF_N, DF_N), dtype=np.uint32)
     par = np.zeros(3, dtype=np.float32)
     has = C.c_int(0)
     rc = lib().cck_build_clearance_field(len(A), _ptr(A), _ptr(B), float(erf_inv_result), _ptr(low), _ptr(high), _ptr(q), _ptr(par), C.byref(has))
@@ -488,7 +495,8 @@ def build_clearance_field(A, B, erf_inv_result, low, high):
         raise CckError(rc, "cck_build_clearance_field")
     if not has.value:
         return None
-    return {"q": q, "icx": par[0], "icy": par[1], "k2": par[2]}
+    return {"q": (q & 255).astype(np.uint8), "q2": ((q >> 8) & 255).astype(np.uint8), "j1": (q >> 16).astype(np.int64),
+            "icx": par[0], "icy": par[1], "k2": par[2]}
 
 
 def belief_distance(ctx, a, b, dim):

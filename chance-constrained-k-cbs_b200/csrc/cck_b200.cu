@@ -38,7 +38,7 @@ struct cck_ctx {
     SvcDev svc{};
     unsigned char* d_tab = nullptr;
     int tab_bytes = 0;
-    unsigned char* d_df = nullptr;     // clearance field (first test of a belief-step, cck_rollout_grid.cuh), CCK_DF_N^2 bytes
+    uint32_t* d_df = nullptr;          // clearance field (first test of a belief-step, cck_rollout_grid.cuh), CCK_DF_N^2 words
     unsigned char* d_gtab = nullptr;   // fp32 box + cell-grid table (Blackmore broad phase, cck_rollout_grid.cuh)
     int gtab_bytes = 0;
     double* d_gexB = nullptr;          // exact fp64 rows in grid-table order
@@ -463,15 +463,16 @@ static void build_grid_table(int M, const double* A, const double* B, const std:
 }
 
 // ---------------------------------------------------------------------------
-// Clearance field: CCK_DF_N x CCK_DF_N cells over the fp32 (inward-rounded) state bounds.  Cell value = floor(16 * D) (0..255),
-// D = a LOWER bound of the Chebyshev clearance between any mean the device maps to the cell and every obstacle's OUTER box:
-//   D_cell = min_o max(dx_o, dy_o),  dx_o / dy_o = gap between the (padded) cell interval and the box interval per axis.
-// A belief with max(ex, ey) <= D (ex = sqrt2 c sqrt(P00), ...) has x - ex >= xhi or x + ex <= xlo or the same in y for
-// EVERY box, which is what the box test proves obstacle by obstacle.  The cell is padded by `pad` per side for the fp32
+// Clearance field: CCK_DF_N x CCK_DF_N cells over the fp32 (inward-rounded) state bounds.  For obstacle o (table row o) and a
+// cell, D_o = max(dx_o, dy_o) >= 0 with dx_o / dy_o = the gap between the (padded) cell interval and the OUTER box interval
+// per axis: a LOWER bound of the Chebyshev clearance between any mean the device maps to the cell and that box.  A belief
+// with max(ex, ey) <= D_o (ex = sqrt2 c sqrt(P00), ...) has x - ex >= xhi or x + ex <= xlo or the same in y: exactly what
+// the box test of obstacle o proves.  Cell word = floor(16 D1) | floor(16 D2) << 8 | j1 << 16 with D1 <= D2 the two smallest
+// D_o and j1 the row attaining D1 (values saturate at 255; one obstacle: D2 = saturated).  The cell is padded by `pad` per side for the fp32
 // roundings of the device's cell function and of the mean itself; the field is built only when every obstacle has a finite
 // outer box (n_grid == M) and the bounds are usable.  Returns false when there is no field.
 // ---------------------------------------------------------------------------
-static bool build_clearance_field(const GridBuild& gb, double c, float blx, float bhx, float bly, float bhy, std::vector<unsigned char>& q,
+static bool build_clearance_field(const GridBuild& gb, double c, float blx, float bhx, float bly, float bhy, std::vector<uint32_t>& q,
                                   float& icx, float& icy, float& k2) {
     GHeader h;
     std::memcpy(&h, gb.buf.data(), sizeof(h));
@@ -488,7 +489,8 @@ static bool build_clearance_field(const GridBuild& gb, double c, float blx, floa
     const double wx = 1.0 / (double)icx, wy = 1.0 / (double)icy;          // cell size in world units
     const double padx = wx / 1024.0 + (std::max(mag, 1.0) + rx) / 1048576.0, pady = wy / 1024.0 + (std::max(mag, 1.0) + ry) / 1048576.0;
     const float* boxes = reinterpret_cast<const float*>(gb.buf.data() + h.off_boxes);
-    std::vector<float> D((size_t)N * N, HUGE_VALF);
+    std::vector<float> D((size_t)N * N, HUGE_VALF), D2((size_t)N * N, HUGE_VALF);
+    std::vector<int> J((size_t)N * N, 0);
     const double reach = 256.0 / CCK_DF_SCALE;      // clearances beyond 255/16 saturate
     for (int o = 0; o < M; ++o) {
         const double xlo = boxes[4 * o], ylo = boxes[4 * o + 1], xhi = boxes[4 * o + 2], yhi = boxes[4 * o + 3];
@@ -502,34 +504,33 @@ static bool build_clearance_field(const GridBuild& gb, double c, float blx, floa
                 const double cx0 = (double)blx + i * wx - padx, cx1 = (double)blx + (i + 1) * wx + padx;
                 const double dx = std::max(xlo - cx1, cx0 - xhi);
                 const float d = (float)std::max(0.0, std::max(dx, dy));
-                float& cell = D[(size_t)j * N + i];
-                if (d < cell) cell = d;
+                const size_t ci = (size_t)j * N + i;
+                if (d < D[ci]) { D2[ci] = D[ci]; D[ci] = d; J[ci] = o; }
+                else if (d < D2[ci]) D2[ci] = d;
             }
         }
     }
     q.assign((size_t)N * N, 0);
-    for (size_t i = 0; i < q.size(); ++i) {
-        const double v = std::floor(std::min((double)D[i], reach) * CCK_DF_SCALE * (1.0 - 1e-6));
-        q[i] = (unsigned char)std::max(0.0, std::min(255.0, v));
-    }
+    auto quant = [&](float d) { return (uint32_t)std::max(0.0, std::min(255.0, std::floor(std::min((double)d, reach) * CCK_DF_SCALE * (1.0 - 1e-6)))); };
+    for (size_t i = 0; i < q.size(); ++i) q[i] = quant(D[i]) | (quant(D2[i]) << 8) | ((uint32_t)J[i] << 16);
     return true;
 }
 
 // Host-only (no GPU, no context): the clearance field cck_set_obstacles builds next to the grid table, for CPU tests of its
-// invariant (a cell's value never exceeds 16 x the true Chebyshev clearance of any point mapped to it).  out: CCK_DF_N^2 bytes
-// (row-major, y-major); params[0..2] = icx, icy, k2.  Returns CCK_OK with *has = 0 when no field is built.
+// invariant (a cell's values never exceed 16 x the true Chebyshev clearances of any point mapped to it).  out: CCK_DF_N^2
+// 32-bit words (row-major, y-major); params[0..2] = icx, icy, k2.  Returns CCK_OK with *has = 0 when no field is built.
 extern "C" int cck_build_clearance_field(int M, const double* A, const double* B, double erf_inv_result, const double* low, const double* high,
-                                         unsigned char* out, float* params, int* has) {
+                                         uint32_t* out, float* params, int* has) {
     if (M < 0 || (M > 0 && (!A || !B)) || !low || !high || !out || !params || !has) return CCK_ERR_INVALID;
     *has = 0;
     if (M == 0) return CCK_OK;
     GridBuild gb;
     std::vector<int> cls_idx(M, 0);
     build_grid_table(M, A, B, cls_idx, erf_inv_result, gb);
-    std::vector<unsigned char> q;
+    std::vector<uint32_t> q;
     float icx, icy, k2;
     if (!build_clearance_field(gb, erf_inv_result, f32_up(low[0]), f32_down(high[0]), f32_up(low[1]), f32_down(high[1]), q, icx, icy, k2)) return CCK_OK;
-    std::memcpy(out, q.data(), q.size());
+    std::memcpy(out, q.data(), q.size() * 4);
     params[0] = icx; params[1] = icy; params[2] = k2;
     *has = 1;
     return CCK_OK;
@@ -652,11 +653,11 @@ extern "C" int cck_set_obstacles(cck_ctx* c, const cck_svc_params* p, const doub
                               keep.blx, keep.bhx, keep.bly, keep.bhy, (int32_t)sizeof(TabHeader), gh.Rm1 + 1.f,
                               boxes_in_smem ? nullptr : reinterpret_cast<const float4*>(c->d_gtab + gh.off_boxes),
                               nullptr, 0.f, 0.f, 0.f};
-        std::vector<unsigned char> dfq;
+        std::vector<uint32_t> dfq;
         float dicx = 0, dicy = 0, dk2 = 0;
         if (!std::getenv("CCK_NO_DF") && build_clearance_field(gb, p->erf_inv_result, keep.blx, keep.bhx, keep.bly, keep.bhy, dfq, dicx, dicy, dk2)) {
-            CK(c, cudaMalloc(&c->d_df, dfq.size()));
-            CK(c, cudaMemcpy(c->d_df, dfq.data(), dfq.size(), cudaMemcpyHostToDevice));
+            CK(c, cudaMalloc(&c->d_df, dfq.size() * 4));
+            CK(c, cudaMemcpy(c->d_df, dfq.data(), dfq.size() * 4, cudaMemcpyHostToDevice));
             c->gconst.df = c->d_df; c->gconst.df_icx = dicx; c->gconst.df_icy = dicy; c->gconst.df_k2 = dk2;
         }
     }
@@ -1632,5 +1633,39 @@ extern "C" int cck_measure_fp64_peak(cck_ctx* c, double* tflops) {
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
     *tflops = best;
+    return CCK_OK;
+}
+
+// out[0..2]: FP64-pipe instructions per second (x 1e12, per lane) of alternating DMUL / DADD, DADD only, DMUL only;
+// out[3..5]: the FP64 rate of the alternating stream with 1, 2, 3 independent fp32 FMULs issued per FP64 instruction
+extern "C" int cck_measure_fp64_rates(cck_ctx* c, double* out) {
+    if (!c || !out) return CCK_ERR_INVALID;
+    CK(c, cudaSetDevice(c->device));
+    double* d = nullptr;
+    CK(c, cudaMalloc(&d, 8));
+    cudaEvent_t e0, e1;
+    CK(c, cudaEventCreate(&e0)); CK(c, cudaEventCreate(&e1));
+    const int iters = 1 << 14, blocks = c->num_sms * 8, threads = 256;
+    for (int mode = 0; mode < 6; ++mode) {
+        double best = 0;
+        for (int rep = 0; rep < 4; ++rep) {
+            CK(c, cudaEventRecord(e0, c->stream));
+            if (mode == 0) k_fp64_rate<0><<<blocks, threads, 0, c->stream>>>(d, iters, 1.0 + rep);
+            else if (mode == 1) k_fp64_rate<1><<<blocks, threads, 0, c->stream>>>(d, iters, 1.0 + rep);
+            else if (mode == 2) k_fp64_rate<2><<<blocks, threads, 0, c->stream>>>(d, iters, 1.0 + rep);
+            else if (mode == 3) k_fp64_mix<1><<<blocks, threads, 0, c->stream>>>(d, iters, 1.0 + rep);
+            else if (mode == 4) k_fp64_mix<2><<<blocks, threads, 0, c->stream>>>(d, iters, 1.0 + rep);
+            else k_fp64_mix<3><<<blocks, threads, 0, c->stream>>>(d, iters, 1.0 + rep);
+            CK(c, cudaEventRecord(e1, c->stream));
+            CK(c, cudaEventSynchronize(e1));
+            c->launches++;
+            float ms = 0;
+            CK(c, cudaEventElapsedTime(&ms, e0, e1));
+            const double inst = 8.0 * (double)iters * blocks * threads;
+            if (rep > 0) best = std::max(best, inst / (ms * 1e-3) / 1e12);
+        }
+        out[mode] = best;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
     return CCK_OK;
 }

@@ -498,4 +498,55 @@ __global__ void __launch_bounds__(256) k_fp64_peak(double* out, int iters, doubl
     if (s == 123.456) out[0] = s;   // keep the chains alive
 }
 
+// Non-fused FP64 instruction rate: MODE 0 alternating DMUL / DADD, 1 DADD only, 2 DMUL only (8 independent chains per
+// thread, __dmul_rn / __dadd_rn are never contracted).  The decision arithmetic of this library may not form FMAs, so
+// this - not the DFMA flop peak - is the attainable rate of its FP64 work.
+template <int MODE>
+__global__ void __launch_bounds__(256) k_fp64_rate(double* out, int iters, double seed) {
+    double a[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] = seed + threadIdx.x + j;
+    const double m = 0.999999, c = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (MODE == 0) a[j] = (i & 1) ? __dmul_rn(a[j], m) : __dadd_rn(a[j], c);
+            else if (MODE == 1) a[j] = __dadd_rn(a[j], c);
+            else a[j] = __dmul_rn(a[j], m);
+        }
+    }
+    double s = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += a[j];
+    if (s == 123.456) out[0] = s;
+}
+
+// Does an FP64 instruction keep the ISSUE port busy for more than one cycle?  NF fp32 FMULs (own chains) per non-fused FP64
+// instruction: if the FP64 rate is unchanged, fp32/int work issues in the shadow of the FP64 pipe; if it drops, it does not.
+template <int NF>
+__global__ void __launch_bounds__(256) k_fp64_mix(double* out, int iters, double seed) {
+    double a[8];
+    float f[8 * (NF > 0 ? NF : 1)];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] = seed + threadIdx.x + j;
+#pragma unroll
+    for (int j = 0; j < 8 * NF; ++j) f[j] = (float)seed + threadIdx.x + j;
+    const double m = 0.999999, c = 1e-9;
+    const float fm = 0.99999f;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            a[j] = (i & 1) ? __dmul_rn(a[j], m) : __dadd_rn(a[j], c);
+#pragma unroll
+            for (int q = 0; q < NF; ++q) f[j * NF + q] = __fmul_rn(f[j * NF + q], fm);
+        }
+    }
+    double s = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += a[j];
+#pragma unroll
+    for (int j = 0; j < 8 * NF; ++j) s += (double)f[j];
+    if (s == 123.456) out[0] = s;
+}
+
 }  // namespace cck

@@ -70,9 +70,10 @@ struct GridConst {
     int32_t off_classes;        // byte offset of the ClassRec array inside the (global) class table
     float Rf;                   // (float)R = Rm1 + 1
     const float4* boxes_global; // non-null: the box arrays are too large for shared memory and are read from global (L1/L2)
-    // clearance field (first test of a belief-step): CCK_DF_N x CCK_DF_N cells over the fp32 state bounds, one byte per cell =
-    // floor(16 * Chebyshev clearance of the cell to the nearest obstacle box), global memory (16 KB: L1-resident)
-    const unsigned char* df;    // null: no field (no obstacles, an obstacle without a box, unusable bounds)
+    // clearance field (first test of a belief-step): CCK_DF_N x CCK_DF_N cells over the fp32 state bounds, one 32-bit word per
+    // cell: bits 0-7 floor(16 * Chebyshev clearance of the cell to the NEAREST obstacle box), bits 8-15 the same for the
+    // SECOND nearest box, bits 16-31 the table row of the nearest box.  Global memory (64 KB, L1/L2-resident).
+    const uint32_t* df;         // null: no field (no obstacles, an obstacle without a box, unusable bounds)
     float df_icx, df_icy;       // cells per unit, shrunk so that a mean strictly inside the bounds lands in [0, CCK_DF_N)
     float df_k2;                // >= 256 * 2 c^2 (1 + 2^-18): variance -> (16 * sqrt2 c sqrt(P))^2, rounded up
 };
@@ -129,36 +130,38 @@ __device__ __forceinline__ bool grid_obstacle(const GridConst& g, const unsigned
 // in, so that the common outcome - bounds proven, operands finite, no gridded obstacle near, no obstacle without a box -
 // leaves through ONE branch (ncu: 21 of 215 instructions per warp-step were BRA/BSSY/BSYNC of five separate rare-path
 // tests).  `enabled` = there is an obstacle table at all.
-// Clearance field lookup for a mean the caller has PROVEN strictly inside the fp32 bounds (`pre`): the squared clearance of
-// its cell in units of 1/16, or 0 when there is no field / the mean is not proven inside.  Issued right after the mean
+// Clearance field lookup for a mean the caller has PROVEN strictly inside the fp32 bounds (`pre`): the word of its cell, or 0
+// (clearances 0: nothing provable) when there is no field / the mean is not proven inside.  Issued right after the mean
 // update so that the load overlaps the covariance recursion.
-__device__ __forceinline__ float df_lookup(const GridConst& g, bool pre, float xf, float yf) {
-    if (!g.df || !pre) return 0.f;
+__device__ __forceinline__ uint32_t df_lookup(const GridConst& g, bool pre, float xf, float yf) {
+    if (!g.df || !pre) return 0u;
     const int cx = __float2int_rz(__fmul_rn(__fsub_rn(xf, g.blx), g.df_icx));
     const int cy = __float2int_rz(__fmul_rn(__fsub_rn(yf, g.bly), g.df_icy));
-    const float q = (float)__ldg(g.df + (cy * CCK_DF_N + cx));
-    return q * q;
+    return __ldg(g.df + (cy * CCK_DF_N + cx));
 }
 
-// `q2` (optional): df_lookup's result for this mean.  If (16 * sqrt2 c sqrt(max(P00, P11)))^2 < q2, the belief's interval
-// stays clear of EVERY obstacle box by Chebyshev distance: proven safe with one compare, before any window arithmetic.
+// `dfw` (optional): df_lookup's word for this mean.  With t = (16 sqrt2 c sqrt(max(P00, P11)))^2:
+//   t < q1^2: the belief's interval stays clear of EVERY obstacle box by Chebyshev distance - proven safe with one compare,
+//             before any window arithmetic;
+//   t < q2^2: it stays clear of every box except possibly the nearest one - that single obstacle is decided by its box
+//             tests / the exact expression, without the cell window and its loops.
 template <bool SPLIT = false, class ExactBounds>
 __device__ __forceinline__ bool grid_check_b(const GridConst& g, const unsigned char* gt, const unsigned char* ctab, const double* exB,
                                              const int32_t* exCls, double c, bool pre, const ExactBounds& exact_bounds, bool enabled, double x, double y,
                                              double Sa0, double Sa1, double Sa2, double Sa3, double Sb0 = 0, double Sb1 = 0, double Sb2 = 0,
-                                             double Sb3 = 0, bool* cov_small_out = nullptr, float q2 = 0.f) {
+                                             double Sb3 = 0, bool* cov_small_out = nullptr, uint32_t dfw = 0u) {
     const GridConst* h = &g;
     const int M = h->M;
     const double P0 = SPLIT ? Sa0 + Sb0 : Sa0, P1 = SPLIT ? Sa1 + Sb1 : Sa1, P2 = SPLIT ? Sa2 + Sb2 : Sa2, P3 = SPLIT ? Sa3 + Sb3 : Sa3;
     const float p0 = __double2float_rn(P0), p3 = __double2float_rn(P3);
-    {
-        // covariance entries finite, non-negative on the diagonal and below 2^100, by their high words (sign bit or NaN
-        // exponent compare as huge unsigned numbers)
-        const bool cov_ok0 = cov_small(P0, P1, P2, P3);
-        if (cov_small_out) *cov_small_out = cov_ok0;
-        // q2 > 0 implies `pre` (df_lookup): bounds proven, mean finite.  NaN variances compare false.
-        if (cov_ok0 & (__fmul_rn(fmaxf(p0, p3), h->df_k2) < q2)) return true;
-    }
+    // covariance entries finite, non-negative on the diagonal and below 2^100, by their high words (sign bit or NaN
+    // exponent compare as huge unsigned numbers)
+    const bool cov_ok = cov_small(P0, P1, P2, P3);
+    if (cov_small_out) *cov_small_out = cov_ok;
+    // a non-zero clearance implies `pre` (df_lookup): bounds proven, mean finite.  NaN variances compare false.
+    const float tq = __fmul_rn(fmaxf(p0, p3), h->df_k2);
+    const float q1 = (float)(dfw & 255u);
+    if (cov_ok & (tq < q1 * q1)) return true;
     const float xf = __double2float_rn(x), yf = __double2float_rn(y);
     // the reference's fp64 expression on obstacle j's own normals
     auto exact = [&](int j) -> bool {
@@ -189,8 +192,12 @@ __device__ __forceinline__ bool grid_check_b(const GridConst& g, const unsigned 
     const bool empty = (uchi < 0.f) | (uclo >= (float)CCK_GRID_COLS) | (urhi < 0.f) | (urlo >= h->Rf);
     // with `pre` (mean strictly inside the fp32 bounds) and a small finite covariance this is all the second fast exit needs -
     // a non-finite or overflowing fp32 intermediate above can only make the window look NON-empty
-    const bool cov_ok = cov_small(P0, P1, P2, P3);
     if (pre & cov_ok & empty & (h->n_grid == M)) return true;
+    {   // only the nearest box can matter (tq < q2^2 bounds the variances, the field bounds the mean: every operand of the
+        // box tests is finite and small)
+        const float q2 = (float)((dfw >> 8) & 255u);
+        if (cov_ok & (tq < q2 * q2)) return grid_obstacle(g, gt, (int)(dfw >> 16), xm, xp, ym, yp, mx, my, exact);
+    }
     if (!pre && !exact_bounds()) return false;
     if (!enabled) return true;
     const float offd = __double2float_rn(fabs(P1) + fabs(P2));
@@ -228,8 +235,8 @@ __device__ __forceinline__ bool grid_check(const GridConst& g, const unsigned ch
     const bool pre = fabs(x) + fabs(y) < 1e30;
     // the clearance field needs the mean strictly inside the fp32 bounds it was built over
     const float xf = __double2float_rn(x), yf = __double2float_rn(y);
-    const float q2 = df_lookup(g, (xf > g.blx) & (xf < g.bhx) & (yf > g.bly) & (yf < g.bhy), xf, yf);
-    return grid_check_b<SPLIT>(g, gt, ctab, exB, exCls, c, pre, [] { return true; }, true, x, y, Sa0, Sa1, Sa2, Sa3, Sb0, Sb1, Sb2, Sb3, nullptr, q2);
+    const uint32_t dfw = df_lookup(g, (xf > g.blx) & (xf < g.bhx) & (yf > g.bly) & (yf < g.bhy), xf, yf);
+    return grid_check_b<SPLIT>(g, gt, ctab, exB, exCls, c, pre, [] { return true; }, true, x, y, Sa0, Sa1, Sa2, Sa3, Sb0, Sb1, Sb2, Sb3, nullptr, dfw);
 }
 
 // PCCBlackmoreSVC::isValid, batched (row a4), through the same broad phase: bounds, then grid_check.
@@ -278,7 +285,7 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // over 4 x 128 threads).  The expansion kernel carries the constraint and goal tests: 128 threads x 3 CTAs leaves it 168
 // registers (no spills); its launches are planner-sized and latency-bound.
 #ifndef CCK_GRID_THREADS
-#define CCK_GRID_THREADS 160
+#define CCK_GRID_THREADS 128
 #endif
 #ifndef CCK_GRID_MINB
 #define CCK_GRID_MINB 4
@@ -391,16 +398,14 @@ __global__ void __launch_bounds__(grid_threads(EXPAND), grid_minb(EXPAND)) k_rol
             a.flags[i] = (uint8_t)((t == steps ? 1 : 0) | (cons_ok ? 2 : 0) | (g ? 4 : 0));
         }
     };
-    // refill (warp-synchronous): idle lanes take their prefetched belief and the warp claims the ones after them.  When four
-    // or more lanes are served, whole quads only (the rest waits for the next round): four consecutive beliefs = one sector
-    // per plane.  A belief with steps <= 0 is answered on the spot; its lane picks up real work in the next round.
+    // refill (warp-synchronous): idle lanes take their prefetched belief and the warp claims the ones after them with one
+    // atomicAdd.  (Serving whole quads only, so that four lanes always fill one 32-byte sector per plane, was measured:
+    // the up-to-three lanes left waiting cost more lane-time than the sectors saved - the sweep is not DRAM-bound.)
+    // A belief with steps <= 0 is answered on the spot; its lane picks up real work in the next round.
     auto take = [&](Lin& A) {
         flush(A);
         const bool cand = !have && nxt >= 0;
-        const unsigned mc = __ballot_sync(0xffffffffu, cand);
-        int nserve = __popc(mc);
-        if (nserve >= 4) nserve &= ~3;
-        const bool serve = cand && __popc(mc & ((1u << lane) - 1u)) < nserve;
+        const bool serve = cand;
         if (serve) {
             cp_async_wait_all();
             i = nxt;
@@ -432,27 +437,29 @@ __global__ void __launch_bounds__(grid_threads(EXPAND), grid_minb(EXPAND)) k_rol
             }
         }
     };
-    // one belief-step of a lane that has work, in place (lin_step is alias-safe)
-    auto advance = [&](Lin& A, Lin& B) {
-        // stash the last valid state, advance A -> B
+    // One belief-step of a lane that has work, in place (lin_step is alias-safe), in two phases: stepA advances the state,
+    // stepB checks the new state and commits.  (x, y, pre, dfw) carry the new mean, its fp32 bounds pre-check and its
+    // clearance-field word from one phase to the other.
+    double x = 0, y = 0;
+    bool pre = false;
+    uint32_t dfw = 0u;
+    auto stepA = [&](Lin& A, bool use_dense) {
+        // stash the last valid state
         stash[0] = make_double2(A.mx, A.my);
         stash[1] = make_double2(A.S[0], A.S[1]); stash[2] = make_double2(A.S[2], A.S[3]);
         stash[3] = make_double2(A.L[0], A.L[1]); stash[4] = make_double2(A.L[2], A.L[3]);
         // the new mean first (UncertainLinearSP.cpp:92-93; the step functions below form the same sums): its clearance-field
         // cell is looked up NOW so that the load is in flight during the covariance recursion
-        const double x = A.mx + dux, y = A.my + duy;
+        x = A.mx + dux; y = A.my + duy;
         // satisfiesBounds (NaN passes): the mean rounded to fp32 strictly inside the inward-rounded bounds proves it
         // (RN is monotone: xf < bhx <= high implies x < high); otherwise the exact fp64 test decides
         const float xf = __double2float_rn(x), yf = __double2float_rn(y);
-        const bool pre = (xf > g.blx) & (xf < g.bhx) & (yf > g.bly) & (yf < g.bhy);
-        const float q2 = df_lookup(g, pre, xf, yf);
-        if (dense) lin_step(A, dux, duy, p, B); else lin_step_diag(A, dux, duy, p, B);
-        bool small;
-        const bool ok = grid_check_b<true>(
-            g, gt, a.tab, a.exB, a.exCls, c, pre,
-            [&] { return !(x - eps > sp.high[0] || x + eps < sp.low[0] || y - eps > sp.high[1] || y + eps < sp.low[1]); }, a.ftab_bytes > 0, x, y,
-            B.S[0], B.S[1], B.S[2], B.S[3], B.L[0], B.L[1], B.L[2], B.L[3], &small, q2);
-        dense = !p.diag || !small;   // the new covariance is finite: the next step may skip the exact-zero terms
+        pre = (xf > g.blx) & (xf < g.bhx) & (yf > g.bly) & (yf < g.bhy);
+        dfw = df_lookup(g, pre, xf, yf);
+        if (use_dense) lin_step(A, dux, duy, p, A); else lin_step_diag(A, dux, duy, p, A);
+    };
+    // commit a valid step / end the rollout
+    auto commit = [&](Lin& B, bool ok) {
         if (ok) {
             if (EXPAND && cons) {   // Sigma + Lambda formed here, not carried across the validity check
                 double s0 = B.S[0], s1 = B.S[1], s2 = B.S[2], s3 = B.S[3];
@@ -471,20 +478,58 @@ __global__ void __launch_bounds__(grid_threads(EXPAND), grid_minb(EXPAND)) k_rol
         // complete (t == steps).  The result is stored by flush(), together with the other finished lanes of the warp.
         if (!ok || t == steps) { have = false; pending = true; }
     };
+    auto stepB = [&](Lin& B) {
+        bool small;
+        const bool ok = grid_check_b<true>(
+            g, gt, a.tab, a.exB, a.exCls, c, pre,
+            [&] { return !(x - eps > sp.high[0] || x + eps < sp.low[0] || y - eps > sp.high[1] || y + eps < sp.low[1]); }, a.ftab_bytes > 0, x, y,
+            B.S[0], B.S[1], B.S[2], B.S[3], B.L[0], B.L[1], B.L[2], B.L[3], &small, dfw);
+        dense = !p.diag || !small;   // the new covariance is finite: the next step may skip the exact-zero terms
+        commit(B, ok);
+    };
     // Lanes are refilled as soon as their rollout ends, but in batches: the take / prefetch / result-store code is ~150
     // instructions that a single finished lane would make the whole warp issue.  Idle lanes therefore wait until
     // CCK_REFILL_MIN lanes of the warp are idle, or at most CCK_REFILL_WAIT iterations (ncu, realistic sweep: the refill
     // path was 24 % of the issue slots at 2.1 active lanes on average).
     int it = 0;
+    bool checked = true;           // false: stepA has run for this lane, stepB is still due (set by the uniform section)
     while (true) {
+        // ---- uniform section: every lane of the warp has work and may take the diagonal-constant step.  The warp then runs
+        // min(steps - t) steps without the per-lane bookkeeping of the general loop (idle ballot, have / dense branches,
+        // per-lane end test): per step ONE vote on "every lane passed the clearance-field test".  The first step some lane
+        // does not pass falls through to the general section, which finishes exactly that step (stepB) for every lane.
+        // An FP64 instruction costs two issue cycles and everything else one (cck_measure_fp64_rates), so the ~50 warp
+        // instructions this saves per step are worth ~20 % on the all-survive sweep.
+        if (!EXPAND && g.df != nullptr && __all_sync(0xffffffffu, have && !dense)) {
+            int nf = (int)__reduce_min_sync(0xffffffffu, (unsigned)(steps - t));
+            while (nf > 0) {
+                stepA(cur, false);
+                const double P0 = cur.S[0] + cur.L[0], P1 = cur.S[1] + cur.L[1], P2 = cur.S[2] + cur.L[2], P3 = cur.S[3] + cur.L[3];
+                const float q1 = (float)(dfw & 255u);
+                const bool fast = cov_small(P0, P1, P2, P3) & (__fmul_rn(fmaxf(__double2float_rn(P0), __double2float_rn(P3)), g.df_k2) < q1 * q1);
+                if (!__all_sync(0xffffffffu, fast)) { checked = false; break; }
+                if (TRAJ && t < a.traj_T) {
+                    double* tp = a.traj + (int64_t)t * 10 * a.traj_ld + i;
+                    tp[0] = cur.mx; tp[a.traj_ld] = cur.my;
+#pragma unroll
+                    for (int f = 0; f < 4; ++f) { tp[(2 + f) * a.traj_ld] = cur.S[f]; tp[(6 + f) * a.traj_ld] = cur.L[f]; }
+                }
+                ++t; --nf;
+            }
+            if (checked && t == steps) { have = false; pending = true; }
+        }
+        if (!checked) {            // warp-uniform: finish the step the uniform section started
+            stepB(cur);
+            checked = true;
+        }
         const unsigned idle = __ballot_sync(0xffffffffu, !have);
         if (idle) {
             if (__popc(idle) >= CCK_REFILL_MIN || (++it & (CCK_REFILL_WAIT - 1)) == 0) {
                 take(cur);
-                if (__all_sync(0xffffffffu, !have && nxt < 0)) break;   // nothing running and nothing prefetched (a lane the quad rule skipped is served next round)
+                if (__all_sync(0xffffffffu, !have && nxt < 0)) break;   // nothing running and nothing prefetched
             }
         }
-        if (have) advance(cur, cur);
+        if (have) { stepA(cur, dense); stepB(cur); }
     }
 }
 

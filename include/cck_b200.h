@@ -227,6 +227,11 @@ int cck_select_winner_dev(cck_ctx* ctx, void* stream, int64_t n, const double* c
  * the roofline denominator for the obstacle-check kernels (MEASURED_PEAKS.json has no
  * FP64 entry). */
 int cck_measure_fp64_peak(cck_ctx* ctx, double* tflops);
+/* out[0..2]: NON-fused FP64 instruction rates (1e12 instructions/s per lane): alternating DMUL/DADD, DADD only, DMUL only.
+ * The decision arithmetic may not be contracted into FMAs, so these are the attainable rates of the path's FP64 work.
+ * out[3..5]: the FP64 rate of the alternating stream when 1, 2, 3 independent fp32 instructions are issued per FP64
+ * instruction (is the issue port shared?  it tells how much fp32/int work the FP64 pipe hides). */
+int cck_measure_fp64_rates(cck_ctx* ctx, double* out6);
 
 /* Host-only (no GPU, no context): the serialised fp32 box + cell-grid table that cck_set_obstacles builds for the
  * PCCBlackmoreSVC broad phase (PCCBlackmoreSVC.cpp:54-75 is what it must never contradict).  Exposed so that the
@@ -235,15 +240,16 @@ int cck_measure_fp64_peak(cck_ctx* ctx, double* tflops);
 int cck_build_grid_table(int M, const double* A, const double* B, double erf_inv_result, unsigned char* out, int64_t cap,
                          int64_t* bytes, int32_t* order);
 
-/* Host-only: the clearance field built next to the grid table - CCK_DF_N x CCK_DF_N (128 x 128) bytes over the fp32 state
- * bounds, value = floor(16 x a lower bound of the Chebyshev clearance between any mean mapped to the cell and every
- * obstacle's outer box).  It is the FIRST test of a belief-step (one byte load + one compare proves "safe w.r.t. every
- * obstacle" for a belief whose sqrt2 c sqrt(P) interval is smaller than the clearance); everything it cannot prove goes on to
- * the cell-grid broad phase and the exact decision.  params[0..2] = cells per unit in x, in y, and the factor that turns a
+/* Host-only: the clearance field built next to the grid table - CCK_DF_N x CCK_DF_N (128 x 128) 32-bit words over the fp32
+ * state bounds: bits 0-7 floor(16 x a lower bound of the Chebyshev clearance between any mean mapped to the cell and the
+ * NEAREST obstacle's outer box), bits 8-15 the same for the second nearest box, bits 16-31 the grid-table row of the nearest
+ * one (order[] of cck_build_grid_table).  It is the FIRST test of a belief-step: one load + one compare proves "safe w.r.t.
+ * every obstacle" for a belief whose sqrt2 c sqrt(P) interval is smaller than the clearance, a second compare reduces the
+ * decision to the nearest obstacle alone; everything else goes on to the cell-grid broad phase and the exact decision.  params[0..2] = cells per unit in x, in y, and the factor that turns a
  * variance into the squared 1/16-unit interval half-width.  *has = 0: no field (M = 0, an obstacle without an axis-aligned
  * box, unusable bounds).  For CPU tests of the invariant. */
 int cck_build_clearance_field(int M, const double* A, const double* B, double erf_inv_result, const double* low, const double* high,
-                              unsigned char* out, float* params, int* has);
+                              uint32_t* out, float* params, int* has);
 
 /* ---- belief-space nearest neighbours over a device-resident tree ----
  * RealVectorBeliefSpace::distance (src/Spaces/RealVectorBeliefSpace.cpp:16-62):
