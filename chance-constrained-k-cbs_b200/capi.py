@@ -20,7 +20,7 @@ OK, ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_NODEVICE = 0, 1, 2, 3, 4
 MODEL_LINEAR2D, MODEL_UNICYCLE = 0, 1
 SVC_BLACKMORE, SVC_ADAPTIVE, SVC_CHISQUARED = 0, 1, 2
 PVC_BLACKMORE, PVC_BOUNDINGBOX, PVC_CHISQUARED, PVC_ADAPTIVE_BLACKMORE, PVC_ADAPTIVE_BOUNDINGBOX = range(5)
-FLAG_FULL, FLAG_CONS_OK, FLAG_GOAL = 1, 2, 4
+FLAG_FULL, FLAG_CONS_OK, FLAG_GOAL, FLAG_COV_TABLE = 1, 2, 4, 8
 
 
 class CckError(RuntimeError):
@@ -65,7 +65,7 @@ SYMBOLS = [
     "cck_propagate", "cck_propagate_dev", "cck_is_valid", "cck_is_valid_dev",
     "cck_propagate_while_valid", "cck_propagate_while_valid_dev",
     "cck_validate_plan", "cck_validate_plan_dev",
-    "cck_set_constraints", "cck_satisfies_constraints", "cck_satisfies_constraints_dev", "cck_build_clearance_field", "cck_measure_fp64_rates",
+    "cck_set_constraints", "cck_satisfies_constraints", "cck_satisfies_constraints_dev", "cck_build_clearance_field", "cck_measure_fp64_rates", "cck_set_cov_table",
     "cck_expand_batch", "cck_expand_batch_dev", "cck_rollout_summary_dev", "cck_select_winner_dev", "cck_measure_fp64_peak",
     "cck_tree_create", "cck_tree_destroy", "cck_tree_clear", "cck_tree_size", "cck_tree_append", "cck_tree_update",
     "cck_tree_select", "cck_tree_nearest", "cck_tree_witness_batch", "cck_belief_distance", "cck_belief_distance_lower", "cck_belief_distance_cols", "cck_belief_distance_cols_near", "cck_build_grid_table",
@@ -131,6 +131,7 @@ def lib():
     L.cck_validate_plan.argtypes = [vp, C.c_int, vp, vp, i64, C.POINTER(ConflictRun)]
     L.cck_validate_plan_dev.argtypes = [vp, vp, C.c_int, vp, C.c_int, vp, i64, vp]
     L.cck_set_constraints.argtypes = [vp, C.c_int, vp, vp, vp, vp]
+    L.cck_set_cov_table.argtypes = [vp, vp, C.c_int]
     L.cck_satisfies_constraints.argtypes = [vp, i64, vp, i64, C.c_int32, vp, vp, vp]
     L.cck_satisfies_constraints_dev.argtypes = [vp, vp, i64, vp, i64, C.c_int32, vp, vp, vp]
     L.cck_expand_batch.argtypes = [vp, i64, vp, i64, vp, i64, vp, vp, vp, C.POINTER(GoalParams), vp, i64, vp, vp, vp, vp]
@@ -337,6 +338,12 @@ class Context:
         if run.first_step < 0:
             return None
         return (run.a, run.b, run.first_step, run.run_len)
+
+    def set_cov_table(self, root_cov, n_steps):
+        """Covariance table of a low-level tree (cck_set_cov_table); root_cov = [Sigma row-major, Lambda row-major]."""
+        rc = None if root_cov is None else np.ascontiguousarray(root_cov, dtype=np.float64)
+        self._keep.append(rc)
+        self._ck(self.L.cck_set_cov_table(self.h, _ptr(rc), int(n_steps)))
 
     def set_constraints(self, ent_step, pair_ab, mu2, cov4):
         n = len(ent_step)

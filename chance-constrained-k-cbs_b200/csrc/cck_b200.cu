@@ -56,6 +56,8 @@ struct cck_ctx {
     unsigned long long* d_key = nullptr;
     cck_conflict_run* d_run = nullptr;
 
+    double* d_cov_tab = nullptr;       // covariance table of the planner's tree (cck_set_cov_table)
+    int cov_tab_n = 0;
     unsigned char* d_cons = nullptr;   // constraint table (nullptr = no constraints)
     size_t cons_cap = 0;
     int cons_bytes = 0;                // size of the current constraint table (staged into shared memory when small)
@@ -135,7 +137,7 @@ extern "C" int cck_ctx_destroy(cck_ctx* c) {
     for (int i = 0; i < CCK_SLOTS; ++i) { if (c->pipe[i]) { cudaStreamSynchronize(c->pipe[i]); cudaStreamDestroy(c->pipe[i]); } cudaFree(c->d_scratch[i]); }
     cudaFree(c->d_df); cudaFree(c->d_gtab); cudaFree(c->d_gexB); cudaFree(c->d_gexCls);
     cudaFree(c->d_tab); cudaFree(c->d_pvc_A); cudaFree(c->d_pvc_B); cudaFree(c->d_pvc_radii); cudaFree(c->d_pvc_order);
-    cudaFree(c->d_key); cudaFree(c->d_run); cudaFree(c->d_cons);
+    cudaFree(c->d_key); cudaFree(c->d_run); cudaFree(c->d_cons); cudaFree(c->d_cov_tab);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return CCK_OK;
@@ -327,6 +329,7 @@ extern "C" int cck_set_model(cck_ctx* c, const cck_model_params* p) {
         c->uni.sparse = ok ? 1 : 0; c->uni.pad = 0;
     }
     c->has_model = true;
+    if (c->d_cov_tab) { cudaSetDevice(c->device); cudaStreamSynchronize(c->stream); cudaFree(c->d_cov_tab); c->d_cov_tab = nullptr; c->cov_tab_n = 0; }   // built for the old model
     return CCK_OK;
 }
 
@@ -896,8 +899,34 @@ extern "C" int cck_expand_batch_dev(cck_ctx* c, void* stream, int64_t n, const d
     a.tab = c->d_tab; a.tab_bytes = c->tab_bytes; a.duration = c->model.dt;
     a.parent_step = parent_step; a.parent_cost = parent_cost; a.cost = cost; a.goal_dist = goal_dist; a.flags = flags;
     a.goal = *goal; a.cons = c->d_cons;
+    a.cov_tab = c->d_cov_tab; a.cov_tab_n = c->cov_tab_n;
     a.cons_smem_bytes = (c->d_cons && c->cons_bytes <= CCK_CONS_SMEM_MAX) ? c->cons_bytes : 0;   // small tables are copied into shared memory by each CTA
     return launch_rollout<true>(c, pick(c, stream), a);
+}
+
+// Covariance table of a low-level tree (see RolloutArgs::cov_tab): entries for absolute steps 0 .. n_steps-1 from the root
+// covariance root_cov = [Sigma row-major, Lambda row-major] (2 dim^2 doubles).  n_steps <= 0 removes the table.
+extern "C" int cck_set_cov_table(cck_ctx* c, const double* root_cov, int n_steps) {
+    int rc = check_ready(c, false);
+    if (rc) return rc;
+    CK(c, cudaSetDevice(c->device));
+    CK(c, cudaStreamSynchronize(c->stream));
+    cudaFree(c->d_cov_tab); c->d_cov_tab = nullptr; c->cov_tab_n = 0;
+    if (n_steps <= 0) return CCK_OK;
+    if (!root_cov || n_steps > (1 << 20)) return fail(c, CCK_ERR_INVALID, "bad covariance table arguments");
+    const int dim = c->model.dim, per = 2 * dim * dim;
+    double* d_root = nullptr;
+    CK(c, cudaMalloc(&c->d_cov_tab, (size_t)n_steps * per * 8));
+    CK(c, cudaMalloc(&d_root, per * 8));
+    CK(c, cudaMemcpy(d_root, root_cov, per * 8, cudaMemcpyHostToDevice));
+    if (c->model.model == CCK_MODEL_LINEAR2D) k_cov_table_lin<<<1, 32, 0, c->stream>>>(c->d_cov_tab, n_steps, c->lin, d_root);
+    else k_cov_table_uni<<<1, 32, 0, c->stream>>>(c->d_cov_tab, n_steps, c->uni, d_root);
+    c->launches++;
+    const cudaError_t e = cudaStreamSynchronize(c->stream);
+    cudaFree(d_root);
+    if (e != cudaSuccess) { cudaFree(c->d_cov_tab); c->d_cov_tab = nullptr; c->err = std::string("k_cov_table: ") + cudaGetErrorString(e); return CCK_ERR_CUDA; }
+    c->cov_tab_n = n_steps;
+    return CCK_OK;
 }
 
 // ---------------------------------------------------------------------------

@@ -25,6 +25,13 @@ struct RolloutArgs {
     const int32_t* parent_step; const double* parent_cost;
     double* cost; double* goal_dist; uint8_t* flags;
     cck_goal_params goal;
+    // Covariance table of the planner's tree (EXPAND kernels): the covariance recursion does not depend on the mean or the
+    // control (UncertainLinearSP.cpp:98-104, UncertainUnicycleSP.cpp:210-220), and every node of a low-level tree descends from
+    // the same start covariance, so the node at absolute step s carries cov_tab[s] = (Sigma_s, Lambda_s) - computed once by
+    // k_cov_table with the very instruction sequence of the step functions.  A candidate whose parent covariance equals
+    // cov_tab[parent_step] BIT FOR BIT reads its next covariances from the table instead of recomputing them; any other
+    // candidate takes the normal step.  Entry s at cov_tab + s * 2 * dim * dim (Sigma row-major, then Lambda).
+    const double* cov_tab; int32_t cov_tab_n;
     const unsigned char* cons;   // constraint table (global memory)
     int32_t cons_smem_bytes;     // > 0: the table is small, every CTA copies it into shared memory first (multiple of 16)
     // staged table: the fp32 box/cell-grid table (Blackmore; exact rows exB/exCls stay in global memory for the rare
@@ -258,6 +265,34 @@ __global__ void __launch_bounds__(128) k_rollout_lin(const __grid_constant__ Rol
         }
     }
     if (!waited) stage_wait((uint32_t)a.tab_bytes, bar);
+}
+
+// ---------------------------------------------------------------------------
+// covariance table of the planner's tree (see RolloutArgs::cov_tab): one thread iterates the model's own step
+// ---------------------------------------------------------------------------
+__global__ void k_cov_table_lin(double* __restrict__ tab, int n, const __grid_constant__ LinDev p, const double* __restrict__ root) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    Lin s, o;
+    s.mx = s.my = 0;
+    for (int f = 0; f < 4; ++f) { s.S[f] = root[f]; s.L[f] = root[4 + f]; }
+    for (int k = 0; k < n; ++k) {
+        for (int f = 0; f < 4; ++f) { tab[(size_t)k * 8 + f] = s.S[f]; tab[(size_t)k * 8 + 4 + f] = s.L[f]; }
+        // the diagonal-constant step where the rollout kernels would take it (finite covariance), else the dense one: the
+        // two agree except for the sign of an exact zero (cck_device.cuh), and the table must hold what the kernels compute
+        const bool diag = p.diag && cov_small(s.S[0] + s.L[0], s.S[1] + s.L[1], s.S[2] + s.L[2], s.S[3] + s.L[3]);
+        if (diag) lin_step_diag(s, 0.0, 0.0, p, o); else lin_step(s, 0.0, 0.0, p, o);
+        s = o;
+    }
+}
+__global__ void k_cov_table_uni(double* __restrict__ tab, int n, const __grid_constant__ UniDev p, const double* __restrict__ root) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    double S[16], L[16], So[16], Lo[16];
+    for (int f = 0; f < 16; ++f) { S[f] = root[f]; L[f] = root[16 + f]; }
+    for (int k = 0; k < n; ++k) {
+        for (int f = 0; f < 16; ++f) { tab[(size_t)k * 32 + f] = S[f]; tab[(size_t)k * 32 + 16 + f] = L[f]; }
+        uni_cov_step(S, L, p, So, Lo);     // the dense step: bit-identical to the sparse one for finite inputs (cck_rollout_uni.cuh)
+        for (int f = 0; f < 16; ++f) { S[f] = So[f]; L[f] = Lo[f]; }
+    }
 }
 
 // ---------------------------------------------------------------------------

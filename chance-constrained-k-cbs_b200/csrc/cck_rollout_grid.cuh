@@ -77,7 +77,9 @@ struct GridConst {
     float df_icx, df_icy;       // cells per unit, shrunk so that a mean strictly inside the bounds lands in [0, CCK_DF_N)
     float df_k2;                // >= 256 * 2 c^2 (1 + 2^-18): variance -> (16 * sqrt2 c sqrt(P))^2, rounded up
 };
+#ifndef CCK_DF_N
 #define CCK_DF_N 128
+#endif
 #define CCK_DF_SCALE 16.0
 
 #define CCK_GRID_COLS 64
@@ -293,10 +295,10 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 __host__ __device__ constexpr int grid_threads(bool expand) { return expand ? 128 : CCK_GRID_THREADS; }
 __host__ __device__ constexpr int grid_minb(bool expand) { return expand ? 3 : CCK_GRID_MINB; }
 #ifndef CCK_REFILL_MIN
-#define CCK_REFILL_MIN 6      // idle lanes of a warp that trigger a refill ...
+#define CCK_REFILL_MIN 10     // idle lanes of a warp that trigger a refill ...
 #endif
 #ifndef CCK_REFILL_WAIT
-#define CCK_REFILL_WAIT 4     // ... or this many loop iterations with an idle lane (power of two)
+#define CCK_REFILL_WAIT 8    // ... or this many loop iterations with an idle lane (power of two)
 #endif
 // the work counter hands out ranges of 2^range_log2 consecutive beliefs, round-robin over the CTAs: 256 for the
 // big sweeps (coalesced refills), 128 = one belief per lane for planner-sized batches (latency: every candidate of a
@@ -367,6 +369,7 @@ __global__ void __launch_bounds__(grid_threads(EXPAND), grid_minb(EXPAND)) k_rol
 
     bool have = false, pending = false;
     bool dense = true;             // this lane's next step must be the dense lin_step (see lin_step_diag's preconditions)
+    bool use_tab = false;          // EXPAND: this candidate's covariances come from the tree's covariance table (RolloutArgs::cov_tab)
     Lin cur;
     double dux = 0, duy = 0;
     int steps = 0, t = 0, pstep = 0;
@@ -395,7 +398,7 @@ __global__ void __launch_bounds__(grid_threads(EXPAND), grid_minb(EXPAND)) k_rol
             double gd;
             const bool g = goal_ok(a.goal, sp, B.mx, B.my, B.S[0] + B.L[0], B.S[1] + B.L[1], B.S[2] + B.L[2], B.S[3] + B.L[3], &gd);
             a.goal_dist[i] = gd;
-            a.flags[i] = (uint8_t)((t == steps ? 1 : 0) | (cons_ok ? 2 : 0) | (g ? 4 : 0));
+            a.flags[i] = (uint8_t)((t == steps ? 1 : 0) | (cons_ok ? 2 : 0) | (g ? 4 : 0) | (use_tab ? 8 : 0));
         }
     };
     // refill (warp-synchronous): idle lanes take their prefetched belief and the warp claims the ones after them with one
@@ -433,6 +436,18 @@ __global__ void __launch_bounds__(grid_threads(EXPAND), grid_minb(EXPAND)) k_rol
             } else {
                 t = 0; cons_ok = true;
                 dense = !p.diag || !cov_small(A.S[0] + A.L[0], A.S[1] + A.L[1], A.S[2] + A.L[2], A.S[3] + A.L[3]);
+                if (EXPAND) {      // parent covariance bit-identical to the table's entry for its depth, and the segment inside the table
+                    use_tab = false;
+                    if (a.cov_tab && pstep >= 0 && pstep + steps < a.cov_tab_n) {
+                        const double* e = a.cov_tab + (size_t)pstep * 8;
+                        bool same = true;
+#pragma unroll
+                        for (int f = 0; f < 4; ++f)
+                            same = same && __double_as_longlong(A.S[f]) == __double_as_longlong(__ldg(e + f)) &&
+                                   __double_as_longlong(A.L[f]) == __double_as_longlong(__ldg(e + 4 + f));
+                        use_tab = same;
+                    }
+                }
                 have = true;
             }
         }
@@ -456,6 +471,14 @@ __global__ void __launch_bounds__(grid_threads(EXPAND), grid_minb(EXPAND)) k_rol
         const float xf = __double2float_rn(x), yf = __double2float_rn(y);
         pre = (xf > g.blx) & (xf < g.bhx) & (yf > g.bly) & (yf < g.bhy);
         dfw = df_lookup(g, pre, xf, yf);
+        if (EXPAND && use_tab) {   // the covariances of absolute step pstep + t + 1, as k_cov_table_lin computed them
+            const double2* e = reinterpret_cast<const double2*>(a.cov_tab + (size_t)(pstep + t + 1) * 8);
+            const double2 s01 = __ldg(e), s23 = __ldg(e + 1), l01 = __ldg(e + 2), l23 = __ldg(e + 3);
+            A.mx = x; A.my = y;
+            A.S[0] = s01.x; A.S[1] = s01.y; A.S[2] = s23.x; A.S[3] = s23.y;
+            A.L[0] = l01.x; A.L[1] = l01.y; A.L[2] = l23.x; A.L[3] = l23.y;
+            return;
+        }
         if (use_dense) lin_step(A, dux, duy, p, A); else lin_step_diag(A, dux, duy, p, A);
     };
     // commit a valid step / end the rollout

@@ -119,6 +119,7 @@ __global__ void __launch_bounds__(CCK_UNI_THREADS, 2) k_rollout_uni2(const __gri
     const bool has_obstacles = reinterpret_cast<const TabHeader*>(a.tab)->M > 0;
 
     bool have = false, done = false, dense = false, pending = false;
+    bool use_tab = false;          // EXPAND: covariances from the tree's covariance table (RolloutArgs::cov_tab)
     double v[4], u[4], S[16], L[16], v0[4];
     double sr = 0, cr = 1, pcost = 0;
     int steps = 0, t = 0, pstep = 0;
@@ -143,7 +144,7 @@ __global__ void __launch_bounds__(CCK_UNI_THREADS, 2) k_rollout_uni2(const __gri
             double gd;
             const bool g = goal_ok(a.goal, sp, v[0], v[1], S[0] + L[0], S[1] + L[1], S[4] + L[4], S[5] + L[5], &gd);
             a.goal_dist[i] = gd;
-            a.flags[i] = (uint8_t)((r == steps ? 1 : 0) | (cons_ok ? 2 : 0) | (g ? 4 : 0));
+            a.flags[i] = (uint8_t)((r == steps ? 1 : 0) | (cons_ok ? 2 : 0) | (g ? 4 : 0) | (use_tab && steps > 0 ? 8 : 0));
         }
     };
 
@@ -184,6 +185,18 @@ __global__ void __launch_bounds__(CCK_UNI_THREADS, 2) k_rollout_uni2(const __gri
 #pragma unroll
             for (int f = 0; f < 16; ++f) mag = mag + (fabs(S[f]) + fabs(L[f]));
             dense = !p.sparse || !(mag < 1e300);      // non-reference sparsity, or a non-finite (or absurd) covariance: 0*x is not an exact zero any more
+            if (EXPAND) {          // parent covariance bit-identical to the table's entry for its depth, and the segment inside the table
+                use_tab = false;
+                if (a.cov_tab && pstep >= 0 && pstep + steps < a.cov_tab_n) {
+                    const double* e = a.cov_tab + (size_t)pstep * 32;
+                    bool same = true;
+#pragma unroll
+                    for (int f = 0; f < 16; ++f)
+                        same = same && __double_as_longlong(S[f]) == __double_as_longlong(__ldg(e + f)) &&
+                               __double_as_longlong(L[f]) == __double_as_longlong(__ldg(e + 16 + f));
+                    use_tab = same;
+                }
+            }
             t = 0;
             have = true;
         }
@@ -211,7 +224,14 @@ __global__ void __launch_bounds__(CCK_UNI_THREADS, 2) k_rollout_uni2(const __gri
 #pragma unroll
             for (int f = 0; f < 4; ++f) v[f] = vn[f];
         }
-        if (!dense) {
+        if (EXPAND && use_tab) {   // the covariances of absolute step pstep + t + 1, as k_cov_table_uni computed them
+            const double2* e = reinterpret_cast<const double2*>(a.cov_tab + (size_t)(pstep + t + 1) * 32);
+#pragma unroll
+            for (int f = 0; f < 8; ++f) {
+                const double2 sv = __ldg(e + f), lv = __ldg(e + 8 + f);
+                S[2 * f] = sv.x; S[2 * f + 1] = sv.y; L[2 * f] = lv.x; L[2 * f + 1] = lv.y;
+            }
+        } else if (!dense) {
             uni_cov_step_sparse(S, L, p);
         } else {
             double SL[32];

@@ -397,6 +397,10 @@ public:
     // satisfiesConstraints(path, constraints)  (MinkowskiSumBlackmorePVC.cpp:64-104)
     bool satisfiesConstraints(const Trajectory& path, const std::vector<ConstraintPtr>& constraints) const {
         installConstraints(constraints);
+        return satisfiesConstraintsInstalled(path);
+    }
+    // the same check against the constraints already on the device (installConstraints)
+    bool satisfiesConstraintsInstalled(const Trajectory& path) const {
         const int W = belief_width(dim_), T = (int)path.size();
         std::vector<double> buf((size_t)T * W);
         for (int t = 0; t < T; ++t) for (int f = 0; f < W; ++f) buf[(size_t)t * W + f] = path[t].v[f];   // ld = 1 path

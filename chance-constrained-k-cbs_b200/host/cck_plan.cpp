@@ -1,7 +1,7 @@
 // cck_plan — command-line driver mirroring the reference's K-CBS CLI (demos/main.cpp:23-47) for the
 // belief models, running the batched GPU low-level planner under the K-CBS search.
 //   cck_plan -m maps/x.map -s scens/x.scen -k 2 [--solver K-CBS] [--lowlevel BSST] [--svc Blackmore]
-//            [--pvc Blackmore] [-p 0.9] [-t 300] [--K 1024] [--seed 1] [--lltime 5] [--devices 1] [--output plan.txt]
+//            [--pvc Blackmore] [-p 0.9] [-t 300] [--K 1024] [--seed 1] [--lltime 5] [--devices 1] [--prune] [--output plan.txt]
 //            [--export DIR]   (the reference's exportBeliefPlan files: DIR/agentNN.txt, DIR/agentNN_covs.txt; DIR must exist)
 // Prints one JSON line; --output writes the plan as text: per robot a line "robot r T W" followed by T rows.
 #include <cstdio>
@@ -17,6 +17,7 @@ int main(int argc, char** argv) {
     int k = 1, K = 1024, devices = 1;
     double p_safe = 0.9, time_s = 300.0, lltime = 5.0;
     uint64_t seed = 1;
+    bool prune = false;      // stock-SST pruning of old representatives (dead code in the reference's file, see PlannerParams::prune)
     for (int i = 1; i < argc; ++i) {
         const std::string a = argv[i];
         auto next = [&]() -> std::string { if (i + 1 >= argc) { std::fprintf(stderr, "missing value for %s\n", a.c_str()); std::exit(2); } return argv[++i]; };
@@ -33,6 +34,7 @@ int main(int argc, char** argv) {
         else if (a == "--K") K = std::atoi(next().c_str());
         else if (a == "--seed") seed = std::strtoull(next().c_str(), nullptr, 10);
         else if (a == "--devices") devices = std::atoi(next().c_str());
+        else if (a == "--prune") prune = true;
         else if (a == "-o" || a == "--output") output = next();
         else if (a == "--export") export_dir = next();
         else { std::fprintf(stderr, "unknown flag %s\n", a.c_str()); return 2; }
@@ -41,7 +43,7 @@ int main(int argc, char** argv) {
     try {
         auto inst = std::make_shared<Instance>(map, scen, k, p_safe, svc, pvc);
         PlannerParams prm;
-        prm.K = K; prm.seed = seed;
+        prm.K = K; prm.seed = seed; prm.prune = prune;
         KCBS kcbs(inst, svc, pvc, prm, lltime, devices);
         KCBSResult r = kcbs.solve(time_s);
         int64_t launches = 0, cands = 0, nodes = 0;

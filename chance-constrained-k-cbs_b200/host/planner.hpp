@@ -61,6 +61,10 @@ struct PlannerParams {
     double goal_threshold = 2.0, goal_p_safe = 0.95;   // ChanceConstrainedGoal(si, goal, 2.0, 0.95)  (OmplSetUp.cpp:239)
     int min_steps = 1, max_steps = 10;
     uint64_t seed = 1;
+    // Stock SST deactivates the old representative of a witness and prunes childless inactive nodes.  The reference's file does
+    // NOT: `inactive_` is only ever assigned inside `while (oldRep->inactive_ && ...)` (ConstraintRespectingBSST.cpp:388-404,
+    // :517-531), so that loop is dead code, every node stays selectable and the tree is never pruned.  false = as written.
+    bool prune = false;
 };
 
 // The solution as the reference's PathControl holds it (ConstraintRespectingBSST.cpp:327-349): tree-node states,
@@ -88,7 +92,7 @@ public:
         bool inactive = false;
         int numChildren = 0;
     };
-    struct Witness { int rep; };
+    struct Witness { int rep; };     // rep < 0: the witness a constraint-rejected candidate left behind (its rep_ is the reference's scratch motion)
 
     BatchedBSST(InstancePtr inst, int robot, const std::string& svc_name, const std::string& pvc_name, PlannerParams prm, int device = 0)
         : inst_(std::move(inst)), robot_(robot), prm_(prm), rng_(prm.seed + 7919 * (uint64_t)robot) {
@@ -125,6 +129,9 @@ public:
         start_[0] = r.getStartLocation().x_; start_[1] = r.getStartLocation().y_;
         if (dim_ == 4) { start_[2] = 0.0; start_[3] = 0.1; }
         for (int i = 0; i < dim_; ++i) { start_[dim_ + i * dim_ + i] = 0.01; start_[dim_ + dim_ * dim_ + i * dim_ + i] = 0.01; }
+        // every node of this robot's trees descends from the start covariance: the expansion kernel reads (Sigma_s, Lambda_s)
+        // of absolute step s from a table instead of re-running the Kalman step (cck_set_cov_table)
+        gpu_->check(cck_set_cov_table(gpu_->get(), start_.data() + dim_, 4096), "cck_set_cov_table");
         goal_.gx = r.getGoalLocation().x_; goal_.gy = r.getGoalLocation().y_;
         goal_.threshold = prm_.goal_threshold; goal_.sc = cck_chi2_quantile_2dof(prm_.goal_p_safe);
         warmup();
@@ -163,6 +170,7 @@ public:
     const GpuContextPtr& gpu() const { return gpu_; }
     int dim() const { return dim_; }
     const PlannerStats& stats() const { return stats_; }
+    bool startStateValid() const { return start_valid_ != 0; }         // false after solve(): OMPL's INVALID_START
     const SegmentPath& lastSolutionPath() const { return last_path_; }   // segments of the last trajectory solve() returned
 
     // ConstraintRespectingPlanner::updateConstraints + clear
@@ -173,6 +181,14 @@ public:
     Trajectory solve(double seconds, double* cost_out = nullptr) {
         const auto t0 = std::chrono::steady_clock::now();
         pvc_->installConstraints(constraints_);
+        // PlannerInputStates::nextStart() (ConstraintRespectingBSST.cpp:186): a start state the validity checker rejects is
+        // skipped and the planner returns INVALID_START ("There are no valid initial states!")
+        if (start_valid_ < 0) {
+            uint8_t v = 0;
+            gpu_->check(cck_is_valid(gpu_->get(), 1, start_.data(), 1, &v), "cck_is_valid (start state)");
+            start_valid_ = v ? 1 : 0;
+        }
+        if (!start_valid_) return {};
         if (motions_.empty()) {
             Motion m; m.state = start_;
             motions_.push_back(m);
@@ -180,6 +196,12 @@ public:
             nodes_dev_->append(1, start_.data(), 1, &zero);      // one record: SoA with ld = 1 is the record itself
             witnesses_.push_back(Witness{0});
             wit_dev_->append(1, start_.data(), 1, &zero);
+        }
+        // the reference's satisfiesConstraints walks the whole root-to-node path, start state (time 0) included: a constraint at
+        // step 0 that the start state violates rejects every candidate, so the low-level search cannot succeed
+        if (!constraints_.empty()) {
+            Trajectory st{BeliefState{dim_, start_}};
+            if (!pvc_->satisfiesConstraintsInstalled(st)) { stats_.seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); return {}; }
         }
         const int K = prm_.K;
         std::vector<double> bel((size_t)W_ * K), ctrl((size_t)dim_ * K), out((size_t)W_ * K), pcost(K), cost(K), gdist(K), samples((size_t)W_ * K);
@@ -238,6 +260,10 @@ public:
 private:
     double uni(double lo, double hi) { return lo + (hi - lo) * std::uniform_real_distribution<double>(0.0, 1.0)(rng_); }
 
+    // Deviations of the batched commit from the one-candidate-at-a-time reference (documented in DESIGN.md section 7): all K
+    // parents of a launch are selected before any of its candidates is committed, so a candidate cannot have a node created by
+    // the same launch as its parent (and, with prm.prune, a node deactivated by an earlier candidate of the launch can still
+    // gain a child); constraints at absolute step 0 are checked once per solve() on the start state, not once per candidate.
     // Commit the survivors of one launch.  The reference handles one candidate at a time: findClosestWitness
     // (:150-178) sees every witness created so far, including those of earlier candidates of the same batch.
     // Here: cck_tree_witness_batch finds each survivor's nearest PRE-BATCH witness, runs the greedy new-witness scan on the
@@ -257,13 +283,13 @@ private:
             auto secs = [](auto a, auto b) { return std::chrono::duration<double>(b - a).count(); };
             const auto t1 = now();
             // ONE call: nearest existing witness of every survivor, which survivors become new witnesses (greedy in sample
-            // order, on the device) and each survivor's nearest new witness among its predecessors.  A survivor the
-            // constraints reject creates a witness only to drop it again (:300-306), so it is not eligible.
+            // order, on the device) and each survivor's nearest new witness among its predecessors.  Every survivor is
+            // eligible: findClosestWitness (:258) runs BEFORE satisfiesConstraints (:300), so a candidate the constraints
+            // reject still leaves its new witness behind (with rep_ == rmotion, the scratch motion: rep -1 here).
             std::vector<int32_t> widx(S), near(S);
             std::vector<double> wdist(S), near_dist(S);
-            std::vector<uint8_t> fresh_dev(S), elig(S, 1);
-            if (!constraints_.empty()) for (int s = 0; s < S; ++s) elig[s] = (flags[surv[c0 + s]] & 2) ? 1 : 0;
-            gpu_->check(cck_tree_witness_batch(wit_dev_->get(), S, q.data(), S, prm_.pruning_radius, constraints_.empty() ? nullptr : elig.data(),
+            std::vector<uint8_t> fresh_dev(S);
+            gpu_->check(cck_tree_witness_batch(wit_dev_->get(), S, q.data(), S, prm_.pruning_radius, nullptr,
                                                widx.data(), wdist.data(), near.data(), near_dist.data(), fresh_dev.data()), "cck_tree_witness_batch");
             stats_.launches += 5;
             const auto t2 = now();
@@ -281,14 +307,12 @@ private:
                 if (near[s] >= 0 && wit_of[near[s]] >= 0 && near_dist[s] < cd) { cd = near_dist[s]; w = wit_of[near[s]]; }
                 const int idx = (int)motions_.size();
                 bool is_new = false;
-                if (w < 0 || cd > prm_.pruning_radius) { witnesses_.push_back(Witness{idx}); w = (int)witnesses_.size() - 1; fresh.emplace_back(s, w); wit_of[s] = w; is_new = true; }
-                if (elig[s] && is_new != (fresh_dev[s] != 0)) throw std::logic_error("witness batch: device and host disagree on a new witness");
+                if (w < 0 || cd > prm_.pruning_radius) { witnesses_.push_back(Witness{-1}); w = (int)witnesses_.size() - 1; fresh.emplace_back(s, w); wit_of[s] = w; is_new = true; }
+                if (is_new != (fresh_dev[s] != 0)) throw std::logic_error("witness batch: device and host disagree on a new witness");
                 Witness& wit = witnesses_[w];
-                if (!(is_new || cost[j] < motions_[wit.rep].accCost)) continue;
-                if (!constraints_.empty() && !(flags[j] & 2)) {                 // satisfiesConstraints failed (:300)
-                    if (is_new) { witnesses_.pop_back(); fresh.pop_back(); wit_of[s] = -1; }
-                    continue;
-                }
+                // :261 `rep_ == rmotion || cost better`: true for a fresh witness and for one whose creator was rejected below
+                if (!(wit.rep < 0 || cost[j] < motions_[wit.rep].accCost)) continue;
+                if (!constraints_.empty() && !(flags[j] & 2)) continue;         // satisfiesConstraints failed (:300): the witness stays, without a representative
                 Motion m;
                 m.state.resize(W_);
                 for (int f = 0; f < W_; ++f) m.state[f] = out[(size_t)f * K + j];
@@ -296,7 +320,8 @@ private:
                 m.steps = steps[j]; m.parent = parent[j]; m.depth = motions_[parent[j]].depth + steps[j]; m.accCost = cost[j];
                 motions_.push_back(m);
                 new_nodes.push_back(s);
-                if (!is_new) { prune(wit.rep, deact); wit.rep = idx; }
+                if (wit.rep >= 0 && prm_.prune) prune(wit.rep, deact);
+                wit.rep = idx;                                                   // linkRep (:301)
                 motions_[parent[j]].numChildren++;
                 stats_.accepted++;
                 const double c00 = m.state[dim_] + m.state[dim_ + dim_ * dim_], c11 = m.state[dim_ + dim_ + 1] + m.state[dim_ + dim_ * dim_ + dim_ + 1];
@@ -392,6 +417,7 @@ private:
     std::vector<Motion> motions_;
     std::vector<Witness> witnesses_;
     std::unique_ptr<DeviceTree> nodes_dev_, wit_dev_;
+    int start_valid_ = -1;                                             // isValid(start), evaluated once (-1: not yet)
     double max_eig_ = 10.0;                                            // :221
     PlannerStats stats_;
     SegmentPath last_path_;

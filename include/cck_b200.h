@@ -193,12 +193,22 @@ int cck_satisfies_constraints_dev(cck_ctx* ctx, void* stream, int64_t n_paths, c
  * accumulated cost.  One launch does propagateWhileValid, the constraint check on the new
  * segment (entries set by cck_set_constraints), the EuclideanPathLengthObjective increment
  * and ChanceConstrainedGoal::isSatisfied.  flags bit0: propCd==cd, bit1: constraints ok,
- * bit2: goal satisfied. */
+ * bit2: goal satisfied, bit3 (diagnostic): the covariances came from the tree's covariance table
+ * (cck_set_cov_table) instead of the Kalman step - same bits either way. */
 typedef struct cck_goal_params {
     double gx, gy;      /* goal location */
     double threshold;   /* goalTollorance = 2.0 (OmplSetUp.cpp:185) */
     double sc;          /* chi2_2 quantile of 0.95 (BeliefSpaceGoals.cpp:110) */
 } cck_goal_params;
+/* Optional: the covariance table of ONE low-level tree.  The covariance recursion of both models does not depend on the mean
+ * or the control (UncertainLinearSP.cpp:98-104, UncertainUnicycleSP.cpp:210-220), so every tree node at absolute step s
+ * carries the same (Sigma_s, Lambda_s), determined by the root covariance root_cov = [Sigma row-major, Lambda row-major]
+ * (the start state's 0.01 I, OmplSetUp.cpp:232-236).  With a table installed, cck_expand_batch reads a candidate's
+ * covariances from it instead of running the Kalman step - but ONLY for a candidate whose parent covariance is bit-identical
+ * to the table's entry for parent_step and whose segment ends inside the table; every other candidate is computed as usual,
+ * so results never depend on the table.  Entries are produced by the kernels' own step functions.  n_steps <= 0 removes it;
+ * cck_set_model removes it too. */
+int cck_set_cov_table(cck_ctx* ctx, const double* root_cov, int n_steps);
 int cck_expand_batch_dev(cck_ctx* ctx, void* stream, int64_t n, const double* bel, int64_t ld, const double* ctrl,
                          int64_t ldc, const int32_t* steps, const int32_t* parent_step, const double* parent_cost,
                          const cck_goal_params* goal, double* out, int64_t ldo, int32_t* valid_steps,

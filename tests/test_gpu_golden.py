@@ -227,3 +227,61 @@ def _segment_ok(opvc, seg, first_step, dim, cons):
     far = seg[:1].copy(); far[0, :2] = [-500.0, -500.0]
     path = np.concatenate([np.repeat(far, first_step, axis=0), seg])
     return opvc.satisfies_constraints(path, dim, 0, cons)
+
+
+@pytest.mark.parametrize("model", ["linear", "unicycle"])
+def test_expand_batch_cov_table_is_bit_identical(K, O, W, ctx, model):
+    """cck_set_cov_table: a candidate whose parent covariance is the tree's covariance at its depth reads its next
+    covariances from the table instead of running the Kalman step - same bits as computing them (the
+    recursion is control-independent, UncertainLinearSP.cpp:98-104); any other candidate is computed as usual."""
+    dim = 2 if model == "linear" else 4
+    Wd = K.width(dim)
+    rng = np.random.default_rng(8)
+    centres = W.synthetic_obstacles(40, seed=77)[:, :] % 20
+    world = O.World.synthetic(centres, 20.0, 20.0, 2, 0.9)
+    svc = O.Svc(world, O.SVC_BLACKMORE, dim)
+    ctx.set_model(K.MODEL_LINEAR2D if dim == 2 else K.MODEL_UNICYCLE)
+    ctx.set_obstacles(K.SVC_BLACKMORE, svc.low, svc.high, svc.A, svc.B, svc.centres, svc.rects, erf_inv_result=svc.erf_inv_result)
+    # the tree's covariances by depth, from the DEVICE's own single-step propagator (what a planner's nodes carry)
+    depth_max = 40
+    cur = K.aos_to_soa(O.default_beliefs(1, dim))
+    if dim == 4:
+        cur[3] = 0.1
+    zero_u = np.zeros((dim, 1))
+    if dim == 4:
+        zero_u[:, 0] = [5.0, 5.0, 0.0, 0.5]
+    covs = [cur[dim:, 0].copy()]
+    for _ in range(depth_max + 12):
+        cur = ctx.propagate(cur, zero_u)
+        covs.append(cur[dim:, 0].copy())
+    n = 2000
+    bel, ctrl = W.synthetic_beliefs(n, model, seed=14)
+    bel[0] = rng.uniform(1, 18, n); bel[1] = rng.uniform(1, 18, n)
+    pstep = rng.integers(0, depth_max, size=n).astype(np.int32)
+    on_tree = rng.uniform(size=n) < 0.7
+    for i in range(n):
+        if on_tree[i]:
+            bel[dim:, i] = covs[pstep[i]]
+        else:
+            bel[dim:, i] *= 0.02
+    if dim == 4:
+        ctrl[0] = rng.uniform(-1, 20, n); ctrl[1] = rng.uniform(-1, 20, n)
+    steps = rng.integers(0, 11, size=n).astype(np.int32)
+    pcost = rng.uniform(0, 5, n)
+    goal = (12.0, 12.0)
+    ref = ctx.expand_batch(bel, ctrl, steps, pstep, pcost, goal)
+    assert not (ref[4] & K.FLAG_COV_TABLE).any()
+    ctx.set_cov_table(covs[0], depth_max + 11)
+    got = ctx.expand_batch(bel, ctrl, steps, pstep, pcost, goal)
+    used = (got[4] & K.FLAG_COV_TABLE) != 0
+    assert np.array_equal(used, on_tree & (steps > 0)), "the table must be used exactly for the on-tree candidates"
+    for a_, b_ in zip(ref[:4], got[:4]):
+        assert np.array_equal(a_.view(np.uint64) if a_.dtype == np.float64 else a_, b_.view(np.uint64) if b_.dtype == np.float64 else b_)
+    assert np.array_equal(ref[4], got[4] & 7)
+    # a segment that would run past the end of the table is computed, not read
+    ctx.set_cov_table(covs[0], 5)
+    short = ctx.expand_batch(bel, ctrl, steps, pstep, pcost, goal)
+    assert np.array_equal((short[4] & K.FLAG_COV_TABLE) != 0, on_tree & (steps > 0) & (pstep + steps < 5))
+    assert np.array_equal(short[0].view(np.uint64), ref[0].view(np.uint64))
+    ctx.set_cov_table(None, 0)
+    assert not (ctx.expand_batch(bel, ctrl, steps, pstep, pcost, goal)[4] & K.FLAG_COV_TABLE).any()

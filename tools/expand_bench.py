@@ -48,6 +48,18 @@ def main():
     dev = torch.device("cuda", 0)
     res = {"model": a.model, "M": int(len(g["centres"])), "agents": k, "rows": []}
     rng = np.random.default_rng(5)
+    # the tree's covariances by depth (what a planner's nodes carry): the device's own single-step propagator from 0.01 I
+    cur = K.aos_to_soa(O.default_beliefs(1, dim))
+    if dim == 4:
+        cur[3] = 0.1
+    u0 = np.zeros((dim, 1))
+    if dim == 4:
+        u0[:, 0] = [5.0, 5.0, 0.0, 0.5]
+    covs = [cur[dim:, 0].copy()]
+    for _ in range(45):
+        cur = ctx.propagate(cur, u0)
+        covs.append(cur[dim:, 0].copy())
+    covs = np.array(covs)
     for Kc in (256, 4096, 65536):
         bel, ctrl = W.synthetic_beliefs(Kc, a.model, seed=100 + Kc)
         bel[0] = rng.uniform(0, float(g["x_max"]) - 1, Kc); bel[1] = rng.uniform(0, float(g["y_max"]) - 1, Kc)
@@ -57,6 +69,7 @@ def main():
         steps = rng.integers(1, 11, size=Kc).astype(np.int32)
         pstep = rng.integers(0, 30, size=Kc).astype(np.int32)
         pcost = rng.uniform(0, 5, Kc)
+        bel[dim:] = covs[pstep].T                      # parents are tree nodes: covariance = the tree's covariance at their depth
         goal = (float(g["goals"][0, 0]), float(g["goals"][0, 1]))
         # host-pointer call (what the planner issues)
         for _ in range(3):
@@ -66,7 +79,7 @@ def main():
         for _ in range(reps):
             ctx.expand_batch(bel, ctrl, steps, pstep, pcost, goal)
         host_us = (time.perf_counter() - t0) / reps * 1e6
-        # device-resident
+        # device-resident, without and with the tree's covariance table (cck_set_cov_table)
         Wd = K.width(dim)
         d = {n_: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for n_, v in dict(bel=bel, ctrl=ctrl, steps=steps, pstep=pstep, pcost=pcost).items()}
         d_out = torch.empty((Wd, Kc), dtype=torch.float64, device=dev); d_valid = torch.empty(Kc, dtype=torch.int32, device=dev)
@@ -88,6 +101,20 @@ def main():
         torch.cuda.synchronize()
         dev_us = e0.elapsed_time(e1) / 100 * 1e3
         assert np.array_equal(d_valid.cpu().numpy(), valid)
+        ref_out = d_out.cpu().numpy().copy()
+        ctx.set_cov_table(covs[0], 45)
+        for _ in range(5):
+            launch()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(100):
+            launch()
+        e1.record()
+        torch.cuda.synchronize()
+        tab_us = e0.elapsed_time(e1) / 100 * 1e3
+        tab_frac = float(((d_fl.cpu().numpy() & K.FLAG_COV_TABLE) != 0).mean())
+        assert np.array_equal(d_out.cpu().numpy().view(np.uint64), ref_out.view(np.uint64)), "covariance table changed a result"
+        ctx.set_cov_table(None, 0)
         # CPU: the oracle's propagateWhileValid on the same candidates, one thread
         aos_b, aos_c = K.soa_to_aos(bel), K.soa_to_aos(ctrl)
         n_cpu = min(Kc, 4096)
@@ -98,7 +125,7 @@ def main():
         units = int(np.minimum(valid + 1, steps).sum())
         row = {"K": Kc, "belief_steps": units, "full_fraction": float(((fl & 1) != 0).mean()),
                "host_call_us": host_us, "host_candidates_per_s": Kc / host_us * 1e6,
-               "device_launch_us": dev_us, "device_candidates_per_s": Kc / dev_us * 1e6, "device_belief_steps_per_s": units / dev_us * 1e6,
+               "device_launch_us": dev_us, "device_launch_us_cov_table": tab_us, "cov_table_fraction": tab_frac, "device_candidates_per_s": Kc / dev_us * 1e6, "device_belief_steps_per_s": units / dev_us * 1e6,
                "cpu_oracle_us_per_candidate_1thread": cpu_us_per_cand, "host_call_vs_cpu": cpu_us_per_cand * Kc / host_us}
         res["rows"].append(row)
         print(json.dumps(row), flush=True)

@@ -18,12 +18,17 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HOST = os.path.join(ROOT, "chance-constrained-k-cbs_b200", "host")
 GOLDEN = os.path.join(ROOT, "tests", "golden")
-# (label, fixture, agents, seed-count scale): the conflict-heavy k >= 6 case is sampled with fewer seeds
-CONFIGS = [("config1 empty-8-8 linear k=2", "config1_empty8_linear_k2", 2, 1.0),
-           ("config2 random-32-32-10 linear k=4", "config2_random32_10_linear_k4", 4, 1.0),
-           ("config2 random-32-32-10 linear k=6 (first 6 rows of the k=8 scenario)", "config2_random32_10_linear_k8", 6, 0.25),
-           ("config3 random-32-32-5 unicycle k=4", "config3_random32_5_unicycle_k4", 4, 1.0),
-           ("config4 narrowPassage linear k=2", "config4_narrow_linear_k2", 2, 1.0)]
+# (label, fixture, agents, seed-count scale, p_safe): the conflict-heavy k >= 6 cases are sampled with fewer seeds.
+# config 4 runs at p_safe = 0.8: at the CLI default 0.9 the reference's own start state of Robot 0 at (2, 1) is INVALID for
+# PCCBlackmoreSVC (sqrt2 c sqrt(0.02) = 0.32337 > 0.32322 = gap to the wall's inflated box), so OMPL skips it and the
+# reference answers "There are no valid initial states" - as do both planners here.
+CONFIGS = [("config1 empty-8-8 linear k=2", "config1_empty8_linear_k2", 2, 1.0, 0.9),
+           ("config2 random-32-32-10 linear k=4", "config2_random32_10_linear_k4", 4, 1.0, 0.9),
+           ("config2 random-32-32-10 linear k=6 (first 6 rows of the k=8 scenario)", "config2_random32_10_linear_k8", 6, 0.2, 0.9),
+           ("config2 random-32-32-10 linear k=8", "config2_random32_10_linear_k8", 8, 0.2, 0.9),
+           ("config3 random-32-32-5 unicycle k=4", "config3_random32_5_unicycle_k4", 4, 1.0, 0.9),
+           ("config4 narrowPassage linear k=2 (p_safe 0.8)", "config4_narrow_linear_k2", 2, 1.0, 0.8)]
+ORACLE_PLAN = os.path.join(ROOT, "oracle", "_build", "cck_oracle_plan")
 
 
 def write_instance(d, g, name):
@@ -49,35 +54,72 @@ def main():
     ap.add_argument("--K", type=int, default=1024)
     ap.add_argument("--only", default="")
     ap.add_argument("--out", default="")
+    ap.add_argument("--cpu", action="store_true", help="also run the CPU arm: the reference's one-candidate-at-a-time loop on the oracle (oracle/cck_oracle_plan.cpp)")
+    ap.add_argument("--cpu-only", action="store_true")
+    ap.add_argument("--cpu-jobs", type=int, default=1, help="CPU-arm seeds run concurrently (each run is single-threaded, like the reference)")
+    ap.add_argument("--prune", action="store_true", help="stock-SST pruning in both arms (not what the reference's file does)")
     a = ap.parse_args()
-    subprocess.check_call(["make", "-C", HOST, "-s"])
+    if not a.cpu_only:
+        subprocess.check_call(["make", "-C", HOST, "-s"])
+    if a.cpu or a.cpu_only:
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "-s"])
+    extra = ["--prune"] if a.prune else []
     res = {}
+
+    def stats(runs, nseeds):
+        ok = [r for r in runs if r.get("solved")]
+        t = np.array([r["seconds"] for r in ok]) if ok else np.array([np.nan])
+        return {"seeds": nseeds, "solved": len(ok), "seconds_median": float(np.median(t)), "seconds_q25": float(np.percentile(t, 25)),
+                "seconds_q75": float(np.percentile(t, 75)), "seconds_p90": float(np.percentile(t, 90)), "seconds_min": float(np.min(t)), "seconds_max": float(np.max(t)),
+                "candidates_median": float(np.median([r["candidates"] for r in ok])) if ok else None,
+                "cbs_nodes_median": float(np.median([r["cbs_nodes"] for r in ok])) if ok else None}
+
     with tempfile.TemporaryDirectory() as d:
-        for label, fx, k, scale in CONFIGS:
+        for label, fx, k, scale, p_safe in CONFIGS:
             if a.only and a.only not in label:
                 continue
             g = np.load(os.path.join(GOLDEN, fx + ".npz"))
             mp, sc = write_instance(d, g, fx)
             runs = []
             nseeds = max(1, int(round(a.seeds * scale)))
+            cpu = None
+            if a.cpu or a.cpu_only:
+                from concurrent.futures import ThreadPoolExecutor
+
+                def one(seed):
+                    try:
+                        o = subprocess.run([ORACLE_PLAN, "-m", mp, "-s", sc, "-k", str(k), "-p", str(p_safe), "-t", str(a.time), "--seed", str(seed),
+                                            "--lltime", str(min(a.time, 20.0))] + extra, capture_output=True, text=True, timeout=a.time + 60)
+                        return json.loads(o.stdout.strip().splitlines()[-1])
+                    except Exception as e:  # noqa: BLE001
+                        return {"solved": False, "seconds": a.time, "error": str(e)[:200]}
+                with ThreadPoolExecutor(max_workers=max(1, a.cpu_jobs)) as ex:
+                    cruns = list(ex.map(one, range(1, nseeds + 1)))
+                cpu = stats(cruns, nseeds)
+                cpu.update({"impl": "CPU oracle planner, one candidate per iteration, single thread per solve", "concurrent_solves": a.cpu_jobs})
+                if a.cpu_only:
+                    res[label] = {"cpu": cpu, "time_limit_s": a.time, "p_safe": p_safe}
+                    print(label, json.dumps(res[label]), flush=True)
+                    continue
             for seed in range(1, nseeds + 1):
                 out = None
                 try:
-                    out = subprocess.run([os.path.join(HOST, "cck_plan"), "-m", mp, "-s", sc, "-k", str(k), "-t", str(a.time), "--K", str(a.K),
-                                          "--seed", str(seed), "--lltime", str(min(a.time, 20.0))], capture_output=True, text=True, timeout=a.time + 60)
+                    out = subprocess.run([os.path.join(HOST, "cck_plan"), "-m", mp, "-s", sc, "-k", str(k), "-p", str(p_safe), "-t", str(a.time), "--K", str(a.K),
+                                          "--seed", str(seed), "--lltime", str(min(a.time, 20.0))] + extra, capture_output=True, text=True, timeout=a.time + 60)
                     runs.append(json.loads(out.stdout.strip().splitlines()[-1]))
                 except Exception as e:  # noqa: BLE001
                     err = (out.stderr if "out" in dir() and out is not None else "")[-300:]
                     runs.append({"solved": False, "seconds": a.time, "error": str(e)[:200], "stderr": err})
                     print(f"  seed {seed}: failed: {str(e)[:80]} | {err.strip()[-200:]}", flush=True)
             ok = [r for r in runs if r.get("solved")]
-            t = np.array([r["seconds"] for r in ok]) if ok else np.array([np.nan])
-            res[label] = {"seeds": nseeds, "solved": len(ok), "time_limit_s": a.time, "K": a.K,
-                          "seconds_median": float(np.median(t)), "seconds_mean": float(np.mean(t)), "seconds_p90": float(np.percentile(t, 90)),
-                          "seconds_min": float(np.min(t)), "seconds_max": float(np.max(t)),
-                          "launches_median": float(np.median([r["launches"] for r in ok])) if ok else None,
-                          "candidates_median": float(np.median([r["candidates"] for r in ok])) if ok else None,
-                          "cbs_nodes_median": float(np.median([r["cbs_nodes"] for r in ok])) if ok else None}
+            res[label] = stats(runs, nseeds)
+            res[label].update({"time_limit_s": a.time, "K": a.K, "p_safe": p_safe,
+                               "launches_median": float(np.median([r["launches"] for r in ok])) if ok else None})
+            if cpu:
+                res[label]["cpu"] = cpu
+                res[label]["cpu_seconds_median"], res[label]["cpu_solved"] = cpu["seconds_median"], cpu["solved"]
+                if ok and cpu["solved"]:
+                    res[label]["speedup_median"] = cpu["seconds_median"] / res[label]["seconds_median"]
             if ok and "phase_seconds" in ok[0]:      # where the wall clock goes (medians; planner phases are summed over robots)
                 res[label]["root_seconds_median"] = float(np.median([r["root_seconds"] for r in ok]))
                 res[label]["validate_seconds_median"] = float(np.median([r["validate_seconds"] for r in ok]))
