@@ -19,7 +19,7 @@ _ROOT = os.path.dirname(_PKG)
 OK, ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_NODEVICE = 0, 1, 2, 3, 4
 MODEL_LINEAR2D, MODEL_UNICYCLE = 0, 1
 SVC_BLACKMORE, SVC_ADAPTIVE, SVC_CHISQUARED = 0, 1, 2
-PVC_BLACKMORE, PVC_BOUNDINGBOX, PVC_CHISQUARED, PVC_ADAPTIVE_BLACKMORE, PVC_ADAPTIVE_BOUNDINGBOX = range(5)
+PVC_BLACKMORE, PVC_BOUNDINGBOX, PVC_CHISQUARED, PVC_ADAPTIVE_BLACKMORE, PVC_ADAPTIVE_BOUNDINGBOX, PVC_BLACKMORE2, PVC_CDFGRID = range(7)
 FLAG_FULL, FLAG_CONS_OK, FLAG_GOAL, FLAG_COV_TABLE = 1, 2, 4, 8
 
 
@@ -42,7 +42,7 @@ class SvcParams(C.Structure):
 
 
 class PvcParams(C.Structure):
-    _fields_ = [("kind", C.c_int32), ("k", C.c_int32), ("dim", C.c_int32), ("reserved", C.c_int32),
+    _fields_ = [("kind", C.c_int32), ("k", C.c_int32), ("dim", C.c_int32), ("grid_n", C.c_int32),
                 ("c_pair", C.c_double), ("p_coll_agnts", C.c_double), ("sc", C.c_double),
                 ("radii", C.POINTER(C.c_double)), ("pair_A", C.POINTER(C.c_double)), ("pair_B", C.POINTER(C.c_double)),
                 ("map_order", C.POINTER(C.c_int32))]
@@ -65,7 +65,7 @@ SYMBOLS = [
     "cck_propagate", "cck_propagate_dev", "cck_is_valid", "cck_is_valid_dev",
     "cck_propagate_while_valid", "cck_propagate_while_valid_dev",
     "cck_validate_plan", "cck_validate_plan_dev",
-    "cck_set_constraints", "cck_satisfies_constraints", "cck_satisfies_constraints_dev", "cck_build_clearance_field", "cck_measure_fp64_rates", "cck_set_cov_table",
+    "cck_set_constraints", "cck_satisfies_constraints", "cck_satisfies_constraints_dev", "cck_build_clearance_field", "cck_measure_fp64_rates", "cck_set_cov_table", "cck_chisq_pairs_disjoint",
     "cck_expand_batch", "cck_expand_batch_dev", "cck_rollout_summary_dev", "cck_select_winner_dev", "cck_measure_fp64_peak",
     "cck_tree_create", "cck_tree_destroy", "cck_tree_clear", "cck_tree_size", "cck_tree_append", "cck_tree_update",
     "cck_tree_select", "cck_tree_nearest", "cck_tree_witness_batch", "cck_belief_distance", "cck_belief_distance_lower", "cck_belief_distance_cols", "cck_belief_distance_cols_near", "cck_build_grid_table",
@@ -132,6 +132,7 @@ def lib():
     L.cck_validate_plan_dev.argtypes = [vp, vp, C.c_int, vp, C.c_int, vp, i64, vp]
     L.cck_set_constraints.argtypes = [vp, C.c_int, vp, vp, vp, vp]
     L.cck_set_cov_table.argtypes = [vp, vp, C.c_int]
+    L.cck_chisq_pairs_disjoint.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp, C.c_double, vp]
     L.cck_satisfies_constraints.argtypes = [vp, i64, vp, i64, C.c_int32, vp, vp, vp]
     L.cck_satisfies_constraints_dev.argtypes = [vp, vp, i64, vp, i64, C.c_int32, vp, vp, vp]
     L.cck_expand_batch.argtypes = [vp, i64, vp, i64, vp, i64, vp, vp, vp, C.POINTER(GoalParams), vp, i64, vp, vp, vp, vp]
@@ -282,13 +283,13 @@ class Context:
         self._ck(self.L.cck_set_obstacles(self.h, C.byref(p), _ptr(A_), _ptr(B_), _ptr(c_), _ptr(r_), M))
         self.M = M
 
-    def set_pvc(self, kind, k, dim, radii, pair_A, pair_B, map_order, c_pair=0.0, p_coll_agnts=0.0, sc=0.0):
+    def set_pvc(self, kind, k, dim, radii, pair_A, pair_B, map_order, c_pair=0.0, p_coll_agnts=0.0, sc=0.0, grid_n=2):
         radii = np.ascontiguousarray(radii, dtype=np.float64)
         pair_A = np.ascontiguousarray(pair_A, dtype=np.float64)
         pair_B = np.ascontiguousarray(pair_B, dtype=np.float64)
         map_order = np.ascontiguousarray(map_order, dtype=np.int32)
         p = PvcParams()
-        p.kind, p.k, p.dim = kind, k, dim
+        p.kind, p.k, p.dim, p.grid_n = kind, k, dim, int(grid_n)
         p.c_pair, p.p_coll_agnts, p.sc = c_pair, p_coll_agnts, sc
         p.radii = radii.ctypes.data_as(C.POINTER(C.c_double))
         p.pair_A = pair_A.ctypes.data_as(C.POINTER(C.c_double))
@@ -338,6 +339,14 @@ class Context:
         if run.first_step < 0:
             return None
         return (run.a, run.b, run.first_step, run.run_len)
+
+    def chisq_pairs_disjoint(self, mu_a, cov_a, rad_a, mu_b, cov_b, rad_b, sc):
+        """CentralizedChiSquaredBoundarySVC's agent-agent decagon test; SoA inputs mu [2, n], cov [4, n], rad [n]."""
+        arrs = [np.ascontiguousarray(x, dtype=np.float64) for x in (mu_a, cov_a, rad_a, mu_b, cov_b, rad_b)]
+        n = arrs[0].shape[1]
+        out = np.zeros(n, dtype=np.uint8)
+        self._ck(self.L.cck_chisq_pairs_disjoint(self.h, n, *[_ptr(x) for x in arrs], float(sc), _ptr(out)))
+        return out.astype(bool)
 
     def set_cov_table(self, root_cov, n_steps):
         """Covariance table of a low-level tree (cck_set_cov_table); root_cov = [Sigma row-major, Lambda row-major]."""
@@ -594,10 +603,10 @@ def robot_map_order(k):
     return np.array(sorted(range(k), key=lambda i: f"Robot {i}"), dtype=np.int32)
 
 
-def install_pvc(ctx, kind, dim, radii, p_safe_agents, chi_p=0.9):
+def install_pvc(ctx, kind, dim, radii, p_safe_agents, chi_p=0.9, grid_n=2):
     """Build the plan-validity-checker constants the reference constructors compute
     (MinkowskiSumBlackmorePVC.cpp:4-30, BoundingBoxBlackmorePVC.cpp:4-32, ChiSquaredBoundaryPVC.cpp:4-20,
-    demos/main.cpp:105-138) with the library's host builders and install them in `ctx`."""
+    Blackmore2PVC.cpp:4-30, CDFGridPVC.cpp:4-38 with grid_n = disk_steps_; demos/main.cpp:105-138) with the library's host builders and install them in `ctx`."""
     radii = np.ascontiguousarray(radii, dtype=np.float64)
     k = len(radii)
     p_coll_agnts = 1 - p_safe_agents
@@ -610,7 +619,7 @@ def install_pvc(ctx, kind, dim, radii, p_safe_agents, chi_p=0.9):
         for b in range(a + 1, k):
             A[a * k + b], B[a * k + b] = build_pair_halfplanes(radii[a], radii[b], bb)
     sc = chi2_quantile_2dof(chi_p)
-    ctx.set_pvc(kind, k, dim, radii, A, B, robot_map_order(k), c_pair=c_pair, p_coll_agnts=p_coll_agnts, sc=sc)
+    ctx.set_pvc(kind, k, dim, radii, A, B, robot_map_order(k), c_pair=c_pair, p_coll_agnts=p_coll_agnts, sc=sc, grid_n=grid_n)
     return {"c_pair": c_pair, "p_coll_dist": p_coll_dist, "pair_A": A, "pair_B": B, "sc": sc}
 
 

@@ -682,8 +682,9 @@ extern "C" int cck_set_pvc(cck_ctx* c, const cck_pvc_params* p) {
     if (!c || !p) return CCK_ERR_INVALID;
     if (p->k < 1 || p->k > CCK_MAX_ROBOTS) return fail(c, CCK_ERR_INVALID, "k out of range");
     if (p->dim != 2 && p->dim != 4) return fail(c, CCK_ERR_INVALID, "pvc dim must be 2 or 4");
-    if (p->kind < 0 || p->kind > 4) return fail(c, CCK_ERR_INVALID, "unknown pvc kind");
-    if (!p->radii || !p->map_order || (p->kind != CCK_PVC_CHISQUARED && (!p->pair_A || !p->pair_B)))
+    if (p->kind < 0 || p->kind > 6) return fail(c, CCK_ERR_INVALID, "unknown pvc kind");
+    if (p->kind == CCK_PVC_CDFGRID && (p->grid_n < 2 || p->grid_n > 64)) return fail(c, CCK_ERR_INVALID, "CDFGrid needs 2 <= grid_n <= 64");
+    if (!p->radii || !p->map_order || (p->kind != CCK_PVC_CHISQUARED && p->kind != CCK_PVC_CDFGRID && (!p->pair_A || !p->pair_B)))
         return fail(c, CCK_ERR_INVALID, "pvc tables missing");
     CK(c, cudaSetDevice(c->device));
     const int k = p->k;
@@ -703,7 +704,7 @@ extern "C" int cck_set_pvc(cck_ctx* c, const cck_pvc_params* p) {
     CK(c, cudaMemcpy(c->d_pvc_radii, c->pvc_radii.data(), k * 8, cudaMemcpyHostToDevice));
     CK(c, cudaMemcpy(c->d_pvc_order, c->pvc_order.data(), k * 4, cudaMemcpyHostToDevice));
     PvcDev& d = c->pvc;
-    d.kind = p->kind; d.k = k; d.dim = p->dim; d.n_pairs = k * (k - 1) / 2;
+    d.kind = p->kind; d.k = k; d.dim = p->dim; d.n_pairs = k * (k - 1) / 2; d.grid_n = p->grid_n; d.pad = 0;
     d.c_pair = p->c_pair; d.p_coll_agnts = p->p_coll_agnts; d.sc = p->sc;
     d.radii = c->d_pvc_radii; d.pair_A = c->d_pvc_A; d.pair_B = c->d_pvc_B; d.map_order = c->d_pvc_order;
     c->has_pvc = true;
@@ -979,7 +980,7 @@ extern "C" int cck_set_constraints(cck_ctx* c, int n_entries, const int32_t* ent
     h.n_entries = n_entries; h.max_step = max_step;
     h.off_first = sizeof(ConsHeader);
     h.off_entries = (h.off_first + (max_step + 2) * 4 + 15) & ~15;
-    h.pvc_kind = c->pvc.kind; h.dim = c->pvc.dim; h.k = c->pvc.k;
+    h.pvc_kind = c->pvc.kind; h.dim = c->pvc.dim; h.k = c->pvc.k; h.grid_n = c->pvc.grid_n;
     h.c_pair = c->pvc.c_pair; h.p_coll_agnts = c->pvc.p_coll_agnts; h.sc = c->pvc.sc;
     const size_t total = h.off_entries + (size_t)n_entries * sizeof(ConsEntry);
     std::vector<unsigned char> buf(total, 0);
@@ -1058,6 +1059,38 @@ static cudaError_t d2h_planes(void* dst, int64_t ld_dst, const void* src, size_t
     return cudaMemcpy2DAsync(dst, (size_t)ld_dst * elem, src, (size_t)cnt * elem, (size_t)cnt * elem, planes, cudaMemcpyDeviceToHost, s);
 }
 
+
+// CentralizedChiSquaredBoundarySVC's agent-agent decagon test for n pairs (host pointers; SoA: mu [2][n], cov [4][n])
+extern "C" int cck_chisq_pairs_disjoint(cck_ctx* c, int64_t n, const double* mu_a, const double* cov_a, const double* rad_a, const double* mu_b,
+                                        const double* cov_b, const double* rad_b, double sc, uint8_t* out) {
+    if (!c) return CCK_ERR_INVALID;
+    if (n < 0 || (n > 0 && (!mu_a || !cov_a || !rad_a || !mu_b || !cov_b || !rad_b || !out))) return fail(c, CCK_ERR_INVALID, "bad arguments");
+    if (n == 0) return CCK_OK;
+    CK(c, cudaSetDevice(c->device));
+    int rc;
+    const size_t b1 = al256((size_t)n * 8), total = 14 * b1 + al256((size_t)n);
+    if ((rc = ensure_scratch(c, 0, total))) return rc;
+    unsigned char* p = (unsigned char*)c->d_scratch[0];
+    cudaStream_t s = c->pipe[0];
+    double* d_mua = (double*)p; double* d_cova = (double*)(p + 2 * b1); double* d_rada = (double*)(p + 6 * b1);
+    double* d_mub = (double*)(p + 7 * b1); double* d_covb = (double*)(p + 9 * b1); double* d_radb = (double*)(p + 13 * b1);
+    uint8_t* d_out = p + 14 * b1;
+    // planes are packed at pitch n inside the al256-sized slots (2 resp. 4 planes each fit: al256(n*8) >= n*8)
+    CK(c, cudaMemcpyAsync(d_mua, mu_a, (size_t)n * 16, cudaMemcpyHostToDevice, s)); CK(c, cudaMemcpyAsync(d_cova, cov_a, (size_t)n * 32, cudaMemcpyHostToDevice, s));
+    CK(c, cudaMemcpyAsync(d_rada, rad_a, (size_t)n * 8, cudaMemcpyHostToDevice, s));
+    CK(c, cudaMemcpyAsync(d_mub, mu_b, (size_t)n * 16, cudaMemcpyHostToDevice, s)); CK(c, cudaMemcpyAsync(d_covb, cov_b, (size_t)n * 32, cudaMemcpyHostToDevice, s));
+    CK(c, cudaMemcpyAsync(d_radb, rad_b, (size_t)n * 8, cudaMemcpyHostToDevice, s));
+    SvcDev sp = c->svc;
+    const double two_pi = 2.0 * M_PI, diff = two_pi / 10.0;      // point_circle(10), as in cck_set_obstacles
+    double ang = 0;
+    for (int i = 0; i < 10; ++i, ang -= diff) { sp.dec_cos[i] = std::cos(ang); sp.dec_sin[i] = std::sin(ang); }
+    k_chisq_pairs<<<grid_for(c, n, 128, 8), 128, 0, s>>>(n, d_mua, d_cova, d_rada, d_mub, d_covb, d_radb, sc, sp, d_out);
+    c->launches++;
+    CK(c, cudaGetLastError());
+    CK(c, cudaMemcpyAsync(out, d_out, (size_t)n, cudaMemcpyDeviceToHost, s));
+    CK(c, cudaStreamSynchronize(s));
+    return CCK_OK;
+}
 
 extern "C" int cck_propagate(cck_ctx* c, int64_t n, const double* bel, int64_t ld, const double* ctrl, int64_t ldc, double duration,
                              double* out, int64_t ldo) {

@@ -46,7 +46,7 @@ struct RolloutArgs {
 struct ConsHeader {
     int32_t n_entries, max_step;       // entries cover steps [0, max_step]
     int32_t off_first, off_entries;    // byte offsets: int32 first[max_step+2]; ConsEntry entries[n]
-    int32_t pvc_kind, dim, k, pad;
+    int32_t pvc_kind, dim, k, grid_n;  // grid_n: CDFGridPVC's disk_steps_
     double c_pair, p_coll_agnts;
     double sc, pad2;                   // ChiSquaredBoundaryPVC: chi2_2 quantile (ChiSquaredBoundaryPVC.cpp:19)
 };
@@ -73,6 +73,102 @@ __device__ __forceinline__ bool pair_safe_halfplanes(const double* A, const doub
     return safe;
 }
 
+// Blackmore2PVC::isSafe_ (Blackmore2PVC.cpp:169-192): smallest half-plane collision probability against p_coll_agnts_
+__device__ __forceinline__ bool pair_safe_blackmore2(const double* A, const double* B, double mx, double my, double S0, double S1, double S2,
+                                                     double S3, double p_coll_agnts) {
+    double p_obs = DBL_MAX;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const double a0 = A[2 * i], a1 = A[2 * i + 1];
+        const double t0 = a0 * S0 + a1 * S2;
+        const double t1 = a0 * S1 + a1 * S3;
+        const double pv2 = t0 * a0 + t1 * a1;
+        const double PV = sqrt(2 * pv2);
+        const double pc = 0.5 + 0.5 * erf((B[i] - (mx * a0 + my * a1)) / PV);
+        if (pc < p_obs) p_obs = pc;
+    }
+    return !(p_obs > p_coll_agnts);
+}
+
+// Eigen::EigenSolver<Matrix2d> as CDFGridPVC uses it, in closed form (see oracle/cck_oracle.hpp::eig2_general for the contract)
+__device__ __forceinline__ void eig2_general(const double* M, double* lam, double* V) {
+    const double a = M[0], b = M[1], c = M[2], d = M[3];
+    V[0] = 1; V[1] = 0; V[2] = 0; V[3] = 1;
+    if (b == 0 && c == 0) { lam[0] = a; lam[1] = d; return; }
+    const double h = (a - d) / 2, disc = h * h + b * c, m = (a + d) / 2;
+    if (!(disc >= 0)) { lam[0] = lam[1] = m; return; }
+    const double sq = sqrt(disc);
+    lam[0] = m + sq; lam[1] = m - sq;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        double vx, vy;
+        if (fabs(b) >= fabs(c)) { vx = b; vy = lam[j] - a; } else { vx = lam[j] - d; vy = c; }
+        const double n = sqrt(vx * vx + vy * vy);
+        V[0 + j] = vx / n; V[2 + j] = vy / n;
+    }
+}
+__device__ __forceinline__ double cdf_rect(double x1, double y1, double x2, double y2) {   // CDFGridPVC.cpp:293-306
+    const double r2 = 1.4142135623730951;   // sqrt(2)
+    const double ex1 = 1 + erf(x1 / r2), ex2 = 1 + erf(x2 / r2), ey1 = 1 + erf(y1 / r2), ey2 = 1 + erf(y2 / r2);
+    const double p1 = (1.0 / 2.0) * ex1 * (1.0 / 2.0) * ey1, p2 = (1.0 / 2.0) * ex2 * (1.0 / 2.0) * ey1;
+    const double p3 = (1.0 / 2.0) * ex2 * (1.0 / 2.0) * ey2, p4 = (1.0 / 2.0) * ex1 * (1.0 / 2.0) * ey2;
+    return p3 - p2 - p4 + p1;
+}
+// CDFGridPVC::isSafe_ (CDFGridPVC.cpp:182-291); belief a = (mua, ca), belief b = (mub, cb), box half-side r_sum, grid n
+__device__ __forceinline__ bool pair_safe_cdfgrid(const double* mua, const double* ca, const double* mub, const double* cb, double r_sum, int n,
+                                                  double p_coll_agnts) {
+    const double T0 = mua[0] - mub[0], T1 = mua[1] - mub[1];
+    double S[4], lam[2], V[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) S[i] = ca[i] + cb[i];
+    eig2_general(S, lam, V);
+    const double l0 = sqrt(lam[0]), l1 = sqrt(lam[1]);
+    const double invdet = 1.0 / (l0 * l1 - 0.0 * 0.0);
+    const double Li00 = l1 * invdet, Li11 = l0 * invdet;
+    const double R0 = V[0] * Li00 + V[1] * 0.0, R1 = V[0] * 0.0 + V[1] * Li11, R2 = V[2] * Li00 + V[3] * 0.0, R3 = V[2] * 0.0 + V[3] * Li11;
+    double px[4], py[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const double vx = (k == 0 || k == 3) ? -r_sum : r_sum, vy = (k < 2) ? -r_sum : r_sum;
+        const double ex = -vx + T0, ey = -vy + T1;
+        px[k] = R0 * ex + R2 * ey;
+        py[k] = R1 * ex + R3 * ey;
+    }
+    double x_low = px[0], x_high = px[0], y_low = py[0], y_high = py[0];
+#pragma unroll
+    for (int k = 1; k < 4; ++k) {   // std::min / std::max semantics (a NaN candidate never replaces the running value)
+        x_low = px[k] < x_low ? px[k] : x_low; x_high = x_high < px[k] ? px[k] : x_high;
+        y_low = py[k] < y_low ? py[k] : y_low; y_high = y_high < py[k] ? py[k] : y_high;
+    }
+    double prob = 0;
+    if (n == 2) {
+        prob += cdf_rect(x_low, y_low, x_high, y_high);
+    } else if (n > 2) {
+        double area2 = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { const int k1 = (k + 1) & 3; area2 += px[k] * py[k1] - px[k1] * py[k]; }
+        const double sg = area2 >= 0 ? 1.0 : -1.0;
+        auto inside = [&](double x, double y) {
+            bool in = true;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int k1 = (k + 1) & 3;
+                const double cr = (px[k1] - px[k]) * (y - py[k]) - (py[k1] - py[k]) * (x - px[k]);
+                if (sg * cr < 0) in = false;
+            }
+            return in;
+        };
+        const double dx = (x_high - x_low) / (n - 1), dy = (y_high - y_low) / (n - 1);
+        for (int ix = 0; ix != n - 1; ++ix)
+            for (int iy = 0; iy != n - 1; ++iy) {
+                const double x1 = x_low + dx * ix, x2 = (ix + 1 == n - 1) ? x_high : x_low + dx * (ix + 1);
+                const double y1 = y_low + dy * iy, y2 = (iy + 1 == n - 1) ? y_high : y_low + dy * (iy + 1);
+                if (inside(x1, y1) || inside(x2, y1) || inside(x2, y2) || inside(x1, y2)) prob += cdf_rect(x1, y1, x2, y2);
+            }
+    }
+    return prob < p_coll_agnts;
+}
+
 // All constraint entries that fall on absolute step `s` against the belief (mu, cov).
 __device__ __forceinline__ bool constraints_ok_at(const unsigned char* cons, int s, double mx, double my, double C0,
                                                   double C1, double C2, double C3) {
@@ -91,6 +187,15 @@ __device__ __forceinline__ bool constraints_ok_at(const unsigned char* cons, int
             const double dist = sqrt(dx * dx + dy * dy);
             const double boundary = (la * h->sc + ent[e].rad[0]) + (lb * h->sc + ent[e].rad[1]);
             ok = dist > boundary;
+            continue;
+        }
+        if (h->pvc_kind == CCK_PVC_BLACKMORE2) {      // Blackmore2PVC.cpp:64-104
+            ok = pair_safe_blackmore2(ent[e].A, ent[e].B, dx, dy, S0, S1, S2, S3, h->p_coll_agnts);
+            continue;
+        }
+        if (h->pvc_kind == CCK_PVC_CDFGRID) {         // CDFGridPVC.cpp:72-109: the planning robot's belief first
+            const double mua[2] = {mx, my}, ca[4] = {C0, C1, C2, C3};
+            ok = pair_safe_cdfgrid(mua, ca, ent[e].mu, ent[e].cov, ent[e].rad[0] + ent[e].rad[1], h->grid_n, h->p_coll_agnts);
             continue;
         }
         double c = h->c_pair;
@@ -299,7 +404,7 @@ __global__ void k_cov_table_uni(double* __restrict__ tab, int n, const __grid_co
 // PlanValidityChecker::validatePlan
 // ---------------------------------------------------------------------------
 struct PvcDev {
-    int32_t kind, k, dim, n_pairs;
+    int32_t kind, k, dim, n_pairs, grid_n, pad;
     double c_pair, p_coll_agnts, sc;
     const double* radii;       // [k]
     const double* pair_A;      // [k*k*8]
@@ -338,7 +443,16 @@ __device__ __forceinline__ bool pvc_pair_safe(const PvcDev& pv, const double* tr
         const double boundary = (la * pv.sc + pv.radii[a]) + (lb * pv.sc + pv.radii[b]);
         return dist > boundary;
     }
+    if (pv.kind == CCK_PVC_CDFGRID) {                         // CDFGridPVC.cpp:111-151: r = r_a + r_b (getBoundingBox_, :330-351)
+        const int lo = a < b ? a : b, hi = a < b ? b : a;
+        return pair_safe_cdfgrid(mua, ca, mub, cb, pv.radii[lo] + pv.radii[hi], pv.grid_n, pv.p_coll_agnts);
+    }
     const double dx = mua[0] - mub[0], dy = mua[1] - mub[1];
+    if (pv.kind == CCK_PVC_BLACKMORE2) {                      // Blackmore2PVC.cpp:125-167
+        const int lo = a < b ? a : b, hi = a < b ? b : a;
+        return pair_safe_blackmore2(pv.pair_A + ((int64_t)lo * pv.k + hi) * 8, pv.pair_B + ((int64_t)lo * pv.k + hi) * 4, dx, dy, ca[0] + cb[0],
+                                    ca[1] + cb[1], ca[2] + cb[2], ca[3] + cb[3], pv.p_coll_agnts);
+    }
     double c = pv.c_pair;
     if (pv.kind == CCK_PVC_ADAPTIVE_BLACKMORE || pv.kind == CCK_PVC_ADAPTIVE_BOUNDINGBOX) {
         // createEtaMap_ (AdaptiveRiskBlackmorePVC.cpp:179-206): sum over the active robots in map order
@@ -462,6 +576,44 @@ __global__ void __launch_bounds__(128) k_constraints(int64_t n_paths, int dim, c
             good = constraints_ok_at(cons, s, b[0], b[ld], C0, C1, C2, C3);
         }
         ok[i] = good ? 1 : 0;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// CentralizedChiSquaredBoundarySVC's agent-agent test (CentralizedChiSquaredBoundarySVC.cpp:70-99), batched: the 10-gon of
+// radius lambda_max(cov_a) * sc + rad_a around mu_a against the one of agent b; out = 1 iff bg::disjoint (touching is NOT
+// disjoint).  Separating axes of two convex polygons: the edge normals of both.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_chisq_pairs(int64_t n, const double* __restrict__ mu_a, const double* __restrict__ cov_a,
+                                                     const double* __restrict__ rad_a, const double* __restrict__ mu_b,
+                                                     const double* __restrict__ cov_b, const double* __restrict__ rad_b, double sc,
+                                                     const __grid_constant__ SvcDev sp, uint8_t* __restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double ra = (max_eig_real_2x2(cov_a[i], cov_a[n + i], cov_a[2 * n + i], cov_a[3 * n + i]) * sc + rad_a[i]);
+        const double rb = (max_eig_real_2x2(cov_b[i], cov_b[n + i], cov_b[2 * n + i], cov_b[3 * n + i]) * sc + rad_b[i]);
+        double ax[11], ay[11], bx[11], by[11];
+#pragma unroll
+        for (int k = 0; k < 10; ++k) {
+            ax[k] = mu_a[i] + ra * sp.dec_cos[k]; ay[k] = mu_a[n + i] + ra * sp.dec_sin[k];
+            bx[k] = mu_b[i] + rb * sp.dec_cos[k]; by[k] = mu_b[n + i] + rb * sp.dec_sin[k];
+        }
+        ax[10] = ax[0]; ay[10] = ay[0]; bx[10] = bx[0]; by[10] = by[0];
+        bool sep = false;
+        for (int pass = 0; pass < 2 && !sep; ++pass) {
+            const double* ex = pass ? bx : ax; const double* ey = pass ? by : ay;
+            for (int e = 0; e < 10 && !sep; ++e) {
+                const double nx = ey[e + 1] - ey[e], ny = ex[e] - ex[e + 1];
+                if (nx == 0 && ny == 0) continue;
+                double amin = nx * ax[0] + ny * ay[0], amax = amin, bmin = nx * bx[0] + ny * by[0], bmax = bmin;
+#pragma unroll
+                for (int j = 1; j < 10; ++j) {
+                    const double da = nx * ax[j] + ny * ay[j], db = nx * bx[j] + ny * by[j];
+                    amin = fmin(amin, da); amax = fmax(amax, da); bmin = fmin(bmin, db); bmax = fmax(bmax, db);
+                }
+                sep = (amax < bmin) || (bmax < amin);
+            }
+        }
+        out[i] = sep ? 1 : 0;
     }
 }
 

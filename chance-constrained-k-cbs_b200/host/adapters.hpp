@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <cstring>
 #include <fstream>
+#include <limits>
 #include <map>
 #include <memory>
 #include <sstream>
@@ -292,6 +293,109 @@ public:
 };
 
 // ---------------------------------------------------------------------------
+// Centralized variants: the composite state of k agents is a RealVectorBeliefSpace(2k) state whose
+// sigma_ / lambda_ carry one 2x2 block per agent on the diagonal.
+// ---------------------------------------------------------------------------
+// CentralizedUncertainLinearStatePropagator(si)  (include/StatePropogators/CentralizedUncertainLinearSP.h:17-70,
+// src/StatePropogators/CentralizedUncertainLinearSP.cpp:42-102): singleAgentPropogate_ is the single-agent linear step with
+// the same constants (F = H = I, Q = R = 0.01 I, A_cl = (1 - 0.3) I, mean += duration_ * u), applied to every agent's block;
+// entries of the result outside the diagonal blocks are left as they are.  ONE cck_propagate over the k agents.
+class CentralizedUncertainLinearStatePropagator : public oc::StatePropagator {
+public:
+    CentralizedUncertainLinearStatePropagator(const oc::SpaceInformationPtr& si, GpuContextPtr gpu)
+        : oc::StatePropagator(si.get()), gpu_(std::move(gpu)), k_((int)si->getStateSpace()->getDimension() / 2) {
+        install_model(gpu_, CCK_MODEL_LINEAR2D, si->getPropagationStepSize());
+    }
+    void propagate(const ob::State* state, const oc::Control* control, const double duration, ob::State* result) const override {
+        const auto* s = state->as<RealVectorBeliefSpace::StateType>();
+        auto* r = result->as<RealVectorBeliefSpace::StateType>();
+        const double* u = control->as<oc::RealVectorControlSpace::ControlType>()->values;
+        std::vector<double> in((size_t)10 * k_), ctl((size_t)2 * k_), out((size_t)10 * k_);
+        for (int a = 0; a < k_; ++a) {
+            in[0 * k_ + a] = s->values[2 * a]; in[1 * k_ + a] = s->values[2 * a + 1];
+            for (int i = 0; i < 2; ++i) for (int j = 0; j < 2; ++j) {
+                in[(2 + i * 2 + j) * k_ + a] = s->sigma_(2 * a + i, 2 * a + j);
+                in[(6 + i * 2 + j) * k_ + a] = s->lambda_(2 * a + i, 2 * a + j);
+            }
+            ctl[a] = u[2 * a]; ctl[k_ + a] = u[2 * a + 1];
+        }
+        gpu_->check(cck_propagate(gpu_->get(), k_, in.data(), k_, ctl.data(), k_, duration, out.data(), k_), "cck_propagate (centralized)");
+        if (r->sigma_.n != 2 * k_) { r->sigma_ = Mat(2 * k_); r->lambda_ = Mat(2 * k_); }
+        for (int a = 0; a < k_; ++a) {
+            r->values[2 * a] = out[0 * k_ + a]; r->values[2 * a + 1] = out[1 * k_ + a];
+            for (int i = 0; i < 2; ++i) for (int j = 0; j < 2; ++j) {
+                r->sigma_(2 * a + i, 2 * a + j) = out[(2 + i * 2 + j) * k_ + a];
+                r->lambda_(2 * a + i, 2 * a + j) = out[(6 + i * 2 + j) * k_ + a];
+            }
+        }
+    }
+    bool canPropagateBackward() const override { return false; }
+private:
+    GpuContextPtr gpu_;
+    int k_;
+};
+
+// CentralizedChiSquaredBoundarySVC(si, instance, accep_prob)  (include/StateValidityCheckers/CentralizedChiSquaredBoundarySVC.h,
+// src/StateValidityCheckers/CentralizedChiSquaredBoundarySVC.cpp:24-99): bounds of the composite state; per agent the decagon
+// of radius lambda_max(SIGMA block only - not Sigma + Lambda) * sc + r_a against every inflated obstacle (ONE cck_is_valid
+// over the k agents, with Lambda = 0 and the block symmetrised from its lower triangle as SelfAdjointEigenSolver reads it);
+// then every agent pair's decagons must be disjoint (ONE cck_chisq_pairs_disjoint; see the note on the reference's
+// uninitialised solver_a2 in the oracle).
+class CentralizedChiSquaredBoundarySVC : public ob::StateValidityChecker {
+public:
+    CentralizedChiSquaredBoundarySVC(const oc::SpaceInformationPtr& si, GpuContextPtr gpu, InstancePtr inst, double accep_prob)
+        : ob::StateValidityChecker(si.get()), gpu_(std::move(gpu)), inst_(std::move(inst)), k_((int)inst_->getRobots().size()) {
+        sc_ = cck_chi2_quantile_2dof(accep_prob);                                          // :8
+        const auto& b = si->getStateSpace()->as<ob::RealVectorStateSpace>()->getBounds();
+        low_ = b.low; high_ = b.high;
+        install_model(gpu_, CCK_MODEL_LINEAR2D, si->getPropagationStepSize());
+        cck_svc_params p{};
+        p.kind = CCK_SVC_CHISQUARED; p.dim = 2;
+        // the composite bounds are checked here (satisfiesBounds on all 2k values); the kernel gets agent 0's (x, y) bounds,
+        // which set_up_CentralizedBSST_Problem repeats for every agent (OmplSetUp.cpp:367-376)
+        for (int i = 0; i < 2; ++i) { p.low[i] = low_[i]; p.high[i] = high_[i]; }
+        const ObstacleTables t = build_tables(*inst_, inst_->getRobots()[0]);              // all robots share one bounding radius in the scenario files
+        p.p_collision = 1 - accep_prob; p.sc = sc_; p.max_rad = inst_->getRobots()[0].getBoundingRadius();
+        gpu_->check(cck_set_obstacles(gpu_->get(), &p, t.A.data(), t.B.data(), t.centres.data(), t.rects.data(), t.M), "cck_set_obstacles");
+    }
+    bool isValid(const ob::State* state) const override {
+        const auto* s = state->as<RealVectorBeliefSpace::StateType>();
+        for (int d = 0; d < 2 * k_; ++d)                                                    // RealVectorStateSpace::satisfiesBounds
+            if (s->values[d] - std::numeric_limits<double>::epsilon() > high_[d] || s->values[d] + std::numeric_limits<double>::epsilon() < low_[d]) return false;
+        std::vector<double> in((size_t)10 * k_, 0.0);
+        for (int a = 0; a < k_; ++a) {
+            in[0 * k_ + a] = s->values[2 * a]; in[1 * k_ + a] = s->values[2 * a + 1];
+            const double s00 = s->sigma_(2 * a, 2 * a), s10 = s->sigma_(2 * a + 1, 2 * a), s11 = s->sigma_(2 * a + 1, 2 * a + 1);
+            in[2 * k_ + a] = s00; in[3 * k_ + a] = s10; in[4 * k_ + a] = s10; in[5 * k_ + a] = s11;    // lower triangle, Lambda planes stay 0
+        }
+        std::vector<uint8_t> ok(k_);
+        gpu_->check(cck_is_valid(gpu_->get(), k_, in.data(), k_, ok.data()), "cck_is_valid (centralized)");
+        for (int a = 0; a < k_; ++a) if (!ok[a]) return false;
+        const int np = k_ * (k_ - 1) / 2;
+        if (np == 0) return true;
+        std::vector<double> mua((size_t)2 * np), cova((size_t)4 * np), rada(np), mub((size_t)2 * np), covb((size_t)4 * np), radb(np);
+        int q = 0;
+        for (int a = 0; a < k_; ++a)
+            for (int b = a + 1; b < k_; ++b, ++q) {
+                mua[q] = in[a]; mua[np + q] = in[k_ + a]; mub[q] = in[b]; mub[np + q] = in[k_ + b];
+                for (int f = 0; f < 4; ++f) { cova[(size_t)f * np + q] = in[(2 + f) * k_ + a]; covb[(size_t)f * np + q] = in[(2 + f) * k_ + b]; }
+                rada[q] = inst_->getRobots()[a].getBoundingRadius(); radb[q] = inst_->getRobots()[b].getBoundingRadius();
+            }
+        std::vector<uint8_t> dj(np);
+        gpu_->check(cck_chisq_pairs_disjoint(gpu_->get(), np, mua.data(), cova.data(), rada.data(), mub.data(), covb.data(), radb.data(), sc_, dj.data()),
+                    "cck_chisq_pairs_disjoint");
+        for (int i = 0; i < np; ++i) if (!dj[i]) return false;
+        return true;
+    }
+private:
+    GpuContextPtr gpu_;
+    InstancePtr inst_;
+    int k_;
+    double sc_ = 0;
+    std::vector<double> low_, high_;
+};
+
+// ---------------------------------------------------------------------------
 // Conflicts, constraints, plan validity checkers
 // ---------------------------------------------------------------------------
 struct Conflict {                                   // include/utils/Conflict.h:6-13
@@ -326,7 +430,7 @@ using ConstraintPtr = std::shared_ptr<BeliefConstraint>;
 // AdaptiveRiskBlackmorePVC / AdaptiveRiskBoundingBoxPVC.
 class BeliefPVC {
 public:
-    BeliefPVC(GpuContextPtr gpu, InstancePtr inst, int kind, int dim, double p_safe_arg, double step_size, std::string name)
+    BeliefPVC(GpuContextPtr gpu, InstancePtr inst, int kind, int dim, double p_safe_arg, double step_size, std::string name, int grid_n = 2)
         : gpu_(std::move(gpu)), inst_(std::move(inst)), kind_(kind), dim_(dim), step_(step_size), name_(std::move(name)) {
         k_ = (int)inst_->getRobots().size();
         std::vector<double> radii(k_), A((size_t)k_ * k_ * 8, 0.0), B((size_t)k_ * k_ * 4, 0.0);
@@ -338,7 +442,7 @@ public:
         for (int i = 0; i < k_; ++i) order[i] = i;
         std::sort(order.begin(), order.end(), [&](int x, int y) { return inst_->getRobots()[x].getName() < inst_->getRobots()[y].getName(); });   // std::map order (quirk 6)
         cck_pvc_params p{};
-        p.kind = kind; p.k = k_; p.dim = dim;
+        p.kind = kind; p.k = k_; p.dim = dim; p.grid_n = grid_n;
         p.p_coll_agnts = 1 - p_safe_arg;                                                 // BeliefPVC.cpp:7
         const double p_coll_dist = k_ > 1 ? p.p_coll_agnts / (k_ - 1) : p.p_coll_agnts;  // MinkowskiSumBlackmorePVC.cpp:7-8
         p.c_pair = cck_erf_inv(1 - (2 * p_coll_dist));
@@ -427,6 +531,12 @@ inline PlanValidityCheckerPtr make_pvc(const std::string& name, GpuContextPtr g,
     if (name == "ChiSquared") return std::make_shared<BeliefPVC>(g, inst, CCK_PVC_CHISQUARED, dim, 0.9, step, "ChiSquaredBoundaryPVC");
     if (name == "AdaptiveBlackmore") return std::make_shared<BeliefPVC>(g, inst, CCK_PVC_ADAPTIVE_BLACKMORE, dim, pa, step, "AdaptiveRiskBlackmorePVC");
     if (name == "AdaptiveBoundingBox") return std::make_shared<BeliefPVC>(g, inst, CCK_PVC_ADAPTIVE_BOUNDINGBOX, dim, pa, step, "AdaptiveRiskBoundingBoxPVC");
+    if (name == "Blackmore2") return std::make_shared<BeliefPVC>(g, inst, CCK_PVC_BLACKMORE2, dim, pa, step, "Blackmore2PVC");     // not reachable from the reference CLI
+    if (name.rfind("CDFGrid", 0) == 0) {                                  // `--pvc CDFGrid-n` (demos/main.cpp:126-134: token after '-')
+        const size_t dash = name.find('-');
+        const int disks = dash == std::string::npos ? 0 : std::atoi(name.c_str() + dash + 1);
+        return std::make_shared<BeliefPVC>(g, inst, CCK_PVC_CDFGRID, dim, pa, step, "CDFGridPVC(" + std::to_string(disks) + ")", disks);
+    }
     throw std::runtime_error("unknown --pvc " + name);   // the reference asserts (demos/main.cpp:40,109-137)
 }
 

@@ -83,6 +83,50 @@ int main(int argc, char** argv) {
         REQUIRE(!pv->satisfiesConstraints(plan[0], {con}));
         Trajectory stay(plan[0].size(), plan[0][0]);
         REQUIRE(pv->satisfiesConstraints(stay, {con}));
+        // ---- centralized variants: composite state of k = 2 agents ----
+        {
+            const int k = 2;
+            auto cspace4 = std::make_shared<RealVectorBeliefSpace>(2 * k);
+            ob::RealVectorBounds b4(2 * k);
+            for (int a = 0; a < k; ++a) { b4.setLow(2 * a, -1); b4.setHigh(2 * a, inst->getDimensions()[0]); b4.setLow(2 * a + 1, -1); b4.setHigh(2 * a + 1, inst->getDimensions()[1]); }
+            cspace4->setBounds(b4);
+            auto ctl4 = std::make_shared<oc::RealVectorControlSpace>(cspace4, 2 * k);
+            auto si4 = std::make_shared<oc::SpaceInformation>(cspace4, ctl4);
+            si4->setPropagationStepSize(0.5);                                             // OmplSetUp.cpp:357
+            auto g4 = std::make_shared<GpuContext>(0);
+            si4->setStatePropagator(std::make_shared<CentralizedUncertainLinearStatePropagator>(si4, g4));
+            auto g5 = std::make_shared<GpuContext>(0);
+            si4->setStateValidityChecker(std::make_shared<CentralizedChiSquaredBoundarySVC>(si4, g5, inst, 0.9));
+            ob::State* cs = si4->allocState();
+            ob::State* cr = si4->allocState();
+            oc::Control* cc = si4->allocControl();
+            auto* cb = cs->as<RealVectorBeliefSpace::StateType>();
+            cb->values[0] = 1.0; cb->values[1] = 2.0; cb->values[2] = 5.0; cb->values[3] = 2.0;
+            cb->sigma_(0, 1) = cb->sigma_(1, 0) = 0.002; cb->sigma_(0, 3) = 0.5;          // an off-block entry: must not influence anything
+            double* cu = cc->as<oc::RealVectorControlSpace::ControlType>()->values;
+            cu[0] = 1.0; cu[1] = 0.0; cu[2] = -1.0; cu[3] = 0.5;
+            REQUIRE(si4->isValid(cs));
+            si4->getStatePropagator()->propagate(cs, cc, 0.5, cr);
+            auto* rb = cr->as<RealVectorBeliefSpace::StateType>();
+            // each agent's block against the single-agent batched propagator on a context with the same step size
+            auto g6 = std::make_shared<GpuContext>(0);
+            install_model(g6, CCK_MODEL_LINEAR2D, 0.5);
+            for (int a = 0; a < k; ++a) {
+                double in1[10], u1[2] = {cu[2 * a], cu[2 * a + 1]}, out1[10];
+                in1[0] = cb->values[2 * a]; in1[1] = cb->values[2 * a + 1];
+                for (int i = 0; i < 2; ++i) for (int j = 0; j < 2; ++j) { in1[2 + 2 * i + j] = cb->sigma_(2 * a + i, 2 * a + j); in1[6 + 2 * i + j] = cb->lambda_(2 * a + i, 2 * a + j); }
+                g6->check(cck_propagate(g6->get(), 1, in1, 1, u1, 1, 0.5, out1, 1), "single");
+                REQUIRE(rb->values[2 * a] == out1[0] && rb->values[2 * a + 1] == out1[1]);
+                for (int i = 0; i < 2; ++i) for (int j = 0; j < 2; ++j) REQUIRE(rb->sigma_(2 * a + i, 2 * a + j) == out1[2 + 2 * i + j] && rb->lambda_(2 * a + i, 2 * a + j) == out1[6 + 2 * i + j]);
+            }
+            REQUIRE(rb->values[0] == 1.0 + 0.5 * 1.0 && rb->values[2] == 5.0 + 0.5 * -1.0);
+            // agents on top of each other: the decagons meet -> invalid; outside the bounds -> invalid
+            cb->values[2] = 1.2; cb->values[3] = 2.1;
+            REQUIRE(!si4->isValid(cs));
+            cb->values[2] = 5.0; cb->values[3] = 2.0; cb->values[1] = -1.5;
+            REQUIRE(!si4->isValid(cs));
+            std::printf("centralized adapters OK\n");
+        }
         std::printf("host_selftest OK\n");
         return 0;
     } catch (const std::exception& e) {

@@ -459,7 +459,7 @@ public:
             const double secs = ll_seconds_;
             roots.push_back(std::async(k > 1 ? std::launch::async : std::launch::deferred, [pl, secs, seconds, &elapsed] {
                 Trajectory t;
-                while (t.empty() && elapsed() < seconds) t = pl->solve(secs);
+                while (t.empty() && elapsed() < seconds && pl->startStateValid()) t = pl->solve(secs);   // INVALID_START is final
                 return t;
             }));
         }

@@ -47,6 +47,8 @@ extern "C" {
 #define CCK_PVC_CHISQUARED 2           /* ChiSquaredBoundaryPVC      */
 #define CCK_PVC_ADAPTIVE_BLACKMORE 3   /* AdaptiveRiskBlackmorePVC   */
 #define CCK_PVC_ADAPTIVE_BOUNDINGBOX 4 /* AdaptiveRiskBoundingBoxPVC */
+#define CCK_PVC_BLACKMORE2 5           /* Blackmore2PVC  (src/PlanValidityCheckers/Blackmore2PVC.cpp:169-192) */
+#define CCK_PVC_CDFGRID 6              /* CDFGridPVC(n)  (src/PlanValidityCheckers/CDFGridPVC.cpp:182-291; `--pvc CDFGrid-n`) */
 
 typedef struct cck_ctx cck_ctx;
 
@@ -79,12 +81,13 @@ typedef struct cck_pvc_params {
     int32_t kind;          /* CCK_PVC_* */
     int32_t k;             /* number of robots (<= CCK_MAX_ROBOTS) */
     int32_t dim;           /* 2 or 4: selects getDistribution_'s sub-block (BeliefPVC.cpp:84-113) */
-    int32_t reserved;
+    int32_t grid_n;        /* CDFGridPVC: disk_steps_ (grid points per axis, >= 2); ignored by the other kinds */
     double c_pair;         /* erf_inv(1 - 2*p_coll_dist) (MinkowskiSumBlackmorePVC.cpp:178) */
     double p_coll_agnts;   /* Adaptive PVCs: 1 - p_safe_agnts (BeliefPVC.cpp:7) */
     double sc;             /* ChiSquared PVC: chi2_2 quantile (ChiSquaredBoundaryPVC.cpp:19) */
     const double* radii;      /* [k] bounding radii */
-    const double* pair_A;     /* [k*k][4][2] half-plane normals, entry [a*k+b] valid for a<b */
+    const double* pair_A;     /* [k*k][4][2] half-plane normals, entry [a*k+b] valid for a<b (Blackmore2: Minkowski sum of the
+                                 bounding squares; CDFGrid does not read them: its box is +-(r_a + r_b)) */
     const double* pair_B;     /* [k*k][4] */
     const int32_t* map_order; /* [k] robot indices in std::map<std::string,...> name order (quirk 6) */
 } cck_pvc_params;
@@ -160,6 +163,15 @@ int cck_propagate_while_valid(cck_ctx* ctx, int64_t n, const double* bel, int64_
 int cck_propagate_while_valid_dev(cck_ctx* ctx, void* stream, int64_t n, const double* bel, int64_t ld,
                                   const double* ctrl, int64_t ldc, const int32_t* steps, double* out, int64_t ldo,
                                   int32_t* valid_steps, double* traj, int64_t traj_ld, int32_t traj_T);
+
+/* ---- CentralizedChiSquaredBoundarySVC's agent-agent test (src/StateValidityCheckers/CentralizedChiSquaredBoundarySVC.cpp:70-99) ----
+ * for n pairs: 10-gon of radius lambda_max(cov_a) * sc + rad_a around mu_a vs the one of agent b; out[i] = 1 iff disjoint
+ * (touching is not).  SoA host arrays: mu [2][n], cov [4][n] (row-major 2x2), rad [n].  (The agent-obstacle half of that
+ * checker is cck_is_valid with CCK_SVC_CHISQUARED on the agents' 2-D blocks; the centralized propagator,
+ * CentralizedUncertainLinearSP.cpp:42-102, is cck_propagate over the agents' 2-D blocks - same constants as the
+ * single-agent linear model.) */
+int cck_chisq_pairs_disjoint(cck_ctx* ctx, int64_t n, const double* mu_a, const double* cov_a, const double* rad_a, const double* mu_b,
+                             const double* cov_b, const double* rad_b, double sc, uint8_t* out);
 
 /* ---- PlanValidityChecker::validatePlan ----------------------------------
  * replaces {MinkowskiSumBlackmore,BoundingBoxBlackmore,ChiSquaredBoundary,AdaptiveRisk*}PVC::validatePlan

@@ -30,6 +30,7 @@
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
+#include <limits>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -712,6 +713,15 @@ inline bool svc_is_valid(const Svc& s, const double* values, const double* cov2,
     return true;
 }
 
+// CentralizedChiSquaredBoundarySVC's agent-agent test (CentralizedChiSquaredBoundarySVC.cpp:70-99): decagons of radius
+// lambda_max * sc + r around the two means must be disjoint.  NOTE the reference computes the second radius from
+// `solver_a2.eigenvalues()` although it called `solver_a1.compute(sigma_a2)` (:79-82): solver_a2 is never computed, so the
+// value is undefined there; the evident intent (lambda_max of sigma_a2) is what is restated here and in the kernel.
+inline bool chisq_pair_disjoint(const double* mu_a, const double* cov_a, double rad_a, const double* mu_b, const double* cov_b, double rad_b, double sc) {
+    const double ra = (max_eig_real_2x2(cov_a) * sc + rad_a), rb = (max_eig_real_2x2(cov_b) * sc + rad_b);
+    return convex_disjoint(decagon(mu_a[0], mu_a[1], ra), decagon(mu_b[0], mu_b[1], rb));
+}
+
 template <int D>
 inline void cov_block2(const Belief<D>& b, double* c) {   // (Sigma+Lambda).block<2,2>(0,0)
     c[0] = b.S[0] + b.L[0];         c[1] = b.S[1] + b.L[1];
@@ -800,7 +810,8 @@ inline Dist2 get_distribution(const Belief<D>& b) {
     return d;
 }
 
-enum PvcKind { PVC_BLACKMORE = 0, PVC_BOUNDINGBOX = 1, PVC_CHISQUARED = 2, PVC_ADAPTIVE_BLACKMORE = 3, PVC_ADAPTIVE_BOUNDINGBOX = 4 };
+enum PvcKind { PVC_BLACKMORE = 0, PVC_BOUNDINGBOX = 1, PVC_CHISQUARED = 2, PVC_ADAPTIVE_BLACKMORE = 3, PVC_ADAPTIVE_BOUNDINGBOX = 4,
+               PVC_BLACKMORE2 = 5, PVC_CDFGRID = 6 };   // Blackmore2PVC, CDFGridPVC(n)
 
 struct Pvc {
     int kind = PVC_BLACKMORE;
@@ -812,6 +823,7 @@ struct Pvc {
     double p_coll_dist = 0;            // p_coll_agnts / (k-1)  (MinkowskiSumBlackmorePVC.cpp:7-8)
     double c_pair = 0;                 // erf_inv(1 - 2 p_coll_dist)   (:178)
     double sc = 0;                     // chi2 quantile of the ctor arg (ChiSquaredBoundaryPVC.cpp:19)
+    int grid_n = 2;                    // CDFGridPVC: disk_steps_ (CDFGridPVC.cpp:5, `--pvc CDFGrid-n`, demos/main.cpp:126-134)
     std::vector<int> map_order;        // robot indices in std::map<std::string,...> order (quirk 6)
 };
 
@@ -836,7 +848,7 @@ inline Pvc make_pvc(int kind, const std::vector<RobotShape>& robots, double p_sa
     }
     for (int a = 0; a < p.k; ++a)
         for (int b = a + 1; b < p.k; ++b) {
-            Ring poly = (kind == PVC_BOUNDINGBOX || kind == PVC_ADAPTIVE_BOUNDINGBOX)
+            Ring poly = (kind == PVC_BOUNDINGBOX || kind == PVC_ADAPTIVE_BOUNDINGBOX || kind == PVC_CDFGRID)   // CDFGridPVC.cpp:32: getBoundingBox_
                             ? bounding_box_ring(robots[a].bounding_rad, robots[b].bounding_rad)
                             : minkowski_sum(robots[a].bounding, robots[b].bounding);
             p.pair_hp[(size_t)a * p.k + b] = half_planes(poly);
@@ -872,6 +884,102 @@ inline bool pair_is_safe_chisq(const Dist2& a, double rad_a, const Dist2& b, dou
     return dist > boundary;
 }
 
+// Blackmore2PVC::isSafe_ / ImprovedHyperplaneCCValidityChecker (Blackmore2PVC.cpp:169-192): the smallest of the four
+// half-plane collision probabilities 1/2 + 1/2 erf((B_i - a_i.mu) / sqrt(2 a_i^T Sigma a_i)) against p_coll_agnts_ (NOT
+// p_coll_dist_, which the constructor computes and never uses).
+inline bool pair_is_safe_blackmore2(const HalfPlanes& hp, const double* mu_ab, const double* S_ab, double p_coll_agnts) {
+    double p_obs = std::numeric_limits<double>::max();
+    for (int i = 0; i < 4; ++i) {
+        const double a0 = hp.A[i][0], a1 = hp.A[i][1];
+        const double t0 = a0 * S_ab[0] + a1 * S_ab[2];
+        const double t1 = a0 * S_ab[1] + a1 * S_ab[3];
+        const double pv2 = t0 * a0 + t1 * a1;
+        const double PV = std::sqrt(2 * pv2);
+        const double pc = 0.5 + 0.5 * std::erf((hp.B[i] - (mu_ab[0] * a0 + mu_ab[1] * a1)) / PV);
+        if (pc < p_obs) p_obs = pc;
+    }
+    return !(p_obs > p_coll_agnts);
+}
+
+// Eigen::EigenSolver<Matrix2d> as CDFGridPVC uses it (CDFGridPVC.cpp:189-193): real parts of the eigenvalues and of the
+// normalised eigenvectors of a general real 2x2.  Restated in closed form; Eigen's RealSchur may return the pair in the other
+// order or an eigenvector with the other sign - the grid probability below is invariant under both (the standard normal is
+// symmetric under axis swaps and reflections).  Diagonal input: (a, d) and the identity, as Eigen.  Complex pair (cannot
+// happen for a sum of covariances): real part tr/2 twice, identity - not pinned.
+inline void eig2_general(const double* M, double* lam, double* V) {
+    const double a = M[0], b = M[1], c = M[2], d = M[3];
+    V[0] = 1; V[1] = 0; V[2] = 0; V[3] = 1;
+    if (b == 0 && c == 0) { lam[0] = a; lam[1] = d; return; }
+    const double h = (a - d) / 2, disc = h * h + b * c, m = (a + d) / 2;
+    if (!(disc >= 0)) { lam[0] = lam[1] = m; return; }
+    const double sq = std::sqrt(disc);
+    lam[0] = m + sq; lam[1] = m - sq;
+    for (int j = 0; j < 2; ++j) {
+        double vx, vy;
+        if (std::fabs(b) >= std::fabs(c)) { vx = b; vy = lam[j] - a; } else { vx = lam[j] - d; vy = c; }
+        const double n = std::sqrt(vx * vx + vy * vy);
+        V[0 + j] = vx / n; V[2 + j] = vy / n;          // column j
+    }
+}
+
+inline double cdf_rect(double x1, double y1, double x2, double y2) {           // CDFGridPVC.cpp:293-306
+    auto p = [](double x, double y) { return (1.0 / 2.0) * (1 + std::erf(x / std::sqrt(2))) * (1.0 / 2.0) * (1 + std::erf(y / std::sqrt(2))); };
+    const double p1 = p(x1, y1), p2 = p(x2, y1), p3 = p(x2, y2), p4 = p(x1, y2);
+    return p3 - p2 - p4 + p1;
+}
+
+// CDFGridPVC::isSafe_ (CDFGridPVC.cpp:182-291): whiten the difference distribution, map the bounding box of r_a + r_b into
+// the whitened frame, lay an n x n grid over ITS bounding box and sum the standard-normal mass of every cell that has a corner
+// inside (or on) the mapped box; n == 2: the whole bounding box.  `eigen_vals` is a default-constructed Matrix2d in the
+// reference, whose off-diagonal entries are never written: they are taken as 0 here (what a zero-initialised stack gives).
+inline bool pair_is_safe_cdfgrid(const double* mu_a, const double* cov_a, const double* mu_b, const double* cov_b, double r_sum, int n, double p_coll_agnts,
+                                 double* prob_out = nullptr) {
+    const double T[2] = {mu_a[0] - mu_b[0], mu_a[1] - mu_b[1]};
+    double S[4], lam[2], V[4];
+    for (int i = 0; i < 4; ++i) S[i] = cov_a[i] + cov_b[i];
+    eig2_general(S, lam, V);
+    const double l0 = std::sqrt(lam[0]), l1 = std::sqrt(lam[1]);            // LLT of diag(lam): L = diag(sqrt)
+    const double invdet = 1.0 / (l0 * l1 - 0.0 * 0.0);                      // L.inverse(): 2x2 adjugate * (1/det)
+    const double Li00 = l1 * invdet, Li11 = l0 * invdet;
+    const double R[4] = {V[0] * Li00 + V[1] * 0.0, V[0] * 0.0 + V[1] * Li11, V[2] * Li00 + V[3] * 0.0, V[2] * 0.0 + V[3] * Li11};   // eigen_vecs * L^-1
+    const double vx[4] = {-r_sum, r_sum, r_sum, -r_sum}, vy[4] = {-r_sum, -r_sum, r_sum, r_sum};   // getBoundingBox_ after correct(): BL, BR, TR, TL
+    double px[4], py[4];
+    for (int k = 0; k < 4; ++k) {                                            // R^T * ((-V_mat).colwise() + T)
+        const double ex = -vx[k] + T[0], ey = -vy[k] + T[1];
+        px[k] = R[0] * ex + R[2] * ey;
+        py[k] = R[1] * ex + R[3] * ey;
+    }
+    double x_low = px[0], x_high = px[0], y_low = py[0], y_high = py[0];
+    for (int k = 1; k < 4; ++k) { x_low = std::min(x_low, px[k]); x_high = std::max(x_high, px[k]); y_low = std::min(y_low, py[k]); y_high = std::max(y_high, py[k]); }
+    double prob = 0;
+    if (n == 2) {
+        prob += cdf_rect(x_low, y_low, x_high, y_high);                     // the box meets the polygon it bounds
+    } else if (n > 2) {
+        // orientation of the mapped quadrilateral (R^T may reflect): point inside-or-on <=> all edge cross products have its sign or are 0
+        double area2 = 0;
+        for (int k = 0; k < 4; ++k) { const int k1 = (k + 1) & 3; area2 += px[k] * py[k1] - px[k1] * py[k]; }
+        const double sg = area2 >= 0 ? 1.0 : -1.0;
+        auto inside = [&](double x, double y) {
+            for (int k = 0; k < 4; ++k) {
+                const int k1 = (k + 1) & 3;
+                const double cr = (px[k1] - px[k]) * (y - py[k]) - (py[k1] - py[k]) * (x - px[k]);
+                if (sg * cr < 0) return false;
+            }
+            return true;
+        };
+        const double dx = (x_high - x_low) / (n - 1), dy = (y_high - y_low) / (n - 1);       // linspace_ (:308-328)
+        auto gx = [&](int i) { return i == n - 1 ? x_high : x_low + dx * i; };
+        auto gy = [&](int i) { return i == n - 1 ? y_high : y_low + dy * i; };
+        for (int ix = 0; ix != n - 1; ++ix)
+            for (int iy = 0; iy != n - 1; ++iy) {
+                const double x1 = gx(ix), x2 = gx(ix + 1), y1 = gy(iy), y2 = gy(iy + 1);
+                if (inside(x1, y1) || inside(x2, y1) || inside(x2, y2) || inside(x1, y2)) prob += cdf_rect(x1, y1, x2, y2);
+            }
+    }
+    if (prob_out) *prob_out = prob;
+    return prob < p_coll_agnts;
+}
+
 // createEtaMap_ (AdaptiveRiskBlackmorePVC.cpp:179-206): `active` = robot indices
 // present in states_map, in map order; returns eta for robot `b` seen from `a`.
 inline double adaptive_eta(const Pvc& p, const std::vector<int>& active, const std::vector<Dist2>& dist, int a, int b) {
@@ -900,6 +1008,13 @@ inline bool check_for_conflicts(const Pvc& p, const std::vector<int>& active, co
             bool safe;
             if (p.kind == PVC_CHISQUARED) {
                 safe = pair_is_safe_chisq(dist[a], p.radii[a], dist[b], p.radii[b], p.sc);
+            } else if (p.kind == PVC_CDFGRID) {
+                safe = pair_is_safe_cdfgrid(dist[a].mu, dist[a].cov, dist[b].mu, dist[b].cov, p.radii[std::min(a, b)] + p.radii[std::max(a, b)], p.grid_n, p.p_coll_agnts);
+            } else if (p.kind == PVC_BLACKMORE2) {
+                const double mu_ab[2] = {dist[a].mu[0] - dist[b].mu[0], dist[a].mu[1] - dist[b].mu[1]};
+                double S_ab[4];
+                for (int i = 0; i < 4; ++i) S_ab[i] = dist[a].cov[i] + dist[b].cov[i];
+                safe = pair_is_safe_blackmore2(p.pair_hp[(size_t)std::min(a, b) * p.k + std::max(a, b)], mu_ab, S_ab, p.p_coll_agnts);
             } else {
                 const double mu_ab[2] = {dist[a].mu[0] - dist[b].mu[0], dist[a].mu[1] - dist[b].mu[1]};
                 double S_ab[4];
@@ -993,6 +1108,17 @@ inline bool satisfies_constraints(const Pvc& p, const std::vector<Belief<D>>& pa
             const Dist2 db = get_distribution<D>(c.states[idx]);
             if (p.kind == PVC_CHISQUARED) {
                 if (!pair_is_safe_chisq(da, p.radii[a], db, p.radii[b], p.sc)) return false;
+                continue;
+            }
+            if (p.kind == PVC_CDFGRID) {      // CDFGridPVC.cpp:72-109: constrained robot's belief first
+                if (!pair_is_safe_cdfgrid(da.mu, da.cov, db.mu, db.cov, p.radii[std::min(a, b)] + p.radii[std::max(a, b)], p.grid_n, p.p_coll_agnts)) return false;
+                continue;
+            }
+            if (p.kind == PVC_BLACKMORE2) {   // Blackmore2PVC.cpp:64-104
+                const double m2[2] = {da.mu[0] - db.mu[0], da.mu[1] - db.mu[1]};
+                double S2[4];
+                for (int i = 0; i < 4; ++i) S2[i] = da.cov[i] + db.cov[i];
+                if (!pair_is_safe_blackmore2(p.pair_hp[(size_t)std::min(a, b) * p.k + std::max(a, b)], m2, S2, p.p_coll_agnts)) return false;
                 continue;
             }
             const double mu_ab[2] = {da.mu[0] - db.mu[0], da.mu[1] - db.mu[1]};

@@ -224,7 +224,12 @@ void* orc_pvc_create(void* w, int kind, double p_safe_arg) {
     h->pvc = make_pvc(kind, shapes, p_safe_arg);
     return h;
 }
+void orc_pvc_set_grid_n(void* p, int n) { ((PvcH*)p)->pvc.grid_n = n; }     // CDFGridPVC's disk_steps_
 void orc_pvc_free(void* p) { delete (PvcH*)p; }
+// CDFGridPVC::isSafe_ in isolation: collision mass of n pairs (mu[2], cov[4] each), radius sum r, grid n
+void orc_cdfgrid_prob(long n, const double* mu_a, const double* cov_a, const double* mu_b, const double* cov_b, double r_sum, int grid_n, double* prob) {
+    for (long i = 0; i < n; ++i) pair_is_safe_cdfgrid(mu_a + 2 * i, cov_a + 4 * i, mu_b + 2 * i, cov_b + 4 * i, r_sum, grid_n, 1.0, prob + i);
+}
 // out: p_coll_agnts, p_coll_dist, c_pair, sc
 void orc_pvc_info(void* p, double* out) {
     const Pvc& v = ((PvcH*)p)->pvc;
@@ -293,6 +298,12 @@ int orc_satisfies_constraints(void* p, int dim, int path_len, const double* path
     };
     if (dim == 2) return run(std::integral_constant<int, 2>{});
     return run(std::integral_constant<int, 4>{});
+}
+
+// CentralizedChiSquaredBoundarySVC agent-agent test for n pairs (AoS: mu[n][2], cov[n][4], rad[n])
+void orc_chisq_pairs_disjoint(long n, const double* mu_a, const double* cov_a, const double* rad_a, const double* mu_b, const double* cov_b,
+                              const double* rad_b, double sc, unsigned char* out) {
+    for (long i = 0; i < n; ++i) out[i] = chisq_pair_disjoint(mu_a + 2 * i, cov_a + 4 * i, rad_a[i], mu_b + 2 * i, cov_b + 4 * i, rad_b[i], sc) ? 1 : 0;
 }
 
 // ChanceConstrainedGoal::isSatisfied over a batch: out_ok[n], out_dist[n]

@@ -16,7 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "_build", "libcck_oracle.so")
 
 SVC_BLACKMORE, SVC_ADAPTIVE, SVC_CHISQUARED = 0, 1, 2
-PVC_BLACKMORE, PVC_BOUNDINGBOX, PVC_CHISQUARED, PVC_ADAPTIVE_BLACKMORE, PVC_ADAPTIVE_BOUNDINGBOX = range(5)
+PVC_BLACKMORE, PVC_BOUNDINGBOX, PVC_CHISQUARED, PVC_ADAPTIVE_BLACKMORE, PVC_ADAPTIVE_BOUNDINGBOX, PVC_BLACKMORE2, PVC_CDFGRID = range(7)
 
 
 def build(force=False):
@@ -65,6 +65,9 @@ def lib():
         L.orc_svc_tables.argtypes = [vp, dp, dp, dp, dp]
         L.orc_svc_override_tables.argtypes = [vp, C.c_int, dp, dp, C.c_double]
         L.orc_svc_set_max_rad.argtypes = [vp, C.c_double]
+        L.orc_pvc_set_grid_n.argtypes = [vp, C.c_int]
+        L.orc_chisq_pairs_disjoint.argtypes = [C.c_long, dp, dp, dp, dp, dp, dp, C.c_double, C.POINTER(C.c_ubyte)]
+        L.orc_cdfgrid_prob.argtypes = [C.c_long, dp, dp, dp, dp, C.c_double, C.c_int, dp]
         L.orc_propagate.argtypes = [C.c_int, C.c_double, C.c_double, C.c_long, dp, dp, dp]
         L.orc_is_valid.argtypes = [vp, C.c_int, C.c_long, dp, u8p, u64p]
         L.orc_rollout.argtypes = [vp, C.c_int, C.c_double, C.c_long, dp, dp, ip, dp, ip, dp, C.c_int, u64p, C.c_int]
@@ -265,10 +268,12 @@ def propagate_n(belief, control, steps, dim, dt=0.2):
 
 
 class Pvc:
-    def __init__(self, world, kind=PVC_BLACKMORE, p_safe_arg=-1.0):
+    def __init__(self, world, kind=PVC_BLACKMORE, p_safe_arg=-1.0, grid_n=2):
         L = lib()
         self.world, self.kind, self.k = world, kind, world.n_robots
         self.h = L.orc_pvc_create(world.h, kind, p_safe_arg)
+        if kind == PVC_CDFGRID:
+            L.orc_pvc_set_grid_n(self.h, int(grid_n))
         info = np.zeros(4)
         L.orc_pvc_info(self.h, _dp(info))
         self.p_coll_agnts, self.p_coll_dist, self.c_pair, self.sc = info
@@ -304,6 +309,23 @@ class Pvc:
             lib().orc_pvc_free(self.h)
         except Exception:
             pass
+
+
+def cdfgrid_prob(mu_a, cov_a, mu_b, cov_b, r_sum, grid_n):
+    """CDFGridPVC::isSafe_'s collision mass for n belief pairs (CDFGridPVC.cpp:182-291)."""
+    mu_a, cov_a, mu_b, cov_b = (_f64(x) for x in (mu_a, cov_a, mu_b, cov_b))
+    out = np.zeros(len(mu_a))
+    lib().orc_cdfgrid_prob(len(mu_a), _dp(mu_a), _dp(cov_a), _dp(mu_b), _dp(cov_b), float(r_sum), int(grid_n), _dp(out))
+    return out
+
+
+def chisq_pairs_disjoint(mu_a, cov_a, rad_a, mu_b, cov_b, rad_b, sc):
+    """CentralizedChiSquaredBoundarySVC's agent-agent decagon test (AoS mu [n, 2], cov [n, 4], rad [n])."""
+    mu_a, cov_a, rad_a, mu_b, cov_b, rad_b = (_f64(x) for x in (mu_a, cov_a, rad_a, mu_b, cov_b, rad_b))
+    out = np.zeros(len(mu_a), dtype=np.uint8)
+    lib().orc_chisq_pairs_disjoint(len(mu_a), _dp(mu_a), _dp(cov_a), _dp(rad_a), _dp(mu_b), _dp(cov_b), _dp(rad_b), float(sc),
+                                   out.ctypes.data_as(C.POINTER(C.c_ubyte)))
+    return out.astype(bool)
 
 
 def goal(beliefs, dim, gx, gy, threshold=2.0, p_safe=0.95):

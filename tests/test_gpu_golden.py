@@ -285,3 +285,28 @@ def test_expand_batch_cov_table_is_bit_identical(K, O, W, ctx, model):
     assert np.array_equal(short[0].view(np.uint64), ref[0].view(np.uint64))
     ctx.set_cov_table(None, 0)
     assert not (ctx.expand_batch(bel, ctrl, steps, pstep, pcost, goal)[4] & K.FLAG_COV_TABLE).any()
+
+
+def test_chisq_pairs_disjoint_vs_oracle(K, O, ctx):
+    """CentralizedChiSquaredBoundarySVC's agent-agent decagon test (CentralizedChiSquaredBoundarySVC.cpp:70-99): bit-exact
+    against the oracle, including pairs a few ulps from tangency."""
+    rng = np.random.default_rng(21)
+    n = 20000
+    mu_a = rng.uniform(0, 8, (n, 2))
+    L = rng.uniform(0.02, 0.3, (2, n, 3))
+    cov = [np.stack([l[:, 0] ** 2, l[:, 0] * l[:, 1], l[:, 0] * l[:, 1], l[:, 1] ** 2 + l[:, 2] ** 2], axis=1) for l in L]
+    rad = rng.uniform(0.1, 0.3, (2, n))
+    sc = K.chi2_quantile_2dof(0.9)
+    lam = [0.5 * (c[:, 0] + c[:, 3]) + np.sqrt((0.5 * (c[:, 0] + c[:, 3])) ** 2 - (c[:, 0] * c[:, 3] - c[:, 1] * c[:, 2])) for c in cov]
+    ra, rb = lam[0] * sc + rad[0], lam[1] * sc + rad[1]
+    ang = rng.uniform(0, 2 * np.pi, n)
+    # distances spread around the tangency range, a third right on a vertex-vertex contact
+    d = (ra + rb) * rng.uniform(0.85, 1.1, n)
+    k = np.arange(0, n, 3)
+    ang[k] = rng.integers(0, 10, len(k)) * (2 * np.pi / 10)
+    d[k] = (ra + rb)[k] * (1 + rng.uniform(-3e-15, 3e-15, len(k)))
+    mu_b = mu_a + np.stack([d * np.cos(ang), d * np.sin(ang)], axis=1)
+    got = ctx.chisq_pairs_disjoint(mu_a.T, cov[0].T, rad[0], mu_b.T, cov[1].T, rad[1], sc)
+    ref = O.chisq_pairs_disjoint(mu_a, cov[0], rad[0], mu_b, cov[1], rad[1], sc)
+    assert np.array_equal(got, ref)
+    assert 0.2 < ref.mean() < 0.8

@@ -58,13 +58,31 @@ def test_adapters_match_batched_launch(tmp_path):
     assert "host_selftest OK" in out.stdout
 
 
-@pytest.mark.parametrize("fixture,k,tmax", [("config1_empty8_linear_k2", 2, 120), ("config4_narrow_linear_k2", 2, 180)])
-def test_kcbs_plan_verified_by_oracle(O, tmp_path, fixture, k, tmax):
+def test_invalid_start_state_is_reported_like_ompl(O, tmp_path):
+    """narrowPassage at the CLI default p_safe = 0.9: Robot 0's start state (2, 1) fails PCCBlackmoreSVC by 1.4e-4
+    (sqrt2 c sqrt(0.02) = 0.32337 > 0.32322 = gap to the wall's inflated box), so OMPL's PlannerInputStates::nextStart skips
+    it and the reference's low-level planner reports INVALID_START (ConstraintRespectingBSST.cpp:186-199).  The batched planner
+    must do the same, at once - not search from an invalid root."""
     build_host()
-    g = np.load(os.path.join(GOLDEN, fixture + ".npz"))
+    g = np.load(os.path.join(GOLDEN, "config4_narrow_linear_k2.npz"))
+    world = O.World.synthetic(g["centres"], float(g["x_max"]), float(g["y_max"]), 2, 0.9)
+    b0 = O.default_beliefs(2, 2); b0[:, :2] = g["starts"]
+    assert O.Svc(world, O.SVC_BLACKMORE, 2).is_valid(b0)[0].tolist() == [False, True]
+    mp, sc = write_instance(tmp_path, g, "narrow")
+    out = subprocess.run([os.path.join(HOST, "cck_plan"), "-m", mp, "-s", sc, "-k", "2", "-t", "30", "--K", "512", "--seed", "3", "--lltime", "20"],
+                         capture_output=True, text=True, timeout=120)
+    res = json.loads(out.stdout.strip().splitlines()[-1])
+    assert not res["solved"] and res["seconds"] < 5.0 and res["candidates"] == 0
+
+
+@pytest.mark.parametrize("fixture,k,tmax,p_safe", [("config1_empty8_linear_k2", 2, 120, 0.9), ("config4_narrow_linear_k2", 2, 180, 0.8)])
+def test_kcbs_plan_verified_by_oracle(O, tmp_path, fixture, k, tmax, p_safe):
+    build_host()
+    g = dict(np.load(os.path.join(GOLDEN, fixture + ".npz")))
+    g["p_safe"] = p_safe
     mp, sc = write_instance(tmp_path, g, fixture)
     plan_path = str(tmp_path / "plan.txt")
-    out = subprocess.run([os.path.join(HOST, "cck_plan"), "-m", mp, "-s", sc, "-k", str(k), "-t", str(tmax), "--K", "512", "--seed", "3",
+    out = subprocess.run([os.path.join(HOST, "cck_plan"), "-m", mp, "-s", sc, "-k", str(k), "-p", str(p_safe), "-t", str(tmax), "--K", "512", "--seed", "3",
                           "--lltime", "20", "-o", plan_path], capture_output=True, text=True, timeout=tmax + 120)
     assert out.returncode == 0, out.stdout + out.stderr
     res = json.loads(out.stdout.strip().splitlines()[-1])

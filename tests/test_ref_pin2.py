@@ -380,3 +380,101 @@ def test_cuda_chisq_pvc_vs_reference_vectors(K, ctx):
     ctx.set_model(K.MODEL_UNICYCLE)
     _cuda_pvc_block(K, ctx, g3(), "pcs_", K.PVC_CHISQUARED, 4)
     _cuda_pvc_block(K, ctx, g3(), "pbm_", K.PVC_BLACKMORE, 4)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Blackmore2PVC, CDFGridPVC(n) - the reference's own Blackmore2PVC.cpp / CDFGridPVC.cpp compiled in
+# oracle/_ref (EigenSolver / LLT / erf through the stand-ins)
+# ---------------------------------------------------------------------------------------------------------------
+F4 = [("pb2_", "PVC_BLACKMORE2", 2), ("cdf2_", "PVC_CDFGRID", 2), ("cdf5_", "PVC_CDFGRID", 5)]
+
+
+def cdfgrid_band(O, g, trajs, dim, n, eps=1e-9):
+    """True if some pair test of the plan has its grid probability within eps of p_coll_agnts (the CDF-grid threshold)."""
+    rad = float(g["bounding_rad"][0])
+    p_coll = 1 - float(g["p_safe_agents"])
+    T = max(len(t) for t in trajs)
+    k = len(trajs)
+    for t in range(T + 1):
+        st = [tr[min(t, len(tr) - 1)] for tr in trajs]
+        for a in range(k):
+            for b in range(a + 1, k):
+                pr = O.cdfgrid_prob([st[a][:2]], [st[a][2:6] + st[a][6:10]], [st[b][:2]], [st[b][2:6] + st[b][6:10]], 2 * rad, n)[0]
+                if abs(pr - p_coll) < eps:
+                    return True
+    return False
+
+
+@pytest.mark.parametrize("tag,kind,n", F4)
+def test_f4_plan_checkers_vs_reference(O, tag, kind, n):
+    g = g2()
+    w = oracle_world(O, g)
+    pv = O.Pvc(w, getattr(O, kind), grid_n=n)
+    assert pv.p_coll_agnts == g[tag + "info"][0]
+    want, sat = g[tag + "conflicts"], g[tag + "satisfies"]
+    n_conf = 0
+    for i, trajs in plans_of(g, tag):
+        got = pv.validate_plan(trajs, 2)
+        exp = [tuple(int(x) for x in r[1:]) for r in want[want[:, 0] == i]]
+        assert got == exp, (tag, i)
+        n_conf += bool(exp)
+        if exp:
+            a, other = exp[0][0], exp[0][1]
+            steps = [e[2] for e in exp]
+            cst = np.array([trajs[other][min(s, len(trajs[other]) - 1)] for s in steps])
+            for j in range(sat.shape[1]):
+                probe = g[tag + "probe_states"][i, j, :g[tag + "probe_len"][i, j]]
+                assert pv.satisfies_constraints(probe, 2, a, [(other, steps, cst)]) == bool(sat[i, j]), (tag, i, j)
+    assert n_conf >= 10 and (sat == 1).any() and (sat == 0).any()
+
+
+def test_cdfgrid_probability_is_basis_invariant(O):
+    """The closed-form eigenvectors may differ from Eigen's in order and sign: the grid mass must not care (standard normal
+    symmetric under axis swaps / reflections), and for n -> large it approaches the exact mass of the box."""
+    rng = np.random.default_rng(4)
+    n = 300
+    mu_a, mu_b = rng.uniform(-1, 1, (n, 2)), rng.uniform(-1, 1, (n, 2))
+    L = rng.uniform(0.05, 0.3, (n, 3))
+    cov = np.stack([L[:, 0] ** 2, L[:, 0] * L[:, 1], L[:, 0] * L[:, 1], L[:, 1] ** 2 + L[:, 2] ** 2], axis=1)
+    p = O.cdfgrid_prob(mu_a, cov, mu_b, cov, 0.35, 5)
+    # mirror the whole configuration in x: same probability
+    fx = np.array([-1.0, 1.0])
+    covm = cov * np.array([1.0, -1.0, -1.0, 1.0])
+    pm = O.cdfgrid_prob(mu_a * fx, covm, mu_b * fx, covm, 0.35, 5)
+    assert np.allclose(p, pm, rtol=1e-12, atol=1e-15)
+    # swap x and y
+    sw = cov[:, [3, 2, 1, 0]]
+    ps = O.cdfgrid_prob(mu_a[:, ::-1], sw, mu_b[:, ::-1], sw, 0.35, 5)
+    assert np.allclose(p, ps, rtol=1e-12, atol=1e-15)
+    assert (p >= 0).all() and (p <= 1.0 + 1e-12).all()
+    # n = 2 integrates the bounding box of the mapped square: an upper bound of every finer grid's covered mass? not in general
+    # (cells are counted whole), but both bound the exact mass of the square from above
+    p2 = O.cdfgrid_prob(mu_a, cov, mu_b, cov, 0.35, 2)
+    p40 = O.cdfgrid_prob(mu_a, cov, mu_b, cov, 0.35, 40)
+    assert (p2 >= p40 - 1e-12).all() and (p >= p40 - 1e-12).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag,kind,n", F4)
+def test_cuda_f4_plan_checkers_vs_reference_vectors(K, O, ctx, tag, kind, n):
+    g = g2()
+    k = int(g["k"])
+    ctx.set_model(K.MODEL_LINEAR2D)
+    rad = K.rect_robot_bounding_radius()
+    K.install_pvc(ctx, getattr(K, kind), 2, [rad] * k, float(g["p_safe_agents"]), grid_n=n)
+    want, sat = g[tag + "conflicts"], g[tag + "satisfies"]
+    for i, trajs in plans_of(g, tag):
+        exp = want[want[:, 0] == i]
+        run = ctx.validate_plan([K.aos_to_soa(t) for t in trajs])
+        wanted = None if len(exp) == 0 else (int(exp[0, 1]), int(exp[0, 2]), int(exp[0, 3]), len(exp))
+        if run != wanted:      # device erf vs the reference build's: only inside the band
+            assert kind == "PVC_CDFGRID" and cdfgrid_band(O, g, trajs, 2, n), (tag, i, run, wanted)
+            continue
+        if wanted is None:
+            continue
+        a, other, steps = wanted[0], wanted[1], [int(x) for x in exp[:, 3]]
+        cst = np.array([trajs[other][min(s, len(trajs[other]) - 1)] for s in steps])
+        ctx.set_constraints(*K.constraint_entries(k, 2, a, [(other, steps, cst)]))
+        soa = np.ascontiguousarray(g[tag + "probe_states"][i].transpose(1, 2, 0))
+        ok = ctx.satisfies_constraints(soa, g[tag + "probe_len"][i], np.zeros(sat.shape[1], dtype=np.int32))
+        assert np.array_equal(ok, sat[i].astype(bool)), (tag, i)
