@@ -187,6 +187,19 @@ def main():
     out.update(pvc_block(w, R.PVC2_BLACKMORE2, 2, k, 911, 60, tag="pb2_"))
     for n_steps in (2, 5):
         out.update(pvc_block(w, R.PVC2_CDFGRID, 2, k, 912 + n_steps, 40, n_steps=n_steps, tag=f"cdf{n_steps}_"))
+    # CentralizedUncertainLinearStatePropagator: composite states of k = 3 agents, step size 0.5 (OmplSetUp.cpp:357)
+    kc, nc = 3, 400
+    rngc = rng_of(31)
+    Wc = 2 * kc + 2 * (2 * kc) ** 2
+    cs = np.zeros((nc, Wc))
+    cs[:, :2 * kc] = rngc.uniform(0, 30, (nc, 2 * kc))
+    full = rngc.uniform(-0.01, 0.01, (nc, 2, 2 * kc, 2 * kc))              # arbitrary off-block entries: the propagator must ignore them
+    for a_ in range(kc):
+        for which in range(2):
+            full[:, which, 2 * a_:2 * a_ + 2, 2 * a_:2 * a_ + 2] = spd(rngc, nc, 2, 0.03, 0.2).reshape(nc, 2, 2)
+    cs[:, 2 * kc:] = full.reshape(nc, -1)
+    cu = rngc.uniform(-1, 1, (nc, 2 * kc))
+    out.update(central_k=kc, central_states=cs, central_controls=cu, central_propagate=R.central_propagate(kc, cs, cu, 0.5))
     np.savez_compressed(os.path.join(out_dir, "ref2_config2_random32_10_linear_k4.npz"), **out)
     print("config2: M", w.n_obstacles, "cs valid %.2f" % out["cs_is_valid"].mean(), "cs full %.2f" % (out["cs_rollout_valid"] == steps).mean(),
           "goal ok %.2f" % ok.mean(), "pcs", len(out["pcs_conflicts"]), "pb2", len(out["pb2_conflicts"]), "cdf2", len(out["cdf2_conflicts"]),

@@ -18,7 +18,7 @@ SOURCES = ["src/utils/common.cpp", "src/utils/Instance.cpp", "src/utils/Conflict
            "src/PlanValidityCheckers/MinkowskiSumBlackmorePVC.cpp", "src/PlanValidityCheckers/BoundingBoxBlackmorePVC.cpp",
            "src/Spaces/RealVectorBeliefSpace.cpp", "src/StatePropogators/UncertainUnicycleSP.cpp", "src/Goals/BeliefSpaceGoals.cpp",
            "src/StateValidityCheckers/ChiSquaredBoundarySVC.cpp", "src/PlanValidityCheckers/ChiSquaredBoundaryPVC.cpp",
-           "src/PlanValidityCheckers/CDFGridPVC.cpp", "src/PlanValidityCheckers/Blackmore2PVC.cpp"]
+           "src/PlanValidityCheckers/CDFGridPVC.cpp", "src/PlanValidityCheckers/Blackmore2PVC.cpp", "src/StatePropogators/CentralizedUncertainLinearSP.cpp"]
 
 
 def available():
@@ -92,6 +92,7 @@ def lib():
         L.ref2_satisfies_constraints.restype = C.c_int
         L.ref2_satisfies_constraints.argtypes = [vp, C.c_int, dp, C.c_int, C.c_int, ip, ip, ip, dp]
         L.ref2_independent_check.argtypes = [vp, C.c_long, dp, dp, u8]
+        L.ref2_central_propagate.argtypes = [C.c_int, C.c_long, dp, dp, C.c_double, dp]
         _lib = L
     return _lib
 
@@ -318,3 +319,13 @@ class Pvc2:
         out = np.zeros(len(a), dtype=np.uint8)
         lib().ref2_independent_check(self.h, len(a), _dp(a), _dp(b), _u8(out))
         return out.astype(bool)
+
+
+def central_propagate(k, states, controls, step=0.5):
+    """CentralizedUncertainLinearStatePropagator::propagate (CentralizedUncertainLinearSP.cpp:42-70) on n composite states of
+    k agents: records [2k values | Sigma (2k x 2k) | Lambda (2k x 2k)], controls [n, 2k].  Entries outside the agents'
+    diagonal blocks are left at the allocState default of the result state."""
+    s, u = np.ascontiguousarray(states, dtype=np.float64), np.ascontiguousarray(controls, dtype=np.float64)
+    out = np.zeros_like(s)
+    lib().ref2_central_propagate(k, len(s), _dp(s), _dp(u), step, _dp(out))
+    return out

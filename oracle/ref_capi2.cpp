@@ -32,6 +32,7 @@
 #include "StateValidityCheckers/ChiSquaredBoundarySVC.h"
 #include "StatePropogators/UncertainLinearSP.h"
 #include "StatePropogators/UncertainUnicycleSP.h"
+#include "StatePropogators/CentralizedUncertainLinearSP.h"
 #include "Goals/BeliefSpaceGoals.h"
 #include "PlanValidityCheckers/MinkowskiSumBlackmorePVC.h"
 #include "PlanValidityCheckers/BoundingBoxBlackmorePVC.h"
@@ -195,6 +196,28 @@ void ref2_goal(int dim, long n, const double* bel, double gx, double gy, double 
         dist[i] = d;
     }
     space->freeState(st);
+}
+
+// CentralizedUncertainLinearStatePropagator::propagate (src/StatePropogators/CentralizedUncertainLinearSP.cpp:42-70) on n
+// composite states of k agents (dimension 2k)
+void ref2_central_propagate(int k, long n, const double* states, const double* ctrl, double step, double* out) {
+    const int dim = 2 * k, W = width(dim);
+    auto space = std::make_shared<RealVectorBeliefSpace>(dim);
+    auto si = std::make_shared<oc::SpaceInformation>(space);
+    si->setPropagationStepSize(step);
+    CentralizedUncertainLinearStatePropagator prop(si);
+    auto* a = space->allocState()->as<BState>();
+    auto* r = space->allocState()->as<BState>();
+    oc::RealVectorControlSpace::ControlType c;
+    std::vector<double> cv(dim);
+    c.values = cv.data();
+    for (long i = 0; i < n; ++i) {
+        load(a, states + i * W, dim);
+        for (int j = 0; j < dim; ++j) cv[j] = ctrl[i * dim + j];
+        prop.propagate(a, &c, step, r);
+        store(r, out + i * W, dim);
+    }
+    space->freeState(a); space->freeState(r);
 }
 
 }  // extern "C"

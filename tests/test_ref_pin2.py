@@ -478,3 +478,25 @@ def test_cuda_f4_plan_checkers_vs_reference_vectors(K, O, ctx, tag, kind, n):
         soa = np.ascontiguousarray(g[tag + "probe_states"][i].transpose(1, 2, 0))
         ok = ctx.satisfies_constraints(soa, g[tag + "probe_len"][i], np.zeros(sat.shape[1], dtype=np.int32))
         assert np.array_equal(ok, sat[i].astype(bool)), (tag, i)
+
+
+def test_centralized_propagator_vs_reference(O):
+    """CentralizedUncertainLinearStatePropagator::propagate (the reference's CentralizedUncertainLinearSP.cpp compiled in
+    oracle/_ref): every agent's 2x2 blocks advance exactly like a single-agent linear belief with step size 0.5, whatever sits
+    outside the blocks; the rest of the result keeps the allocState default 0.01 I."""
+    g = g2()
+    k = int(g["central_k"])
+    cs, cu, want = g["central_states"], g["central_controls"], g["central_propagate"]
+    n, d = len(cs), 2 * k
+    S = cs[:, d:d + d * d].reshape(n, d, d); L = cs[:, d + d * d:].reshape(n, d, d)
+    Sw = want[:, d:d + d * d].reshape(n, d, d); Lw = want[:, d + d * d:].reshape(n, d, d)
+    for a in range(k):
+        b = np.concatenate([cs[:, 2 * a:2 * a + 2], S[:, 2 * a:2 * a + 2, 2 * a:2 * a + 2].reshape(n, 4), L[:, 2 * a:2 * a + 2, 2 * a:2 * a + 2].reshape(n, 4)], axis=1)
+        got = O.propagate(b, cu[:, 2 * a:2 * a + 2], 2, dt=0.5)
+        assert np.array_equal(got[:, :2], want[:, 2 * a:2 * a + 2])
+        assert np.array_equal(got[:, 2:6], Sw[:, 2 * a:2 * a + 2, 2 * a:2 * a + 2].reshape(n, 4))
+        assert np.array_equal(got[:, 6:10], Lw[:, 2 * a:2 * a + 2, 2 * a:2 * a + 2].reshape(n, 4))
+    off = np.ones((d, d), dtype=bool)
+    for a in range(k):
+        off[2 * a:2 * a + 2, 2 * a:2 * a + 2] = False
+    assert (Sw[:, off] == 0).all() and (Lw[:, off] == 0).all()        # result state: allocState default, off-diagonal zeros
