@@ -65,7 +65,7 @@ SYMBOLS = [
     "cck_propagate", "cck_propagate_dev", "cck_is_valid", "cck_is_valid_dev",
     "cck_propagate_while_valid", "cck_propagate_while_valid_dev",
     "cck_validate_plan", "cck_validate_plan_dev",
-    "cck_set_constraints", "cck_satisfies_constraints", "cck_satisfies_constraints_dev", "cck_build_clearance_field", "cck_measure_fp64_rates", "cck_set_cov_table", "cck_chisq_pairs_disjoint",
+    "cck_set_constraints", "cck_satisfies_constraints", "cck_satisfies_constraints_dev", "cck_build_clearance_field", "cck_measure_fp64_rates", "cck_set_cov_table", "cck_chisq_pairs_disjoint", "cck_host_pair_safe", "cck_host_chisq_pair_disjoint",
     "cck_expand_batch", "cck_expand_batch_dev", "cck_rollout_summary_dev", "cck_select_winner_dev", "cck_measure_fp64_peak",
     "cck_tree_create", "cck_tree_destroy", "cck_tree_clear", "cck_tree_size", "cck_tree_append", "cck_tree_update",
     "cck_tree_select", "cck_tree_nearest", "cck_tree_witness_batch", "cck_belief_distance", "cck_belief_distance_lower", "cck_belief_distance_cols", "cck_belief_distance_cols_near", "cck_build_grid_table",
@@ -132,6 +132,8 @@ def lib():
     L.cck_validate_plan_dev.argtypes = [vp, vp, C.c_int, vp, C.c_int, vp, i64, vp]
     L.cck_set_constraints.argtypes = [vp, C.c_int, vp, vp, vp, vp]
     L.cck_set_cov_table.argtypes = [vp, vp, C.c_int]
+    L.cck_host_pair_safe.argtypes = [C.c_int, vp, vp, vp, vp, vp, vp, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int]
+    L.cck_host_chisq_pair_disjoint.argtypes = [vp, vp, C.c_double, vp, vp, C.c_double, C.c_double]
     L.cck_chisq_pairs_disjoint.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp, C.c_double, vp]
     L.cck_satisfies_constraints.argtypes = [vp, i64, vp, i64, C.c_int32, vp, vp, vp]
     L.cck_satisfies_constraints_dev.argtypes = [vp, vp, i64, vp, i64, C.c_int32, vp, vp, vp]
@@ -595,6 +597,12 @@ def aos_to_soa(b):
 
 def soa_to_aos(b):
     return np.ascontiguousarray(np.asarray(b).T)
+
+
+def host_pair_safe(kind, mu_a, cov_a, mu_b, cov_b, A8, B4, rad_a, rad_b, c_pair=0.0, p_coll_agnts=0.0, sc=0.0, grid_n=2):
+    """Host-only: the kernels' pair-test source compiled for the CPU (cck_host_pair_safe), one pair."""
+    arrs = [np.ascontiguousarray(x, dtype=np.float64) for x in (mu_a, cov_a, mu_b, cov_b, A8, B4)]
+    return lib().cck_host_pair_safe(int(kind), *[_ptr(x) for x in arrs], float(rad_a), float(rad_b), float(c_pair), float(p_coll_agnts), float(sc), int(grid_n))
 
 
 def robot_map_order(k):

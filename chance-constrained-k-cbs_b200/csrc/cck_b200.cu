@@ -905,6 +905,37 @@ extern "C" int cck_expand_batch_dev(cck_ctx* c, void* stream, int64_t n, const d
     return launch_rollout<true>(c, pick(c, stream), a);
 }
 
+// Host-only test hook (no GPU, no context): the pair test of plan-validity-checker `kind`, evaluated by the SAME source
+// functions the validatePlan / satisfiesConstraints kernels call (cck_kernels.cuh, compiled here for the host), so that their
+// logic can be checked against the oracle on a CPU-only machine.  Kinds with a data-dependent risk allocation (adaptive) take
+// c_pair as given.  Returns 1 safe, 0 unsafe, -1 bad kind.
+extern "C" int cck_host_pair_safe(int kind, const double* mu_a, const double* cov_a, const double* mu_b, const double* cov_b, const double* A8,
+                                  const double* B4, double rad_a, double rad_b, double c_pair, double p_coll_agnts, double sc, int grid_n) {
+    const double dx = mu_a[0] - mu_b[0], dy = mu_a[1] - mu_b[1];
+    const double S0 = cov_a[0] + cov_b[0], S1 = cov_a[1] + cov_b[1], S2 = cov_a[2] + cov_b[2], S3 = cov_a[3] + cov_b[3];
+    switch (kind) {
+        case CCK_PVC_BLACKMORE: case CCK_PVC_BOUNDINGBOX: case CCK_PVC_ADAPTIVE_BLACKMORE: case CCK_PVC_ADAPTIVE_BOUNDINGBOX:
+            return pair_safe_halfplanes(A8, B4, dx, dy, S0, S1, S2, S3, c_pair) ? 1 : 0;
+        case CCK_PVC_CHISQUARED: {
+            const double la = max_eig_real_2x2(cov_a[0], cov_a[1], cov_a[2], cov_a[3]), lb = max_eig_real_2x2(cov_b[0], cov_b[1], cov_b[2], cov_b[3]);
+            const double dist = std::sqrt(dx * dx + dy * dy);
+            return dist > (la * sc + rad_a) + (lb * sc + rad_b) ? 1 : 0;
+        }
+        case CCK_PVC_BLACKMORE2: return pair_safe_blackmore2(A8, B4, dx, dy, S0, S1, S2, S3, p_coll_agnts) ? 1 : 0;
+        case CCK_PVC_CDFGRID: return pair_safe_cdfgrid(mu_a, cov_a, mu_b, cov_b, rad_a + rad_b, grid_n, p_coll_agnts) ? 1 : 0;
+        default: return -1;
+    }
+}
+
+// Host-only test hook: CentralizedChiSquaredBoundarySVC's agent-agent decagon test by the kernel's own source (k_chisq_pairs)
+extern "C" int cck_host_chisq_pair_disjoint(const double* mu_a, const double* cov_a, double rad_a, const double* mu_b, const double* cov_b, double rad_b, double sc) {
+    double dc[10], ds[10];
+    const double two_pi = 2.0 * M_PI, diff = two_pi / 10.0;
+    double ang = 0;
+    for (int i = 0; i < 10; ++i, ang -= diff) { dc[i] = std::cos(ang); ds[i] = std::sin(ang); }
+    return chisq_pair_disjoint(mu_a[0], mu_a[1], cov_a[0], cov_a[1], cov_a[2], cov_a[3], rad_a, mu_b[0], mu_b[1], cov_b[0], cov_b[1], cov_b[2], cov_b[3], rad_b, sc, dc, ds) ? 1 : 0;
+}
+
 // Covariance table of a low-level tree (see RolloutArgs::cov_tab): entries for absolute steps 0 .. n_steps-1 from the root
 // covariance root_cov = [Sigma row-major, Lambda row-major] (2 dim^2 doubles).  n_steps <= 0 removes the table.
 extern "C" int cck_set_cov_table(cck_ctx* c, const double* root_cov, int n_steps) {

@@ -266,7 +266,7 @@ __device__ __forceinline__ bool bounds_ok(const SvcDev& sp, const double* v) {
     return ok;
 }
 
-__device__ __forceinline__ double max_eig_real_2x2(double m0, double m1, double m2, double m3) {
+__host__ __device__ __forceinline__ double max_eig_real_2x2(double m0, double m1, double m2, double m3) {
     const double tr = m0 + m3;
     const double det = m0 * m3 - m1 * m2;
     const double h = tr / 2;

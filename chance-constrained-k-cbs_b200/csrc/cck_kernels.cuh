@@ -57,7 +57,7 @@ struct ConsEntry {
 };
 static_assert(sizeof(ConsHeader) == 64 && sizeof(ConsEntry) == 160, "constraint table records");
 
-__device__ __forceinline__ bool pair_safe_halfplanes(const double* A, const double* B, double mx, double my, double S0,
+__host__ __device__ __forceinline__ bool pair_safe_halfplanes(const double* A, const double* B, double mx, double my, double S0,
                                                      double S1, double S2, double S3, double c) {
     bool safe = false;
 #pragma unroll
@@ -74,7 +74,7 @@ __device__ __forceinline__ bool pair_safe_halfplanes(const double* A, const doub
 }
 
 // Blackmore2PVC::isSafe_ (Blackmore2PVC.cpp:169-192): smallest half-plane collision probability against p_coll_agnts_
-__device__ __forceinline__ bool pair_safe_blackmore2(const double* A, const double* B, double mx, double my, double S0, double S1, double S2,
+__host__ __device__ __forceinline__ bool pair_safe_blackmore2(const double* A, const double* B, double mx, double my, double S0, double S1, double S2,
                                                      double S3, double p_coll_agnts) {
     double p_obs = DBL_MAX;
 #pragma unroll
@@ -91,7 +91,7 @@ __device__ __forceinline__ bool pair_safe_blackmore2(const double* A, const doub
 }
 
 // Eigen::EigenSolver<Matrix2d> as CDFGridPVC uses it, in closed form (see oracle/cck_oracle.hpp::eig2_general for the contract)
-__device__ __forceinline__ void eig2_general(const double* M, double* lam, double* V) {
+__host__ __device__ __forceinline__ void eig2_general(const double* M, double* lam, double* V) {
     const double a = M[0], b = M[1], c = M[2], d = M[3];
     V[0] = 1; V[1] = 0; V[2] = 0; V[3] = 1;
     if (b == 0 && c == 0) { lam[0] = a; lam[1] = d; return; }
@@ -107,7 +107,7 @@ __device__ __forceinline__ void eig2_general(const double* M, double* lam, doubl
         V[0 + j] = vx / n; V[2 + j] = vy / n;
     }
 }
-__device__ __forceinline__ double cdf_rect(double x1, double y1, double x2, double y2) {   // CDFGridPVC.cpp:293-306
+__host__ __device__ __forceinline__ double cdf_rect(double x1, double y1, double x2, double y2) {   // CDFGridPVC.cpp:293-306
     const double r2 = 1.4142135623730951;   // sqrt(2)
     const double ex1 = 1 + erf(x1 / r2), ex2 = 1 + erf(x2 / r2), ey1 = 1 + erf(y1 / r2), ey2 = 1 + erf(y2 / r2);
     const double p1 = (1.0 / 2.0) * ex1 * (1.0 / 2.0) * ey1, p2 = (1.0 / 2.0) * ex2 * (1.0 / 2.0) * ey1;
@@ -115,7 +115,7 @@ __device__ __forceinline__ double cdf_rect(double x1, double y1, double x2, doub
     return p3 - p2 - p4 + p1;
 }
 // CDFGridPVC::isSafe_ (CDFGridPVC.cpp:182-291); belief a = (mua, ca), belief b = (mub, cb), box half-side r_sum, grid n
-__device__ __forceinline__ bool pair_safe_cdfgrid(const double* mua, const double* ca, const double* mub, const double* cb, double r_sum, int n,
+__host__ __device__ __forceinline__ bool pair_safe_cdfgrid(const double* mua, const double* ca, const double* mub, const double* cb, double r_sum, int n,
                                                   double p_coll_agnts) {
     const double T0 = mua[0] - mub[0], T1 = mua[1] - mub[1];
     double S[4], lam[2], V[4];
@@ -584,37 +584,41 @@ __global__ void __launch_bounds__(128) k_constraints(int64_t n_paths, int dim, c
 // radius lambda_max(cov_a) * sc + rad_a around mu_a against the one of agent b; out = 1 iff bg::disjoint (touching is NOT
 // disjoint).  Separating axes of two convex polygons: the edge normals of both.
 // ---------------------------------------------------------------------------
+// one pair; dec_cos / dec_sin: the ten directions of point_circle(10)
+__host__ __device__ __forceinline__ bool chisq_pair_disjoint(double mxa, double mya, double c0a, double c1a, double c2a, double c3a, double rada, double mxb,
+                                                             double myb, double c0b, double c1b, double c2b, double c3b, double radb, double sc,
+                                                             const double* dec_cos, const double* dec_sin) {
+    const double ra = (max_eig_real_2x2(c0a, c1a, c2a, c3a) * sc + rada);
+    const double rb = (max_eig_real_2x2(c0b, c1b, c2b, c3b) * sc + radb);
+    double ax[11], ay[11], bx[11], by[11];
+    for (int k = 0; k < 10; ++k) {
+        ax[k] = mxa + ra * dec_cos[k]; ay[k] = mya + ra * dec_sin[k];
+        bx[k] = mxb + rb * dec_cos[k]; by[k] = myb + rb * dec_sin[k];
+    }
+    ax[10] = ax[0]; ay[10] = ay[0]; bx[10] = bx[0]; by[10] = by[0];
+    bool sep = false;
+    for (int pass = 0; pass < 2 && !sep; ++pass) {
+        const double* ex = pass ? bx : ax; const double* ey = pass ? by : ay;
+        for (int e = 0; e < 10 && !sep; ++e) {
+            const double nx = ey[e + 1] - ey[e], ny = ex[e] - ex[e + 1];
+            if (nx == 0 && ny == 0) continue;
+            double amin = nx * ax[0] + ny * ay[0], amax = amin, bmin = nx * bx[0] + ny * by[0], bmax = bmin;
+            for (int j = 1; j < 10; ++j) {
+                const double da = nx * ax[j] + ny * ay[j], db = nx * bx[j] + ny * by[j];
+                amin = da < amin ? da : amin; amax = amax < da ? da : amax; bmin = db < bmin ? db : bmin; bmax = bmax < db ? db : bmax;
+            }
+            sep = (amax < bmin) || (bmax < amin);
+        }
+    }
+    return sep;
+}
 __global__ void __launch_bounds__(128) k_chisq_pairs(int64_t n, const double* __restrict__ mu_a, const double* __restrict__ cov_a,
                                                      const double* __restrict__ rad_a, const double* __restrict__ mu_b,
                                                      const double* __restrict__ cov_b, const double* __restrict__ rad_b, double sc,
                                                      const __grid_constant__ SvcDev sp, uint8_t* __restrict__ out) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const double ra = (max_eig_real_2x2(cov_a[i], cov_a[n + i], cov_a[2 * n + i], cov_a[3 * n + i]) * sc + rad_a[i]);
-        const double rb = (max_eig_real_2x2(cov_b[i], cov_b[n + i], cov_b[2 * n + i], cov_b[3 * n + i]) * sc + rad_b[i]);
-        double ax[11], ay[11], bx[11], by[11];
-#pragma unroll
-        for (int k = 0; k < 10; ++k) {
-            ax[k] = mu_a[i] + ra * sp.dec_cos[k]; ay[k] = mu_a[n + i] + ra * sp.dec_sin[k];
-            bx[k] = mu_b[i] + rb * sp.dec_cos[k]; by[k] = mu_b[n + i] + rb * sp.dec_sin[k];
-        }
-        ax[10] = ax[0]; ay[10] = ay[0]; bx[10] = bx[0]; by[10] = by[0];
-        bool sep = false;
-        for (int pass = 0; pass < 2 && !sep; ++pass) {
-            const double* ex = pass ? bx : ax; const double* ey = pass ? by : ay;
-            for (int e = 0; e < 10 && !sep; ++e) {
-                const double nx = ey[e + 1] - ey[e], ny = ex[e] - ex[e + 1];
-                if (nx == 0 && ny == 0) continue;
-                double amin = nx * ax[0] + ny * ay[0], amax = amin, bmin = nx * bx[0] + ny * by[0], bmax = bmin;
-#pragma unroll
-                for (int j = 1; j < 10; ++j) {
-                    const double da = nx * ax[j] + ny * ay[j], db = nx * bx[j] + ny * by[j];
-                    amin = fmin(amin, da); amax = fmax(amax, da); bmin = fmin(bmin, db); bmax = fmax(bmax, db);
-                }
-                sep = (amax < bmin) || (bmax < amin);
-            }
-        }
-        out[i] = sep ? 1 : 0;
-    }
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = chisq_pair_disjoint(mu_a[i], mu_a[n + i], cov_a[i], cov_a[n + i], cov_a[2 * n + i], cov_a[3 * n + i], rad_a[i], mu_b[i], mu_b[n + i],
+                                     cov_b[i], cov_b[n + i], cov_b[2 * n + i], cov_b[3 * n + i], rad_b[i], sc, sp.dec_cos, sp.dec_sin) ? 1 : 0;
 }
 
 // ---------------------------------------------------------------------------

@@ -173,6 +173,15 @@ int cck_propagate_while_valid_dev(cck_ctx* ctx, void* stream, int64_t n, const d
 int cck_chisq_pairs_disjoint(cck_ctx* ctx, int64_t n, const double* mu_a, const double* cov_a, const double* rad_a, const double* mu_b,
                              const double* cov_b, const double* rad_b, double sc, uint8_t* out);
 
+/* Host-only test hook (no GPU): the pair test (*PVC::isSafe_) of plan-validity-checker `kind` evaluated on the host by the same
+ * source functions the validatePlan / satisfiesConstraints kernels call; lets CPU-only tests compare the kernels' logic with
+ * the oracle.  1 safe, 0 unsafe, -1 unknown kind. */
+int cck_host_pair_safe(int kind, const double* mu_a, const double* cov_a, const double* mu_b, const double* cov_b, const double* A8,
+                       const double* B4, double rad_a, double rad_b, double c_pair, double p_coll_agnts, double sc, int grid_n);
+
+int cck_host_chisq_pair_disjoint(const double* mu_a, const double* cov_a, double rad_a, const double* mu_b, const double* cov_b, double rad_b,
+                                 double sc);   /* same, for cck_chisq_pairs_disjoint's kernel source (one pair, row-major cov) */
+
 /* ---- PlanValidityChecker::validatePlan ----------------------------------
  * replaces {MinkowskiSumBlackmore,BoundingBoxBlackmore,ChiSquaredBoundary,AdaptiveRisk*}PVC::validatePlan
  * on already-interpolated trajectories (one belief per dt).  traj: robot r, plane f,

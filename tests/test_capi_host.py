@@ -72,3 +72,65 @@ def test_no_cpu_fallback_without_gpu(K):
     with pytest.raises(K.CckError) as e:
         K.Context(0)
     assert e.value.code == K.capi.ERR_NODEVICE
+
+
+def test_kernel_pair_tests_on_the_host_match_the_oracle(K, O):
+    """The pair tests (*PVC::isSafe_) the validatePlan / satisfiesConstraints kernels call are plain functions of
+    cck_kernels.cuh; cck_host_pair_safe runs that very source compiled for the host.  Against the oracle, pair by pair, for
+    the five kinds without a data-dependent risk allocation - bit-exact verdicts (same libm on both sides), including the
+    Blackmore2 and CDF-grid checkers and non-symmetric / degenerate covariances."""
+    rng = np.random.default_rng(33)
+    n = 4000
+    world = O.World.synthetic(np.zeros((0, 2)), 20.0, 20.0, 4, 0.9)
+    rad = K.rect_robot_bounding_radius()
+    mu_a, mu_b = rng.uniform(0, 3, (n, 2)), rng.uniform(0, 3, (n, 2))
+    mu_b[::5] = mu_a[::5] + rng.uniform(-0.6, 0.6, (len(mu_a[::5]), 2))        # close pairs
+    L = rng.uniform(0.01, 0.3, (2, n, 3))
+    cov = [np.stack([l[:, 0] ** 2, l[:, 0] * l[:, 1], l[:, 0] * l[:, 1], l[:, 1] ** 2 + l[:, 2] ** 2], axis=1) for l in L]
+    cov[0][::7, 1] += 1e-3                                                      # non-symmetric (what the unicycle recursion produces)
+    cov[1][::11] = [0.02, 0.0, 0.0, 0.02]                                       # multiples of I: the linear model's covariances
+    cov[0][::11] = [0.02, 0.0, 0.0, 0.02]
+    cov[1][3::13] = [0.03, 0.0, 0.0, 0.01]                                      # diagonal, unequal
+    beliefs = [np.concatenate([m, c, np.zeros((n, 4))], axis=1) for m, c in ((mu_a, cov[0]), (mu_b, cov[1]))]   # Sigma = cov, Lambda = 0
+    cases = [(K.PVC_BLACKMORE, O.PVC_BLACKMORE, 2), (K.PVC_BOUNDINGBOX, O.PVC_BOUNDINGBOX, 2), (K.PVC_CHISQUARED, O.PVC_CHISQUARED, 2),
+             (K.PVC_BLACKMORE2, O.PVC_BLACKMORE2, 2), (K.PVC_CDFGRID, O.PVC_CDFGRID, 2), (K.PVC_CDFGRID, O.PVC_CDFGRID, 3), (K.PVC_CDFGRID, O.PVC_CDFGRID, 6)]
+    for kk, ok_, gn in cases:
+        pv = O.Pvc(world, ok_, grid_n=gn)
+        A, B = K.build_pair_halfplanes(rad, rad, kk == K.PVC_BOUNDINGBOX)
+        oA, oB = pv.pair_halfplanes(0, 1)
+        if kk not in (K.PVC_CHISQUARED, K.PVC_CDFGRID):
+            assert np.array_equal(A, oA) and np.array_equal(B, oB)
+        unsafe = 0
+        for i in range(n):
+            got = K.host_pair_safe(kk, mu_a[i], cov[0][i], mu_b[i], cov[1][i], A, B, rad, rad, c_pair=pv.c_pair, p_coll_agnts=pv.p_coll_agnts, sc=pv.sc, grid_n=gn)
+            # the oracle's verdict for the same pair: a two-robot, one-step plan conflicts iff the pair is unsafe
+            conf = pv.validate_plan([beliefs[0][i:i + 1], beliefs[1][i:i + 1]] + [np.array([[100.0 + 10 * r, 100.0, 1e-4, 0, 0, 1e-4, 0, 0, 0, 0]]) for r in range(2)], 2)
+            want = 0 if (conf and conf[0][:2] == (0, 1) and conf[0][2] == 0) else 1
+            assert got == want, (kk, gn, i)
+            unsafe += 1 - want
+        assert 0.02 * n < unsafe < 0.9 * n, (kk, gn, unsafe)
+
+
+def test_kernel_decagon_pair_test_on_the_host_matches_the_oracle(K, O):
+    """k_chisq_pairs' source compiled for the host against the oracle, incl. vertex-vertex contacts a few ulps either way."""
+    rng = np.random.default_rng(21)
+    n = 6000
+    mu_a = rng.uniform(0, 8, (n, 2))
+    L = rng.uniform(0.02, 0.3, (2, n, 3))
+    cov = [np.ascontiguousarray(np.stack([l[:, 0] ** 2, l[:, 0] * l[:, 1], l[:, 0] * l[:, 1], l[:, 1] ** 2 + l[:, 2] ** 2], axis=1)) for l in L]
+    rad = rng.uniform(0.1, 0.3, (2, n))
+    sc = K.chi2_quantile_2dof(0.9)
+    lam = [0.5 * (c[:, 0] + c[:, 3]) + np.sqrt((0.5 * (c[:, 0] + c[:, 3])) ** 2 - (c[:, 0] * c[:, 3] - c[:, 1] * c[:, 2])) for c in cov]
+    ra, rb = lam[0] * sc + rad[0], lam[1] * sc + rad[1]
+    ang = rng.uniform(0, 2 * np.pi, n)
+    d = (ra + rb) * rng.uniform(0.85, 1.1, n)
+    k = np.arange(0, n, 3)
+    ang[k] = rng.integers(0, 10, len(k)) * (2 * np.pi / 10)
+    d[k] = (ra + rb)[k] * (1 + rng.uniform(-3e-15, 3e-15, len(k)))
+    mu_b = np.ascontiguousarray(mu_a + np.stack([d * np.cos(ang), d * np.sin(ang)], axis=1))
+    ref = O.chisq_pairs_disjoint(mu_a, cov[0], rad[0], mu_b, cov[1], rad[1], sc)
+    L_ = K.lib()
+    got = np.array([L_.cck_host_chisq_pair_disjoint(mu_a[i].ctypes.data, cov[0][i].ctypes.data, float(rad[0][i]), mu_b[i].ctypes.data, cov[1][i].ctypes.data,
+                                                     float(rad[1][i]), float(sc)) for i in range(n)], dtype=bool)
+    assert np.array_equal(got, ref)
+    assert 0.2 < ref.mean() < 0.8
