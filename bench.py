@@ -254,9 +254,10 @@ class Clocks:
 # oracle on the seeded workload (bench runs at N = 1 re-count them live; these are the values those runs print)
 HPS_RECORDED = {"linear/all_survive": 533.99, "linear/dense_survive": 475.6, "linear/realistic": 400.0,
                 "unicycle/all_survive": 533.99, "unicycle/realistic": 400.0}
-# FP64-pipe instructions per belief-step on the hot path, from the ncu source view (profiles/): linear 70 (lin_step_diag) + 5
-# (Sigma+Lambda, |P01|+|P10|); unicycle 316 DMUL + 251 DADD + 32 DFMA + 10 DSETP
-FP64_INST = {"linear": 75.0, "linear_dense": 95.0, "unicycle": 609.0}
+# FP64 arithmetic instructions per belief-step on the hot path, from the ncu source view (profiles/r2c_*): linear 34 DMUL + 30
+# DADD + 5 DFMA (the division) = 69 - the diagonal-constant Kalman step, the mean update, Sigma+Lambda and |P01|+|P10|; unicycle
+# 316 DMUL + 251 DADD + 32 DFMA + 10 DSETP (round-1 capture, kernel unchanged)
+FP64_INST = {"linear": 69.0, "linear_dense": 89.0, "unicycle": 609.0}
 
 
 def pin_to_gpu_cpus(index):
@@ -614,6 +615,7 @@ def run_ours(args):
         except Exception:
             pass
         fp64_peak = ctx.measure_fp64_peak()
+        fp64_rates = ctx.measure_fp64_rates()
         key = lambda v: f"{args.model}/{v}"       # noqa: E731
         # ---- cpu_baseline + parity (N = 1 only: the oracle is test infrastructure and is timed once per box) ----
         parity = None
@@ -661,7 +663,9 @@ def run_ours(args):
         f_prop = 60.0 if dim == 2 else 700.0
         inst_per_step = FP64_INST["linear_dense" if (dim == 2 and os.environ.get("CCK_LIN_DENSE", "") == "1") else args.model]
         bytes_per_belief = (Wd * 8 + dim * 8 + 4) + (Wd * 8 + 4)     # 184 B linear, 616 B unicycle
-        issue_peak = fp64_peak / 2.0      # FP64-pipe instructions/s per lane: one DFMA = 2 flop = one instruction
+        # FP64-pipe instructions/s per lane that NON-fused code can reach: alternating DMUL / DADD chains measured live (18.2 T/s on
+        # this pool's B200s; the DFMA flop peak / 2 = 17.4 T/s is the same pipe rate seen through fused instructions)
+        issue_peak = fp64_rates["dmul_dadd"]
         traffic_tab = {}
         try:
             traffic_tab = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
@@ -711,13 +715,17 @@ def run_ours(args):
             # results), so every flop is its own instruction and the attainable rate is the ISSUE rate = measured DFMA flop peak / 2;
             # the fraction against the DFMA flop peak itself is given next to it.
             "roofline": {"bound": "fp64", "achieved": exec_tinst, "peak": issue_peak, "unit": "TFLOP/s", "frac": exec_tinst / issue_peak,
-                         "peak_dfma_flop": fp64_peak, "frac_of_dfma_flop_peak": exec_tinst / fp64_peak,
+                         "peak_dfma_flop": fp64_peak, "frac_of_dfma_flop_peak": exec_tinst / fp64_peak, "fp64_rates_measured": fp64_rates,
                          "traffic": traffic, "fp64_inst_per_belief_step": inst_per_step,
                          "f_alg_frac": hv["f_alg_frac"],
-                         "how": "one DADD/DMUL = one flop = one FP64-pipe instruction per lane; peak = DFMA-chain microbenchmark run live on this GPU "
-                                "(MEASURED_PEAKS.json has no FP64 entry), halved for `peak` because no FMA may be formed; f_alg_frac is SURVEY 8(d)'s "
-                                "credited figure (oracle-counted flops of the reference's un-strength-reduced algorithm vs the DFMA flop peak): it "
-                                "exceeds 1 because the fp32 broad phase proves most half-planes without evaluating them"},
+                         "how": "one DADD/DMUL = one flop = one FP64-pipe instruction per lane (no FMA may be formed: bit-exact results); peak = "
+                                "the rate of alternating DMUL/DADD chains measured live on this GPU (MEASURED_PEAKS.json has no FP64 entry), "
+                                "peak_dfma_flop = the DFMA-chain flop peak; fp64_rates_measured also shows the FP64 rate when 1-3 independent fp32 "
+                                "instructions are issued per FP64 instruction - it drops, i.e. an FP64 instruction costs about two issue cycles and "
+                                "every other instruction one, which is why the kernel's fraction is bounded by its instruction mix (69 FP64 of 120 "
+                                "per warp-step: 2*69 / (2*69 + 51) = 0.73); f_alg_frac is SURVEY 8(d)'s credited figure (oracle-counted flops of the "
+                                "reference's un-strength-reduced algorithm vs the DFMA flop peak): it exceeds 1 because the broad phase proves most "
+                                "half-planes without evaluating them"},
             "roofline_hbm": {"bound": "hbm", "achieved": B * bytes_per_belief / (kern_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                              "frac": B * bytes_per_belief / (kern_ms * 1e-3) / 1e9 / hbm_peak,
                              "peak_source": "MEASURED_PEAKS.json (burst copy)" if "hbm_gbs" in peaks else "fallback 6650", "bytes_per_belief": bytes_per_belief},
@@ -739,16 +747,18 @@ def allsum_cached(x, world):
 
 def solve_sample():
     try:
-        out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "solve_bench.py"), "--seeds", "5", "--time", "20", "--only", "k=4"],
-                             capture_output=True, text=True, timeout=300)
+        out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "solve_bench.py"), "--seeds", "5", "--time", "20", "--only", "k=4", "--cpu", "--cpu-jobs", "5"],
+                             capture_output=True, text=True, timeout=400)
         solve = {}
         for ln in out.stdout.splitlines():
             if ln.startswith("config"):
                 lab, js = ln.split(" {", 1)
                 d = json.loads("{" + js)
-                solve[lab] = {k: d[k] for k in d if k in ("seeds", "solved", "seconds_median", "seconds_p90", "K", "candidates_median", "cbs_nodes_median",
-                                                          "cpu_seconds_median", "cpu_solved")}
-        solve["how"] = "K-CBS over the batched GPU BSST (host/cck_plan), instances rebuilt from tests/golden; wall seconds per solve"
+                solve[lab] = {k: d[k] for k in d if k in ("seeds", "solved", "seconds_median", "seconds_q25", "seconds_q75", "seconds_p90", "K", "candidates_median",
+                                                          "cbs_nodes_median", "cpu_seconds_median", "cpu_solved", "speedup_median")}
+        solve["how"] = ("K-CBS over the batched GPU BSST (host/cck_plan) next to the CPU arm (oracle/cck_oracle_plan: the reference's planner loop, one "
+                        "candidate per iteration, single-threaded like the reference); same instances (rebuilt from tests/golden), same seeds; wall "
+                        "seconds per solve; 50-seed distributions: profiles/r2d_solve_times.json")
         return solve
     except Exception as e:  # noqa: BLE001
         return {"error": str(e)[:200]}

@@ -74,7 +74,8 @@ SYMBOLS = [
 
 def build(force=False, verbose=False):
     """Compile libcck_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
-    src = [os.path.join(_PKG, "csrc", f) for f in ("cck_b200.cu", "cck_kernels.cuh", "cck_device.cuh", "cck_rollout_bm.cuh", "cck_rollout_grid.cuh", "cck_rollout_uni.cuh", "cck_tree.cuh")]
+    import glob
+    src = sorted(glob.glob(os.path.join(_PKG, "csrc", "*.cu")) + glob.glob(os.path.join(_PKG, "csrc", "*.cuh")))
     src.append(os.path.join(_ROOT, "include", "cck_b200.h"))
     if not force and os.path.exists(_SO) and all(os.path.getmtime(_SO) >= os.path.getmtime(s) for s in src):
         return _SO

@@ -22,7 +22,7 @@
 //     distance >= |mu1 - mu2|^2 over a uniform grid of the means: same answers as a linear scan.
 // The random stream cannot match the reference's (it is never seeded there), so results are statistical, like the GPU planner's.
 //
-//   cck_oracle_plan -m x.map -s x.scen -k 2 [--svc Blackmore] [--pvc Blackmore] [-p 0.9] [-t 300] [--lltime 20] [--seed 1] [--prune]
+//   cck_oracle_plan -m x.map -s x.scen -k 2 [--svc Blackmore] [--pvc Blackmore] [-p 0.9] [-t 300] [--lltime 20] [--seed 1] [--prune] [-o plan.txt]
 // Prints one JSON line in the format of host/cck_plan.
 #include <algorithm>
 #include <chrono>
@@ -222,6 +222,8 @@ public:
         return tr;
     }
     double last_cost() const { return cost_; }
+    // OMPL answers INVALID_START when the only start state fails the validity checker (:186-195)
+    bool start_valid() const { double c2[4]; cov_block2(start_, c2); return svc_is_valid(svc_, start_.v, c2); }
 
 private:
     double uni(double lo, double hi) { return lo + (hi - lo) * std::uniform_real_distribution<double>(0.0, 1.0)(rng_); }
@@ -265,7 +267,8 @@ private:
     MeanGrid<D> nodes_, wits_;
 };
 
-struct Result { bool solved = false; double seconds = 0, cost = 0; int cbs_nodes = 0, replans = 0; long long iterations = 0, tree_nodes = 0; };
+struct Result { bool solved = false; double seconds = 0, cost = 0; int cbs_nodes = 0, replans = 0; long long iterations = 0, tree_nodes = 0;
+                std::vector<std::vector<std::vector<double>>> plan; };   // plan[robot][state][W]
 
 template <int D, class Model>
 Result kcbs(const Instance& inst, int svc_kind, int pvc_kind, Params prm, double seconds, double ll_seconds, Model model) {
@@ -286,7 +289,7 @@ Result kcbs(const Instance& inst, int svc_kind, int pvc_kind, Params prm, double
     for (int r = 0; r < k; ++r) {                                                                 // KCBS.cpp:213-228
         pl[r]->set_constraints({});
         std::vector<Belief<D>> t;
-        while (t.empty() && now_s() - t0 < seconds) t = pl[r]->solve(ll_seconds);
+        while (t.empty() && pl[r]->start_valid() && now_s() - t0 < seconds) t = pl[r]->solve(ll_seconds);
         if (t.empty()) { res.seconds = now_s() - t0; return res; }
         root->cost += 0.2 * (double)(t.size() - 1);
         root->plan.push_back(std::move(t));
@@ -296,7 +299,14 @@ Result kcbs(const Instance& inst, int svc_kind, int pvc_kind, Params prm, double
         auto cur = pq.top(); pq.pop();
         res.cbs_nodes++;
         const std::vector<Conflict> confs = validate_plan<D>(pvc, cur->plan);                    // :289
-        if (confs.empty()) { res.solved = true; res.cost = cur->cost; break; }
+        if (confs.empty()) {
+            res.solved = true; res.cost = cur->cost;
+            for (const auto& tr : cur->plan) {
+                res.plan.emplace_back();
+                for (const auto& b : tr) res.plan.back().emplace_back((const double*)&b, (const double*)&b + sizeof(b) / sizeof(double));
+            }
+            break;
+        }
         const int agents[2] = {confs.front().a, confs.front().b};
         for (int i = 0; i < 2; ++i) {                                                             // :389-467
             const int a = agents[i];
@@ -323,7 +333,7 @@ std::string slurp(const std::string& p) { std::ifstream f(p); std::stringstream 
 }  // namespace
 
 int main(int argc, char** argv) {
-    std::string map, scen, svc = "Blackmore", pvc = "Blackmore";
+    std::string map, scen, svc = "Blackmore", pvc = "Blackmore", output;
     int k = 1;
     double p_safe = 0.9, time_s = 300.0, lltime = 20.0;
     Params prm;
@@ -340,6 +350,7 @@ int main(int argc, char** argv) {
         else if (a == "--lltime") lltime = std::atof(next().c_str());
         else if (a == "--seed") prm.seed = std::strtoull(next().c_str(), nullptr, 10);
         else if (a == "--prune") prm.prune = true;
+        else if (a == "-o" || a == "--output") output = next();
         else if (a == "--K" || a == "--devices") next();     // accepted for CLI compatibility with cck_plan, meaningless here (K = 1)
         else { std::fprintf(stderr, "unknown flag %s\n", a.c_str()); return 2; }
     }
@@ -355,5 +366,13 @@ int main(int argc, char** argv) {
     std::printf("{\"solved\": %s, \"seconds\": %.6f, \"cost\": %.6f, \"cbs_nodes\": %d, \"replans\": %d, \"launches\": 0, \"candidates\": %lld, "
                 "\"tree_nodes\": %lld, \"obstacles\": %zu, \"agents\": %d, \"K\": 1, \"impl\": \"cpu-oracle\", \"prune\": %s}\n",
                 r.solved ? "true" : "false", r.seconds, r.cost, r.cbs_nodes, r.replans, r.iterations, r.tree_nodes, inst.obstacles.size(), k, prm.prune ? "true" : "false");
+    if (!output.empty() && r.solved) {     // same text format as host/cck_plan: "robot r T W" then T rows
+        FILE* f = std::fopen(output.c_str(), "w");
+        for (int i = 0; i < k; ++i) {
+            std::fprintf(f, "robot %d %zu %zu\n", i, r.plan[i].size(), r.plan[i][0].size());
+            for (const auto& st : r.plan[i]) { for (double v : st) std::fprintf(f, "%.17g ", v); std::fprintf(f, "\n"); }
+        }
+        std::fclose(f);
+    }
     return r.solved ? 0 : 1;
 }

@@ -134,3 +134,13 @@ def test_kernel_decagon_pair_test_on_the_host_matches_the_oracle(K, O):
                                                      float(rad[1][i]), float(sc)) for i in range(n)], dtype=bool)
     assert np.array_equal(got, ref)
     assert 0.2 < ref.mean() < 0.8
+
+
+def test_build_entry_points_run_without_a_gpu(K):
+    """__graft_entry__.build() is the driver's "does it build" check: every source it names must exist and the in-tree
+    library must be up to date with them (a stale source list once made it raise FileNotFoundError)."""
+    so = K.capi.build()
+    assert os.path.exists(so)
+    srcs = [f for f in os.listdir(os.path.join(os.path.dirname(so), "csrc")) if f.endswith((".cu", ".cuh"))]
+    assert "cck_b200.cu" in srcs and "cck_rollout_grid.cuh" in srcs
+    assert all(os.path.getmtime(so) >= os.path.getmtime(os.path.join(os.path.dirname(so), "csrc", f)) for f in srcs)
