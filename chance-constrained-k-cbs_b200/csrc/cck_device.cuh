@@ -47,6 +47,7 @@ struct UniDev { double F[16], Acl[16], Q[16], R[16], gains[8], acc_lo, acc_hi, t
 // ---------------------------------------------------------------------------
 // PTX helpers: mbarrier + TMA 1-D bulk copy (cp.async.bulk -> SASS UBLKCP)
 // ---------------------------------------------------------------------------
+#ifndef CCK_HOSTSIM
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -73,6 +74,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
+#define CCK_OPAQUE4(a, b, c, d) asm volatile("" : "+d"(a), "+d"(b), "+d"(c), "+d"(d))
+#else   // tests/hostsim (CPU execution of the kernels, test infrastructure): the copy is made at once, the barrier is a flag
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t) { *bar = 0; }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t*, uint32_t) {}
+__device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) { memcpy(smem_dst, gmem_src, bytes); *bar = 1; }
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t) { while (*(volatile uint64_t*)bar == 0) sim::yield(); }
+#define CCK_OPAQUE4(a, b, c, d) ((void)0)
+#endif
 
 // Stage `bytes` (multiple of 16) of the obstacle table into shared memory.  Thread 0
 // issues the bulk copy; callers overlap their own global loads and then call

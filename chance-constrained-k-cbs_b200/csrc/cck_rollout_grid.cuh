@@ -100,9 +100,13 @@ __host__ __device__ __forceinline__ float grid_cellf(float v, float g0, float ic
 
 // MUFU.SQRT: max relative error 2^-23 (PTX ISA, sqrt.approx.f32), denormal inputs flushed to zero
 __device__ __forceinline__ float sqrt_approx(float v) {
+#ifndef CCK_HOSTSIM
     float r;
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
     return r;
+#else
+    return sqrtf(v);   // tests/hostsim: within the error bound the callers already allow for
+#endif
 }
 
 // One obstacle the broad phase could not skip: outer box (proves safe), inner box (proves unsafe:
@@ -170,7 +174,7 @@ __device__ __forceinline__ bool grid_check_b(const GridConst& g, const unsigned 
         const ClassRec* cls = reinterpret_cast<const ClassRec*>(ctab + h->off_classes);   // a kernel constant: no header load
         if (SPLIT) {
             double s0 = Sa0, s1 = Sa1, s2 = Sa2, s3 = Sa3;
-            asm volatile("" : "+d"(s0), "+d"(s1), "+d"(s2), "+d"(s3));
+            CCK_OPAQUE4(s0, s1, s2, s3);
             return bm_exact_obstacle(cls[exCls[j]].A, exB + (size_t)j * 4, x, y, s0 + Sb0, s1 + Sb1, s2 + Sb2, s3 + Sb3, c);
         }
         return bm_exact_obstacle(cls[exCls[j]].A, exB + (size_t)j * 4, x, y, P0, P1, P2, P3, c);
@@ -272,6 +276,7 @@ __global__ void __launch_bounds__(256) k_is_valid_grid(int64_t n, int dim, const
 // cp.async (LDGSTS): per-lane prefetch of the NEXT belief into shared memory while the current
 // rollout runs, so a refill never exposes HBM latency to the warp.
 // ---------------------------------------------------------------------------
+#ifndef CCK_HOSTSIM
 __device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem)), "l"(__cvta_generic_to_global(gmem)) : "memory");
 }
@@ -280,6 +285,12 @@ __device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+#else   // tests/hostsim: plain copies
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) { memcpy(smem, gmem, 8); }
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) { memcpy(smem, gmem, 4); }
+__device__ __forceinline__ void cp_async_commit() {}
+__device__ __forceinline__ void cp_async_wait_all() {}
+#endif
 
 // shared-memory carve-up (T = CCK_GRID_THREADS): [mbarrier 16 B][grid table][work counter 16 B][stash T x 80 B]
 //                         [prefetch slots: 13 planes x T doubles][2 planes x T ints]
@@ -486,7 +497,7 @@ __global__ void __launch_bounds__(grid_threads(EXPAND), grid_minb(EXPAND)) k_rol
         if (ok) {
             if (EXPAND && cons) {   // Sigma + Lambda formed here, not carried across the validity check
                 double s0 = B.S[0], s1 = B.S[1], s2 = B.S[2], s3 = B.S[3];
-                asm volatile("" : "+d"(s0), "+d"(s1), "+d"(s2), "+d"(s3));
+                CCK_OPAQUE4(s0, s1, s2, s3);
                 cons_ok = cons_ok && constraints_ok_at(cons, pstep + t + 1, x, y, s0 + B.L[0], s1 + B.L[1], s2 + B.L[2], s3 + B.L[3]);
             }
             if (TRAJ && t < a.traj_T) {

@@ -1,5 +1,21 @@
 """Shared helpers for the parity tests: build matching oracle / product configurations."""
+import os
+
 import numpy as np
+
+HOSTSIM = os.environ.get("CCK_HOSTSIM", "") == "1"      # tests/hostsim: the kernels run on the CPU, "device" memory is host memory
+
+
+def torch_device():
+    """Where the device-pointer entry points expect their tensors: cuda:0 (tests/hostsim: plain host memory)."""
+    import torch
+    return torch.device("cpu") if HOSTSIM else torch.device("cuda", 0)
+
+
+def torch_sync():
+    import torch
+    if not HOSTSIM:
+        torch.cuda.synchronize()
 
 
 def oracle_synth(O, W, M, variant, kind, dim, k_agents=4, p_safe=0.9, seed=None):

@@ -10,6 +10,7 @@ decided by the reference's fp64 expression, so verdicts must stay bit-identical 
 import numpy as np
 import pytest
 
+import helpers
 from helpers import install_from_oracle_svc, oracle_synth
 
 pytestmark = pytest.mark.gpu
@@ -303,7 +304,7 @@ def test_traj_T_is_enforced(K, W, ctx):
     out, valid, traj = ctx.propagate_while_valid(bel, ctrl, steps, traj_T=8)
     assert (valid == 8).all() and np.array_equal(traj[7], out)
     import torch
-    dev = torch.device("cuda", 0)
+    dev = helpers.torch_device()
     d_b, d_c, d_s = (torch.from_numpy(x).to(dev) for x in (bel, ctrl, steps))
     d_o = torch.empty_like(d_b); d_v = torch.empty(n, dtype=torch.int32, device=dev)
     T = 4

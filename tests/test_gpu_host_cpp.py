@@ -8,6 +8,7 @@ import subprocess
 import numpy as np
 import pytest
 
+import helpers
 from conftest import GOLDEN, ROOT
 
 pytestmark = pytest.mark.gpu
@@ -74,7 +75,8 @@ def test_invalid_start_state_is_reported_like_ompl(O, tmp_path):
     res = json.loads(out.stdout.strip().splitlines()[-1])
     # no search from the invalid root: the run ends at once instead of spending its time limit (Robot 1's own root plan is
     # found in milliseconds meanwhile; no constraint-tree node is ever expanded)
-    assert not res["solved"] and res["seconds"] < 5.0 and res["cbs_nodes"] == 0 and res["replans"] == 0
+    # (tests/hostsim runs the kernels on the CPU: Robot 1's root plan alone takes about 10 s there)
+    assert not res["solved"] and res["seconds"] < (25.0 if helpers.HOSTSIM else 5.0) and res["cbs_nodes"] == 0 and res["replans"] == 0
 
 
 @pytest.mark.parametrize("fixture,k,tmax,p_safe", [("config1_empty8_linear_k2", 2, 120, 0.9), ("config4_narrow_linear_k2", 2, 180, 0.8)])

@@ -7,6 +7,7 @@ checkers (device erfinv vs Boost-style erf_inv) exact outside the band.
 import numpy as np
 import pytest
 
+import helpers
 from helpers import assert_rollout_mismatches_in_band, band_mask_halfplane, install_from_oracle_svc, oracle_synth
 
 pytestmark = pytest.mark.gpu
@@ -197,7 +198,7 @@ def test_launch_count_and_errors(K, W, ctx):
     bel, ctrl = W.synthetic_beliefs(100, "linear")
     ctx.propagate(bel, ctrl)
     assert ctx.launch_count == before + 1
-    assert ctx.num_sms >= 100
+    assert ctx.num_sms >= 100 or helpers.HOSTSIM
 
 
 def test_summary_and_winner_records(K, W, ctx):
@@ -208,12 +209,12 @@ def test_summary_and_winner_records(K, W, ctx):
     bel, ctrl = W.synthetic_beliefs(n, "linear", seed=4)
     steps = np.random.default_rng(0).integers(0, T + 1, n).astype(np.int32)
     out, valid = ctx.propagate_while_valid(bel, ctrl, steps)
-    dev = torch.device("cuda", 0)
+    dev = helpers.torch_device()
     d_steps, d_valid = torch.from_numpy(steps).to(dev), torch.from_numpy(valid).to(dev)
     d_sum = torch.zeros(3, dtype=torch.int64, device=dev)
     ctx.rollout_summary_dev(None, n, d_steps, d_valid, d_sum)
     ctx.synchronize()
-    torch.cuda.synchronize()
+    helpers.torch_sync()
     ref = [int((valid == steps).sum()), int(np.where(steps > 0, np.minimum(valid + 1, steps), 0).sum()), int(valid.sum())]
     assert d_sum.tolist() == ref
     rng = np.random.default_rng(1)
@@ -225,9 +226,9 @@ def test_summary_and_winner_records(K, W, ctx):
     rec = torch.zeros(2, dtype=torch.float64, device=dev)
     ctx.select_winner_dev(None, n, d_cost, d_flags, 3, 1000, rec)
     ctx.synchronize()
-    torch.cuda.synchronize()
+    helpers.torch_sync()
     assert rec.tolist() == [-1.0, float(1000 + adm[10])]
     ctx.select_winner_dev(None, n, d_cost, torch.zeros_like(d_flags), 3, 0, rec)
     ctx.synchronize()
-    torch.cuda.synchronize()
+    helpers.torch_sync()
     assert rec.tolist() == [float("inf"), -1.0]
