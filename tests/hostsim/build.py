@@ -18,7 +18,10 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "chance-constrained-k-cbs_b200", "csrc")
-OUT = os.path.join(HERE, "_build")
+# CCK_HOSTSIM_ASAN=1: AddressSanitizer build (out-of-bounds accesses of "device" buffers abort with a report), run with
+#   LD_PRELOAD=$(g++ -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0:detect_stack_use_after_return=0
+ASAN = os.environ.get("CCK_HOSTSIM_ASAN", "") == "1"
+OUT = os.path.join(HERE, "_build", "asan") if ASAN else os.path.join(HERE, "_build")
 SO = os.path.join(OUT, "libcck_b200.so")
 
 LAUNCH = re.compile(r"(\b[A-Za-z_]\w*(?:<[^<>();]*>)?)\s*<<<(.+?)>>>\s*\(")
@@ -52,6 +55,8 @@ def build(force=False, verbose=False):
            "-Wno-unused-variable", "-Wno-unknown-pragmas", "-Wno-unused-but-set-variable", "-Wno-sign-compare",
            "-I", os.path.join(HERE, "shim"), "-include", os.path.join(HERE, "cuda_sim.hpp"),
            "-o", SO, os.path.join(gen, "cck_b200_sim.cpp"), "-pthread"]
+    if ASAN:
+        cmd[1:1] = ["-fsanitize=address", "-fno-omit-frame-pointer"]
     out = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or out.returncode != 0:
         print(out.stdout[-6000:], out.stderr[-12000:])
