@@ -64,7 +64,7 @@ SYMBOLS = [
     "cck_build_obstacle_tables", "cck_build_pair_halfplanes",
     "cck_propagate", "cck_propagate_dev", "cck_is_valid", "cck_is_valid_dev",
     "cck_propagate_while_valid", "cck_propagate_while_valid_dev",
-    "cck_validate_plan", "cck_validate_plan_dev",
+    "cck_validate_plan", "cck_validate_plan_dev", "cck_validate_plan_range", "cck_validate_plan_range_dev",
     "cck_set_constraints", "cck_satisfies_constraints", "cck_satisfies_constraints_dev", "cck_build_clearance_field", "cck_measure_fp64_rates", "cck_set_cov_table", "cck_chisq_pairs_disjoint", "cck_host_pair_safe", "cck_host_chisq_pair_disjoint",
     "cck_expand_batch", "cck_expand_batch_dev", "cck_rollout_summary_dev", "cck_select_winner_dev", "cck_measure_fp64_peak",
     "cck_tree_create", "cck_tree_destroy", "cck_tree_clear", "cck_tree_size", "cck_tree_append", "cck_tree_update",
@@ -131,6 +131,8 @@ def lib():
     L.cck_propagate_while_valid_dev.argtypes = [vp, vp, i64, vp, i64, vp, i64, vp, vp, i64, vp, vp, i64, C.c_int32]
     L.cck_validate_plan.argtypes = [vp, C.c_int, vp, vp, i64, C.POINTER(ConflictRun)]
     L.cck_validate_plan_dev.argtypes = [vp, vp, C.c_int, vp, C.c_int, vp, i64, vp]
+    L.cck_validate_plan_range.argtypes = [vp, C.c_int, vp, vp, i64, C.c_int, C.c_int, C.POINTER(ConflictRun), C.POINTER(C.c_uint64)]
+    L.cck_validate_plan_range_dev.argtypes = [vp, vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, vp, i64, vp, vp]
     L.cck_set_constraints.argtypes = [vp, C.c_int, vp, vp, vp, vp]
     L.cck_set_cov_table.argtypes = [vp, vp, C.c_int]
     L.cck_host_pair_safe.argtypes = [C.c_int, vp, vp, vp, vp, vp, vp, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int]
@@ -342,6 +344,20 @@ class Context:
         if run.first_step < 0:
             return None
         return (run.a, run.b, run.first_step, run.run_len)
+
+    def validate_plan_range(self, trajs, t_begin, t_end=-1):
+        """One rank's share of a sharded conflict search: first conflict within the steps [t_begin, t_end) of the plan.
+        -> record [key, a, b, first_step, run_len] (int64; key < 0: none) for sharding.gather_conflict."""
+        k = len(trajs)
+        lens = np.array([t.shape[1] for t in trajs], dtype=np.int32)
+        W, T = trajs[0].shape[0], int(lens.max())
+        buf = np.zeros((k, W, T))
+        for r, t in enumerate(trajs):
+            buf[r, :, :t.shape[1]] = t
+        run, key = ConflictRun(), C.c_uint64(0)
+        self._ck(self.L.cck_validate_plan_range(self.h, k, _ptr(lens), _ptr(buf), T, int(t_begin), int(t_end), C.byref(run), C.byref(key)))
+        kv = -1 if key.value == 0xFFFFFFFFFFFFFFFF else int(key.value)
+        return np.array([kv, run.a, run.b, run.first_step, run.run_len], dtype=np.int64)
 
     def chisq_pairs_disjoint(self, mu_a, cov_a, rad_a, mu_b, cov_b, rad_b, sc):
         """CentralizedChiSquaredBoundarySVC's agent-agent decagon test; SoA inputs mu [2, n], cov [4, n], rad [n]."""

@@ -964,26 +964,34 @@ extern "C" int cck_set_cov_table(cck_ctx* c, const double* root_cov, int n_steps
 // ---------------------------------------------------------------------------
 // validatePlan
 // ---------------------------------------------------------------------------
-extern "C" int cck_validate_plan_dev(cck_ctx* c, void* stream, int k, const int32_t* lens_dev, int max_len, const double* traj,
-                                     int64_t ld, cck_conflict_run* out_dev) {
+// Scans the steps [t_begin, t_end) for the first conflict; the follow-up of the winning pair always covers the whole plan.
+extern "C" int cck_validate_plan_range_dev(cck_ctx* c, void* stream, int k, const int32_t* lens_dev, int max_len, int t_begin, int t_end,
+                                           const double* traj, int64_t ld, cck_conflict_run* out_dev, unsigned long long* key_out_dev) {
     if (!c) return CCK_ERR_INVALID;
     if (!c->has_pvc) return fail(c, CCK_ERR_INVALID, "cck_set_pvc has not been called");
     if (k != c->pvc.k) return fail(c, CCK_ERR_INVALID, "k differs from cck_set_pvc");
     if (max_len < 1 || ld < max_len) return fail(c, CCK_ERR_INVALID, "bad max_len/ld");
+    if (t_begin < 0 || t_end > max_len || t_begin > t_end) return fail(c, CCK_ERR_INVALID, "bad step range");
     CK(c, cudaSetDevice(c->device));
     cudaStream_t s = pick(c, stream);
     CK(c, cudaMemsetAsync(c->d_key, 0xff, sizeof(unsigned long long), s));
-    if (c->pvc.n_pairs > 0) {
+    if (c->pvc.n_pairs > 0 && t_end > t_begin) {
         const int warps_per_block = 4;
-        int blocks = (max_len + warps_per_block - 1) / warps_per_block;
+        int blocks = (t_end - t_begin + warps_per_block - 1) / warps_per_block;
         if (blocks > c->num_sms * 8) blocks = c->num_sms * 8;
-        k_validate_steps<<<blocks, 128, 0, s>>>(c->pvc, traj, ld, lens_dev, max_len, c->d_key);
+        k_validate_steps<<<blocks, 128, 0, s>>>(c->pvc, traj, ld, lens_dev, t_begin, t_end, c->d_key);
         c->launches++;
     }
     k_validate_finalize<<<1, 256, 0, s>>>(c->pvc, traj, ld, lens_dev, max_len, c->d_key, out_dev);
     c->launches++;
+    if (key_out_dev) CK(c, cudaMemcpyAsync(key_out_dev, c->d_key, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, s));
     CK(c, cudaGetLastError());
     return CCK_OK;
+}
+
+extern "C" int cck_validate_plan_dev(cck_ctx* c, void* stream, int k, const int32_t* lens_dev, int max_len, const double* traj,
+                                     int64_t ld, cck_conflict_run* out_dev) {
+    return cck_validate_plan_range_dev(c, stream, k, lens_dev, max_len, 0, max_len, traj, ld, out_dev, nullptr);
 }
 
 // ---------------------------------------------------------------------------
@@ -1295,7 +1303,9 @@ extern "C" int cck_expand_batch(cck_ctx* c, int64_t n, const double* bel, int64_
                         goal_dist, flags);
 }
 
-extern "C" int cck_validate_plan(cck_ctx* c, int k, const int32_t* lens, const double* traj, int64_t ld, cck_conflict_run* out) {
+// t_end < 0: the whole plan.  key_out (optional): (first_step << 32 | rank of the pair in map order), ~0 = no conflict in the range.
+extern "C" int cck_validate_plan_range(cck_ctx* c, int k, const int32_t* lens, const double* traj, int64_t ld, int t_begin, int t_end,
+                                       cck_conflict_run* out, unsigned long long* key_out) {
     if (!c) return CCK_ERR_INVALID;
     if (!c->has_pvc) return fail(c, CCK_ERR_INVALID, "cck_set_pvc has not been called");
     if (!lens || !traj || !out || k != c->pvc.k) return fail(c, CCK_ERR_INVALID, "bad arguments");
@@ -1303,18 +1313,28 @@ extern "C" int cck_validate_plan(cck_ctx* c, int k, const int32_t* lens, const d
     int max_len = 0;
     for (int r = 0; r < k; ++r) { if (lens[r] < 1) return fail(c, CCK_ERR_INVALID, "empty trajectory"); max_len = std::max(max_len, lens[r]); }
     if (ld < max_len) return fail(c, CCK_ERR_INVALID, "ld < max trajectory length");
+    if (t_end < 0) t_end = max_len;
+    if (t_end > max_len) t_end = max_len;
+    if (t_begin > t_end) t_begin = t_end;
     const int W = c->pvc.dim + 2 * c->pvc.dim * c->pvc.dim;
     const size_t b_traj = al256((size_t)k * W * max_len * 8), b_len = al256((size_t)k * 4);
     int rc;
-    if ((rc = ensure_scratch(c, 0, b_traj + b_len))) return rc;
+    if ((rc = ensure_scratch(c, 0, b_traj + b_len + 256))) return rc;
     unsigned char* p = (unsigned char*)c->d_scratch[0];
     cudaStream_t s = c->pipe[0];
     CK(c, h2d_planes(p, traj, 8, max_len, ld, k * W, s));
     CK(c, cudaMemcpyAsync(p + b_traj, lens, (size_t)k * 4, cudaMemcpyHostToDevice, s));
-    if ((rc = cck_validate_plan_dev(c, s, k, (int32_t*)(p + b_traj), max_len, (double*)p, max_len, c->d_run))) return rc;
+    unsigned long long* d_keyout = (unsigned long long*)(p + b_traj + b_len);
+    if ((rc = cck_validate_plan_range_dev(c, s, k, (int32_t*)(p + b_traj), max_len, t_begin, t_end, (double*)p, max_len, c->d_run,
+                                          key_out ? d_keyout : nullptr))) return rc;
     CK(c, cudaMemcpyAsync(out, c->d_run, sizeof(cck_conflict_run), cudaMemcpyDeviceToHost, s));
+    if (key_out) CK(c, cudaMemcpyAsync(key_out, d_keyout, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
     CK(c, cudaStreamSynchronize(s));
     return CCK_OK;
+}
+
+extern "C" int cck_validate_plan(cck_ctx* c, int k, const int32_t* lens, const double* traj, int64_t ld, cck_conflict_run* out) {
+    return cck_validate_plan_range(c, k, lens, traj, ld, 0, -1, out, nullptr);
 }
 
 extern "C" int cck_satisfies_constraints(cck_ctx* c, int64_t n_paths, const double* path, int64_t ld, int32_t max_len,

@@ -488,13 +488,14 @@ __device__ __forceinline__ void rank_to_pair(int rank, int k, int& ia, int& ib) 
 // first unsafe pair of that step (checkForConflicts_, MinkowskiSumBlackmorePVC.cpp:125-167).
 // first_rank[t] = rank of that pair or INT_MAX.  An atomicMin on (t<<32 | rank) yields the
 // earliest conflict of the plan.
+// [t_begin, t_end): the steps this launch scans (the whole plan, or one rank's share of it: cck_validate_plan_range).
 __global__ void __launch_bounds__(128) k_validate_steps(const __grid_constant__ PvcDev pv, const double* __restrict__ traj,
-                                                        int64_t ld, const int32_t* __restrict__ lens, int max_states,
+                                                        int64_t ld, const int32_t* __restrict__ lens, int t_begin, int t_end,
                                                         unsigned long long* __restrict__ best_key) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
-    for (int t = warp; t < max_states; t += nwarps) {
+    for (int t = t_begin + warp; t < t_end; t += nwarps) {
         // steps later than an already-found conflict cannot win
         unsigned long long cur = 0;
         if (lane == 0) cur = *reinterpret_cast<volatile unsigned long long*>(best_key);

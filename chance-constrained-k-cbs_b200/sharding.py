@@ -1,7 +1,8 @@
 """Multi-GPU host logic: independent units (beliefs / candidates / CBS child replans) are
 block-partitioned over the ranks of one node; tables are replicated; no data-path collective.
 Only per-rank RESULT RECORDS cross NVLink (torch.distributed, NCCL on GPUs; gloo in CPU tests):
-the rollout summary (3 x int64) and the expansion winner (cost, global index)."""
+the rollout summary (3 x int64), the expansion winner (cost, global index) and the earliest conflict of a plan
+(key, a, b, first_step, run_len)."""
 import torch
 import torch.distributed as dist
 
@@ -43,3 +44,28 @@ def gather_winner(local2, group=None):
         if c < best_c or (c == best_c and i < best_i):
             best_c, best_i = c, int(i)
     return best_c, best_i
+
+
+def gather_conflict(local5, group=None):
+    """Sharded validatePlan: every rank scans its own range of steps (cck_validate_plan_range) and contributes
+    [key, a, b, first_step, run_len] (int64; key = first_step << 32 | pair rank in std::map order, < 0: no conflict in the
+    range).  all-gather -> the record with the smallest key = what the reference's validatePlan reports:
+    (a, b, first_step, run_len), or None when no rank found a conflict."""
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        parts = [torch.zeros_like(local5) for _ in range(dist.get_world_size(group))]
+        dist.all_gather(parts, local5, group=group)
+        recs = torch.stack(parts).cpu()
+    else:
+        recs = local5.reshape(1, 5).cpu()
+    return pick_conflict(recs.tolist())
+
+
+def pick_conflict(records):
+    """The earliest conflict among per-range records [key, a, b, first_step, run_len]: smallest non-negative key."""
+    best = None
+    for rec in records:
+        if rec[0] < 0:
+            continue
+        if best is None or rec[0] < best[0]:
+            best = rec
+    return None if best is None else (int(best[1]), int(best[2]), int(best[3]), int(best[4]))

@@ -189,6 +189,15 @@ int cck_host_chisq_pair_disjoint(const double* mu_a, const double* cov_a, double
 int cck_validate_plan(cck_ctx* ctx, int k, const int32_t* lens, const double* traj, int64_t ld, cck_conflict_run* out);
 int cck_validate_plan_dev(cck_ctx* ctx, void* stream, int k, const int32_t* lens_dev, int max_len, const double* traj,
                           int64_t ld, cck_conflict_run* out_dev);
+/* Sharded conflict search (the pair x step tests are independent up to the final "earliest (step, pair order)" argmin;
+ * one rank scans only the steps [t_begin, t_end) of the replicated plan; t_end < 0 = to the end).  out = the first conflict
+ * INSIDE the range with the follow-up run over the WHOLE plan (a = -1 when the range is conflict free); key_out (optional) =
+ * first_step << 32 | rank of the pair in std::map order, all ones when there is none: the record with the smallest key over
+ * the ranks is what validatePlan returns (sharding.gather_conflict all-gathers {key, a, b, first_step, run_len}). */
+int cck_validate_plan_range(cck_ctx* ctx, int k, const int32_t* lens, const double* traj, int64_t ld, int t_begin, int t_end,
+                            cck_conflict_run* out, unsigned long long* key_out);
+int cck_validate_plan_range_dev(cck_ctx* ctx, void* stream, int k, const int32_t* lens_dev, int max_len, int t_begin, int t_end,
+                                const double* traj, int64_t ld, cck_conflict_run* out_dev, unsigned long long* key_out_dev);
 
 /* ---- PlanValidityChecker::satisfiesConstraints, batched ------------------
  * Constraints (BeliefConstraint, include/Constraints/BeliefConstraint.h:8-16) are

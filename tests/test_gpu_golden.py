@@ -116,6 +116,46 @@ def test_validate_plan_semantics_vs_oracle(K, O, ctx):
                 assert run == (ref[0][0], ref[0][1], ref[0][2], len(ref)), (trial, kind, run, ref[0], len(ref))
 
 
+def test_validate_plan_sharded_over_step_ranges(K, O, ctx):
+    """the conflict search shards over time steps - every rank scans its own range of the replicated plan
+    (cck_validate_plan_range) and the record with the smallest (step, pair-order) key is validatePlan's answer, follow-up run
+    included (it is always taken over the whole plan)."""
+    from cck_b200 import sharding
+    rng = np.random.default_rng(11)
+    k, dim = 12, 2
+    world = O.World.synthetic(np.zeros((0, 2)), 40.0, 40.0, k, 0.9)
+    rad = K.rect_robot_bounding_radius()
+    ctx.set_model(K.MODEL_LINEAR2D)
+    seen_conflict = seen_free = False
+    for trial in range(5):
+        trajs = []
+        for r in range(k):
+            b0 = O.default_beliefs(1, dim)[0]
+            ang = rng.uniform(0, 2 * np.pi)
+            far = 9.0 if trial < 4 else 1000.0 * (r + 1)           # last trial: nobody ever meets
+            b0[:2] = [20 + far * np.cos(ang), 20 + far * np.sin(ang)]
+            u = -np.array([np.cos(ang), np.sin(ang)]) * rng.uniform(0.6, 1.0)
+            trajs.append(np.concatenate([b0[None, :], O.propagate_n(b0, u, int(rng.integers(5, 70)), dim)]))
+        soa = [K.aos_to_soa(t) for t in trajs]
+        T = max(len(t) for t in trajs)
+        for kind in (K.PVC_BLACKMORE, K.PVC_CHISQUARED):
+            K.install_pvc(ctx, kind, dim, [rad] * k, 0.9 if kind == K.PVC_CHISQUARED else world.p_safe_agents)
+            ref = O.Pvc(world, kind).validate_plan(trajs, dim)
+            want = None if not ref else (ref[0][0], ref[0][1], ref[0][2], len(ref))
+            assert ctx.validate_plan(soa) == want
+            for n_ranks in (1, 2, 3, 8):
+                recs = [ctx.validate_plan_range(soa, *sharding.shard_bounds(T, r, n_ranks)) for r in range(n_ranks)]
+                assert sharding.pick_conflict([x.tolist() for x in recs]) == want, (trial, kind, n_ranks)
+                if want is not None:      # ranges that end before the first conflict report none; the key carries the step
+                    for r, x in enumerate(recs):
+                        lo, hi = sharding.shard_bounds(T, r, n_ranks)
+                        assert (x[0] < 0) if hi <= want[2] else True
+                        assert x[0] < 0 or (lo <= (x[0] >> 32) < hi and x[3] == (x[0] >> 32))
+            seen_conflict |= want is not None
+            seen_free |= want is None
+    assert seen_conflict and seen_free
+
+
 def test_satisfies_constraints_vs_oracle(K, O, ctx):
     rng = np.random.default_rng(9)
     k, dim = 3, 2

@@ -42,6 +42,14 @@ def _worker(rank, world, port, n, q):
                            dtype=torch.int64)
     w = sharding.gather_winner(local_w)
     s = sharding.gather_summary(local_s)
+    # sharded conflict search: rank 0 found (step 40, pair rank 3) in its range of steps, rank 1 (step 12, pair rank 7) and,
+    # in a second plan, nothing; a third plan has the same step on both ranks - the lower pair rank wins
+    key = lambda t, r: (t << 32) | r       # noqa: E731
+    c1 = sharding.gather_conflict(torch.tensor([key(40, 3), 2, 5, 40, 6] if rank == 0 else [key(12, 7), 1, 9, 12, 2], dtype=torch.int64))
+    c2 = sharding.gather_conflict(torch.tensor([key(40, 3), 2, 5, 40, 6] if rank == 0 else [-1, -1, -1, -1, 0], dtype=torch.int64))
+    c3 = sharding.gather_conflict(torch.tensor([key(7, 9), 4, 6, 7, 1] if rank == 0 else [key(7, 2), 0, 3, 7, 5], dtype=torch.int64))
+    c4 = sharding.gather_conflict(torch.tensor([-1, -1, -1, -1, 0], dtype=torch.int64))
+    assert c1 == (1, 9, 12, 2) and c2 == (2, 5, 40, 6) and c3 == (0, 3, 7, 5) and c4 is None, (c1, c2, c3, c4)
     gc = np.where(ok, cost, np.inf)
     q.put((rank, lo, hi, w, s.tolist(), (float(gc.min()), int(np.argmin(gc))),
            [int((valid == steps).sum()), int(np.minimum(valid + 1, steps).sum()), int(valid.sum())]))
@@ -84,3 +92,5 @@ def test_single_process_gather_is_identity():
     assert sharding.gather_winner(torch.tensor([3.5, 17.0], dtype=torch.float64)) == (3.5, 17)
     assert sharding.gather_winner(torch.tensor([float("inf"), -1.0], dtype=torch.float64)) == (float("inf"), -1)
     assert sharding.gather_summary(torch.tensor([1, 2, 3])).tolist() == [1, 2, 3]
+    assert sharding.gather_conflict(torch.tensor([(3 << 32) | 1, 0, 2, 3, 4], dtype=torch.int64)) == (0, 2, 3, 4)
+    assert sharding.gather_conflict(torch.tensor([-1, -1, -1, -1, 0], dtype=torch.int64)) is None
