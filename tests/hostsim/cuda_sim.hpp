@@ -156,10 +156,19 @@ inline void run_block(Block& B) {
         f.ctx.uc_link = &B.main;
         makecontext(&f.ctx, (void (*)())trampoline, 0);
     }
+    // CCK_HOSTSIM_SCHED=reverse | random[:seed]: the order in which runnable threads are resumed between rendez-vous points.
+    // A kernel whose results depend on it has a race (a missing __syncthreads / __syncwarp, an unordered shared-memory update).
+    static const int sched = [] { const char* e = std::getenv("CCK_HOSTSIM_SCHED"); return !e ? 0 : (e[0] == 'r' && e[1] == 'e') ? 1 : (e[0] == 'r' && e[1] == 'a') ? 2 : 0; }();
+    static uint64_t rng = [] { const char* e = std::getenv("CCK_HOSTSIM_SCHED"); const char* c = e ? std::strchr(e, ':') : nullptr; return c ? std::strtoull(c + 1, nullptr, 10) * 2 + 1 : 0x9E3779B97F4A7C15ull; }();
+    std::vector<int> order(n);
+    for (int i = 0; i < n; ++i) order[i] = sched == 1 ? n - 1 - i : i;
     for (;;) {
         bool any = false;
         const long p0 = B.progress;
-        for (int i = 0; i < n; ++i) {
+        if (sched == 2)
+            for (int i = n - 1; i > 0; --i) { rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17; std::swap(order[i], order[(int)(rng % (uint64_t)(i + 1))]); }
+        for (int oi = 0; oi < n; ++oi) {
+            const int i = order[oi];
             if (B.fibers[i].done) continue;
             any = true;
             g_cur = &B.fibers[i];
