@@ -355,6 +355,28 @@ __device__ __forceinline__ double adaptive_c(const SvcDev& sp, const unsigned ch
 
 // ChiSquaredBoundarySVC: decagon of circumradius lambda_max*sc + r_robot vs every inflated
 // rectangle, separating-axis test (touching = not disjoint).
+// The separating-axis test of decagon (px, py: 10 vertices + the closing one) vs rectangle, written exactly as the oracle's
+// convex_disjoint: running minima / maxima that start at +-inf and are replaced only when a comparison is TRUE, so NaN
+// projections are never taken.  A decagon with NaN vertices (NaN / inf covariance) is therefore "separated" from every
+// rectangle - the state is valid - whereas fmin / fmax of the fast path below would carry the NaN into comparisons that are
+// all false (found by tests/hostsim/fuzz_rollout.py --generic).  Used for non-finite or huge operands only.
+__device__ __noinline__ bool chisq_disjoint_literal(const double* px, const double* py, double xlo, double ylo, double xhi, double yhi) {
+    const double rx[5] = {xlo, xhi, xhi, xlo, xlo}, ry[5] = {ylo, ylo, yhi, yhi, ylo};
+    for (int pass = 0; pass < 2; ++pass) {
+        const double* ex = pass ? rx : px; const double* ey = pass ? ry : py;
+        const int ne = pass ? 4 : 10;
+        for (int i = 0; i < ne; ++i) {
+            const double nx = ey[i + 1] - ey[i], ny = ex[i] - ex[i + 1];
+            if (nx == 0 && ny == 0) continue;
+            double amin = HUGE_VAL, amax = -HUGE_VAL, bmin = HUGE_VAL, bmax = -HUGE_VAL;
+            for (int j = 0; j < 11; ++j) { const double d = nx * px[j] + ny * py[j]; amin = d < amin ? d : amin; amax = amax < d ? d : amax; }
+            for (int j = 0; j < 5; ++j) { const double d = nx * rx[j] + ny * ry[j]; bmin = d < bmin ? d : bmin; bmax = bmax < d ? d : bmax; }
+            if (amax < bmin || bmax < amin) return true;
+        }
+    }
+    return false;
+}
+
 __device__ __forceinline__ bool chisq_check(const SvcDev& sp, const unsigned char* tab, double x, double y, double P0,
                                             double P1, double P2, double P3) {
     const TabHeader* h = reinterpret_cast<const TabHeader*>(tab);
@@ -365,6 +387,13 @@ __device__ __forceinline__ bool chisq_check(const SvcDev& sp, const unsigned cha
 #pragma unroll
     for (int i = 0; i < 10; ++i) { px[i] = x + boundary * sp.dec_cos[i]; py[i] = y + boundary * sp.dec_sin[i]; }
     px[10] = px[0]; py[10] = py[0];
+    if (!(fabs(x) < 1e150 && fabs(y) < 1e150 && fabs(boundary) < 1e150)) {     // NaN compares false: the literal test decides
+        for (int o = 0; o < h->M; ++o) {
+            const double4 r = rc[o];
+            if (!chisq_disjoint_literal(px, py, r.x, r.y, r.z, r.w)) return false;
+        }
+        return true;
+    }
     double dxmin = px[0], dxmax = px[0], dymin = py[0], dymax = py[0];
 #pragma unroll
     for (int i = 1; i < 10; ++i) {

@@ -603,8 +603,10 @@ __host__ __device__ __forceinline__ bool chisq_pair_disjoint(double mxa, double 
         for (int e = 0; e < 10 && !sep; ++e) {
             const double nx = ey[e + 1] - ey[e], ny = ex[e] - ex[e + 1];
             if (nx == 0 && ny == 0) continue;
-            double amin = nx * ax[0] + ny * ay[0], amax = amin, bmin = nx * bx[0] + ny * by[0], bmax = bmin;
-            for (int j = 1; j < 10; ++j) {
+            // running extrema start at +-inf and move only on a TRUE comparison (the oracle's std::min / std::max): NaN projections
+            // are never taken, so a decagon with NaN vertices is "separated" from everything
+            double amin = HUGE_VAL, amax = -HUGE_VAL, bmin = HUGE_VAL, bmax = -HUGE_VAL;
+            for (int j = 0; j < 10; ++j) {
                 const double da = nx * ax[j] + ny * ay[j], db = nx * bx[j] + ny * by[j];
                 amin = da < amin ? da : amin; amax = amax < da ? da : amax; bmin = db < bmin ? db : bmin; bmax = bmax < db ? db : bmax;
             }

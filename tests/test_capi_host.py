@@ -128,7 +128,13 @@ def test_kernel_decagon_pair_test_on_the_host_matches_the_oracle(K, O):
     ang[k] = rng.integers(0, 10, len(k)) * (2 * np.pi / 10)
     d[k] = (ra + rb)[k] * (1 + rng.uniform(-3e-15, 3e-15, len(k)))
     mu_b = np.ascontiguousarray(mu_a + np.stack([d * np.cos(ang), d * np.sin(ang)], axis=1))
-    ref = O.chisq_pairs_disjoint(mu_a, cov[0], rad[0], mu_b, cov[1], rad[1], sc)
+    # degenerate covariances (NaN / inf / hugely negative entries): non-finite decagons; the oracle's separating-axis test never
+    # takes a NaN projection, the kernel's must not either
+    bad = np.arange(5, n, 7)
+    for j, i in enumerate(bad):
+        cov[j % 2][i, j % 4] = [np.nan, np.inf, -np.inf, -1e300, 1e300][j % 5]
+    with np.errstate(all="ignore"):
+        ref = O.chisq_pairs_disjoint(mu_a, cov[0], rad[0], mu_b, cov[1], rad[1], sc)
     L_ = K.lib()
     got = np.array([L_.cck_host_chisq_pair_disjoint(mu_a[i].ctypes.data, cov[0][i].ctypes.data, float(rad[0][i]), mu_b[i].ctypes.data, cov[1][i].ctypes.data,
                                                      float(rad[1][i]), float(sc)) for i in range(n)], dtype=bool)
