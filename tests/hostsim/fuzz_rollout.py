@@ -51,6 +51,8 @@ def main():
                     "kinds on random ragged plans with degenerate states mixed in")
     ap.add_argument("--tree", action="store_true", help="fuzz the belief-space distance, selectNode and nearest-witness queries instead "
                     "(non-symmetric, near-singular, negative-definite and non-finite covariances mixed in)")
+    ap.add_argument("--expand", action="store_true", help="fuzz cck_expand_batch instead: rollout + constraint check on the new segment + cost + "
+                    "goal test in one launch, both models, constraints of the exact plan-checker kinds, with and without the covariance table")
     a = ap.parse_args()
     if os.environ.get("CCK_HOSTSIM", "") == "1" and not os.environ.get("CCK_SO"):
         sys.path.insert(0, HERE)
@@ -67,6 +69,8 @@ def main():
         return fuzz_pvc(a, K, O, ctx, t_end)
     if a.tree:
         return fuzz_tree(a, K, O, ctx, t_end)
+    if a.expand:
+        return fuzz_expand(a, K, O, ctx, t_end)
     case = 0
     total_beliefs = total_steps = died = 0
     while (a.cases and case < a.cases) or (not a.cases and time.time() < t_end):
@@ -157,6 +161,109 @@ def main():
             print(f"{case} cases, {total_beliefs} beliefs, {total_steps} valid belief-steps, {died} rollouts ended early: all bit-identical", flush=True)
     print(f"fuzz ok: {case} cases, {total_beliefs} beliefs, {total_steps} valid belief-steps, {died} rollouts ended early, 0 mismatches "
           f"(seed {a.seed}, library {K.capi._SO})")
+    ctx.close()
+
+
+def fuzz_expand(a, K, O, ctx, t_end):
+    from cck_b200 import workloads as W
+    sim = os.environ.get("CCK_HOSTSIM", "") == "1"
+    rad = K.rect_robot_bounding_radius()
+    kinds = [K.PVC_BLACKMORE, K.PVC_BOUNDINGBOX, K.PVC_CHISQUARED, K.PVC_BLACKMORE2] + ([K.PVC_CDFGRID] if sim else [])
+    okind = {K.PVC_BLACKMORE: O.PVC_BLACKMORE, K.PVC_BOUNDINGBOX: O.PVC_BOUNDINGBOX, K.PVC_CHISQUARED: O.PVC_CHISQUARED,
+             K.PVC_BLACKMORE2: O.PVC_BLACKMORE2, K.PVC_CDFGRID: O.PVC_CDFGRID}
+    case = cands = 0
+    while (a.cases and case < a.cases) or (not a.cases and time.time() < t_end):
+        seed = a.seed * 1000003 + case
+        rng = np.random.default_rng(seed)
+        model = "linear" if case % 2 == 0 else "unicycle"
+        dim = 2 if model == "linear" else 4
+        if dim == 4 and not sim:      # device sincos: needs the band logic of the GPU tests, not a bit-exact fuzz
+            case += 1
+            continue
+        k = int(rng.choice([2, 3, 5]))
+        M = int(rng.choice([0, 7, 40]))
+        cells = rng.choice(20 * 20, size=M, replace=False)
+        centres = np.stack([cells % 20, cells // 20], axis=1).astype(np.float64)
+        wld = O.World.synthetic(centres, 20.0, 20.0, k, float(rng.choice([0.8, 0.9, 0.99])))
+        svc = O.Svc(wld, O.SVC_BLACKMORE, dim)
+        kind = kinds[int(rng.integers(len(kinds)))]
+        grid_n = int(rng.choice([2, 3, 5]))
+        opvc = O.Pvc(wld, okind[kind], grid_n=grid_n) if kind == K.PVC_CDFGRID else O.Pvc(wld, okind[kind])
+        ctx.set_model(K.MODEL_LINEAR2D if dim == 2 else K.MODEL_UNICYCLE)
+        ctx.set_obstacles(K.SVC_BLACKMORE, svc.low, svc.high, svc.A, svc.B, svc.centres, svc.rects, erf_inv_result=svc.erf_inv_result)
+        K.install_pvc(ctx, kind, dim, [rad] * k, 0.9 if kind == K.PVC_CHISQUARED else wld.p_safe_agents, grid_n=grid_n)
+        n = 256
+        bel, ctrl = W.synthetic_beliefs(n, model, seed=seed % 100000)
+        bel[0] = rng.uniform(0, 19, n); bel[1] = rng.uniform(0, 19, n)
+        bel[0, ::2] = rng.uniform(8.0, 12.0, (n + 1) // 2); bel[1, ::2] = rng.uniform(8.0, 12.0, (n + 1) // 2)
+        bel[dim:] *= 10.0 ** rng.uniform(-3, -1)
+        if dim == 4:
+            ctrl[0] = rng.uniform(-1, 20, n); ctrl[1] = rng.uniform(-1, 20, n)
+        steps = rng.integers(0, 11, size=n).astype(np.int32)
+        pstep = rng.integers(0, 30, size=n).astype(np.int32)
+        pcost = rng.uniform(0, 5, n)
+        cons = []
+        for other in range(1, k):
+            ob = O.default_beliefs(1, dim)[0]
+            ob[:2] = rng.uniform(8.5, 11.5, 2)
+            if dim == 4:
+                ob[3] = 0.1
+            ob[dim:] *= 10.0 ** rng.uniform(-1, 0.5)
+            st = sorted(set(int(x) for x in rng.integers(0, 40, 12)))
+            cons.append((other, st, np.repeat(ob[None, :], len(st), axis=0)))
+        ctx.set_constraints(*K.constraint_entries(k, dim, 0, cons))
+        goal = (float(rng.uniform(5, 15)), float(rng.uniform(5, 15)))
+        # half of the cases with the covariance table of a tree rooted at the default start covariance: candidates whose
+        # parent covariance is the tree's get it (same bits), all others are computed
+        use_tab = case % 4 >= 2
+        if use_tab:
+            cur = K.aos_to_soa(O.default_beliefs(1, dim))
+            if dim == 4:
+                cur[3] = 0.1
+            zero_u = np.zeros((dim, 1))
+            covs = [cur[dim:, 0].copy()]
+            for _ in range(45):
+                cur = ctx.propagate(cur, zero_u)
+                covs.append(cur[dim:, 0].copy())
+            for i in range(0, n, 2):
+                bel[dim:, i] = covs[pstep[i]]
+            ctx.set_cov_table(covs[0], 44)
+        else:
+            ctx.set_cov_table(None, 0)
+        aos_b, aos_c = K.soa_to_aos(bel), K.soa_to_aos(ctrl)
+        with np.errstate(all="ignore"):
+            out, valid, cost, gd, fl = ctx.expand_batch(bel, ctrl, steps, pstep, pcost, goal)
+            ref_out, ref_valid, _, traj = svc.rollout(aos_b, aos_c, steps, traj_stride=10)
+            g_ok, g_d = O.goal(ref_out, dim, goal[0], goal[1])
+        ref_cost = pcost + np.sqrt(((aos_b[:, :dim] - ref_out[:, :dim]) ** 2).sum(axis=1))
+        ref_c = np.ones(n, bool)
+        for i in range(n):
+            v = int(ref_valid[i])
+            if v:
+                far = traj[i, :1].copy(); far[0, :2] = [-500.0, -500.0]
+                path = np.concatenate([np.repeat(far, int(pstep[i]) + 1, axis=0), traj[i, :v]])
+                ref_c[i] = opvc.satisfies_constraints(path, dim, 0, cons)
+        problems = []
+        if not np.array_equal(valid, ref_valid): problems.append(("valid_steps", np.flatnonzero(valid != ref_valid)))
+        if not np.array_equal(K.soa_to_aos(out), ref_out, equal_nan=True): problems.append(("finals", np.flatnonzero((K.soa_to_aos(out) != ref_out).any(axis=1))))
+        if not np.allclose(cost, ref_cost, rtol=1e-15, atol=0): problems.append(("cost", np.flatnonzero(cost != ref_cost)))
+        if not np.array_equal(gd, g_d): problems.append(("goal_dist", np.flatnonzero(gd != g_d)))
+        if not np.array_equal((fl & K.FLAG_GOAL) != 0, g_ok): problems.append(("goal flag", np.flatnonzero(((fl & K.FLAG_GOAL) != 0) != g_ok)))
+        if not np.array_equal((fl & K.FLAG_FULL) != 0, ref_valid == steps): problems.append(("full flag", np.flatnonzero(((fl & K.FLAG_FULL) != 0) != (ref_valid == steps))))
+        if not np.array_equal((fl & K.FLAG_CONS_OK) != 0, ref_c): problems.append(("constraint flag", np.flatnonzero(((fl & K.FLAG_CONS_OK) != 0) != ref_c)))
+        if use_tab:
+            want_tab = (np.arange(n) % 2 == 0) & (steps > 0) & (pstep + steps <= 44)
+            if not np.array_equal((fl & K.FLAG_COV_TABLE) != 0, want_tab): problems.append(("cov-table flag", np.flatnonzero(((fl & K.FLAG_COV_TABLE) != 0) != want_tab)))
+        if problems:
+            print(f"MISMATCH expand case {case} seed {seed} {model} pvc kind {kind} grid_n {grid_n} k {k} M {M} table {use_tab}: "
+                  + "; ".join(f"{name} at {idx[:5]}" for name, idx in problems))
+            sys.exit(1)
+        cands += n
+        case += 1
+        if case % 20 == 0:
+            print(f"{case} cases, {cands} candidates: all identical", flush=True)
+    print(f"fuzz ok (batched expansion): {case} cases, {cands} candidates, 0 mismatches (seed {a.seed}, library {K.capi._SO})")
+    ctx.set_cov_table(None, 0)
     ctx.close()
 
 
