@@ -53,6 +53,8 @@ def main():
                     "(non-symmetric, near-singular, negative-definite and non-finite covariances mixed in)")
     ap.add_argument("--expand", action="store_true", help="fuzz cck_expand_batch instead: rollout + constraint check on the new segment + cost + "
                     "goal test in one launch, both models, constraints of the exact plan-checker kinds, with and without the covariance table")
+    ap.add_argument("--witness", action="store_true", help="fuzz cck_tree_witness_batch instead: the witness rules of one launch (nearest "
+                    "existing witness, which survivors become witnesses, nearest same-launch witness) against a sequential replay")
     a = ap.parse_args()
     if os.environ.get("CCK_HOSTSIM", "") == "1" and not os.environ.get("CCK_SO"):
         sys.path.insert(0, HERE)
@@ -71,6 +73,8 @@ def main():
         return fuzz_tree(a, K, O, ctx, t_end)
     if a.expand:
         return fuzz_expand(a, K, O, ctx, t_end)
+    if a.witness:
+        return fuzz_witness(a, K, O, ctx, t_end)
     case = 0
     total_beliefs = total_steps = died = 0
     while (a.cases and case < a.cases) or (not a.cases and time.time() < t_end):
@@ -160,6 +164,77 @@ def main():
         if case % 20 == 0:
             print(f"{case} cases, {total_beliefs} beliefs, {total_steps} valid belief-steps, {died} rollouts ended early: all bit-identical", flush=True)
     print(f"fuzz ok: {case} cases, {total_beliefs} beliefs, {total_steps} valid belief-steps, {died} rollouts ended early, 0 mismatches "
+          f"(seed {a.seed}, library {K.capi._SO})")
+    ctx.close()
+
+
+def fuzz_witness(a, K, O, ctx, t_end):
+    def beliefs(rng, n, dim, spread):
+        b = np.zeros((n, K.width(dim)))
+        b[:, :dim] = rng.uniform(0, spread, (n, dim))
+        for off in (dim, dim + dim * dim):
+            L = np.zeros((n, dim, dim))
+            idx = np.tril_indices(dim)
+            L[:, idx[0], idx[1]] = rng.uniform(0.05, 0.3, (n, len(idx[0])))
+            b[:, off:off + dim * dim] = np.einsum("nij,nkj->nik", L, L).reshape(n, dim * dim)
+        return b
+
+    case = surv = new = adopt = 0
+    while (a.cases and case < a.cases) or (not a.cases and time.time() < t_end):
+        seed = a.seed * 1000003 + case
+        rng = np.random.default_rng(seed)
+        dim = int(rng.choice([2, 4]))
+        spread = float(rng.choice([3.0, 10.0, 25.0]))
+        pr = float(rng.choice([0.1, 0.5, 2.0]))
+        nw = int(rng.choice([0, 1, 60, 400]))
+        n = int(rng.choice([1, 33, 200, 700, 1024]))       # CCK_WIT_MAX = 1024 survivors per call
+        wit = beliefs(rng, max(nw, 1), dim, spread)[:nw]
+        b = beliefs(rng, n, dim, spread)
+        if n > 50:
+            b[10:30] = b[9]                                                       # identical survivors
+            b[30:50, :dim] = b[29, :dim] + rng.normal(0, 0.3 * pr, (20, dim))    # a cluster around the pruning radius
+        elig = (rng.random(n) < rng.uniform(0.2, 1.0)) if rng.uniform() < 0.5 else None
+        tree = K.Tree(ctx, dim)
+        if nw:
+            tree.append(K.aos_to_soa(wit), np.zeros(nw))
+        widx, wdist, near, ndist, fresh = tree.witness_batch(K.aos_to_soa(b), pr, elig)
+        if nw:
+            ridx, rdist = O.nearest_witness(wit, b, dim)
+        else:
+            ridx, rdist = np.full(n, -1, dtype=np.int32), np.full(n, np.inf)
+        ok = np.array_equal(widx, ridx) and np.array_equal(wdist, rdist)
+        created, why = [], ""
+        for s_ in range(n):
+            if not ok:
+                why = "nearest existing witness"
+                break
+            cd, best = rdist[s_], -1
+            if created:
+                d = O.belief_distance(b[created], np.repeat(b[s_:s_ + 1], len(created), axis=0), dim)
+                for f, df in zip(created, d):
+                    if df < cd:
+                        cd, best = df, f
+            keeps = (cd > pr) and (elig is None or bool(elig[s_]))
+            if bool(fresh[s_]) != keeps:
+                ok, why = False, f"fresh[{s_}] got {bool(fresh[s_])} want {keeps}"
+            elif best >= 0 and cd <= pr:
+                if not (near[s_] == best and ndist[s_] == cd):
+                    ok, why = False, f"near[{s_}] got {near[s_]} ({ndist[s_]}) want {best} ({cd})"
+                adopt += 1
+            elif near[s_] != -1:
+                ok, why = False, f"near[{s_}] got {near[s_]} want -1"
+            if keeps:
+                created.append(s_)
+        tree.close()
+        if not ok:
+            print(f"MISMATCH witness case {case} seed {seed} dim {dim} existing {nw} survivors {n} radius {pr} eligibility {elig is not None}: {why}")
+            sys.exit(1)
+        surv += n
+        new += len(created)
+        case += 1
+        if case % 50 == 0:
+            print(f"{case} cases, {surv} survivors, {new} new witnesses, {adopt} same-launch adoptions: all identical", flush=True)
+    print(f"fuzz ok (witness batch): {case} cases, {surv} survivors, {new} new witnesses, {adopt} same-launch adoptions, 0 mismatches "
           f"(seed {a.seed}, library {K.capi._SO})")
     ctx.close()
 
