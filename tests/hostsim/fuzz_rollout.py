@@ -148,6 +148,16 @@ def main():
             ref_out, ref_valid, _ = svc.rollout(aos, ctrl, steps, nthreads=8)
         got = K.soa_to_aos(out)
         same = np.array_equal(v_got, v_ref) and np.array_equal(valid, ref_valid) and np.array_equal(got, ref_out, equal_nan=True)
+        if same and case % 4 == 0:      # trajectory mode (TRAJ kernels): every valid intermediate state, same rollout
+            with np.errstate(all="ignore"):
+                out2, valid2, tr = ctx.propagate_while_valid(bel, ctl, steps, traj_T=50)
+                _, _, _, rtr = svc.rollout(aos, ctrl, steps, traj_stride=50)
+            same = np.array_equal(valid2, ref_valid) and np.array_equal(K.soa_to_aos(out2), ref_out, equal_nan=True)
+            tr = tr.transpose(2, 0, 1)                                   # [n, T, W]
+            mask = np.arange(50)[None, :] < ref_valid[:, None]           # only the valid steps are defined
+            same = same and np.array_equal(tr[mask], rtr[mask], equal_nan=True)
+            if not same:
+                print(f"MISMATCH (trajectory mode) case {case} seed {seed}")
         if not same:
             b1 = np.flatnonzero(v_got != v_ref)
             b2 = np.flatnonzero(valid != ref_valid)

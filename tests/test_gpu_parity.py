@@ -232,3 +232,57 @@ def test_summary_and_winner_records(K, W, ctx):
     ctx.synchronize()
     helpers.torch_sync()
     assert rec.tolist() == [float("inf"), -1.0]
+
+
+@pytest.mark.parametrize("model", ["linear", "unicycle"])
+def test_leading_dimensions_are_honoured(K, O, W, ctx, model):
+    """Every batch argument of the C ABI carries its own leading dimension (plane f of item i at base[f*ld + i]); the planner
+    passes ld = capacity > n.  Strided calls must give the contiguous results bit for bit and must not touch the padding."""
+    P = K.capi._ptr
+    L = K.capi.lib()
+    dim = 2 if model == "linear" else 4
+    Wd = K.width(dim)
+    world, svc = oracle_synth(O, W, 102, "realistic", 0, dim, seed=5)
+    install_from_oracle_svc(K, ctx, svc, K.MODEL_LINEAR2D if dim == 2 else K.MODEL_UNICYCLE)
+    n, ld, ldc, ldo, ldt, T = 777, 1000, 901, 1203, 811, 12
+    bel, ctrl = W.synthetic_beliefs(n, model, seed=3)
+    bel[dim:] *= 0.05
+    steps = np.random.default_rng(1).integers(0, T + 1, n).astype(np.int32)
+    ref_p = ctx.propagate(bel, ctrl)
+    ref_v = ctx.is_valid(bel)
+    ref_out, ref_valid, ref_traj = ctx.propagate_while_valid(bel, ctrl, steps, traj_T=T)
+    sentinel = -7.25
+    b2 = np.full((Wd, ld), sentinel); b2[:, :n] = bel
+    c2 = np.full((dim, ldc), sentinel); c2[:, :n] = ctrl
+    o2 = np.full((Wd, ldo), sentinel)
+    assert L.cck_propagate(ctx.h, n, P(b2), ld, P(c2), ldc, 0.2, P(o2), ldo) == 0
+    assert np.array_equal(o2[:, :n], ref_p, equal_nan=True) and (o2[:, n:] == sentinel).all()
+    v2 = np.full(n + 5, 9, dtype=np.uint8)
+    assert L.cck_is_valid(ctx.h, n, P(b2), ld, P(v2)) == 0
+    assert np.array_equal(v2[:n].astype(bool), ref_v) and (v2[n:] == 9).all()
+    o3 = np.full((Wd, ldo), sentinel)
+    val = np.full(n + 3, -5, dtype=np.int32)
+    tr = np.full((T, Wd, ldt), sentinel)
+    assert L.cck_propagate_while_valid(ctx.h, n, P(b2), ld, P(c2), ldc, P(steps), P(o3), ldo, P(val), P(tr), ldt, T) == 0
+    assert np.array_equal(val[:n], ref_valid) and (val[n:] == -5).all()
+    assert np.array_equal(o3[:, :n], ref_out, equal_nan=True) and (o3[:, n:] == sentinel).all()
+    mask = (np.arange(T)[:, None] < ref_valid[None, :])                   # [T, n]: the valid steps of every belief
+    assert np.array_equal(tr[:, :, :n].transpose(0, 2, 1)[mask], ref_traj.transpose(0, 2, 1)[mask], equal_nan=True)
+    assert (tr[:, :, n:] == sentinel).all()
+    # batched expansion with strides
+    rad = K.rect_robot_bounding_radius()
+    K.install_pvc(ctx, K.PVC_BLACKMORE, dim, [rad, rad], world.p_safe_agents)
+    other = O.default_beliefs(1, dim)[0]; other[:2] = [30.0, 30.0]
+    ctx.set_constraints(*K.constraint_entries(2, dim, 0, [(1, list(range(3, 20)), np.repeat(other[None, :], 17, axis=0))]))
+    pstep = np.random.default_rng(2).integers(0, 10, n).astype(np.int32)
+    pcost = np.random.default_rng(3).uniform(0, 3, n)
+    st1 = np.maximum(steps, 1).astype(np.int32)
+    ref = ctx.expand_batch(bel, ctrl, st1, pstep, pcost, (30.0, 30.0))
+    g = K.capi.GoalParams(30.0, 30.0, 2.0, K.chi2_quantile_2dof(0.95))
+    o4 = np.full((Wd, ldo), sentinel)
+    val4, cost4, gd4, fl4 = np.zeros(n, dtype=np.int32), np.zeros(n), np.zeros(n), np.zeros(n, dtype=np.uint8)
+    import ctypes
+    assert L.cck_expand_batch(ctx.h, n, P(b2), ld, P(c2), ldc, P(st1), P(pstep), P(pcost), ctypes.byref(g), P(o4), ldo, P(val4), P(cost4), P(gd4), P(fl4)) == 0
+    assert np.array_equal(o4[:, :n], ref[0], equal_nan=True) and (o4[:, n:] == sentinel).all()
+    assert np.array_equal(val4, ref[1]) and np.array_equal(cost4, ref[2]) and np.array_equal(gd4, ref[3]) and np.array_equal(fl4, ref[4])
+    ctx.set_constraints([], [], np.zeros((0, 2)), np.zeros((0, 4)))
