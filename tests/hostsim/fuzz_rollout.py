@@ -520,7 +520,8 @@ def fuzz_generic(a, K, O, ctx, t_end):
     while (a.cases and case < a.cases) or (not a.cases and time.time() < t_end):
         seed = a.seed * 1000003 + case
         rng = np.random.default_rng(seed)
-        model, kind = [("unicycle", O.SVC_BLACKMORE), ("unicycle", O.SVC_CHISQUARED), ("linear", O.SVC_CHISQUARED)][case % 3]
+        model, kind = [("unicycle", O.SVC_BLACKMORE), ("unicycle", O.SVC_CHISQUARED), ("linear", O.SVC_CHISQUARED),
+                       ("linear", O.SVC_ADAPTIVE), ("unicycle", O.SVC_ADAPTIVE)][case % 5]
         dim = 2 if model == "linear" else 4
         world = int(rng.choice([8, 32, 64]))
         M = min(int(rng.choice([0, 7, 40, 102, 256])), world * world // 2)
@@ -546,7 +547,20 @@ def fuzz_generic(a, K, O, ctx, t_end):
             out, valid = ctx.propagate_while_valid(bel, ctl, steps)
             ref_out, ref_valid, _ = svc.rollout(aos, ctrl, steps, nthreads=8)
         got = K.soa_to_aos(out)
-        if sim or dim == 2:
+        if kind == O.SVC_ADAPTIVE:
+            # erf_inv at data-dependent arguments (Boost restatement in the oracle, erfinv in the kernels): a first-violation
+            # step may differ only where the deciding state is inside the +-1e-6 band; everything else bit-identical
+            import helpers
+            with np.errstate(all="ignore"):
+                try:
+                    agree = helpers.assert_rollout_mismatches_in_band(O, svc, aos, ctrl, valid, ref_valid)
+                    same = np.array_equal(got[agree], ref_out[agree], equal_nan=True) if (sim or dim == 2) else \
+                        np.allclose(got[agree], ref_out[agree], rtol=1e-9, atol=1e-12, equal_nan=True)
+                    same = same and agree.mean() > 0.995
+                except AssertionError as e:
+                    print("  ", e)
+                    same = False
+        elif sim or dim == 2:
             same = np.array_equal(valid, ref_valid) and np.array_equal(got, ref_out, equal_nan=True)
         else:
             agree = valid == ref_valid
