@@ -26,7 +26,17 @@
 //  * the common outcome of a step (bounds proven in fp32, covariance finite, window misses the grid, no obstacle without
 //    a box) leaves grid_check through ONE branch; the Kalman step skips the exact zeros of the reference's diagonal
 //    Q, R, A_cl (lin_step_diag) while the lane's covariance is known finite.  171 instructions per warp-step, 75 of
-//    them FP64 (profiles/r1o_*).
+//    them FP64 at the end of round 1 (profiles/r1o_*).
+// Round 2 (profiles/r2c_*):
+//  * a CLEARANCE FIELD is the first test of a step: 128 x 128 cells over the state bounds, per cell the quantised Chebyshev
+//    clearances to the nearest and second-nearest obstacle box (lower bounds) and the nearest box's row.  One fp32 compare
+//    proves the step against ALL obstacles, a second one leaves a single obstacle to decide; only then the cell window.
+//  * a WARP-UNIFORM fast section: while every lane has work and finite covariance, the warp runs min(steps left) steps of
+//    nothing but the Kalman step, the field lookup and that compare, with one vote per step; the first unproven step falls
+//    through to the general path.  120 executed instructions per warp-step, 69 of them FP64 (34 DMUL, 30 DADD, 5 DFMA);
+//    statically 124 / 69 (tools/sass_loop_mix.py, tests/test_sass_static.py).
+//  * the refill is warp-aggregated: a ballot counts the lanes that want work, ONE atomicAdd per warp hands out consecutive
+//    beliefs.
 #pragma once
 #include "cck_kernels.cuh"
 
@@ -294,9 +304,10 @@ __device__ __forceinline__ void cp_async_wait_all() {}
 
 // shared-memory carve-up (T = CCK_GRID_THREADS): [mbarrier 16 B][grid table][work counter 16 B][stash T x 80 B]
 //                         [prefetch slots: 13 planes x T doubles][2 planes x T ints]
-// Sweeps (EXPAND = false): 5 warps x 4 CTAs = 20 warps per SM at <= 96 registers (measured: +4 % on the realistic sweep
-// over 4 x 128 threads).  The expansion kernel carries the constraint and goal tests: 128 threads x 3 CTAs leaves it 168
-// registers (no spills); its launches are planner-sized and latency-bound.
+// Sweeps (EXPAND = false, profiles/r2c_so_sweep.txt): 4 warps x 4 CTAs at 122 registers is the shipped shape; 5 warps x 4 CTAs
+// needs a 96-register cap, under which the round-2 kernel spills (164.6 -> 143.6 G belief-steps/s).  The expansion kernel
+// carries the constraint and goal tests: 128 threads x 3 CTAs leaves it 170 registers (160 used, no spills); its launches
+// are planner-sized and latency-bound.
 #ifndef CCK_GRID_THREADS
 #define CCK_GRID_THREADS 128
 #endif

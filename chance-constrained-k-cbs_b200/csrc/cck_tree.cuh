@@ -14,7 +14,10 @@
 //   mean[DIM] | cov[DIM*DIM] | sqrtcov[DIM*DIM] | cost ; plus an `active` byte plane.
 // sqrtcov is filled once per item at append time.  One CTA scans all items for one query; lanes
 // reduce (key, index) pairs lexicographically so ties resolve to the lowest index, exactly like the
-// sequential scan.
+// sequential scan.  A NaN distance (a rank-deficient covariance whose product gets a slightly negative eigenvalue under
+// operatorSqrt, or non-finite inputs) has no defined answer: a sequential scan keeps its first item if THAT distance is
+// NaN and the reference's GNAT is undefined; distances themselves stay bit-identical to the oracle, NaN included
+// (tests/hostsim/fuzz_rollout.py --tree).
 #pragma once
 #include "cck_device.cuh"
 
