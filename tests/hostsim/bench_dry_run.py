@@ -21,6 +21,7 @@ import build as hostsim_build  # noqa: E402
 so = hostsim_build.build()
 os.environ["CCK_SO"] = so
 os.environ["CCK_HOSTSIM"] = "1"
+os.environ.setdefault("CCK_HOSTSIM_DEVICES", os.environ.get("WORLD_SIZE", "1"))
 os.environ["LD_LIBRARY_PATH"] = os.path.dirname(so) + ":" + os.environ.get("LD_LIBRARY_PATH", "")
 
 import torch  # noqa: E402
@@ -77,6 +78,12 @@ torch.cuda.stream = lambda s: contextlib.nullcontext()
 torch.cuda.get_device_name = lambda *a, **k: "hostsim"
 torch.cuda.device_count = lambda: 1
 torch.Tensor.pin_memory = lambda self, *a, **k: self
+# multi-rank dry run (python -m torch.distributed.run --nproc-per-node 2 tests/hostsim/bench_dry_run.py --gpus 2 ...): gloo
+# stands in for NCCL, the collectives and the rank logic of bench.py are the real ones
+import torch.distributed as _dist  # noqa: E402
+
+_init = _dist.init_process_group
+_dist.init_process_group = lambda backend=None, **k: _init("gloo", **{kk: v for kk, v in k.items() if kk != "device_id"})
 
 if len(sys.argv) == 1:
     sys.argv += ["--log2-beliefs", "11", "--steps", "2", "--warmup", "3"]

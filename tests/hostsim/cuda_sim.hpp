@@ -380,7 +380,11 @@ struct cudaDeviceProp {
 };
 inline const char* cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : (e == cudaErrorMemoryAllocation ? "out of memory" : "invalid value"); }
 inline cudaError_t cudaGetLastError() { return cudaSuccess; }
-inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
+inline cudaError_t cudaGetDeviceCount(int* n) {      // CCK_HOSTSIM_DEVICES: pretend to have several (multi-rank dry runs)
+    const char* e = std::getenv("CCK_HOSTSIM_DEVICES");
+    *n = e ? std::max(1, std::atoi(e)) : 1;
+    return cudaSuccess;
+}
 inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) {
     std::memset(p, 0, sizeof(*p));
