@@ -104,7 +104,7 @@ public:
     }
 private:
     int cx(double v) const { return (int)std::floor(v / cell_); }
-    static long long key(int a, int b) { return ((long long)a << 32) ^ (unsigned)b; }
+    static long long key(int a, int b) { return (long long)(((unsigned long long)(unsigned)a << 32) | (unsigned)b); }
     double cell_;
     int max_ring_ = 400;
     std::unordered_map<long long, std::vector<int>> cells_;
